@@ -1,0 +1,145 @@
+/*
+ * pcm_b200.h -- C ABI of libpcm_b200.so, the B200-native (sm_100a) replacement for the native
+ * layer of HaoyiZhu/PointCloudMatters' point-cloud behaviour-cloning training step.
+ *
+ * Conventions (all entry points):
+ *   - plain C, `extern "C"`, raw DEVICE pointers + sizes; no torch / ATen types;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream, which is what the reference launchers always use);
+ *   - the caller owns and allocates every buffer; nothing is allocated inside the library
+ *     (a few launchers keep a tiny per-process scratch, documented where they do);
+ *   - return value: 0 on success, a cudaError_t value (> 0) if the launch failed, or a
+ *     negative PCM_E* code for an argument the kernel cannot honour;
+ *   - `offset` / `new_offset` are int32 CUMULATIVE END indices per cloud (reference convention,
+ *     libs/pointops/functions/query.py:20-22), -1 marks padding in index outputs.
+ *
+ * Each prototype cites the reference interface it replaces (paths relative to the reference
+ * repository root).  The reference's own launchers are `extern "C" void ...(raw pointers)`
+ * declared in libs/pointops/src/<op>/<op>_cuda_kernel.h and exported to Python through the
+ * pybind11 module `pointops._C` (libs/pointops/src/pointops_api.cpp:15-32).
+ */
+#ifndef PCM_B200_H_
+#define PCM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCM_OK 0
+#define PCM_EINVAL (-1)      /* bad argument (null pointer, non-positive size, ...)            */
+#define PCM_EUNSUPPORTED (-2) /* size outside what the kernel supports (e.g. nsample > 128)     */
+
+typedef void *pcm_stream_t; /* cudaStream_t */
+
+/* Library / build identification. */
+int pcm_abi_version(void);
+const char *pcm_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * pointops family
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces farthest_point_sampling_cuda_launcher(int b, int n, const float *xyz,
+ * const int *offset, const int *new_offset, float *tmp, int *idx)
+ * (libs/pointops/src/sampling/sampling_cuda_kernel.h:13; kernel sampling_cuda_kernel.cu:14-129).
+ * `n` is the size of the largest cloud, exactly as the reference caller computes it
+ * (libs/pointops/functions/sampling.py:14-16): it selects the reference's thread-block size and
+ * therefore its tie-break rule, which this kernel reproduces bit-exactly.
+ * `tmp` (n_total floats pre-filled with 1e10, sampling.py:18) is only touched when n > 8192;
+ * it may be NULL otherwise (running minima live in registers). */
+int pcm_farthest_point_sampling(int b, int n, const float *xyz, const int *offset,
+                                const int *new_offset, float *tmp, int *idx, pcm_stream_t stream);
+
+/* Tuning hook (no reference counterpart): force the CTA width (128/256/512/1024, 0 = automatic)
+ * of the register-resident FPS kernel; used by bench / profiling sweeps. */
+int pcm_tune_fps_threads(int threads);
+
+/* Replaces knn_query_cuda_launcher(int m, int nsample, const float *xyz, const float *new_xyz,
+ * const int *offset, const int *new_offset, int *idx, float *dist2)
+ * (libs/pointops/src/knn_query/knn_query_cuda_kernel.h:13; kernel knn_query_cuda_kernel.cu:60-104).
+ * Adds `b` (number of clouds; the reference scans new_offset linearly instead).  Outputs are
+ * bit-identical to the reference including tie order (exact replay of its binary heap).
+ * dist2 receives SQUARED distances (the Python wrapper applies sqrt, query.py:23) and may be
+ * NULL.  nsample <= 128 (reference hard limit, knn_query_cuda_kernel.cu:82-83). */
+int pcm_knn_query(int b, int m, int nsample, const float *xyz, const float *new_xyz,
+                  const int *offset, const int *new_offset, int *idx, float *dist2,
+                  pcm_stream_t stream);
+
+/* Replaces ball_query_cuda_launcher(int m, int nsample, float min_radius, float max_radius,
+ * const float *xyz, const float *new_xyz, const int *offset, const int *new_offset, int *idx,
+ * float *dist2) (libs/pointops/src/ball_query/ball_query_cuda_kernel.h:17-21; kernel
+ * ball_query_cuda_kernel.cu:58-123).  Reproduces the reference's quirks (double-precision 1e-5
+ * test, heap_sort without heapify, index written into dist2 on the strided-subsample branch);
+ * stops collecting at 2048 candidates where the reference overflows its stack arrays. */
+int pcm_ball_query(int b, int m, int nsample, float min_radius, float max_radius,
+                   const float *xyz, const float *new_xyz, const int *offset,
+                   const int *new_offset, int *idx, float *dist2, pcm_stream_t stream);
+
+/* Replaces random_ball_query_cuda_launcher(int m, int nsample, float min_radius,
+ * float max_radius, const int *order, const float *xyz, const float *new_xyz, const int *offset,
+ * const int *new_offset, int *idx, float *dist2)
+ * (libs/pointops/src/random_ball_query/random_ball_query_cuda_kernel.h; kernel .cu:58-108). */
+int pcm_random_ball_query(int b, int m, int nsample, float min_radius, float max_radius,
+                          const int *order, const float *xyz, const float *new_xyz,
+                          const int *offset, const int *new_offset, int *idx, float *dist2,
+                          pcm_stream_t stream);
+
+/* Replace grouping_{forward,backward}_cuda_launcher
+ * (libs/pointops/src/grouping/grouping_cuda_kernel.cu:5-25, launchers :27-41).
+ * backward ACCUMULATES into grad_input (caller zero-fills, functions/grouping.py:30). */
+int pcm_grouping_forward(int m, int nsample, int c, const float *input, const int *idx,
+                         float *output, pcm_stream_t stream);
+int pcm_grouping_backward(int m, int nsample, int c, const float *grad_output, const int *idx,
+                          float *grad_input, pcm_stream_t stream);
+
+/* Replace interpolation_{forward,backward}_cuda_launcher
+ * (libs/pointops/src/interpolation/interpolation_cuda_kernel.cu:5-33).  forward ACCUMULATES into
+ * output (caller zero-fills, functions/interpolation.py:39). */
+int pcm_interpolation_forward(int n, int c, int k, const float *input, const int *idx,
+                              const float *weight, float *output, pcm_stream_t stream);
+int pcm_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx,
+                               const float *weight, float *grad_input, pcm_stream_t stream);
+
+/* Replace aggregation_{forward,backward}_cuda_launcher
+ * (libs/pointops/src/aggregation/aggregation_cuda_kernel.cu:5-39). */
+int pcm_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,
+                            const float *position, const float *weight, const int *idx,
+                            float *output, pcm_stream_t stream);
+int pcm_aggregation_backward(int n, int nsample, int c, int w_c, const float *input,
+                             const float *position, const float *weight, const int *idx,
+                             const float *grad_output, float *grad_input, float *grad_position,
+                             float *grad_weight, pcm_stream_t stream);
+
+/* Replace subtraction_{forward,backward}_cuda_launcher
+ * (libs/pointops/src/subtraction/subtraction_cuda_kernel.cu:5-30). */
+int pcm_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2,
+                            const int *idx, float *output, pcm_stream_t stream);
+int pcm_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output,
+                             float *grad_input1, float *grad_input2, pcm_stream_t stream);
+
+/* Replace attention_{relation,fusion}_step_{forward,backward}_cuda_launcher
+ * (libs/pointops/src/attention/attention_cuda_kernel.cu:9-86, launchers :93-147). */
+int pcm_attention_relation_step_forward(int m, int g, int c, const float *query, const float *key,
+                                        const float *weight, const int *index_target,
+                                        const int *index_refer, float *output,
+                                        pcm_stream_t stream);
+int pcm_attention_relation_step_backward(int m, int g, int c, const float *query,
+                                         float *grad_query, const float *key, float *grad_key,
+                                         const float *weight, float *grad_weight,
+                                         const int *index_target, const int *index_refer,
+                                         const float *grad_output, pcm_stream_t stream);
+int pcm_attention_fusion_step_forward(int m, int g, int c, const float *weight, const float *value,
+                                      const int *index_target, const int *index_refer,
+                                      float *output, pcm_stream_t stream);
+int pcm_attention_fusion_step_backward(int m, int g, int c, const float *weight,
+                                       float *grad_weight, const float *value, float *grad_value,
+                                       const int *index_target, const int *index_refer,
+                                       const float *grad_output, pcm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCM_B200_H_ */

@@ -1,0 +1,36 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libpcm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/pcm_b200.h"
+
+#define PCM_API extern "C" __attribute__((visibility("default")))
+
+#define PCM_FULL_MASK 0xffffffffu
+
+static inline int pcm_launch_status() { return (int)cudaPeekAtLastError(); }
+static inline cudaStream_t pcm_cu_stream(pcm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int pcm_divup(long a, long b) { return (int)((a + b - 1) / b); }
+
+// Reference block-size rule (libs/pointops/src/cuda_utils.h:11-14): largest power of two
+// <= work_size, capped at 1024.  Host-side, same libm expression as the reference launcher.
+int pcm_ref_opt_n_threads(int work_size);
+
+// Squared distance with the reference's FMA contraction (verified in its sm_100a SASS):
+// d = fma(dz,dz, fma(dy,dy, dx*dx)).  Written with explicit intrinsics so that neither -fmad
+// nor instruction scheduling can change the rounding.
+__device__ __forceinline__ float pcm_dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// cloud id of element `i` given cumulative end offsets (first c with i < offset[c]);
+// equals the reference's linear get_bt_idx (knn_query_cuda_kernel.cu:45-56) for i < offset[b-1].
+__device__ __forceinline__ int pcm_cloud_of(int i, const int* __restrict__ offset, int b) {
+    int lo = 0, hi = b - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (i < __ldg(offset + mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}

@@ -1,0 +1,320 @@
+"""GPU parity tests of the sm_100a pointops kernels, called through the drop-in `pointops`
+package (=> through the C ABI of libpcm_b200.so):
+  * bit-exact index outputs against the CPU oracle on seeded inputs incl. tie-heavy sets;
+  * bit-exact against the UNMODIFIED reference kernels (oracle/_ref/libpointops_ref.so);
+  * size-independent properties at BASELINE.json's full sizes (cfg-2 / cfg-4).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointops_oracle as O
+from tests import _ref
+from tests._data import CASES, clouds
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    from pointcloudmatters_b200 import pointops
+
+    return pointops
+
+
+def _dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fps_bit_exact_vs_oracle(P, case):
+    b, n, m, kind, ragged = case
+    xyz, off, noff = clouds(b, n, m, seed=21, kind=kind, ragged=ragged)
+    want = O.farthest_point_sampling(xyz, off, noff)
+    t_xyz, t_off, t_noff = _dev(xyz, off, noff)
+    got = P.farthest_point_sampling(t_xyz, t_off, t_noff)
+    assert got.dtype == torch.int32
+    assert np.array_equal(got.cpu().numpy(), want)
+    # sync-free form used by the training step
+    n_max = int(np.diff(np.concatenate([[0], off])).max())
+    got2 = P.farthest_point_sampling(t_xyz, t_off, t_noff, n_max=n_max, m_total=int(noff[-1]))
+    assert np.array_equal(got2.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("threads", [128, 256, 512, 1024])
+def test_fps_every_cta_width_is_exact(P, threads):
+    from pointcloudmatters_b200._lib import lib
+
+    xyz, off, noff = clouds(3, 1000, 400, seed=5, kind="lattice", ragged=True)
+    want = O.farthest_point_sampling(xyz, off, noff)
+    t_xyz, t_off, t_noff = _dev(xyz, off, noff)
+    assert lib.pcm_tune_fps_threads(threads) == 0
+    try:
+        got = P.farthest_point_sampling(t_xyz, t_off, t_noff)
+    finally:
+        lib.pcm_tune_fps_threads(0)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_large_cloud_generic_kernel(P):
+    xyz, off, noff = clouds(2, 12000, 600, seed=8)
+    want = O.farthest_point_sampling(xyz, off, noff)
+    got = P.farthest_point_sampling(*_dev(xyz, off, noff))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_more_samples_than_points(P):
+    xyz, off, _ = clouds(2, 20, None, seed=1)
+    noff = np.array([30, 60], dtype=np.int32)
+    want = O.farthest_point_sampling(xyz, off, noff)
+    got = P.farthest_point_sampling(*_dev(xyz, off, noff))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("k", [1, 3, 16, 33])
+def test_knn_bit_exact_vs_oracle(P, case, k):
+    b, n, m, kind, ragged = case
+    xyz, off, noff = clouds(b, n, m, seed=22, kind=kind, ragged=ragged)
+    q = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    wi, wd = O.knn_query(k, xyz, off, q, noff)
+    t_xyz, t_off, t_q, t_noff = _dev(xyz, off, q, noff)
+    gi, gd = P.knn_query(k, t_xyz, t_off, t_q, t_noff)
+    assert gi.dtype == torch.int32 and gd.dtype == torch.float32
+    assert np.array_equal(gi.cpu().numpy(), wi)
+    assert np.array_equal(gd.cpu().numpy(), wd)
+
+
+def test_knn_self_query_and_k128(P):
+    xyz, off, _ = clouds(2, 300, None, seed=3, ragged=True)
+    wi, wd = O.knn_query(128, xyz, off)
+    gi, gd = P.knn_query(128, *_dev(xyz, off))
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gd.cpu().numpy(), wd)
+    with pytest.raises(Exception):
+        P.knn_query(129, *_dev(xyz, off))
+
+
+@pytest.mark.parametrize("kind,rmax,rmin,ns", [("uniform", 0.12, 0.0, 16), ("uniform", 0.3, 0.05, 8),
+                                                ("lattice", 0.3, 0.0, 8), ("dup", 0.1, 0.0, 12),
+                                                ("uniform", 2.0, 0.0, 16)])
+def test_ball_query_bit_exact_vs_oracle(P, kind, rmax, rmin, ns):
+    xyz, off, noff = clouds(3, 900, 200, seed=23, kind=kind, ragged=True)
+    q = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    wi, wd = O.ball_query(ns, rmax, rmin, xyz, off, q, noff)
+    t_xyz, t_off, t_q, t_noff = _dev(xyz, off, q, noff)
+    gi, gd = P.ball_query(ns, rmax, rmin, t_xyz, t_off, t_q, t_noff)
+    assert np.array_equal(gi.cpu().numpy(), wi)
+    assert np.array_equal(gd.cpu().numpy(), wd)
+
+
+def test_ball_query_candidate_cap(P):
+    # > 2048 candidates per query: reference overflows its stack arrays (UB); both the oracle and
+    # the kernel stop collecting at 2048.
+    xyz, off, noff = clouds(1, 3000, 64, seed=2)
+    q = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    wi, wd = O.ball_query(16, 5.0, 0.0, xyz, off, q, noff)
+    gi, gd = P.ball_query(16, 5.0, 0.0, *_dev(xyz, off, q, noff))
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gd.cpu().numpy(), wd)
+
+
+def test_random_ball_query_bit_exact_vs_oracle(P):
+    xyz, off, noff = clouds(3, 500, 100, seed=24, ragged=True)
+    q = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    rng = np.random.default_rng(0)
+    starts = np.concatenate([[0], off[:-1]])
+    order = np.concatenate([s + rng.permutation(e - s) for s, e in zip(starts, off)]).astype(np.int32)
+    wi, wd = O.random_ball_query(10, 0.2, 0.0, xyz, off, q, noff, order)
+    t_xyz, t_off, t_q, t_noff, t_order = _dev(xyz, off, q, noff, order)
+    gi, gd = P.random_ball_query(10, 0.2, 0.0, t_xyz, t_off, t_q, t_noff, order=t_order)
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gd.cpu().numpy(), wd)
+    # without an injected order: every index is a genuine hit inside its own cloud
+    gi2, gd2 = P.random_ball_query(10, 0.2, 0.0, t_xyz, t_off, t_q, t_noff)
+    gi2, gd2 = gi2.cpu().numpy(), gd2.cpu().numpy()
+    valid = gi2 >= 0
+    assert (gd2[valid] < 0.2).all() and (gd2[~valid] == np.sqrt(np.float32(1e10))).all()
+
+
+def test_gather_scatter_ops_vs_oracle(P):
+    rng = np.random.default_rng(6)
+    n, m, ns, c = 300, 120, 9, 37
+    inp = rng.standard_normal((n, c)).astype(np.float32)
+    idx = rng.integers(0, n, (m, ns)).astype(np.int32)
+    t_inp, t_idx = _dev(inp, idx)
+    t_inp.requires_grad_(True)
+    out = P.grouping2(t_inp, t_idx)
+    assert np.array_equal(out.detach().cpu().numpy(), O.grouping_forward(inp, idx))
+    go = rng.standard_normal((m, ns, c)).astype(np.float32)
+    out.backward(torch.from_numpy(go).cuda())
+    np.testing.assert_allclose(t_inp.grad.cpu().numpy(), O.grouping_backward(go, idx, n), rtol=1e-5, atol=1e-5)
+
+    # subtraction
+    i1 = rng.standard_normal((n, c)).astype(np.float32)
+    idx2 = rng.integers(0, n, (n, ns)).astype(np.int32)
+    a, bb, ti = _dev(i1, inp, idx2)
+    a.requires_grad_(True); bb.requires_grad_(True)
+    s = P.subtraction(a, bb, ti)
+    assert np.array_equal(s.detach().cpu().numpy(), O.subtraction_forward(i1, inp, idx2))
+    go = rng.standard_normal((n, ns, c)).astype(np.float32)
+    s.backward(torch.from_numpy(go).cuda())
+    g1, g2 = O.subtraction_backward(idx2, go)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(bb.grad.cpu().numpy(), g2, rtol=1e-5, atol=1e-5)
+
+    # aggregation (w_c divides c)
+    c2, w_c = 32, 8
+    inp2 = rng.standard_normal((n, c2)).astype(np.float32)
+    pos = rng.standard_normal((n, ns, c2)).astype(np.float32)
+    wt = rng.standard_normal((n, ns, w_c)).astype(np.float32)
+    ti2, tp, tw, tix = _dev(inp2, pos, wt, idx2)
+    for t in (ti2, tp, tw):
+        t.requires_grad_(True)
+    ag = P.aggregation(ti2, tp, tw, tix)
+    assert np.array_equal(ag.detach().cpu().numpy(), O.aggregation_forward(inp2, pos, wt, idx2))  # same FMA chain
+    go = rng.standard_normal((n, c2)).astype(np.float32)
+    ag.backward(torch.from_numpy(go).cuda())
+    gi, gp, gw = O.aggregation_backward(inp2, pos, wt, idx2, go)
+    np.testing.assert_allclose(ti2.grad.cpu().numpy(), gi, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(tp.grad.cpu().numpy(), gp, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(tw.grad.cpu().numpy(), gw, rtol=1e-4, atol=1e-5)
+
+
+def test_interpolation_vs_oracle(P):
+    xyz, off, noff = clouds(2, 200, 50, seed=12)
+    coarse = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    rng = np.random.default_rng(1)
+    feat = rng.standard_normal((coarse.shape[0], 19)).astype(np.float32)
+    t_c, t_f, t_noff, t_xyz, t_off = _dev(coarse, feat, noff, xyz, off)
+    t_f.requires_grad_(True)
+    out = P.interpolation2(t_c, t_xyz, t_f, t_noff, t_off, 3)
+    idx, dist = O.knn_query(3, coarse, noff, xyz, off)
+    recip = (1.0 / (dist + np.float32(1e-8))).astype(np.float32)
+    w = (recip / recip.sum(1, keepdims=True)).astype(np.float32)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), O.interpolation_forward(feat, idx, w), rtol=1e-5, atol=1e-6)
+    out1 = P.interpolation(t_c, t_xyz, t_f.detach(), t_noff, t_off, 3)
+    np.testing.assert_allclose(out1.cpu().numpy(), out.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(go).cuda())
+    np.testing.assert_allclose(t_f.grad.cpu().numpy(), O.interpolation_backward(go, idx, w, feat.shape[0]), rtol=1e-4, atol=1e-5)
+
+
+def test_scatter_attention_vs_oracle(P):
+    rng = np.random.default_rng(2)
+    n, g, c, m = 60, 4, 24, 500
+    q = rng.standard_normal((n, g, c)).astype(np.float32)
+    k = rng.standard_normal((n, g, c)).astype(np.float32)
+    w = rng.standard_normal((c,)).astype(np.float32)
+    it = rng.integers(0, n, m).astype(np.int32)
+    ir = rng.integers(0, n, m).astype(np.int32)
+    tq, tk, tw, tit, tir = _dev(q, k, w, it, ir)
+    tq.requires_grad_(True); tk.requires_grad_(True)
+    rel = P.attention_relation_step(tq, tk, tw, tit, tir)
+    np.testing.assert_allclose(rel.detach().cpu().numpy(), O.attention_relation_step_forward(q, k, w, it, ir), rtol=1e-4, atol=1e-4)
+    go = rng.standard_normal((m, g)).astype(np.float32)
+    rel.backward(torch.from_numpy(go).cuda())
+    gq, gk, _ = O.attention_relation_step_backward(q, k, w, it, ir, go)
+    np.testing.assert_allclose(tq.grad.cpu().numpy(), gq, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(tk.grad.cpu().numpy(), gk, rtol=1e-3, atol=1e-4)
+
+    aw = rng.standard_normal((m, g)).astype(np.float32)
+    v = rng.standard_normal((n, g, c)).astype(np.float32)
+    taw, tv = _dev(aw, v)
+    taw.requires_grad_(True); tv.requires_grad_(True)
+    fu = P.attention_fusion_step(taw, tv, tit, tir)
+    np.testing.assert_allclose(fu.detach().cpu().numpy(), O.attention_fusion_step_forward(aw, v, it, ir), rtol=1e-3, atol=1e-4)
+    go = rng.standard_normal((n, g, c)).astype(np.float32)
+    fu.backward(torch.from_numpy(go).cuda())
+    gw, gv = O.attention_fusion_step_backward(aw, v, it, ir, go)
+    np.testing.assert_allclose(taw.grad.cpu().numpy(), gw, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(tv.grad.cpu().numpy(), gv, rtol=1e-3, atol=1e-4)
+
+
+def test_knn_query_and_group_matches_reference_semantics(P):
+    xyz, off, noff = clouds(2, 12, 6, seed=4)  # clouds smaller than nsample -> -1 padding
+    rng = np.random.default_rng(0)
+    feat = rng.standard_normal((xyz.shape[0], 5)).astype(np.float32)
+    q = xyz[O.farthest_point_sampling(xyz, off, noff)]
+    t_xyz, t_off, t_q, t_noff, t_f = _dev(xyz, off, q, noff, feat)
+    t_f.requires_grad_(True)
+    grouped, idx = P.knn_query_and_group(t_f, t_xyz, offset=t_off, new_xyz=t_q, new_offset=t_noff, nsample=16, with_xyz=True)
+    wi, _ = O.knn_query(16, xyz, off, q, noff)
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    # reference grouping(): zero row for -1, (xyz[idx] - new_xyz) * sign(idx + 1)
+    xyz_p = np.concatenate([xyz, np.zeros((1, 3), np.float32)])
+    feat_p = np.concatenate([feat, np.zeros((1, 5), np.float32)])
+    gx = (xyz_p[wi] - q[:, None, :]) * np.sign(wi + 1)[..., None]
+    want = np.concatenate([gx, feat_p[wi]], -1).astype(np.float32)
+    assert np.array_equal(grouped.detach().cpu().numpy(), want)
+    grouped.sum().backward()
+    cnt = np.zeros(xyz.shape[0] + 1); np.add.at(cnt, wi.reshape(-1), 1)
+    np.testing.assert_allclose(t_f.grad.cpu().numpy(), np.repeat(cnt[:-1, None], 5, 1), rtol=0, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Against the UNMODIFIED reference kernels on the same device
+# ---------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not _ref.available(), reason="oracle/_ref/libpointops_ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("case", CASES + [(64, 1024, 512, "uniform", False), (8, 4096, 2048, "uniform", False)])
+def test_fps_knn_bit_exact_vs_reference_kernels(P, case):
+    b, n, m, kind, ragged = case
+    xyz, off, noff = clouds(b, n, m, seed=31, kind=kind, ragged=ragged)
+    t_xyz, t_off, t_noff = _dev(xyz, off, noff)
+    ref_fps = _ref.farthest_point_sampling(t_xyz, t_off, t_noff)
+    got_fps = P.farthest_point_sampling(t_xyz, t_off, t_noff)
+    assert torch.equal(ref_fps, got_fps)
+    q = t_xyz[ref_fps.long()].contiguous()
+    for k in (16, 5):
+        ri, rd2 = _ref.knn_query(k, t_xyz, t_off, q, t_noff)
+        gi, gd = P.knn_query(k, t_xyz, t_off, q, t_noff)
+        assert torch.equal(ri, gi)
+        assert torch.equal(torch.sqrt(rd2), gd)
+    # oracle agrees with the reference too (pins the oracle on this box)
+    assert np.array_equal(O.farthest_point_sampling(xyz, off, noff), ref_fps.cpu().numpy())
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "dup"])
+def test_ball_queries_bit_exact_vs_reference_kernels(P, kind):
+    xyz, off, noff = clouds(3, 800, 150, seed=32, kind=kind, ragged=True)
+    t_xyz, t_off, t_noff = _dev(xyz, off, noff)
+    q = t_xyz[_ref.farthest_point_sampling(t_xyz, t_off, t_noff).long()].contiguous()
+    for ns, rmax, rmin in [(16, 0.15, 0.0), (8, 0.4, 0.1)]:
+        ri, rd2 = _ref.ball_query(ns, rmax, rmin, t_xyz, t_off, q, t_noff)
+        gi, gd = P.ball_query(ns, rmax, rmin, t_xyz, t_off, q, t_noff)
+        assert torch.equal(ri, gi)
+        assert torch.equal(torch.sqrt(rd2), gd)
+    rng = np.random.default_rng(3)
+    starts = np.concatenate([[0], off[:-1]])
+    order = torch.from_numpy(np.concatenate([s + rng.permutation(e - s) for s, e in zip(starts, off)]).astype(np.int32)).cuda()
+    ri, rd2 = _ref.random_ball_query(12, 0.2, 0.0, order, t_xyz, t_off, q, t_noff)
+    gi, gd = P.random_ball_query(12, 0.2, 0.0, t_xyz, t_off, q, t_noff, order=order)
+    assert torch.equal(ri, gi) and torch.equal(torch.sqrt(rd2), gd)
+
+
+# ---------------------------------------------------------------------------------------------
+# Full BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,n,m", [(64, 1024, 512), (32, 4096, 2048)])
+def test_full_size_properties(P, b, n, m):
+    xyz, off, noff = clouds(b, n, m, seed=77)
+    t_xyz, t_off, t_noff = _dev(xyz, off, noff)
+    fps = P.farthest_point_sampling(t_xyz, t_off, t_noff, n_max=n, m_total=b * m)
+    f = fps.view(b, m).long()
+    base = (torch.arange(b, device="cuda") * n).view(b, 1)
+    assert ((f >= base) & (f < base + n)).all()  # stays inside its cloud
+    assert (f[:, 0] == base[:, 0]).all()  # first pick = first point
+    assert all(len(torch.unique(r)) == m for r in f)  # no repeats on tie-free data
+    q = t_xyz[fps.long()].contiguous()
+    idx, dist = P.knn_query(16, t_xyz, t_off, q, t_noff)
+    assert (idx[:, 0] == fps).all() and (dist[:, 0] == 0).all()  # a sample's nearest neighbour is itself
+    assert (dist[:, 1:] >= dist[:, :-1]).all()  # ascending
+    il = idx.long()
+    assert ((il >= base.repeat_interleave(m, 0)) & (il < base.repeat_interleave(m, 0) + n)).all()
+    # distances recomputed from the returned indices agree, and nothing closer was missed
+    d = (q.unsqueeze(1) - t_xyz[il]).pow(2).sum(-1).sqrt()
+    torch.testing.assert_close(d, dist, rtol=1e-5, atol=1e-6)
+    full = torch.cdist(q.view(b, m, 3), t_xyz.view(b, n, 3))
+    kth = full.topk(16, dim=-1, largest=False).values[..., -1].reshape(-1)
+    torch.testing.assert_close(kth, dist[:, -1], rtol=1e-4, atol=1e-5)
