@@ -15,8 +15,12 @@
  * /root/reference into oracle/_ref/libpointops_ref.so (oracle/build_ref.sh) and executed on the
  * B200 by tests/test_parity_ref_gpu.py, and against the committed fixtures in tests/golden/.
  *
- * Distance arithmetic (verified in the sm_100a SASS of the reference build: FMUL, FFMA, FFMA):
- *     d = fmaf(dz, dz, fmaf(dy, dy, dx * dx))
+ * Distance arithmetic.  nvcc contracts `dx*dx + dy*dy + dz*dz` of the reference into
+ * FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.) -- the plain multiply lands on the Y term (read off
+ * the sm_100a SASS of the reference build: the FMUL operand is the register loaded from +0x4,
+ * and confirmed 100% bit-exact against kNN distances produced by the reference kernels on a
+ * B200, tests/golden/):
+ *     d = fmaf(dz, dz, fmaf(dx, dx, dy * dy))
  * with dx = x_k - x_last for FPS and dx = q_x - x_k for the query kernels.  Compile with
  * -ffp-contract=off so that gcc never fuses anything we did not write as fmaf().
  *
@@ -43,7 +47,7 @@ static inline float dist2_fps(const float *xyz, int k, float x1, float y1, float
     const float dx = xyz[k * 3 + 0] - x1;
     const float dy = xyz[k * 3 + 1] - y1;
     const float dz = xyz[k * 3 + 2] - z1;
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 static inline float dist2_query(const float *xyz, int i, float qx, float qy, float qz) {
@@ -51,7 +55,7 @@ static inline float dist2_query(const float *xyz, int i, float qx, float qy, flo
     const float dx = qx - xyz[i * 3 + 0];
     const float dy = qy - xyz[i * 3 + 1];
     const float dz = qz - xyz[i * 3 + 2];
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -60,7 +64,10 @@ static inline float dist2_query(const float *xyz, int i, float qx, float qy, flo
  * its launcher (:131-171): one block per cloud, block_size = opt_n_threads(n) where n is the
  * caller-supplied maximum cloud size (functions/sampling.py:14-16).  Thread `tid` scans points
  * start_n+tid, +block_size, ... keeping the FIRST strict maximum (:57-58), then the shared-memory
- * tree reduction keeps the lower thread id on ties (__update, :5-10: `v2 > v1 ? i2 : i1`).
+ * tree reduction keeps the lower SLOT on ties (__update, :5-10: `v2 > v1 ? i2 : i1`).  Because the
+ * tree folds the upper half onto the lower half first, the surviving thread among equal maxima is
+ * the one with the smallest BIT-REVERSED thread id (even beats odd at the last level, ...), not
+ * the smallest thread id; the tree is emulated literally below.
  * `tmp` is the caller-initialised running min-distance buffer (1e10, sampling.py:18).
  * ------------------------------------------------------------------------------------------ */
 ORACLE_API void oracle_farthest_point_sampling(int b, int n, const float *xyz, const int *offset,

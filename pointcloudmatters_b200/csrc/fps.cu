@@ -9,8 +9,9 @@
 //     __syncthreads per round (the reference does a 10-level shared-memory tree with 11 barriers);
 //   * ties are resolved by an explicit priority key that reproduces the reference's implicit
 //     rule: its thread `t` of a BS-wide block scans points t, t+BS, ... keeping the first strict
-//     maximum, and its tree reduction keeps the lower thread id, so among equal distances the
-//     winner minimises (rel % BS, rel / BS) with rel = k - start_n and
+//     maximum, and its shared-memory tree (fold upper half onto lower half, lower slot wins a tie)
+//     lets the thread with the smallest BIT-REVERSED id survive, so among equal distances the
+//     winner minimises (bitrev(rel % BS), rel / BS) with rel = k - start_n and
 //     BS = opt_n_threads(n_max) (cuda_utils.h:11-14).
 // FPS is a chain of M-1 dependent block-wide reductions: it is latency-bound, never HBM-bound
 // (algorithmic traffic 12N+4M bytes per cloud).
@@ -27,14 +28,19 @@ int pcm_ref_opt_n_threads(int work_size) {
 
 namespace {
 
-constexpr int kKeyQBits = 16;  // key = (rel % BS) << 16 | (rel / BS)
+constexpr int kKeyQBits = 16;  // key = bitrev(rel % BS) << 16 | (rel / BS)
 constexpr int kNegOneBits = (int)0xBF800000;  // __float_as_int(-1.0f): below every d >= +0 as a signed int
 
+__device__ __forceinline__ unsigned fps_brev(unsigned r, int bs_log2) {
+    return bs_log2 ? (__brev(r) >> (32 - bs_log2)) : 0u;
+}
 __device__ __forceinline__ unsigned fps_key(int rel, int bs_log2) {
-    return ((unsigned)(rel & ((1 << bs_log2) - 1)) << kKeyQBits) | (unsigned)(rel >> bs_log2);
+    const unsigned r = (unsigned)rel & ((1u << bs_log2) - 1u);
+    return (fps_brev(r, bs_log2) << kKeyQBits) | (unsigned)(rel >> bs_log2);
 }
 __device__ __forceinline__ int fps_rel_of_key(unsigned key, int bs_log2) {
-    return (int)(((key & ((1u << kKeyQBits) - 1u)) << bs_log2) | (key >> kKeyQBits));
+    const unsigned r = fps_brev(key >> kKeyQBits, bs_log2);
+    return (int)(((key & ((1u << kKeyQBits) - 1u)) << bs_log2) | r);
 }
 
 // Block-wide (max distance, then min key) with a single barrier.  Every warp ends up holding
@@ -194,7 +200,7 @@ PCM_API int pcm_farthest_point_sampling(int b, int n, const float* xyz, const in
         return pcm_launch_status();
     }
     int T = g_fps_threads_override;
-    if (T == 0) T = n <= 1024 ? 128 : (n <= 2048 ? 256 : (n <= 4096 ? 512 : 1024));
+    if (T == 0) T = n <= 4096 ? 512 : 1024;  // measured on B200: 512-wide CTAs win for N = 1024..4096
     while (T < 1024 && (n + T - 1) / T > 8) T *= 2;
     const int ppt = (n + T - 1) / T;
     switch (T) {

@@ -17,8 +17,8 @@ def _d2(q, p):
     dx = (q[..., 0] - p[..., 0]).astype(np.float32)
     dy = (q[..., 1] - p[..., 1]).astype(np.float32)
     dz = (q[..., 2] - p[..., 2]).astype(np.float32)
-    t = (dx.astype(np.float64) * dx).astype(np.float32)
-    t = (dy.astype(np.float64) * dy + t).astype(np.float32)
+    t = (dy.astype(np.float64) * dy).astype(np.float32)  # FMUL lands on the y term (reference SASS)
+    t = (dx.astype(np.float64) * dx + t).astype(np.float32)
     return (dz.astype(np.float64) * dz + t).astype(np.float32)
 
 
