@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- BC training-step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # B200-native path (this repository)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host CPU cores
+
+Workload (config.workload): BASELINE.json configs[1] -- ManiSkill2 PickCube, PointNet-MLP +
+set abstraction (FPS + kNN-16) + ACT, N = 1024 points, batch 64 PER GPU (weak scaling), fp32
+master weights, bf16 tensor-core operands, dropout on, synthetic data.
+A "step" = forward + backward + gradient all-reduce + clip(0.5) + AdamW + OneCycleLR.
+
+One JSON line on stdout (rank 0): see the task contract; additionally
+  roofline     -- the dominant kernel of the step, timed live with CUDA events on the launch stream;
+  cpu_baseline -- the oracle port (oracle/act_oracle.py + oracle/pointops_oracle.c) on a bounded
+                  sample of the same workload on this box's host cores (rank 0, N = 1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "bc_train_steps_per_sec"
+UNIT = "steps/s"
+WORKLOAD = "cfg2: ManiSkill2 PickCube, PointNet-MLP + SA(FPS+kNN16) + ACT, N=1024 pts, M=512, bs=64/GPU"
+CFG2 = dict(hidden_dim=512, nhead=8, dim_feedforward=32, enc_layers=4, dec_layers=7, dropout=0.1, num_queries=100,
+            action_dim=7, qpos_dim=9, goal_cond_dim=3, latent_dim=32, kl_weight=10.0, pcd_npoints=512, pcd_nsample=16)
+BATCH_PER_GPU = 64
+N_POINTS = 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (default: BASELINE cfg-2)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-dead-decoder-layers", action="store_true",
+                    help="reported separately: stop the decoder after layer 0 (only [0] is consumed)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated (oracle port), all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample_batch, steps, warmup):
+    """Times `steps` training steps of the oracle port on a `sample_batch`-cloud sample of cfg-2 and
+    scales to the full 64-sample step (per-sample cost is batch-independent: clouds are independent
+    units).  Returns (steps_per_sec_at_full_batch, cores, ms_per_sample_step)."""
+    import torch
+
+    from oracle.act_oracle import build_oracle_policy
+    from pointcloudmatters_b200.data import synthetic_act_batch
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    torch.manual_seed(0)
+    model = build_oracle_policy(CFG2).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.05)
+    batches = [synthetic_act_batch(sample_batch, N_POINTS, seed=1000 + i) for i in range(2)]
+
+    def step(i):
+        b = batches[i % len(batches)]
+        b = {k: (dict(v) if isinstance(v, dict) else v) for k, v in b.items()}
+        b["pcds"].pop("n_max", None)
+        opt.zero_grad(set_to_none=True)
+        out = model(b)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+        opt.step()
+        return float(out["loss"])
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = (time.perf_counter() - t0) / steps
+    full_step_s = dt * (BATCH_PER_GPU / sample_batch)
+    return 1.0 / full_step_s, cores, dt * 1e3
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    v, cores, ms = cpu_reference_run(args.cpu_sample_batch, steps, warmup)
+    sample = (f"{steps} timed + {warmup} warm-up steps of the oracle port (oracle/act_oracle.py + C pointops oracle, "
+              f"fp32, torch CPU) on {args.cpu_sample_batch}/{BATCH_PER_GPU} clouds of cfg-2, scaled x{BATCH_PER_GPU // args.cpu_sample_batch}")
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores; the reference's own "
+                       "pointops has no CPU implementation, so its kernels are the C restatement pinned to them"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from pointcloudmatters_b200 import _lib
+    from pointcloudmatters_b200 import functional as PF
+    from pointcloudmatters_b200.act import build_policy
+    from pointcloudmatters_b200.bc_module import ACTBCModule
+    from pointcloudmatters_b200.data import batch_nbytes, synthetic_act_batch, to_device
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (b200 arm) needs a CUDA device: there is no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    torch.manual_seed(1234)  # identical initial weights on every rank (DDP broadcast equivalent)
+    policy = build_policy(CFG2).to(dev).train()
+    policy.transformer.decoder.skip_dead_layers = bool(args.skip_dead_decoder_layers)
+    total_steps = max(1000, args.steps + args.warmup + 8)
+    module = ACTBCModule(policy, total_steps=total_steps)
+    module.configure_optimizers()
+
+    # per-rank shard of the global batch: distinct synthetic batches, pinned on the host
+    n_pool = 4
+    host = [synthetic_act_batch(args.batch, N_POINTS, seed=1000 + rank * 97 + i, pin=True) for i in range(n_pool)]
+    resident = [to_device(b, dev) for b in host]
+    for r, h in zip(resident, host):
+        r["pcds"]["n_max"] = h["pcds"]["n_max"]
+    h2d = batch_nbytes(host[0])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(batches, steps, from_host):
+        """Time exactly `steps` steps; returns (seconds, last loss).  Device-timed with CUDA events."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss_host = None
+        for i in range(steps):
+            b = batches[i % len(batches)]
+            if from_host:
+                nm = b["pcds"]["n_max"]
+                b = to_device(b, dev, non_blocking=True)
+                b["pcds"]["n_max"] = nm
+            loss = module.training_step(b, i)
+            if from_host:
+                loss_host = float(loss)  # device->host read of the step result, every step
+        e1.record()
+        barrier()
+        sec = e0.elapsed_time(e1) / 1e3
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), (loss_host if from_host else float(loss))
+
+    # warm-up (also builds the flat parameter / gradient buffers on the first step)
+    run(resident, max(3, args.warmup), False)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    PF.KERNEL_TIMER.enable()
+    lib_l0 = _lib.launch_count()
+    t_wall0 = time.perf_counter()
+    sec, last_loss = run(resident, args.steps, False)
+    t_wall1 = time.perf_counter()
+    launches = _lib.launch_count() - lib_l0
+    kstats = PF.KERNEL_TIMER.summary()
+    PF.KERNEL_TIMER.disable()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    run(host, 2, True)
+    sec_e2e, loss_e2e = run(host, args.steps, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = args.steps * 1.0 / sec  # global steps/s: every rank advances the same global step
+    e2e_value = args.steps * 1.0 / sec_e2e
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    roofline = PF.roofline_for(kstats, peaks, args.batch, N_POINTS, CFG2)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + 385 MB parameter/optimizer state) exceeds the 126 MB L2; "
+                         "4 distinct input batches cycled; no explicit flush",
+                   "dropout": CFG2["dropout"], "decoder_layers_computed": 1 if args.skip_dead_decoder_layers else CFG2["dec_layers"],
+                   "samples_per_sec": value * args.batch * world, "last_loss": last_loss},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * sec_e2e / args.steps, "last_loss": loss_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "kernel_ms_per_step": {k: v["ms_per_step"] for k, v in kstats.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, ms = cpu_reference_run(args.cpu_sample_batch, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"2 timed + 1 warm-up steps of the oracle port on {args.cpu_sample_batch}/"
+                                          f"{BATCH_PER_GPU} clouds of cfg-2 (fp32, torch CPU + C pointops oracle), "
+                                          f"scaled x{BATCH_PER_GPU // args.cpu_sample_batch}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -37,6 +37,8 @@ typedef void *pcm_stream_t; /* cudaStream_t */
 /* Library / build identification. */
 int pcm_abi_version(void);
 const char *pcm_build_info(void);
+/* Number of kernel launches issued by this library in the current process (bench.py gpu_launches). */
+long long pcm_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * pointops family

@@ -38,7 +38,7 @@ def _parse_header(text: str):
     """Return {name: (restype, [argtypes])} for every `int|const char * pcm_*(...)` prototype."""
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(int|const char \*|void)\s*(pcm_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"(long long|int|const char \*|void)\s*(pcm_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -49,7 +49,7 @@ def _parse_header(text: str):
                 else:
                     ty = a.rsplit(" ", 1)[0].replace("const ", "").strip()
                     argtypes.append(_CTYPES[ty])
-        restype = {"int": ctypes.c_int, "const char *": ctypes.c_char_p, "void": None}[ret]
+        restype = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "const char *": ctypes.c_char_p, "void": None}[ret]
         protos[name] = (restype, argtypes)
     return protos
 
@@ -74,7 +74,33 @@ def _load():
     return lib
 
 
-lib = _load()
+class _CountingLib:
+    """Thin proxy over the ctypes handle that counts launches of OUR kernels (bench `gpu_launches`)."""
+
+    def __init__(self, handle):
+        object.__setattr__(self, "_h", handle)
+        object.__setattr__(self, "launches", 0)
+        object.__setattr__(self, "_no_count", {"pcm_abi_version", "pcm_build_info", "pcm_tune_fps_threads", "pcm_launch_count"})
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if name in self._no_count:
+            return fn
+
+        def call(*args):
+            object.__setattr__(self, "launches", self.launches + 1)
+            return fn(*args)
+
+        object.__setattr__(self, name, call)
+        return call
+
+
+lib = _CountingLib(_load())
+
+
+def launch_count() -> int:
+    """Kernel launches issued by libpcm_b200.so so far in this process."""
+    return int(lib.pcm_launch_count())
 
 
 def check(status: int, what: str) -> None:

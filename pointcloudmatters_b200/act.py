@@ -1,0 +1,291 @@
+"""ACT policy for point-cloud observations -- host-side mirror of
+`src/models/components/act/act.py` (`ACTPCD` :312-598, `ACTRLBenchPCD` :707-825, base `ACT`
+:40-309) of HaoyiZhu/PointCloudMatters.  Same constructor kwargs, same `state_dict` keys and
+shapes, same `forward(data_dict) -> data_dict` contract (keys `loss, action_loss, kl_loss, a_hat,
+is_pad_hat, mu, logvar`), so it can be selected with a one-line Hydra `_target_` override.
+
+What changed underneath (B200-first):
+  * FPS / kNN run through the sm_100a kernels of libpcm_b200.so; the per-cloud Python loops and
+    host syncs of the reference (`functions/sampling.py:14-17`, act.py:387-391) are gone: the
+    fixed-M `new_offset` is built on the device and `pcds["n_max"]` (optional Python int, the
+    largest cloud) makes the whole step sync-free;
+  * the set-abstraction head (gather -> Linear -> BatchNorm -> ReLU -> max) is one fused operator;
+  * dense blocks go through pointcloudmatters_b200.functional.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as PF
+from . import pointops
+
+
+def get_sinusoid_encoding_table(n_position, d_hid):
+    """act/utils.py:42-55."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    table = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.FloatTensor(table).unsqueeze(0)
+
+
+class KLDivergence(nn.Module):
+    """loss/misc.py:6-26."""
+
+    def forward(self, mu, logvar):
+        if mu is None:
+            return 0
+        klds = -0.5 * (1 + logvar - mu.pow(2) - logvar.exp())
+        return klds.sum(1).mean(0, True)[0]
+
+
+class ACTPCD(nn.Module):
+    def __init__(self, backbone, transformer, encoder, hidden_dim, num_queries, num_cameras=0, action_dim=8,
+                 qpos_dim=9, env_state_dim=0, latent_dim=32, action_loss=None, klloss=None, kl_weight=20.0,
+                 goal_cond_dim=0, obs_feature_pos_embedding=None, freeze_backbone=False, pcd_nsample=16,
+                 pcd_npoints=1024, sampling="fps", heatmap_th=0.1, ignore_vae=False, use_mask=False,
+                 bg_ratio=0.0, pre_sample=False, in_channels=6):
+        super().__init__()
+        if backbone is None:
+            raise NotImplementedError("state-only ACT (backbone=None) is outside the point-cloud hot path")
+        if use_mask or pre_sample:
+            raise NotImplementedError("use_mask / pre_sample set-abstraction variants (SURVEY.md 8 a4') are not "
+                                      "built yet; all BASELINE configs run with both off")
+        if "fps" not in sampling:
+            raise NotImplementedError(sampling)  # same as the reference (act.py:443-444)
+        self.backbone, self.transformer, self.encoder = backbone, transformer, encoder
+        self.num_queries, self.num_cameras = num_queries, 0
+        self.action_dim, self.qpos_dim, self.env_state_dim = action_dim, qpos_dim, env_state_dim
+        self.hidden_dim, self.kl_weight, self.latent_dim = hidden_dim, kl_weight, latent_dim
+        self.goal_cond_dim, self.freeze_backbone, self.ignore_vae = goal_cond_dim, freeze_backbone, ignore_vae
+        self.obs_feature_pos_embedding = None
+        if freeze_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+        self.action_loss = action_loss if action_loss is not None else nn.MSELoss(reduction="none")
+        self.klloss = klloss if klloss is not None else KLDivergence()
+        # build_encoder (act.py:93-122)
+        self.input_proj_robot_state = nn.Linear(qpos_dim, hidden_dim)
+        self.cls_embed = nn.Embedding(1, hidden_dim)
+        self.encoder_action_proj = nn.Linear(action_dim, hidden_dim)
+        self.encoder_joint_proj = nn.Linear(qpos_dim, hidden_dim)
+        self.latent_proj = nn.Linear(hidden_dim, latent_dim * 2)
+        self.register_buffer("pos_table", get_sinusoid_encoding_table(2 + num_queries, hidden_dim))
+        if goal_cond_dim > 0:
+            self.proj_goal_cond_emb = nn.Linear(goal_cond_dim, hidden_dim)
+        # build_decoder (act.py:124-135)
+        self.action_head = nn.Linear(hidden_dim, action_dim)
+        self.is_pad_head = nn.Linear(hidden_dim, 1)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.latent_out_proj = nn.Linear(latent_dim, hidden_dim)
+        self.additional_pos_embed = nn.Embedding(2 + int(goal_cond_dim > 0), hidden_dim)
+        self.input_proj = None
+        # set-abstraction head (act.py:363-382)
+        self.pcd_nsample, self.pcd_npoints, self.pre_sample = pcd_nsample, pcd_npoints, pre_sample
+        self.linear = nn.Linear(3 + self.backbone.num_channels, hidden_dim, bias=False)
+        self.bn = nn.BatchNorm1d(hidden_dim)
+        self.pool = nn.MaxPool1d(pcd_nsample)
+        self.relu = nn.ReLU(inplace=True)
+        self.sampling, self.use_mask, self.bg_ratio = sampling, use_mask, bg_ratio
+
+    # ---- CVAE posterior (act.py:137-188) ------------------------------------------------------
+    def forward_encoder(self, data_dict):
+        qpos = data_dict["qpos"]
+        actions = data_dict.get("actions", None)
+        is_pad = data_dict.get("is_pad", None)
+        is_training = actions is not None
+        bs = qpos.shape[0]
+        data_dict["is_training"] = is_training
+        if is_training and not self.ignore_vae:
+            action_embed = PF.linear(actions, self.encoder_action_proj.weight, self.encoder_action_proj.bias)
+            qpos_embed = PF.linear(qpos, self.encoder_joint_proj.weight, self.encoder_joint_proj.bias).unsqueeze(1)
+            cls_embed = self.cls_embed.weight.unsqueeze(0).expand(bs, -1, -1)
+            encoder_input = torch.cat([cls_embed, qpos_embed, action_embed], dim=1).permute(1, 0, 2).contiguous()
+            pad = torch.cat([torch.zeros(bs, 2, dtype=torch.bool, device=qpos.device), is_pad], dim=1)
+            pos_embed = self.pos_table.detach().permute(1, 0, 2)
+            cls_out = self.encoder(encoder_input, pos=pos_embed, src_key_padding_mask=pad)[0]
+            latent_info = PF.linear(cls_out, self.latent_proj.weight, self.latent_proj.bias)
+            mu, logvar = latent_info[:, : self.latent_dim], latent_info[:, self.latent_dim:]
+            eps = data_dict.get("_eps", None)  # test hook: injected reparametrisation noise
+            if eps is None:
+                eps = torch.empty_like(mu).normal_()
+            latent_sample = mu + logvar.div(2).exp() * eps
+        else:
+            mu = logvar = None
+            latent_sample = torch.zeros(bs, self.latent_dim, dtype=torch.float32, device=qpos.device)
+        data_dict["mu"], data_dict["logvar"] = mu, logvar
+        data_dict["latent_input"] = PF.linear(latent_sample, self.latent_out_proj.weight, self.latent_out_proj.bias)
+        return data_dict
+
+    # ---- set abstraction (act.py:384-465) ----------------------------------------------------
+    def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None):
+        p, x, o = pxo
+        b = o.shape[0]
+        n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
+        o32 = o.int() if o.dtype != torch.int32 else o
+        idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=n_max, m_total=b * self.pcd_npoints)
+        n_p = p[idx.long(), :].contiguous()
+        knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
+        x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
+        if return_index:
+            return [n_p, x, n_o, idx]
+        return [n_p, x, n_o]
+
+    def coord_embedding_sine(self, coord, temperature=10000):
+        """act.py:467-506 (normalize=False, the only form the reference calls)."""
+        npf = self.hidden_dim // 3
+        pad = self.hidden_dim - npf * 3
+        dim_t = torch.arange(npf, dtype=torch.float32, device=coord.device)
+        dim_t = temperature ** (2 * (dim_t // 2) / npf)
+        parts = []
+        for a in range(3):
+            pa = coord[:, a:a + 1, None] / dim_t
+            parts.append(torch.stack((pa[..., 0::2].sin(), pa[..., 1::2].cos()), dim=2).flatten(1))
+        pos = torch.cat(parts, dim=1)
+        return torch.cat((pos, torch.zeros_like(pos)[:, :pad]), dim=1)
+
+    def forward_pcd_embed(self, pcd_dict):
+        features = self.backbone(pcd_dict)
+        coord, features, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]),
+                                               n_max=pcd_dict.get("n_max", None))
+        pcd_pos = self.coord_embedding_sine(coord)
+        b = pcd_dict["offset"].shape[0]
+        features = features.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)  # (b, c, 1, n)
+        pcd_pos = pcd_pos.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)
+        return features, pcd_pos
+
+    # ---- observation tokens (act.py:553-598) -------------------------------------------------
+    def forward_obs_embed(self, data_dict):
+        qpos = data_dict["qpos"]
+        latent_input = data_dict["latent_input"]
+        pcd_tokens, pcd_pos = self.forward_pcd_embed(data_dict["pcds"])
+        proprio_input = PF.linear(qpos, self.input_proj_robot_state.weight, self.input_proj_robot_state.bias).unsqueeze(0)
+        if self.goal_cond_dim > 0:
+            gc = data_dict["goal_cond"]
+            if gc.dim() > 2:
+                gc = gc.reshape(gc.shape[0], -1)
+                data_dict["goal_cond"] = gc
+            goal = PF.linear(gc, self.proj_goal_cond_emb.weight, self.proj_goal_cond_emb.bias).unsqueeze(0)
+            proprio_input = torch.cat([proprio_input, goal], dim=0)
+        data_dict["src"], data_dict["pos"] = pcd_tokens, pcd_pos
+        data_dict["latent_input"], data_dict["proprio_input"] = latent_input.unsqueeze(0), proprio_input
+        return data_dict
+
+    def _decode(self, data_dict):
+        return self.transformer(data_dict["src"], None, self.query_embed.weight, data_dict["pos"],
+                                data_dict["latent_input"], data_dict["proprio_input"],
+                                self.additional_pos_embed.weight)[0]
+
+    # ---- heads + loss (act.py:255-291) -------------------------------------------------------
+    def forward_decoder(self, data_dict):
+        hs = self._decode(data_dict)
+        data_dict["a_hat"] = PF.linear(hs, self.action_head.weight, self.action_head.bias)
+        data_dict["is_pad_hat"] = PF.linear(hs, self.is_pad_head.weight, self.is_pad_head.bias)
+        return data_dict
+
+    def forward_loss(self, data_dict):
+        total_kld = self.klloss(data_dict["mu"], data_dict["logvar"])
+        action_loss = self.action_loss(data_dict["a_hat"], data_dict["actions"])
+        action_loss = (action_loss * ~data_dict["is_pad"].unsqueeze(-1)).mean()
+        data_dict["action_loss"], data_dict["kl_loss"] = action_loss, total_kld
+        data_dict["loss"] = action_loss + total_kld * self.kl_weight
+        return data_dict
+
+    def forward(self, data_dict):
+        data_dict = self.forward_encoder(data_dict)
+        data_dict = self.forward_obs_embed(data_dict)
+        data_dict = self.forward_decoder(data_dict)
+        if not data_dict["is_training"]:
+            return data_dict
+        return self.forward_loss(data_dict)
+
+
+class ACTRLBenchPCD(ACTPCD):
+    """act.py:707-825: position / rot6d / sigmoid(gripper[, collision]) heads, weighted position loss."""
+
+    def __init__(self, *args, rot_type="6d", collision=False, position_loss_weight=1.0, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.rot_type, self.collision, self.position_loss_weight = rot_type, collision, position_loss_weight
+
+    def forward_decoder(self, data_dict):
+        hs = self._decode(data_dict)
+        a_hat = PF.linear(hs, self.action_head.weight, self.action_head.bias)
+        position = a_hat[..., :3]
+        if self.collision:
+            gripper = torch.cat([torch.sigmoid(a_hat[..., -2:-1]), torch.sigmoid(a_hat[..., -1:])], dim=-1)
+            rot = a_hat[..., 3:-2]
+        else:
+            gripper = torch.sigmoid(a_hat[..., -1:])
+            rot = a_hat[..., 3:-1]
+        if not data_dict["is_training"]:
+            if self.rot_type != "6d":
+                raise NotImplementedError
+            rot = _matrix_to_quaternion(_rotation_6d_to_matrix(rot))
+        data_dict["a_hat"] = torch.cat([position, rot, gripper], dim=-1)
+        data_dict["is_pad_hat"] = PF.linear(hs, self.is_pad_head.weight, self.is_pad_head.bias)
+        return data_dict
+
+    def forward_loss(self, data_dict):
+        total_kld = self.klloss(data_dict["mu"], data_dict["logvar"])
+        action_loss = self.action_loss(data_dict["a_hat"], data_dict["actions"])
+        action_loss = torch.cat([action_loss[..., :3] * self.position_loss_weight, action_loss[..., 3:]], dim=-1)
+        action_loss = (action_loss * ~data_dict["is_pad"].unsqueeze(-1)).mean()
+        data_dict["action_loss"], data_dict["kl_loss"] = action_loss, total_kld
+        data_dict["loss"] = action_loss + total_kld * self.kl_weight
+        return data_dict
+
+
+# rot6d -> matrix -> quaternion for the (non-training) RLBench inference branch
+# (reference: src/utils/rotation_conversions.py, Zhou et al. 2019 / standard w-first quaternion).
+def _rotation_6d_to_matrix(d6):
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = F.normalize(a1, dim=-1)
+    b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    return torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+
+
+def _matrix_to_quaternion(matrix):
+    m = matrix
+    m00, m11, m22 = m[..., 0, 0], m[..., 1, 1], m[..., 2, 2]
+    q_abs = torch.sqrt(torch.clamp(torch.stack([1 + m00 + m11 + m22, 1 + m00 - m11 - m22,
+                                                1 - m00 + m11 - m22, 1 - m00 - m11 + m22], dim=-1), min=0))
+    cand = torch.stack([
+        torch.stack([q_abs[..., 0] ** 2, m[..., 2, 1] - m[..., 1, 2], m[..., 0, 2] - m[..., 2, 0], m[..., 1, 0] - m[..., 0, 1]], -1),
+        torch.stack([m[..., 2, 1] - m[..., 1, 2], q_abs[..., 1] ** 2, m[..., 1, 0] + m[..., 0, 1], m[..., 0, 2] + m[..., 2, 0]], -1),
+        torch.stack([m[..., 0, 2] - m[..., 2, 0], m[..., 1, 0] + m[..., 0, 1], q_abs[..., 2] ** 2, m[..., 1, 2] + m[..., 2, 1]], -1),
+        torch.stack([m[..., 1, 0] - m[..., 0, 1], m[..., 2, 0] + m[..., 0, 2], m[..., 2, 1] + m[..., 1, 2], q_abs[..., 3] ** 2], -1),
+    ], dim=-2)
+    cand = cand / (2.0 * q_abs[..., None].clamp(min=0.1))
+    best = F.one_hot(q_abs.argmax(dim=-1), num_classes=4) > 0.5
+    return cand[best, :].reshape(matrix.shape[:-2] + (4,))
+
+
+def build_policy(cfg: dict, rlbench: bool = False):
+    """Convenience constructor with the reference's maniskill2_act_pcd_model.yaml structure."""
+    from .pointnet import PointNet
+    from .transformer import Transformer, TransformerEncoder
+
+    backbone = PointNet(cfg.get("in_channels", 6), 0)
+    tr = Transformer(d_model=cfg["hidden_dim"], nhead=cfg["nhead"], num_encoder_layers=cfg["enc_layers"],
+                     num_decoder_layers=cfg["dec_layers"], dim_feedforward=cfg["dim_feedforward"],
+                     dropout=cfg["dropout"], normalize_before=False, return_intermediate_dec=True)
+    enc = TransformerEncoder(d_model=cfg["hidden_dim"], nhead=cfg["nhead"], dim_feedforward=cfg["dim_feedforward"],
+                             dropout=cfg["dropout"], num_layers=cfg["enc_layers"], normalize_before=False)
+    kw = dict(backbone=backbone, transformer=tr, encoder=enc, hidden_dim=cfg["hidden_dim"],
+              num_queries=cfg["num_queries"], num_cameras=1, action_dim=cfg["action_dim"], qpos_dim=cfg["qpos_dim"],
+              latent_dim=cfg.get("latent_dim", 32), kl_weight=cfg.get("kl_weight", 10.0),
+              goal_cond_dim=cfg.get("goal_cond_dim", 0), pcd_nsample=cfg.get("pcd_nsample", 16),
+              pcd_npoints=cfg["pcd_npoints"])
+    if rlbench:
+        return ACTRLBenchPCD(**kw, collision=cfg.get("collision", False),
+                             position_loss_weight=cfg.get("position_loss_weight", 1.0))
+    return ACTPCD(**kw)
+
+
+# BASELINE.json configs: model hyper-parameters of maniskill2_act_pcd_model.yaml
+ACT_MODEL_CFG = dict(hidden_dim=512, nhead=8, dim_feedforward=32, enc_layers=4, dec_layers=7, dropout=0.1,
+                     num_queries=100, latent_dim=32, kl_weight=10.0, pcd_nsample=16)

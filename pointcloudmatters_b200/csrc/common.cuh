@@ -9,7 +9,10 @@
 
 #define PCM_FULL_MASK 0xffffffffu
 
-static inline int pcm_launch_status() { return (int)cudaPeekAtLastError(); }
+// every kernel launch in the library is followed by pcm_launch_status(): it bumps the process-wide
+// launch counter (pcm_launch_count(), bench.py's `gpu_launches`) and returns the launch status.
+extern long long g_pcm_launch_count;
+static inline int pcm_launch_status() { ++g_pcm_launch_count; return (int)cudaPeekAtLastError(); }
 static inline cudaStream_t pcm_cu_stream(pcm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int pcm_divup(long a, long b) { return (int)((a + b - 1) / b); }
 

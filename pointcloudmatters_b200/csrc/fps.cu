@@ -18,6 +18,9 @@
 #include "common.cuh"
 #include <math.h>
 
+long long g_pcm_launch_count = 0;
+PCM_API long long pcm_launch_count(void) { return g_pcm_launch_count; }
+
 int pcm_ref_opt_n_threads(int work_size) {
     const int pow_2 = (int)(log((double)work_size) / log(2.0));
     int t = 1 << pow_2;

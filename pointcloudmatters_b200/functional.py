@@ -1,0 +1,180 @@
+"""Operator layer of the B200 training step: every dense / fused op the policy modules use.
+
+Each function is the single call site of one C-ABI kernel family of libpcm_b200.so (through an
+autograd.Function).  Numerics policy (stated tolerance): GEMM / attention operands
+are rounded to bf16 and accumulated in fp32 on the tensor cores; everything else (LayerNorm,
+BatchNorm statistics, softmax statistics, losses, optimizer, master weights) is fp32.
+CUDA only -- there is no CPU fallback; a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ._lib import PcmError
+
+COMPUTE_DTYPE = torch.bfloat16
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise PcmError("pointcloudmatters_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def linear(x, weight, bias=None, relu=False):
+    """y = x @ weight^T (+ bias) (+ ReLU); x (..., K), weight (N, K) fp32 master -> y fp32."""
+    _need_cuda(x)
+    y = F.linear(x.to(COMPUTE_DTYPE), weight.to(COMPUTE_DTYPE)).float()
+    if bias is not None:
+        y = y + bias
+    return F.relu(y) if relu else y
+
+
+def attention(q, k, v, key_padding_mask=None, dropout_p=0.0, training=False):
+    """softmax(q k^T / sqrt(d) + mask) v on (B, h, L, d) / (B, h, S, d) tensors -> (B, h, L, d) fp32."""
+    _need_cuda(q)
+    d = q.shape[-1]
+    scores = (q.to(COMPUTE_DTYPE) @ k.to(COMPUTE_DTYPE).transpose(-1, -2)).float() * (1.0 / math.sqrt(d))
+    if key_padding_mask is not None:
+        B, S = key_padding_mask.shape
+        scores = scores.masked_fill(key_padding_mask.view(B, 1, 1, S), float("-inf"))
+    attn = torch.softmax(scores, dim=-1)
+    if training and dropout_p > 0:
+        attn = F.dropout(attn, dropout_p, True)
+    return (attn.to(COMPUTE_DTYPE) @ v.to(COMPUTE_DTYPE)).float()
+
+
+def multi_head_attention(mha, query, key, value, key_padding_mask=None, training=False):
+    """nn.MultiheadAttention semantics (seq-first (L, B, E) inputs, returns the attended output only;
+    the reference discards the averaged weights it asks for, transformer.py:246-248)."""
+    L, B, E = query.shape
+    S = key.shape[0]
+    h = mha.num_heads
+    d = E // h
+    w, b = mha.in_proj_weight, mha.in_proj_bias
+    if query is key:  # self-attention: q = k = x + pos share one GEMM
+        qk = linear(query, w[: 2 * E], b[: 2 * E])
+        q, k = qk[..., :E], qk[..., E:]
+    else:
+        q = linear(query, w[:E], b[:E])
+        k = linear(key, w[E: 2 * E], b[E: 2 * E])
+    v = linear(value, w[2 * E:], b[2 * E:])
+    q = q.reshape(L, B, h, d).permute(1, 2, 0, 3)
+    k = k.reshape(S, B, h, d).permute(1, 2, 0, 3)
+    v = v.reshape(S, B, h, d).permute(1, 2, 0, 3)
+    o = attention(q, k, v, key_padding_mask, mha.dropout, training)
+    o = o.permute(2, 0, 1, 3).reshape(L, B, E)
+    return linear(o, mha.out_proj.weight, mha.out_proj.bias)
+
+
+def add_dropout_layernorm(x, residual, norm, p, training):
+    """LayerNorm(residual + dropout(x)) -- the post-LN epilogue of every transformer sub-block."""
+    if training and p > 0:
+        x = F.dropout(x, p, True)
+    return F.layer_norm(residual + x, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+
+
+def dropout(x, p, training):
+    return F.dropout(x, p, True) if (training and p > 0) else x
+
+
+def batchnorm_relu(x, bn):
+    """ReLU(BatchNorm1d(x)) over rows of x (R, C); training mode uses batch statistics and updates
+    the running buffers exactly like nn.BatchNorm1d (momentum, unbiased running_var)."""
+    return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
+                               bn.momentum if bn.momentum is not None else 0.0, bn.eps))
+
+
+def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn):
+    """Grouped Linear(3+C -> H, no bias) + BatchNorm1d + ReLU + max over the k neighbours
+    (act.py:446-460).  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H)."""
+    from .pointops import grouping
+
+    g = grouping(knn_idx, feat, p, new_p, with_xyz=True)  # (m, k, 3 + C)
+    m, k, cin = g.shape
+    y = linear(g.reshape(m * k, cin), linear_weight)  # (m*k, H)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    y = batchnorm_relu(y, bn)
+    return y.view(m, k, -1).max(dim=1).values
+
+
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, *, step, lr, beta1, beta2, eps, weight_decay, clip_norm):
+    """Fused clip-by-global-norm + AdamW over flat fp32 buffers (in place); returns the pre-clip
+    gradient norm as a 0-dim device tensor (no host sync).  Same arithmetic as
+    torch.nn.utils.clip_grad_norm_ followed by torch.optim.AdamW (decoupled weight decay)."""
+    _need_cuda(param)
+    norm = torch.linalg.vector_norm(grad)
+    if clip_norm is not None and clip_norm > 0:
+        grad.mul_(torch.clamp(clip_norm / (norm + 1e-6), max=1.0))
+    param.mul_(1.0 - lr * weight_decay)
+    exp_avg.lerp_(grad, 1.0 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1.0 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    denom = (exp_avg_sq.sqrt() / math.sqrt(bc2)).add_(eps)
+    param.addcdiv_(exp_avg, denom, value=-lr / bc1)
+    return norm
+
+
+# ------------------------------------------------------------------------------------------------
+# live kernel timing for bench.py's roofline (CUDA events on the launching stream)
+# ------------------------------------------------------------------------------------------------
+class _KernelTimer:
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def enable(self):
+        self.enabled, self.events = True, {}
+
+    def disable(self):
+        self.enabled = False
+
+    class _Region:
+        def __init__(self, timer, name):
+            self.t, self.name = timer, name
+
+        def __enter__(self):
+            if self.t.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.t.enabled:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.t.events.setdefault(self.name, []).append((self.e0, e1))
+            return False
+
+    def region(self, name):
+        return self._Region(self, name)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.events.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[name] = {"launches": len(ms), "avg_ms": sum(ms) / len(ms), "total_ms": sum(ms)}
+        steps = max((v["launches"] for v in out.values()), default=1)
+        for name, v in out.items():
+            v["ms_per_step"] = v["total_ms"] / max(1, min(steps, v["launches"]))
+        return out
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
+def roofline_for(kstats, peaks, batch, n_points, cfg):
+    """Roofline object for the dominant timed kernel family of the step (bench.py)."""
+    if not kstats:
+        return None
+    name = max(kstats, key=lambda k: kstats[k]["total_ms"])
+    st = kstats[name]
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    return {"kernel": name, "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+            "traffic": None, "avg_launch_ms": st["avg_ms"], "launches_timed": st["launches"], "peak_source": which}

@@ -1,0 +1,158 @@
+"""Data-parallel BC training step -- the B200 replacement for what Lightning + DDP + torch.optim do
+around the reference's `training_step` (configs/trainer/ddp.yaml:4-15,
+src/models/maniskill2_act_bc_module.py:69-86,347-367):
+
+    forward -> backward -> ONE all-reduce of a flat fp32 gradient buffer (NCCL over NVLink)
+            -> clip-by-global-norm(0.5) -> AdamW (lr 5e-5, wd 0.05) -> OneCycleLR step
+
+All parameters are views into one flat fp32 buffer and all gradients views into another, so the
+gradient exchange is a single collective and the optimizer is a single fused kernel launch over
+contiguous memory (no per-parameter loops, no host sync: the clip coefficient stays on device).
+State parity with the reference optimizer: parameters that never receive a gradient
+(`is_pad_head.*`) are skipped entirely like torch.optim.AdamW skips `grad is None`;
+the dead decoder layers receive exact zeros and are therefore only weight-decayed.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class OneCycle:
+    """torch.optim.lr_scheduler.OneCycleLR (two-phase, cos) as a pure function of the step index;
+    config of configs/model/maniskill2_act_pcd_model.yaml:16-25 (reference wrapper
+    src/utils/scheduler.py:102-139 keeps torch's defaults cycle_momentum=True, 0.85 / 0.95)."""
+
+    def __init__(self, max_lr, total_steps, pct_start=0.1, div_factor=100.0, final_div_factor=1000.0,
+                 base_momentum=0.85, max_momentum=0.95, anneal_strategy="cos"):
+        assert anneal_strategy == "cos"
+        self.total_steps = int(total_steps)
+        initial = max_lr / div_factor
+        self.phases = [
+            (float(pct_start * total_steps) - 1, initial, max_lr, max_momentum, base_momentum),
+            (total_steps - 1, max_lr, initial / final_div_factor, base_momentum, max_momentum),
+        ]
+
+    @staticmethod
+    def _cos(start, end, pct):
+        return end + (start - end) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+    def at(self, step_num: int):
+        """(lr, beta1) in force for optimizer step number `step_num` (0-based)."""
+        start_step = 0.0
+        for i, (end_step, lr0, lr1, m0, m1) in enumerate(self.phases):
+            if step_num <= end_step or i == len(self.phases) - 1:
+                pct = (step_num - start_step) / (end_step - start_step)
+                return self._cos(lr0, lr1, pct), self._cos(m0, m1, pct)
+            start_step = end_step
+        raise AssertionError
+
+
+class FlatState:
+    """Flat fp32 parameter / gradient / Adam-moment buffers with per-parameter views."""
+
+    def __init__(self, params: Iterable[nn.Parameter], inactive: Iterable[nn.Parameter] = ()):
+        inactive_ids = {id(p) for p in inactive}
+        params = [p for p in params if p.requires_grad]
+        self.active = [p for p in params if id(p) not in inactive_ids]
+        self.inactive = [p for p in params if id(p) in inactive_ids]
+        ordered = self.active + self.inactive
+        dev = ordered[0].device
+        pad4 = lambda n: (n + 3) // 4 * 4  # keep every view 16-byte aligned for 128-bit accesses
+        self.n_active = sum(pad4(p.numel()) for p in self.active)
+        total = self.n_active + sum(pad4(p.numel()) for p in self.inactive)
+        self.param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(self.n_active, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_active, dtype=torch.float32, device=dev)
+        off = 0
+        for p in ordered:
+            n = p.numel()
+            self.param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.param[off:off + n].view_as(p)
+            old = p.grad
+            p.grad = self.grad[off:off + n].view_as(p)
+            if old is not None:
+                p.grad.copy_(old)
+            off += pad4(n)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class BCTrainer:
+    def __init__(self, policy: nn.Module, lr=5e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
+                 clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None):
+        self.policy = policy
+        self.lr, self.weight_decay, self.betas, self.eps, self.clip_norm = lr, weight_decay, betas, eps, clip_norm
+        sch = dict(pct_start=0.1, div_factor=100.0, final_div_factor=1000.0)
+        sch.update(scheduler or {})
+        self.schedule = OneCycle(max_lr=lr, total_steps=total_steps, **sch)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.flat: FlatState | None = None
+        self.step_num = 0
+        self.last_grad_norm = None
+
+    # -- gradient exchange: ONE collective over the flat buffer -----------------------------------
+    def reduce_gradients(self):
+        if self.world > 1:
+            g = self.flat.grad[: self.flat.n_active]
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            g.mul_(1.0 / self.world)
+
+    def _build_flat(self):
+        inactive = [p for p in self.policy.parameters() if p.requires_grad and p.grad is None]
+        self.flat = FlatState(self.policy.parameters(), inactive)
+
+    def optimizer_step(self):
+        from . import functional as PF
+
+        lr, beta1 = self.schedule.at(min(self.step_num, self.schedule.total_steps - 1))
+        f = self.flat
+        self.last_grad_norm = PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq,
+                                                 step=self.step_num + 1, lr=lr, beta1=beta1, beta2=self.betas[1],
+                                                 eps=self.eps, weight_decay=self.weight_decay, clip_norm=self.clip_norm)
+        self.step_num += 1
+
+    def training_step(self, batch):
+        """One full step on this rank's shard; returns the (detached) loss dict."""
+        if self.flat is not None:
+            self.flat.zero_grad()
+        out = self.policy(batch)
+        out["loss"].backward()
+        if self.flat is None:  # first step: discover never-used parameters, then go flat
+            self._build_flat()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return {k: out[k].detach() for k in ("loss", "action_loss", "kl_loss")}
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    """DistributedSampler-style split of one collated global batch by SAMPLE (contiguous blocks):
+    clouds are independent units, so no data-path collective is needed."""
+    b = batch["qpos"].shape[0]
+    assert b % world == 0, "global batch must divide evenly across ranks"
+    per = b // world
+    lo, hi = rank * per, (rank + 1) * per
+    out = {}
+    for k, v in batch.items():
+        if k == "pcds":
+            off = v["offset"]
+            start = int(off[lo - 1]) if lo > 0 else 0
+            end = int(off[hi - 1])
+            pc = {kk: vv[start:end] for kk, vv in v.items() if torch.is_tensor(vv) and kk != "offset"}
+            pc["offset"] = off[lo:hi] - start
+            for kk, vv in v.items():
+                if not torch.is_tensor(vv):
+                    pc[kk] = vv
+            out[k] = pc
+        elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == b:
+            out[k] = v[lo:hi]
+        else:
+            out[k] = v
+    return out

@@ -1,0 +1,199 @@
+"""DETR-style transformer of ACT -- host-side mirror of
+`src/models/components/act/transformer.py:16-425` (same class names, constructor kwargs, parameter
+names; `nn.MultiheadAttention` / `nn.Linear` / `nn.LayerNorm` are kept purely as PARAMETER
+CONTAINERS so reference checkpoints load key-for-key -- their forward is never called; all
+arithmetic goes through pointcloudmatters_b200.functional -> libpcm_b200.so).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import functional as PF
+
+
+def _check_activation(activation):
+    if activation != "relu":
+        raise NotImplementedError("the B200 path implements the reference's configured activation (relu) only")
+
+
+class TransformerEncoderLayer(nn.Module):
+    """transformer.py:210-283."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__()
+        _check_activation(activation)
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+        self.p = dropout
+
+    def _ffn(self, x):
+        h = PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
+        return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+
+    def forward(self, src, src_mask: Optional[Tensor] = None, src_key_padding_mask: Optional[Tensor] = None,
+                pos: Optional[Tensor] = None):
+        assert src_mask is None, "attn_mask is never used by the reference ACT path"
+        tr = self.training
+        if self.normalize_before:
+            s2 = PF.add_dropout_layernorm(torch.zeros_like(src), src, self.norm1, 0.0, False)
+            qk = s2 if pos is None else s2 + pos
+            src = src + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, s2, src_key_padding_mask, tr), self.p, tr)
+            s2 = PF.add_dropout_layernorm(torch.zeros_like(src), src, self.norm2, 0.0, False)
+            return src + PF.dropout(self._ffn(s2), self.p, tr)
+        qk = src if pos is None else src + pos
+        a = PF.multi_head_attention(self.self_attn, qk, qk, src, src_key_padding_mask, tr)
+        src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr)
+        return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr)
+
+
+class TransformerEncoder(nn.Module):
+    """transformer.py:118-158."""
+
+    def __init__(self, d_model=256, nhead=8, dim_feedforward=2048, dropout=0.1, activation="relu",
+                 normalize_before=False, num_layers=4):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerEncoderLayer(d_model, nhead, dim_feedforward, dropout, activation,
+                                                             normalize_before) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = nn.LayerNorm(d_model) if normalize_before else None
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, pos=None):
+        out = src
+        for layer in self.layers:
+            out = layer(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+        if self.norm is not None:
+            out = PF.add_dropout_layernorm(torch.zeros_like(out), out, self.norm, 0.0, False)
+        return out
+
+
+class TransformerDecoderLayer(nn.Module):
+    """transformer.py:286-404."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__()
+        _check_activation(activation)
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+        self.p = dropout
+
+    def _ffn(self, x):
+        h = PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
+        return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos=None, query_pos=None):
+        assert tgt_mask is None and memory_mask is None and tgt_key_padding_mask is None
+        tr = self.training
+        wq = (lambda t: t if query_pos is None else t + query_pos)
+        mem_k = memory if pos is None else memory + pos
+        if self.normalize_before:
+            ln = (lambda x, n: PF.add_dropout_layernorm(torch.zeros_like(x), x, n, 0.0, False))
+            t2 = ln(tgt, self.norm1)
+            qk = wq(t2)
+            tgt = tgt + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, t2, None, tr), self.p, tr)
+            t2 = ln(tgt, self.norm2)
+            tgt = tgt + PF.dropout(PF.multi_head_attention(self.multihead_attn, wq(t2), mem_k, memory,
+                                                           memory_key_padding_mask, tr), self.p, tr)
+            t2 = ln(tgt, self.norm3)
+            return tgt + PF.dropout(self._ffn(t2), self.p, tr)
+        qk = wq(tgt)
+        a = PF.multi_head_attention(self.self_attn, qk, qk, tgt, None, tr)
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr)
+        a = PF.multi_head_attention(self.multihead_attn, wq(tgt), mem_k, memory, memory_key_padding_mask, tr)
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr)
+        return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr)
+
+
+class TransformerDecoder(nn.Module):
+    """transformer.py:161-207.  `skip_dead_layers` (off by default = like-for-like with the
+    reference) stops after the first layer when only intermediate [0] is consumed downstream."""
+
+    def __init__(self, decoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        import copy
+
+        self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+        self.skip_dead_layers = False
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos=None, query_pos=None):
+        out, inter = tgt, []
+        ln = (lambda x: PF.add_dropout_layernorm(torch.zeros_like(x), x, self.norm, 0.0, False))
+        for li, layer in enumerate(self.layers):
+            out = layer(out, memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos)
+            if self.return_intermediate:
+                inter.append(ln(out))
+                if self.skip_dead_layers and li == 0:
+                    return torch.stack(inter)
+        if self.norm is not None:
+            out = ln(out)
+            if self.return_intermediate:
+                inter[-1] = out
+        if self.return_intermediate:
+            return torch.stack(inter)
+        return out.unsqueeze(0)
+
+
+class Transformer(nn.Module):
+    """transformer.py:16-115."""
+
+    def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                 dropout=0.1, activation="relu", normalize_before=False, return_intermediate_dec=False):
+        super().__init__()
+        self.encoder = TransformerEncoder(d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward,
+                                          dropout=dropout, activation=activation, normalize_before=normalize_before,
+                                          num_layers=num_encoder_layers)
+        layer = TransformerDecoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before)
+        self.decoder = TransformerDecoder(layer, num_decoder_layers, nn.LayerNorm(d_model),
+                                          return_intermediate=return_intermediate_dec)
+        self._reset_parameters()
+        self.d_model = d_model
+        self.nhead = nhead
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, src, mask, query_embed, pos_embed, latent_input=None, proprio_input=None,
+                additional_pos_embed=None):
+        bs = src.shape[0]
+        src = src.flatten(2).permute(2, 0, 1)
+        pos_embed = pos_embed.flatten(2).permute(2, 0, 1)
+        if pos_embed.shape[1] == 1:
+            pos_embed = pos_embed.repeat(1, bs, 1)
+        query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
+        additional_pos_embed = additional_pos_embed.unsqueeze(1).repeat(1, bs, 1)
+        pos_embed = torch.cat([additional_pos_embed, pos_embed], dim=0)
+        if latent_input.dim() == 2:
+            addition_input = torch.stack([latent_input, proprio_input], dim=0)
+        else:
+            addition_input = torch.cat([latent_input, proprio_input], dim=0)
+        src = torch.cat([addition_input, src], dim=0)
+        tgt = torch.zeros_like(query_embed)
+        memory = self.encoder(src, src_key_padding_mask=mask, pos=pos_embed)
+        hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed)
+        return hs.transpose(1, 2)
