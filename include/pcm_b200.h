@@ -141,6 +141,26 @@ int pcm_attention_fusion_step_backward(int m, int g, int c, const float *weight,
                                        const int *index_target, const int *index_refer,
                                        const float *grad_output, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense blocks of the policy.  The reference runs these through
+ * torch.nn (cuBLAS SGEMM, ATen kernels): nn.Linear / MultiheadAttention in-proj / out-proj
+ * (src/models/components/act/transformer.py:220-233,297-314), PointNet's k=1 SubMConv3d layers
+ * (src/models/components/pcd_encoder/pointnet.py:31-55) and the set-abstraction Linear
+ * (src/models/components/act/act.py:368-370,457-459).
+ * ------------------------------------------------------------------------------------------ */
+
+/* C[m,n] (+)= sum_k A(m,k) * B(n,k) (+ bias[n]) (ReLU) on tcgen05 tensor cores: bf16 operands,
+ * fp32 accumulation in tensor memory, TMA-fed 128B-swizzled shared-memory ring.
+ *   a_mn / b_mn = 0: operand stored row-major [rows, K], pitch ld elements (K contiguous);
+ *               = 1: stored row-major [K, rows], pitch ld (rows contiguous) -- lets dX = dY * W and
+ *                    dW = dY^T * X read tensors in place, without transposes.
+ *   c_bf16: C is bf16 (else fp32), pitch ldc.  accumulate: atomically ADD into fp32 C
+ *   (gradient accumulation; implied when split_k > 1).  bias / relu only with split_k == 1.
+ * Base pointers must be 16-byte aligned and lda / ldb multiples of 8 (TMA). */
+int pcm_gemm_bf16(int M, int N, int K, const void *A, int lda, int a_mn, const void *B, int ldb,
+                  int b_mn, void *C, int ldc, int c_bf16, const float *bias, int relu,
+                  int accumulate, int split_k, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

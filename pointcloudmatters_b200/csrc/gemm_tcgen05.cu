@@ -1,0 +1,401 @@
+// gemm_tcgen05.cu -- bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//     C[m, n] (+)= sum_k A(m, k) * B(n, k)   (+ bias[n]) (ReLU)        C: fp32 or bf16
+//
+// Hand-written tcgen05 / TMEM / TMA kernel (inline PTX, no CUTLASS):
+//   * warp 0 (one elected lane): TMA producer -- cp.async.bulk.tensor.2d tiles into a 128B-swizzled
+//     shared-memory ring, completion counted on mbarriers (expect_tx);
+//   * warp 1 (one elected lane): issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BLOCK_N x 16)
+//     with the fp32 accumulator in TENSOR MEMORY, releases ring slots with tcgen05.commit;
+//     the same warp owns tcgen05.alloc / dealloc;
+//   * warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / cast ->
+//     128-byte-per-thread global stores, or red.global.add.f32 for split-K accumulation.
+// Both operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
+// second form lets the backward GEMMs (dX = dY W, dW = dY^T X) read activations / weights in the
+// layout they already have, with no transpose pass.  Shared-memory layouts are the canonical UMMA
+// SWIZZLE_128B layouts (K-major: 8-row x 128 B atoms, SBO = 1024 B; MN-major: 64-element x 8-row
+// atoms, SBO = 1024 B, LBO = BLOCK_K * 128 B) which are exactly what a SWIZZLE_128B TMA box writes.
+// One output tile per CTA; 3-stage ring (96 KB) so that two CTAs share an SM and one CTA's
+// epilogue overlaps the other's main loop.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), sm_100 version field = 1.
+// Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version [46,48), layout_type [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct GemmParams {
+    int M, N, K;
+    int k_blocks_per_split;  // split-K: blockIdx.z covers [z * kbps, min((z+1) * kbps, kblocks))
+    void* C;
+    int ldc;
+    const float* bias;
+    int relu;
+    int c_bf16;
+    int atomic;  // red.global.add.f32 (split-K / gradient accumulation); C must be fp32
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                   const __grid_constant__ CUtensorMap tmap_b,
+                                                                   const GemmParams p) {
+    constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=BF16
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+    const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kb0 = blockIdx.z * p.k_blocks_per_split;
+    const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = tiles + s * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int k0 = (kb0 + i) * BLOCK_K;
+                if (!A_MN) {
+                    tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m_blk * BLOCK_M);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_M / 64; ++c)
+                        tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n_blk * BLOCK_N);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N / 64; ++c)
+                        tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 rows of 128 B
+                    const uint64_t da = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                             : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+                    const uint64_t db = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                             : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                    umma_f16(tmem_base, da, db, IDESC, (i | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        const int row = m_blk * BLOCK_M + quad * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            const int col0 = n_blk * BLOCK_N + c0;
+            if (row < p.M && col0 < p.N) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                const bool full = (col0 + 32 <= p.N);
+                if (p.atomic) {
+                    float* crow = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full || col0 + j < p.N) atomicAdd(crow + j, f[j]);
+                } else if (p.c_bf16) {
+                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+                    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
+                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                            *reinterpret_cast<uint4*>(crow + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* crow = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[j] = f[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t inner, outer, ld;
+    uint32_t box_inner, box_outer;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 tensor map over a row-major [outer, inner] matrix with row pitch `ld` elements,
+// SWIZZLE_128B boxes of box_inner (= 64) x box_outer elements, zero fill out of bounds.
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    static std::mutex mu;
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 700 + (int)r;
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, cudaStream_t st) {
+    constexpr size_t SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, (p.N + BLOCK_N - 1) / BLOCK_N, split_k);
+    gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
+    return pcm_launch_status();
+}
+
+}  // namespace
+
+// C[m, n] (+)= sum_k A(m, k) B(n, k) (+ bias[n]) (ReLU).  a_mn / b_mn = 0: operand stored row-major
+// [rows, K] with pitch ld (K contiguous); = 1: stored row-major [K, rows] with pitch ld (rows
+// contiguous).  c_bf16: output dtype; accumulate: atomically add into fp32 C (required if split_k > 1).
+PCM_API int pcm_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
+                          void* C, int ldc, int c_bf16, const float* bias, int relu, int accumulate, int split_k,
+                          pcm_stream_t stream) {
+    if (M <= 0 || N <= 0) return PCM_OK;
+    if (!A || !B || !C || K <= 0) return PCM_EINVAL;
+    if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return PCM_EUNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
+    if (split_k < 1) split_k = 1;
+    if ((split_k > 1 || accumulate) && c_bf16) return PCM_EINVAL;
+    if (split_k > 1 && (bias || relu)) return PCM_EINVAL;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    if (split_k > kblocks) split_k = kblocks;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.k_blocks_per_split = (kblocks + split_k - 1) / split_k;
+    split_k = (kblocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16;
+    p.atomic = (accumulate || split_k > 1) ? 1 : 0;
+    const int BN = 128;
+    CUtensorMap ta, tb;
+    int r;
+    if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BLOCK_M, &ta);
+    else r = get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BLOCK_K, &ta);
+    if (r) return r;
+    if (!b_mn) r = get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN, &tb);
+    else r = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BLOCK_K, &tb);
+    if (r) return r;
+    cudaStream_t st = pcm_cu_stream(stream);
+    if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, st);
+    if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, st);
+    if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, p, split_k, st);
+    return launch<128, true, true>(ta, tb, p, split_k, st);
+}

@@ -1,0 +1,32 @@
+"""Low-level Python bindings of the dense kernels of libpcm_b200.so (one function per C-ABI entry
+point; tensors in, tensors out, launches on torch's current stream).  `functional.py` builds the
+autograd-aware operators on top of these."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, current_stream, lib, ptr, require_cuda
+
+
+def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32, bias=None, relu=False,
+              accumulate=False, split_k=1):
+    """C[m,n] (+)= sum_k A(m,k) B(n,k) (+bias) (ReLU) on tcgen05 (pcm_gemm_bf16).
+
+    a: bf16, (M, K) if not a_mn else (K, M); b: bf16, (N, K) if not b_mn else (K, N); last dim
+    contiguous.  Returns C (M, N) of out_dtype (fp32 or bf16); with `accumulate` adds into `out`."""
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    check(lib.pcm_gemm_bf16(M, N, K, ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out),
+                            out.stride(0), int(out.dtype == torch.bfloat16), ptr(bias), int(relu), int(accumulate),
+                            int(split_k), current_stream()), "pcm_gemm_bf16")
+    return out
