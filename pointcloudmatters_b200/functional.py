@@ -13,6 +13,7 @@ import math
 import torch
 import torch.nn.functional as F
 
+from . import kernels as K
 from ._lib import PcmError
 
 COMPUTE_DTYPE = torch.bfloat16
@@ -23,12 +24,65 @@ def _need_cuda(t):
         raise PcmError("pointcloudmatters_b200 runs on CUDA tensors only (no CPU fallback)")
 
 
-def linear(x, weight, bias=None, relu=False):
-    """y = x @ weight^T (+ bias) (+ ReLU); x (..., K), weight (N, K) fp32 master -> y fp32."""
+def _split_k_for(m_tiles, n_tiles, kblocks):
+    """Enough CTAs for ~2 waves of the 148 SMs when the output is small and K is long (dW GEMMs)."""
+    want = max(1, (2 * 148 + m_tiles * n_tiles - 1) // (m_tiles * n_tiles))
+    return max(1, min(want, kblocks))
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T (+b) (ReLU) on the tcgen05 GEMM; backward dX = dY W and dW = dY^T X read dY, W, X in
+    place through the MN-major operand forms of the same kernel (no transposes)."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias, relu, out_bf16):
+        xb = x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16)
+        wb = weight.to(torch.bfloat16)
+        y = K.gemm_bf16(xb, wb, bias=bias, relu=relu, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        ctx.relu, ctx.has_bias, ctx.x_dtype = relu, bias is not None, x2.dtype
+        ctx.save_for_backward(xb, wb, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, y = ctx.saved_tensors
+        if ctx.relu:
+            dy = dy * (y > 0)
+        dyb = dy.contiguous() if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        M, N = dyb.shape
+        Kin = xb.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm_bf16(dyb, wb, b_mn=True)  # (M, N) x W(N, Kin) -> (M, Kin)
+            if ctx.x_dtype == torch.bfloat16:
+                dx = dx.to(torch.bfloat16)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((N, Kin), dtype=torch.float32, device=dyb.device)
+            sk = _split_k_for((N + 127) // 128, (Kin + 127) // 128, (M + 63) // 64)
+            K.gemm_bf16(dyb, xb, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=sk)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dx, dw, db, None, None
+
+
+def linear(x, weight, bias=None, relu=False, out_bf16=False):
+    """y = x @ weight^T (+ bias) (+ ReLU); x (..., K) fp32 or bf16, weight (N, K) fp32 master.
+
+    Tensor-core path (pcm_gemm_bf16, tcgen05) whenever TMA's alignment rules allow (K, N multiples
+    of 8); the handful of tiny embedding / head linears with K or N in {1, 3, 6, 7, 9} are plain
+    fp32 library GEMMs (well under 0.1% of the step's FLOPs)."""
     _need_cuda(x)
-    y = F.linear(x.to(COMPUTE_DTYPE), weight.to(COMPUTE_DTYPE)).float()
-    if bias is not None:
-        y = y + bias
+    N, Kin = weight.shape
+    lead = x.shape[:-1]
+    if Kin % 8 == 0 and N % 8 == 0 and Kin >= 16:
+        x2 = x.reshape(-1, Kin)
+        if x2.stride(-1) != 1 or (x2.stride(0) % 8) or (x2.data_ptr() % 16):
+            x2 = x2.contiguous()
+        if weight.stride(-1) != 1:
+            weight = weight.contiguous()
+        y = _LinearTC.apply(x2, weight, bias, relu, out_bf16)
+        return y.view(*lead, N)
+    y = F.linear(x.float(), weight, bias)
     return F.relu(y) if relu else y
 
 
