@@ -45,6 +45,10 @@ def test_policy_matches_reference_fixture(path):
     got_nograd = sorted(k for k, p in model.named_parameters() if p.grad is None)
     assert got_nograd == sorted(nograd)
     worst = {}
+    # gradients whose true value is ~0 (e.g. q/k projections of decoder layer 0's self-attention:
+    # tgt = 0 makes every value row identical, so d(out)/d(scores) = 0) are pure rounding noise on
+    # both sides; compare them on the scale of the whole gradient instead of their own norm.
+    floor = 1e-3 * max(v[0] for v in grads.values())
     for k, p in model.named_parameters():
         if p.grad is None:
             continue
@@ -53,7 +57,8 @@ def test_policy_matches_reference_fixture(path):
             assert got[0] == 0.0, k  # dead decoder layers: exactly zero
             continue
         # norm and strided samples, relative to the tensor's gradient norm
-        err = max(abs(got[0] - want[0]) / max(want[0], 1e-9), np.abs(got[2:] - want[2:]).max() / max(want[0], 1e-9))
+        scale = max(want[0], floor)
+        err = max(abs(got[0] - want[0]) / scale, np.abs(got[2:] - want[2:]).max() / scale)
         worst[k] = err
     bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
     assert not bad, bad

@@ -1,0 +1,35 @@
+"""Per-kernel breakdown of the cfg-2 training step (torch.profiler, CUDA activities).
+Usage: python tools/profile_step.py [steps] -> gpurun_out/profile_step.txt"""
+import sys
+from pathlib import Path
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from pointcloudmatters_b200.act import build_policy  # noqa: E402
+from pointcloudmatters_b200.bc_module import ACTBCModule  # noqa: E402
+from pointcloudmatters_b200.data import synthetic_act_batch, to_device  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+policy = build_policy(bench.CFG2).to(dev).train()
+module = ACTBCModule(policy, total_steps=1000)
+hb = synthetic_act_batch(64, 1024, seed=1)
+b = to_device(hb, dev)
+b["pcds"]["n_max"] = hb["pcds"]["n_max"]
+for i in range(3):
+    module.training_step(b, i)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(steps):
+        module.training_step(b, i)
+    torch.cuda.synchronize()
+tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+out = ROOT / "gpurun_out" / "profile_step.txt"
+out.parent.mkdir(exist_ok=True)
+out.write_text(tab)
+print(tab[-9000:])
