@@ -161,6 +161,37 @@ int pcm_gemm_bf16(int M, int N, int K, const void *A, int lda, int a_mn, const v
                   int b_mn, void *C, int ldc, int c_bf16, const float *bias, int relu,
                   int accumulate, int split_k, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused set-abstraction head.  Replaces, for ACTPCD.pcd_sampling (src/models/components/act/
+ * act.py:446-460) and PCDObsEncoder.pcd_sampling (.../vision/pcd_obs_encoder.py:179-193), the
+ * chain pointops.grouping(with_xyz=True) (libs/pointops/functions/grouping.py:35-59) ->
+ * nn.Linear(3+C -> H, bias=False) -> BatchNorm1d(H) -> ReLU -> MaxPool1d(k).  See
+ * csrc/sa_fused.cu for the reformulation.  W is the Linear weight (H, 3+C) with row pitch ldw;
+ * Pf = feat * W[:, 3:]^T (n, H) fp32 comes from pcm_gemm_bf16; idx (m, k) int32 (-1 = padding).
+ * stats / gstats are zero-initialised (5, H) fp64 accumulators; coef = [a, b, mean, invstd] (4, H).
+ * ------------------------------------------------------------------------------------------ */
+int pcm_sa_gather_stats(int m, int k, int H, const float *Pf, const float *xyz, const float *new_xyz,
+                        const int *idx, const float *W, int ldw, float *ymax, float *ymin,
+                        unsigned char *jmax, unsigned char *jmin, double *stats, pcm_stream_t stream);
+int pcm_sa_bn_finalize(int H, const double *stats, double n_rows, const float *gamma,
+                       const float *beta, float eps, float momentum, int training,
+                       float *running_mean, float *running_var, float *coef, pcm_stream_t stream);
+int pcm_sa_output(int m, int H, const float *ymax, const float *ymin, const unsigned char *jmax,
+                  const unsigned char *jmin, const float *coef, float *out, unsigned char *jsel,
+                  pcm_stream_t stream);
+int pcm_sa_bwd_scatter(int m, int k, int H, const float *dout, const float *out,
+                       const unsigned char *jsel, const int *idx, const float *xyz,
+                       const float *new_xyz, const float *coef, float *dPf, double *gstats,
+                       pcm_stream_t stream);
+int pcm_sa_edge_stats(int m, int k, const int *idx, const float *xyz, const float *new_xyz,
+                      float *cnt, float *sq, double *sdtot, pcm_stream_t stream);
+int pcm_sa_bwd_coef(int H, const double *gstats, const double *fstats, const double *sdtot,
+                    const float *coef, double n_rows, int training, float *ab, float *dW, int ldw,
+                    float *dgamma, float *dbeta, pcm_stream_t stream);
+int pcm_sa_bwd_dense(int n, int H, const float *Pf, const float *xyz, const float *cnt,
+                     const float *sq, const float *W, int ldw, const float *ab, const float *dPf,
+                     void *dPf_bf16, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

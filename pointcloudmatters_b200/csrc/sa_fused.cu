@@ -1,0 +1,369 @@
+// sa_fused.cu -- fused set-abstraction head for sm_100a.
+//
+// Replaces the chain in ACTPCD.pcd_sampling (reference src/models/components/act/act.py:446-460):
+//     grouping(idx, feat, xyz, new_xyz, with_xyz=True)      -> (m, k, 3+C)    1.08 GB at cfg-2
+//     Linear(3+C -> H, bias=False)                          -> (m, k, H)      276 GFLOP fp32 SGEMM
+//     transpose/contiguous, BatchNorm1d(H) (batch stats), ReLU, MaxPool1d(k)   3 more 1 GB passes
+// by an algebraically exact reformulation that never materialises an (m, k, .) tensor:
+//     y[m,j,c] = W[c,:] . [xyz[i]-q_m, feat[i]] = Pf[i,c] + Wx[c,:] . (xyz[i] - q_m),   i = idx[m,j]
+//     Pf = feat Wf^T  -- ONE (n x C) x (C x H) GEMM over SOURCE points on tcgen05 (36 GFLOP);
+//     BatchNorm is a per-channel monotone affine map, so
+//     out[m,c] = ReLU(a_c * (a_c >= 0 ? max_j y : min_j y) + b_c).
+// Forward = one gather pass (pcm_sa_gather_stats: per (m,c) max / min / arg + per-channel sum,
+// sum of squares and sum of y*dxyz in fp64) + BN finalize + an (m x H) elementwise pass.
+// Backward is exact for training-mode BN: dy[m,j,c] = a_c*(delta_{j=j*} dz[m,c] - A_c - xhat*B_c)
+// splits into a SPARSE part (one scatter per (m,c)) and a DENSE part that is affine in y and
+// therefore collapses per source point: dPf[i,c] = cnt_i*(alpha_c + beta_c*Pf[i,c]) +
+// beta_c * Wx[c,:].(cnt_i*xyz_i - SQ_i).  All kernels are HBM/L2-bound gathers: one thread owns 4
+// channels (128-bit loads of a Pf row), a CTA owns a strip of queries, per-channel partial sums
+// live in registers and reach global memory as one fp64 atomic per channel per CTA.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SA_STAT_ROWS = 5;  // s1, s2, sum y*dx, sum y*dy, sum y*dz   (forward)
+                                 // dbeta, dgamma, sparse dWx[0..2]        (backward)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ---- forward gather ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sa_gather_stats_kernel(
+    const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+    const int* __restrict__ idx, const float* __restrict__ W, int ldw, int m, int k, int H,
+    float* __restrict__ ymax, float* __restrict__ ymin, unsigned char* __restrict__ jmax,
+    unsigned char* __restrict__ jmin, double* __restrict__ stats) {
+    const int c0 = threadIdx.x * 4;
+    const bool act = c0 < H;
+    float wx[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wx[v][d] = act ? __ldg(W + (size_t)(c0 + v) * ldw + d) : 0.f;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
+    for (int q = blockIdx.x; q < m; q += gridDim.x) {
+        const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
+        float mx[4], mn[4];
+        int amx[4] = {0, 0, 0, 0}, amn[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { mx[v] = -INFINITY; mn[v] = INFINITY; }
+        const int* qi = idx + (size_t)q * k;
+        for (int j = 0; j < k; ++j) {
+            const int i = __ldg(qi + j);
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i >= 0) {  // -1 = padding: the reference groups an all-zero row (y = 0, still counted by BN)
+                dx = __ldg(xyz + (size_t)i * 3 + 0) - qx;
+                dy = __ldg(xyz + (size_t)i * 3 + 1) - qy;
+                dz = __ldg(xyz + (size_t)i * 3 + 2) - qz;
+                if (act) pf = ld4(Pf + (size_t)i * H + c0);
+            }
+            const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, pv[v])));
+                if (y > mx[v]) { mx[v] = y; amx[v] = j; }
+                if (y < mn[v]) { mn[v] = y; amn[v] = j; }
+                s1[v] += y;
+                s2[v] = fmaf(y, y, s2[v]);
+                sx[v] = fmaf(y, dx, sx[v]);
+                sy[v] = fmaf(y, dy, sy[v]);
+                sz[v] = fmaf(y, dz, sz[v]);
+            }
+        }
+        if (act) {
+            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+            *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<uchar4*>(jmax + (size_t)q * H + c0) = make_uchar4(amx[0], amx[1], amx[2], amx[3]);
+            *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            atomicAdd(stats + 0 * H + c0 + v, (double)s1[v]);
+            atomicAdd(stats + 1 * H + c0 + v, (double)s2[v]);
+            atomicAdd(stats + 2 * H + c0 + v, (double)sx[v]);
+            atomicAdd(stats + 3 * H + c0 + v, (double)sy[v]);
+            atomicAdd(stats + 4 * H + c0 + v, (double)sz[v]);
+        }
+    }
+}
+
+// ---- BatchNorm finalize: coef = [a, b, mean, invstd] (4 x H), running-stat update -------------
+__global__ void sa_bn_finalize_kernel(const double* __restrict__ stats, double n_rows, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, float momentum, int training,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                      float* __restrict__ coef, int H) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    double mean, var;
+    if (training) {
+        mean = stats[c] / n_rows;
+        var = stats[H + c] / n_rows - mean * mean;
+        if (var < 0) var = 0;
+        if (running_mean) {
+            const double unbiased = n_rows > 1 ? var * n_rows / (n_rows - 1) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const double a = (double)gamma[c] * invstd;
+    coef[0 * H + c] = (float)a;
+    coef[1 * H + c] = (float)((double)beta[c] - mean * a);
+    coef[2 * H + c] = (float)mean;
+    coef[3 * H + c] = (float)invstd;
+}
+
+// ---- out = ReLU(a * ext + b); jsel = arg of the selected extreme -------------------------------
+__global__ void __launch_bounds__(256) sa_output_kernel(const float* __restrict__ ymax, const float* __restrict__ ymin,
+                                                        const unsigned char* __restrict__ jmax,
+                                                        const unsigned char* __restrict__ jmin,
+                                                        const float* __restrict__ coef, long total, int H,
+                                                        float* __restrict__ out, unsigned char* __restrict__ jsel) {
+    for (long e = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < total; e += (long)gridDim.x * blockDim.x * 4) {
+        const int c = (int)(e % H);
+        const float4 a = ld4(coef + c), b = ld4(coef + H + c);
+        const float4 hi = ld4(ymax + e), lo = ld4(ymin + e);
+        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = *reinterpret_cast<const uchar4*>(jmin + e);
+        float4 o;
+        uchar4 js;
+        o.x = fmaxf(fmaf(a.x, a.x >= 0.f ? hi.x : lo.x, b.x), 0.f); js.x = a.x >= 0.f ? jh.x : jl.x;
+        o.y = fmaxf(fmaf(a.y, a.y >= 0.f ? hi.y : lo.y, b.y), 0.f); js.y = a.y >= 0.f ? jh.y : jl.y;
+        o.z = fmaxf(fmaf(a.z, a.z >= 0.f ? hi.z : lo.z, b.z), 0.f); js.z = a.z >= 0.f ? jh.z : jl.z;
+        o.w = fmaxf(fmaf(a.w, a.w >= 0.f ? hi.w : lo.w, b.w), 0.f); js.w = a.w >= 0.f ? jh.w : jl.w;
+        *reinterpret_cast<float4*>(out + e) = o;
+        *reinterpret_cast<uchar4*>(jsel + e) = js;
+    }
+}
+
+// ---- backward pass 1: per-channel reductions + sparse scatter ----------------------------------
+// gstats rows: 0 dbeta = sum dz, 1 dgamma = sum dz*xhat_sel, 2..4 sum a*dz*dxyz_sel (sparse dWx)
+__global__ void __launch_bounds__(256) sa_bwd_scatter_kernel(
+    const float* __restrict__ dout, const float* __restrict__ out, const unsigned char* __restrict__ jsel,
+    const int* __restrict__ idx, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+    const float* __restrict__ coef, int m, int k, int H, float* __restrict__ dPf, double* __restrict__ gstats) {
+    const int c0 = threadIdx.x * 4;
+    const bool act = c0 < H;
+    float a[4], b[4], mean[4], invstd[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        a[v] = act ? coef[0 * H + c0 + v] : 0.f;
+        b[v] = act ? coef[1 * H + c0 + v] : 0.f;
+        mean[v] = act ? coef[2 * H + c0 + v] : 0.f;
+        invstd[v] = act ? coef[3 * H + c0 + v] : 0.f;
+    }
+    float g0[4] = {0, 0, 0, 0}, g1[4] = {0, 0, 0, 0}, gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, gz[4] = {0, 0, 0, 0};
+    for (int q = blockIdx.x; q < m; q += gridDim.x) {
+        if (!act) continue;
+        const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
+        const float4 d4 = ld4(dout + (size_t)q * H + c0), o4 = ld4(out + (size_t)q * H + c0);
+        const uchar4 j4 = *reinterpret_cast<const uchar4*>(jsel + (size_t)q * H + c0);
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+        const int jv[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (ov[v] > 0.f && dv[v] != 0.f) {
+                const float dz = dv[v];
+                const float ysel = a[v] != 0.f ? (ov[v] - b[v]) / a[v] : mean[v];
+                g0[v] += dz;
+                g1[v] = fmaf(dz, (ysel - mean[v]) * invstd[v], g1[v]);
+                const int i = __ldg(idx + (size_t)q * k + jv[v]);
+                if (i >= 0) {
+                    const float adz = a[v] * dz;
+                    atomicAdd(dPf + (size_t)i * H + c0 + v, adz);
+                    gx[v] = fmaf(adz, __ldg(xyz + (size_t)i * 3 + 0) - qx, gx[v]);
+                    gy[v] = fmaf(adz, __ldg(xyz + (size_t)i * 3 + 1) - qy, gy[v]);
+                    gz[v] = fmaf(adz, __ldg(xyz + (size_t)i * 3 + 2) - qz, gz[v]);
+                }
+            }
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            atomicAdd(gstats + 0 * H + c0 + v, (double)g0[v]);
+            atomicAdd(gstats + 1 * H + c0 + v, (double)g1[v]);
+            atomicAdd(gstats + 2 * H + c0 + v, (double)gx[v]);
+            atomicAdd(gstats + 3 * H + c0 + v, (double)gy[v]);
+            atomicAdd(gstats + 4 * H + c0 + v, (double)gz[v]);
+        }
+    }
+}
+
+// ---- edge statistics: cnt[i], SQ[i] = sum of q over incoming edges, total sum of dxyz ---------
+__global__ void __launch_bounds__(256) sa_edge_stats_kernel(const int* __restrict__ idx, const float* __restrict__ xyz,
+                                                            const float* __restrict__ new_xyz, long edges, int k,
+                                                            float* __restrict__ cnt, float* __restrict__ sq,
+                                                            double* __restrict__ sdtot) {
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < edges; e += (long)gridDim.x * blockDim.x) {
+        const int i = __ldg(idx + e);
+        if (i < 0) continue;
+        const long q = e / k;
+        const float qx = __ldg(new_xyz + q * 3 + 0), qy = __ldg(new_xyz + q * 3 + 1), qz = __ldg(new_xyz + q * 3 + 2);
+        atomicAdd(cnt + i, 1.0f);
+        atomicAdd(sq + (size_t)i * 3 + 0, qx);
+        atomicAdd(sq + (size_t)i * 3 + 1, qy);
+        atomicAdd(sq + (size_t)i * 3 + 2, qz);
+        tx += __ldg(xyz + (size_t)i * 3 + 0) - qx;
+        ty += __ldg(xyz + (size_t)i * 3 + 1) - qy;
+        tz += __ldg(xyz + (size_t)i * 3 + 2) - qz;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        tx += __shfl_xor_sync(PCM_FULL_MASK, tx, o);
+        ty += __shfl_xor_sync(PCM_FULL_MASK, ty, o);
+        tz += __shfl_xor_sync(PCM_FULL_MASK, tz, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sdtot + 0, (double)tx);
+        atomicAdd(sdtot + 1, (double)ty);
+        atomicAdd(sdtot + 2, (double)tz);
+    }
+}
+
+// ---- backward coefficients: alpha, beta' (2 x H) + the small parameter gradients --------------
+// dW[:, 0:3] (pitch ldw) += sparse + alpha*SDtot + beta'*SYD ; dgamma, dbeta.
+__global__ void sa_bwd_coef_kernel(const double* __restrict__ gstats, const double* __restrict__ fstats,
+                                   const double* __restrict__ sdtot, const float* __restrict__ coef, double n_rows,
+                                   int training, int H, float* __restrict__ ab, float* __restrict__ dW, int ldw,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    const double a = coef[c], mean = coef[2 * H + c], invstd = coef[3 * H + c];
+    const double dbe = gstats[c], dga = gstats[H + c];
+    double alpha = 0.0, betap = 0.0;
+    if (training) {
+        const double A = dbe / n_rows, B = dga / n_rows;
+        betap = -a * B * invstd;
+        alpha = -a * A - betap * mean;
+    }
+    ab[c] = (float)alpha;
+    ab[H + c] = (float)betap;
+    if (dgamma) dgamma[c] = (float)dga;
+    if (dbeta) dbeta[c] = (float)dbe;
+    if (dW) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            dW[(size_t)c * ldw + d] = (float)(gstats[(2 + d) * H + c] + alpha * sdtot[d] + betap * fstats[(2 + d) * H + c]);
+    }
+}
+
+// ---- backward dense part over source points; emits the bf16 operand of the two dPf GEMMs ------
+__global__ void __launch_bounds__(256) sa_bwd_dense_kernel(const float* __restrict__ Pf, const float* __restrict__ xyz,
+                                                           const float* __restrict__ cnt, const float* __restrict__ sq,
+                                                           const float* __restrict__ W, int ldw,
+                                                           const float* __restrict__ ab, int n, int H,
+                                                           const float* __restrict__ dPf,
+                                                           __nv_bfloat16* __restrict__ dPf_bf16) {
+    const int c0 = threadIdx.x * 4;
+    if (c0 >= H) return;
+    float wx[4][3], al[4], be[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wx[v][d] = __ldg(W + (size_t)(c0 + v) * ldw + d);
+        al[v] = ab[c0 + v];
+        be[v] = ab[H + c0 + v];
+    }
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const float cn = __ldg(cnt + i);
+        const float ex = cn * __ldg(xyz + (size_t)i * 3 + 0) - __ldg(sq + (size_t)i * 3 + 0);
+        const float ey = cn * __ldg(xyz + (size_t)i * 3 + 1) - __ldg(sq + (size_t)i * 3 + 1);
+        const float ez = cn * __ldg(xyz + (size_t)i * 3 + 2) - __ldg(sq + (size_t)i * 3 + 2);
+        const float4 pf = ld4(Pf + (size_t)i * H + c0), sp = ld4(dPf + (size_t)i * H + c0);
+        const float pv[4] = {pf.x, pf.y, pf.z, pf.w}, sv[4] = {sp.x, sp.y, sp.z, sp.w};
+        float r[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float wd = fmaf(wx[v][2], ez, fmaf(wx[v][1], ey, wx[v][0] * ex));
+            r[v] = sv[v] + cn * fmaf(be[v], pv[v], al[v]) + be[v] * wd;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dPf_bf16 + (size_t)i * H + c0) = pk;
+    }
+}
+
+inline int sa_threads(int H) { return ((H / 4 + 31) / 32) * 32; }
+inline int sa_grid(long work) { long g = 148L * 8; return (int)(work < g ? (work > 0 ? work : 1) : g); }
+
+}  // namespace
+
+PCM_API int pcm_sa_gather_stats(int m, int k, int H, const float* Pf, const float* xyz, const float* new_xyz,
+                                const int* idx, const float* W, int ldw, float* ymax, float* ymin,
+                                unsigned char* jmax, unsigned char* jmin, double* stats, pcm_stream_t stream) {
+    if (m <= 0) return PCM_OK;
+    if (!Pf || !xyz || !new_xyz || !idx || !W || !ymax || !ymin || !jmax || !jmin || !stats) return PCM_EINVAL;
+    if (H % 4 || H > 4096 || k > 255 || k <= 0) return PCM_EUNSUPPORTED;
+    sa_gather_stats_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, k, H, ymax,
+                                                                                   ymin, jmax, jmin, stats);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_bn_finalize(int H, const double* stats, double n_rows, const float* gamma, const float* beta,
+                               float eps, float momentum, int training, float* running_mean, float* running_var,
+                               float* coef, pcm_stream_t stream) {
+    if (H <= 0) return PCM_OK;
+    if (!stats || !gamma || !beta || !coef || (!training && (!running_mean || !running_var))) return PCM_EINVAL;
+    sa_bn_finalize_kernel<<<pcm_divup(H, 128), 128, 0, pcm_cu_stream(stream)>>>(stats, n_rows, gamma, beta, eps, momentum, training,
+                                                                               running_mean, running_var, coef, H);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_output(int m, int H, const float* ymax, const float* ymin, const unsigned char* jmax,
+                          const unsigned char* jmin, const float* coef, float* out, unsigned char* jsel,
+                          pcm_stream_t stream) {
+    const long total = (long)m * H;
+    if (total <= 0) return PCM_OK;
+    if (!ymax || !ymin || !jmax || !jmin || !coef || !out || !jsel) return PCM_EINVAL;
+    if (H % 4) return PCM_EUNSUPPORTED;
+    sa_output_kernel<<<sa_grid((total / 4 + 255) / 256), 256, 0, pcm_cu_stream(stream)>>>(ymax, ymin, jmax, jmin, coef, total, H, out, jsel);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_bwd_scatter(int m, int k, int H, const float* dout, const float* out, const unsigned char* jsel,
+                               const int* idx, const float* xyz, const float* new_xyz, const float* coef, float* dPf,
+                               double* gstats, pcm_stream_t stream) {
+    if (m <= 0) return PCM_OK;
+    if (!dout || !out || !jsel || !idx || !xyz || !new_xyz || !coef || !dPf || !gstats) return PCM_EINVAL;
+    if (H % 4 || H > 4096) return PCM_EUNSUPPORTED;
+    sa_bwd_scatter_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(dout, out, jsel, idx, xyz, new_xyz, coef, m, k, H,
+                                                                                  dPf, gstats);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_edge_stats(int m, int k, const int* idx, const float* xyz, const float* new_xyz, float* cnt,
+                              float* sq, double* sdtot, pcm_stream_t stream) {
+    const long edges = (long)m * k;
+    if (edges <= 0) return PCM_OK;
+    if (!idx || !xyz || !new_xyz || !cnt || !sq || !sdtot) return PCM_EINVAL;
+    sa_edge_stats_kernel<<<sa_grid((edges + 255) / 256), 256, 0, pcm_cu_stream(stream)>>>(idx, xyz, new_xyz, edges, k, cnt, sq, sdtot);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_bwd_coef(int H, const double* gstats, const double* fstats, const double* sdtot, const float* coef,
+                            double n_rows, int training, float* ab, float* dW, int ldw, float* dgamma, float* dbeta,
+                            pcm_stream_t stream) {
+    if (H <= 0) return PCM_OK;
+    if (!gstats || !fstats || !sdtot || !coef || !ab) return PCM_EINVAL;
+    sa_bwd_coef_kernel<<<pcm_divup(H, 128), 128, 0, pcm_cu_stream(stream)>>>(gstats, fstats, sdtot, coef, n_rows, training, H, ab, dW,
+                                                                            ldw, dgamma, dbeta);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_bwd_dense(int n, int H, const float* Pf, const float* xyz, const float* cnt, const float* sq,
+                             const float* W, int ldw, const float* ab, const float* dPf, void* dPf_bf16,
+                             pcm_stream_t stream) {
+    if (n <= 0) return PCM_OK;
+    if (!Pf || !xyz || !cnt || !sq || !W || !ab || !dPf || !dPf_bf16) return PCM_EINVAL;
+    if (H % 4 || H > 4096) return PCM_EUNSUPPORTED;
+    sa_bwd_dense_kernel<<<sa_grid(n), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, cnt, sq, W, ldw, ab, n, H, dPf,
+                                                                                reinterpret_cast<__nv_bfloat16*>(dPf_bf16));
+    return pcm_launch_status();
+}

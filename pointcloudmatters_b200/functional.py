@@ -141,18 +141,88 @@ def batchnorm_relu(x, bn):
                                bn.momentum if bn.momentum is not None else 0.0, bn.eps))
 
 
+class _SetAbstraction(torch.autograd.Function):
+    """Fused gather + Linear(3+C->H) + BatchNorm1d + ReLU + max over k (csrc/sa_fused.cu)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, gamma, beta, p, new_p, knn_idx, running_mean, running_var, eps, momentum,
+                training):
+        from ._lib import check, current_stream, lib, ptr
+
+        n, C = feat.shape
+        H = weight.shape[0]
+        m, k = knn_idx.shape
+        dev = feat.device
+        st = current_stream()
+        weight = weight.contiguous()
+        featb = feat if feat.dtype == torch.bfloat16 else feat.to(torch.bfloat16)
+        wfb = weight[:, 3:].to(torch.bfloat16).contiguous()
+        Pf = K.gemm_bf16(featb, wfb)  # (n, H) fp32: the only tensor-core work of the layer
+        ymax = torch.empty((m, H), dtype=torch.float32, device=dev)
+        ymin = torch.empty_like(ymax)
+        jmax = torch.empty((m, H), dtype=torch.uint8, device=dev)
+        jmin = torch.empty_like(jmax)
+        stats = torch.zeros((5, H), dtype=torch.float64, device=dev)
+        check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
+                                      ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
+        coef = torch.empty((4, H), dtype=torch.float32, device=dev)
+        check(lib.pcm_sa_bn_finalize(H, ptr(stats), float(m * k), ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                     int(training), ptr(running_mean), ptr(running_var), ptr(coef), st),
+              "pcm_sa_bn_finalize")
+        out = torch.empty((m, H), dtype=torch.float32, device=dev)
+        check(lib.pcm_sa_output(m, H, ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(coef), ptr(out), ptr(jmax), st),
+              "pcm_sa_output")  # jsel overwrites jmax in place
+        ctx.save_for_backward(featb, wfb, Pf, p, new_p, knn_idx, weight, out, jmax, coef, stats)
+        ctx.training = training
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ._lib import check, current_stream, lib, ptr
+
+        featb, wfb, Pf, p, new_p, knn_idx, weight, out, jsel, coef, stats = ctx.saved_tensors
+        n, H = Pf.shape
+        C = featb.shape[1]
+        m, k = knn_idx.shape
+        dev = Pf.device
+        st = current_stream()
+        dout = dout.contiguous().float()
+        dPf = torch.zeros((n, H), dtype=torch.float32, device=dev)
+        gstats = torch.zeros((5, H), dtype=torch.float64, device=dev)
+        check(lib.pcm_sa_bwd_scatter(m, k, H, ptr(dout), ptr(out), ptr(jsel), ptr(knn_idx), ptr(p), ptr(new_p), ptr(coef),
+                                     ptr(dPf), ptr(gstats), st), "pcm_sa_bwd_scatter")
+        cnt = torch.zeros(n, dtype=torch.float32, device=dev)
+        sq = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        sdtot = torch.zeros(3, dtype=torch.float64, device=dev)
+        check(lib.pcm_sa_edge_stats(m, k, ptr(knn_idx), ptr(p), ptr(new_p), ptr(cnt), ptr(sq), ptr(sdtot), st),
+              "pcm_sa_edge_stats")
+        dW = torch.zeros((H, 3 + C), dtype=torch.float32, device=dev)
+        ab = torch.empty((2, H), dtype=torch.float32, device=dev)
+        dgamma = torch.empty(H, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(H, dtype=torch.float32, device=dev)
+        check(lib.pcm_sa_bwd_coef(H, ptr(gstats), ptr(stats), ptr(sdtot), ptr(coef), float(m * k), int(ctx.training),
+                                  ptr(ab), ptr(dW), dW.stride(0), ptr(dgamma), ptr(dbeta), st), "pcm_sa_bwd_coef")
+        dPfb = torch.empty((n, H), dtype=torch.bfloat16, device=dev)
+        check(lib.pcm_sa_bwd_dense(n, H, ptr(Pf), ptr(p), ptr(cnt), ptr(sq), ptr(weight), weight.stride(0), ptr(ab),
+                                   ptr(dPf), ptr(dPfb), st), "pcm_sa_bwd_dense")
+        dfeat = None
+        if ctx.needs_input_grad[0]:
+            dfeat = K.gemm_bf16(dPfb, wfb, b_mn=True)  # (n, H) x Wf(H, C)
+        sk = _split_k_for((H + 127) // 128, (C + 127) // 128, (n + 63) // 64)
+        K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=sk)
+        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
 def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn):
     """Grouped Linear(3+C -> H, no bias) + BatchNorm1d + ReLU + max over the k neighbours
-    (act.py:446-460).  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H)."""
-    from .pointops import grouping
-
-    g = grouping(knn_idx, feat, p, new_p, with_xyz=True)  # (m, k, 3 + C)
-    m, k, cin = g.shape
-    y = linear(g.reshape(m * k, cin), linear_weight)  # (m*k, H)
+    (act.py:446-460) as ONE fused operator.  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H)."""
+    _need_cuda(feat)
+    training = bn.training or (bn.running_mean is None)
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    y = batchnorm_relu(y, bn)
-    return y.view(m, k, -1).max(dim=1).values
+    momentum = bn.momentum if bn.momentum is not None else 0.0
+    return _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
+                                 knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training)
 
 
 def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, *, step, lr, beta1, beta2, eps, weight_decay, clip_norm):
