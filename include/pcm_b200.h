@@ -161,6 +161,31 @@ int pcm_gemm_bf16(int M, int N, int K, const void *A, int lda, int a_mn, const v
                   int b_mn, void *C, int ldc, int c_bf16, const float *bias, int relu,
                   int accumulate, int split_k, pcm_stream_t stream);
 
+/* Batched / scaled form of pcm_gemm_bf16 used by the attention blocks (the reference goes
+ * through nn.MultiheadAttention's math path, transformer.py:246-248,329-340): `batch` stacked
+ * problems share one 2-D tensor per operand (a_rows_total x ., b_rows_total x .); batch z starts
+ * a_batch_rows / b_batch_rows rows further down (for an MN-major operand those rows are the K
+ * dimension, so its K tail must meet zeros in the other operand).  C = alpha * acc.
+ * c_mode 0: plain rows (z * c_batch_rows + m); 1: head-split -- token-major rows r = l*hs_B + b,
+ * columns h*64 + d are written to a (hs_B, hs_nh, hs_L, 64) tensor; 2: head-merge -- batch
+ * z = b*hs_nh + h, row l, column d is written to token-major (l*hs_B + b, h*64 + d), pitch ldc. */
+int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void *A, int lda, int a_mn,
+                     long long a_rows_total, long long a_batch_rows, const void *B, int ldb, int b_mn,
+                     long long b_rows_total, long long b_batch_rows, void *C, int ldc, int c_bf16,
+                     int c_mode, long long c_batch_rows, int hs_B, int hs_nh, int hs_L, float alpha,
+                     const float *bias, int relu, int accumulate, int split_k, pcm_stream_t stream);
+
+/* Row-wise softmax stages of multi-head attention between the batched GEMMs (replaces the
+ * softmax / dropout of nn.MultiheadAttention's math path, transformer.py:246-248).  Buffers are
+ * [Z = B*nh, Lp, Sp] with zero padding.  fwd: S fp32 raw scores -> Y = softmax(scale*S + mask)
+ * (bf16), Zd = dropout(Y) (bf16; pass Zd == Y when p_drop == 0); kpm (B, Sk) bytes, non-zero =
+ * masked key, may be NULL.  bwd (in place on dZ): dS = scale * Y * (dY - <dY, Y>). */
+int pcm_attn_softmax_fwd(int Z, int L, int Lp, int Sk, int Sp, int nh, const float *S,
+                         const unsigned char *kpm, float scale, float p_drop,
+                         unsigned long long seed, void *Y, void *Zd, pcm_stream_t stream);
+int pcm_attn_softmax_bwd(int Z, int L, int Lp, int Sk, int Sp, const void *Y, void *dZ, float scale,
+                         float p_drop, unsigned long long seed, pcm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused set-abstraction head.  Replaces, for ACTPCD.pcd_sampling (src/models/components/act/
  * act.py:446-460) and PCDObsEncoder.pcd_sampling (.../vision/pcd_obs_encoder.py:179-193), the

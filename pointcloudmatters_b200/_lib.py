@@ -26,6 +26,7 @@ _CTYPES = {
     "double": ctypes.c_double,
     "long": ctypes.c_long,
     "long long": ctypes.c_longlong,
+    "unsigned long long": ctypes.c_ulonglong,
     "size_t": ctypes.c_size_t,
     "uint32_t": ctypes.c_uint32,
     "uint64_t": ctypes.c_uint64,

@@ -110,14 +110,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 struct GemmParams {
-    int M, N, K;
-    int k_blocks_per_split;  // split-K: blockIdx.z covers [z * kbps, min((z+1) * kbps, kblocks))
+    int M, N, K;             // per-batch problem size
+    int k_blocks_per_split;  // split-K: slice ks covers [ks * kbps, min((ks+1) * kbps, kblocks))
+    int split_k;             // blockIdx.z = batch * split_k + ks
+    // batching: operand row offset per batch, in rows of the operand's 2-D tensor (for an
+    // MN-major operand the rows are the K dimension)
+    long long a_batch_rows, b_batch_rows;
     void* C;
     int ldc;
+    // output addressing: 0 plain (row = z * c_batch_rows + m), 1 head-split (token-major rows
+    // r = l * hs_B + b, column = h * 64 + d  ->  ((b * hs_nh + h) * hs_L + l) * 64 + d),
+    // 2 head-merge (batch z = b * hs_nh + h, row l, column d -> (l * hs_B + b) * ldc + h * 64 + d)
+    int c_mode;
+    long long c_batch_rows;
+    int hs_B, hs_nh, hs_L;
     const float* bias;
     int relu;
     int c_bf16;
     int atomic;  // red.global.add.f32 (split-K / gradient accumulation); C must be fp32
+    float alpha;  // C = alpha * acc (+ bias)
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -142,7 +153,9 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, n_blk = blockIdx.y;
     const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int kb0 = blockIdx.z * p.k_blocks_per_split;
+    const int zb = blockIdx.z / p.split_k;  // batch index
+    const int kb0 = (blockIdx.z - zb * p.split_k) * p.k_blocks_per_split;
+    const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
     const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
     const int nkb = kb1 - kb0;
 
@@ -171,18 +184,18 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int k0 = (kb0 + i) * BLOCK_K;
                 if (!A_MN) {
-                    tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m_blk * BLOCK_M);
+                    tma_load_2d(sa, &tmap_a, &full_bar[s], k0, a_off + m_blk * BLOCK_M);
                 } else {
 #pragma unroll
                     for (int c = 0; c < BLOCK_M / 64; ++c)
-                        tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, k0);
+                        tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, a_off + k0);
                 }
                 if (!B_MN) {
-                    tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n_blk * BLOCK_N);
+                    tma_load_2d(sb, &tmap_b, &full_bar[s], k0, b_off + n_blk * BLOCK_N);
                 } else {
 #pragma unroll
                     for (int c = 0; c < BLOCK_N / 64; ++c)
-                        tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, k0);
+                        tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, b_off + k0);
                 }
             }
         }
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
     } else {
         // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
-        const int row = m_blk * BLOCK_M + quad * 32 + lane;
+        const int row = m_blk * BLOCK_M + quad * 32 + lane;  // row inside this batch's M
         if (nkb > 0) {
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -230,21 +243,33 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
             const int col0 = n_blk * BLOCK_N + c0;
             if (row < p.M && col0 < p.N) {
                 float f[32];
+                // destination of this thread's 32-column strip (see GemmParams::c_mode)
+                size_t dst;
+                if (p.c_mode == 0) {
+                    dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
+                } else if (p.c_mode == 1) {
+                    const int l = row / p.hs_B, b = row - l * p.hs_B;
+                    const int h = col0 >> 6, d = col0 & 63;
+                    dst = ((size_t)(b * p.hs_nh + h) * p.hs_L + l) * 64 + d;
+                } else {
+                    const int b = zb / p.hs_nh, h = zb - b * p.hs_nh;
+                    dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
+                    float x = __uint_as_float(v[j]) * p.alpha;
                     if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
                     if (p.relu) x = fmaxf(x, 0.f);
                     f[j] = x;
                 }
                 const bool full = (col0 + 32 <= p.N);
                 if (p.atomic) {
-                    float* crow = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                    float* crow = reinterpret_cast<float*>(p.C) + dst;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (full || col0 + j < p.N) atomicAdd(crow + j, f[j]);
                 } else if (p.c_bf16) {
-                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + dst;
                     if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -263,7 +288,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
                             if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
                     }
                 } else {
-                    float* crow = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                    float* crow = reinterpret_cast<float*>(p.C) + dst;
                     if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -347,7 +372,7 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
     constexpr size_t SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
     static bool attr = false;
     if (!attr) {
@@ -356,12 +381,57 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, (p.N + BLOCK_N - 1) / BLOCK_N, split_k);
+    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, (p.N + BLOCK_N - 1) / BLOCK_N, split_k * batch);
     gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
     return pcm_launch_status();
 }
 
 }  // namespace
+
+// Extended entry point: batched, scaled, with head-split / head-merge output addressing (used by
+// the attention GEMMs).  Operand tensor maps span `batch` stacked problems: a_rows_total /
+// b_rows_total are the row counts of the full 2-D operand tensors.
+PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int lda, int a_mn, long long a_rows_total,
+                             long long a_batch_rows, const void* B, int ldb, int b_mn, long long b_rows_total,
+                             long long b_batch_rows, void* C, int ldc, int c_bf16, int c_mode, long long c_batch_rows,
+                             int hs_B, int hs_nh, int hs_L, float alpha, const float* bias, int relu, int accumulate,
+                             int split_k, pcm_stream_t stream) {
+    if (M <= 0 || N <= 0 || batch <= 0) return PCM_OK;
+    if (!A || !B || !C || K <= 0) return PCM_EINVAL;
+    if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return PCM_EUNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
+    if (split_k < 1) split_k = 1;
+    if ((split_k > 1 || accumulate) && c_bf16) return PCM_EINVAL;
+    if (split_k > 1 && (bias || relu)) return PCM_EINVAL;
+    if (c_mode < 0 || c_mode > 2 || (c_mode != 0 && (hs_B <= 0 || hs_nh <= 0))) return PCM_EINVAL;
+    if (c_mode == 1 && (N % 64)) return PCM_EUNSUPPORTED;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    if (split_k > kblocks) split_k = kblocks;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.k_blocks_per_split = (kblocks + split_k - 1) / split_k;
+    split_k = (kblocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+    p.split_k = split_k;
+    p.a_batch_rows = a_batch_rows; p.b_batch_rows = b_batch_rows;
+    p.C = C; p.ldc = ldc; p.c_mode = c_mode; p.c_batch_rows = c_batch_rows;
+    p.hs_B = hs_B; p.hs_nh = hs_nh; p.hs_L = hs_L;
+    p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16; p.alpha = alpha;
+    p.atomic = (accumulate || split_k > 1) ? 1 : 0;
+    const int BN = 128;
+    CUtensorMap ta, tb;
+    int r;
+    if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_M, &ta);
+    else r = get_tensor_map(A, (uint64_t)M, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_K, &ta);
+    if (r) return r;
+    if (!b_mn) r = get_tensor_map(B, (uint64_t)K, (uint64_t)b_rows_total, (uint64_t)ldb, 64, BN, &tb);
+    else r = get_tensor_map(B, (uint64_t)N, (uint64_t)b_rows_total, (uint64_t)ldb, 64, BLOCK_K, &tb);
+    if (r) return r;
+    cudaStream_t st = pcm_cu_stream(stream);
+    if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, batch, st);
+    if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, batch, st);
+    if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, p, split_k, batch, st);
+    return launch<128, true, true>(ta, tb, p, split_k, batch, st);
+}
 
 // C[m, n] (+)= sum_k A(m, k) B(n, k) (+ bias[n]) (ReLU).  a_mn / b_mn = 0: operand stored row-major
 // [rows, K] with pitch ld (K contiguous); = 1: stored row-major [K, rows] with pitch ld (rows
@@ -369,33 +439,6 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 PCM_API int pcm_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
                           void* C, int ldc, int c_bf16, const float* bias, int relu, int accumulate, int split_k,
                           pcm_stream_t stream) {
-    if (M <= 0 || N <= 0) return PCM_OK;
-    if (!A || !B || !C || K <= 0) return PCM_EINVAL;
-    if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
-        return PCM_EUNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
-    if (split_k < 1) split_k = 1;
-    if ((split_k > 1 || accumulate) && c_bf16) return PCM_EINVAL;
-    if (split_k > 1 && (bias || relu)) return PCM_EINVAL;
-    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
-    if (split_k > kblocks) split_k = kblocks;
-    GemmParams p;
-    p.M = M; p.N = N; p.K = K;
-    p.k_blocks_per_split = (kblocks + split_k - 1) / split_k;
-    split_k = (kblocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
-    p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16;
-    p.atomic = (accumulate || split_k > 1) ? 1 : 0;
-    const int BN = 128;
-    CUtensorMap ta, tb;
-    int r;
-    if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BLOCK_M, &ta);
-    else r = get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BLOCK_K, &ta);
-    if (r) return r;
-    if (!b_mn) r = get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN, &tb);
-    else r = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BLOCK_K, &tb);
-    if (r) return r;
-    cudaStream_t st = pcm_cu_stream(stream);
-    if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, st);
-    if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, st);
-    if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, p, split_k, st);
-    return launch<128, true, true>(ta, tb, p, split_k, st);
+    return pcm_gemm_bf16_ex(M, N, K, 1, A, lda, a_mn, a_mn ? K : M, 0, B, ldb, b_mn, b_mn ? K : N, 0, C, ldc, c_bf16, 0, 0,
+                            0, 0, 0, 1.0f, bias, relu, accumulate, split_k, stream);
 }

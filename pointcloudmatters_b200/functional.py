@@ -100,6 +100,111 @@ def attention(q, k, v, key_padding_mask=None, dropout_p=0.0, training=False):
     return (attn.to(COMPUTE_DTYPE) @ v.to(COMPUTE_DTYPE)).float()
 
 
+_WORKSPACE = {}
+
+
+def _workspace(name, shape, dtype, device, zero=False):
+    """Cached scratch tensor.  `zero=True` buffers are zero-filled once; their users only ever write
+    the valid (unpadded) region, so the padding stays zero across reuses."""
+    key = (name, tuple(shape), dtype, str(device))
+    t = _WORKSPACE.get(key)
+    if t is None:
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+        _WORKSPACE[key] = t
+    return t
+
+
+def _ceil64(x):
+    return (x + 63) // 64 * 64
+
+
+class _MHA(torch.autograd.Function):
+    """nn.MultiheadAttention (head_dim 64) as a chain of tcgen05 GEMMs + row-wise softmax kernels:
+    in-proj GEMMs write Q/K/V straight into (B, h, L, 64) (head-split epilogue), S = QK^T and
+    O = PV are batched GEMMs, O lands token-major (head-merge epilogue) for the out-proj GEMM.
+    Backward mirrors it with the MN-major operand forms; nothing is transposed or permuted."""
+
+    @staticmethod
+    def forward(ctx, xq, xk, xv, w_in, b_in, w_out, b_out, nh, kpm, p_drop, same_qk):
+        L, B, E = xq.shape
+        S = xk.shape[0]
+        d = E // nh
+        dev = xq.device
+        bf = torch.bfloat16
+        xq_b = xq.reshape(L * B, E).to(bf)
+        xk_b = xq_b if same_qk else xk.reshape(S * B, E).to(bf)
+        xv_b = xv.reshape(S * B, E).to(bf)
+        wb = w_in.to(bf)
+        wo_b = w_out.to(bf)
+        Z = B * nh
+        Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        Kh = torch.empty((Z * S, 64), dtype=bf, device=dev)
+        Vh = torch.empty((Z * S, 64), dtype=bf, device=dev)
+        K.gemm_ex(L * B, E, E, 1, xq_b, False, 0, wb[:E], False, 0, Qh, c_mode=1, hs=(B, nh, L), ldc=64, bias=b_in[:E])
+        K.gemm_ex(S * B, E, E, 1, xk_b, False, 0, wb[E:2 * E], False, 0, Kh, c_mode=1, hs=(B, nh, S), ldc=64,
+                  bias=b_in[E:2 * E])
+        K.gemm_ex(S * B, E, E, 1, xv_b, False, 0, wb[2 * E:], False, 0, Vh, c_mode=1, hs=(B, nh, S), ldc=64,
+                  bias=b_in[2 * E:])
+        Lp, Sp = _ceil64(L), _ceil64(S)
+        scale = 1.0 / math.sqrt(d)
+        Sbuf = _workspace("attn_scores", (Z * Lp, Sp), torch.float32, dev)
+        K.gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=Lp, ldc=Sp)
+        Y = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev)
+        Zd = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev) if p_drop > 0 else Y
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+        kpm_u8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
+        K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed)
+        O_tok = torch.empty((L * B, E), dtype=bf, device=dev)
+        K.gemm_ex(L, 64, S, Z, Zd, False, Lp, Vh, True, S, O_tok, c_mode=2, hs=(B, nh, L), ldc=E)
+        out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
+        ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
+        ctx.dims = (L, S, B, E, nh, Lp, Sp, scale, p_drop, seed, same_qk)
+        return out.view(L, B, E)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok = ctx.saved_tensors
+        L, S, B, E, nh, Lp, Sp, scale, p_drop, seed, same_qk = ctx.dims
+        dev = dout.device
+        bf = torch.bfloat16
+        Z = B * nh
+        dout2 = dout.reshape(L * B, E)
+        dout_b = dout2.to(bf)
+        # out-proj
+        dWo = torch.zeros((E, E), dtype=torch.float32, device=dev)
+        K.gemm_bf16(dout_b, O_tok, a_mn=True, b_mn=True, out=dWo, accumulate=True,
+                    split_k=_split_k_for(E // 128, E // 128, (L * B + 63) // 64))
+        dbo = dout2.sum(0)
+        dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
+        # softmax backward
+        dP = _workspace("attn_dP", (Z * Lp, Sp), bf, dev, zero=True)
+        K.gemm_ex(L, S, 64, Z, dOh, False, L, Vh, False, S, dP, c_mode=0, c_batch_rows=Lp, ldc=Sp)
+        K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, seed)
+        dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
+        dK_tok = torch.empty((S * B, E), dtype=bf, device=dev)
+        dV_tok = torch.empty((S * B, E), dtype=bf, device=dev)
+        K.gemm_ex(L, 64, S, Z, dP, False, Lp, Kh, True, S, dQ_tok, c_mode=2, hs=(B, nh, L), ldc=E)
+        K.gemm_ex(S, 64, L, Z, dP, True, Lp, Qh, True, L, dK_tok, c_mode=2, hs=(B, nh, S), ldc=E)
+        K.gemm_ex(S, 64, L, Z, Zd, True, Lp, dOh, True, L, dV_tok, c_mode=2, hs=(B, nh, S), ldc=E)
+        # in-proj
+        dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
+        grads_x = []
+        for j, (dtok, xb) in enumerate(((dQ_tok, xq_b), (dK_tok, xk_b), (dV_tok, xv_b))):
+            rows = dtok.shape[0]
+            K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=dW_in[j * E:(j + 1) * E], accumulate=True,
+                        split_k=_split_k_for(E // 128, E // 128, (rows + 63) // 64))
+            grads_x.append(K.gemm_bf16(dtok, wb[j * E:(j + 1) * E], b_mn=True))
+        db_in = torch.cat([dQ_tok.float().sum(0), dK_tok.float().sum(0), dV_tok.float().sum(0)])
+        dxq, dxk, dxv = grads_x
+        if same_qk:
+            dxq = dxq + dxk
+            dxk = None
+        else:
+            dxk = dxk.view(S, B, E)
+        return (dxq.view(L, B, E), dxk, dxv.view(S, B, E), dW_in, db_in, dWo, dbo, None, None, None, None)
+
+
 def multi_head_attention(mha, query, key, value, key_padding_mask=None, training=False):
     """nn.MultiheadAttention semantics (seq-first (L, B, E) inputs, returns the attended output only;
     the reference discards the averaged weights it asks for, transformer.py:246-248)."""
@@ -107,13 +212,15 @@ def multi_head_attention(mha, query, key, value, key_padding_mask=None, training
     S = key.shape[0]
     h = mha.num_heads
     d = E // h
+    if d == 64 and E % 128 == 0:
+        p = mha.dropout if training else 0.0
+        return _MHA.apply(query.contiguous(), key.contiguous(), value.contiguous(), mha.in_proj_weight,
+                          mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p,
+                          query is key)
+    # head sizes other than 64 (test fixtures only): composed from the same linear() + library bmm
     w, b = mha.in_proj_weight, mha.in_proj_bias
-    if query is key:  # self-attention: q = k = x + pos share one GEMM
-        qk = linear(query, w[: 2 * E], b[: 2 * E])
-        q, k = qk[..., :E], qk[..., E:]
-    else:
-        q = linear(query, w[:E], b[:E])
-        k = linear(key, w[E: 2 * E], b[E: 2 * E])
+    q = linear(query, w[:E], b[:E])
+    k = linear(key, w[E: 2 * E], b[E: 2 * E])
     v = linear(value, w[2 * E:], b[2 * E:])
     q = q.reshape(L, B, h, d).permute(1, 2, 0, 3)
     k = k.reshape(S, B, h, d).permute(1, 2, 0, 3)

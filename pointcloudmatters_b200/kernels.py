@@ -30,3 +30,29 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32
                             out.stride(0), int(out.dtype == torch.bfloat16), ptr(bias), int(relu), int(accumulate),
                             int(split_k), current_stream()), "pcm_gemm_bf16")
     return out
+
+
+def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, *, c_mode=0, c_batch_rows=0,
+            hs=(0, 0, 0), ldc=None, alpha=1.0, bias=None, relu=False, accumulate=False, split_k=1):
+    """Batched tcgen05 GEMM with head-split / head-merge output addressing (pcm_gemm_bf16_ex).
+    a, b: 2-D bf16 tensors spanning all batches (last dim contiguous); out: destination tensor."""
+    require_cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    if ldc is None:
+        ldc = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
+    check(lib.pcm_gemm_bf16_ex(M, N, Kd, batch, ptr(a), a.stride(0), int(a_mn), a.shape[0], a_batch_rows,
+                               ptr(b), b.stride(0), int(b_mn), b.shape[0], b_batch_rows, ptr(out), ldc,
+                               int(out.dtype == torch.bfloat16), c_mode, c_batch_rows, hs[0], hs[1], hs[2],
+                               float(alpha), ptr(bias), int(relu), int(accumulate), int(split_k), current_stream()),
+          "pcm_gemm_bf16_ex")
+    return out
+
+
+def attn_softmax_fwd(S, Y, Zd, Z, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed):
+    check(lib.pcm_attn_softmax_fwd(Z, L, Lp, Sk, Sp, nh, ptr(S), ptr(kpm), float(scale), float(p_drop), int(seed),
+                                   ptr(Y), ptr(Zd), current_stream()), "pcm_attn_softmax_fwd")
+
+
+def attn_softmax_bwd(Y, dZ, Z, L, Lp, Sk, Sp, scale, p_drop, seed):
+    check(lib.pcm_attn_softmax_bwd(Z, L, Lp, Sk, Sp, ptr(Y), ptr(dZ), float(scale), float(p_drop), int(seed),
+                                   current_stream()), "pcm_attn_softmax_bwd")
