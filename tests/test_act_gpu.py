@@ -108,8 +108,15 @@ def test_training_steps_track_the_oracle():
     for a, b in zip(losses_g, losses_o):
         assert abs(a - b) <= 3e-2 * abs(b), (losses_g, losses_o)
     # parameters after 5 steps stay close; never-used parameters are untouched on both sides
+    # Adam's normalised update moves every element by <= ~lr per step, so two runs can drift
+    # apart by at most a few lr per element; near-zero-initialised tensors (BatchNorm / Linear
+    # biases) are therefore compared in absolute terms, the whole parameter vector relatively.
     sd_o = oracle.state_dict()
+    num = den = 0.0
     for k, v in policy.state_dict().items():
         if v.dtype.is_floating_point and "running" not in k:
-            assert _rel_l2(v.cpu().numpy(), sd_o[k].numpy()) <= 2e-2, k
+            a, b = v.cpu().double(), sd_o[k].double()
+            assert float((a - b).abs().max()) <= 5 * lr, k
+            num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
+    assert (num / den) ** 0.5 <= 5e-3
     assert torch.equal(policy.is_pad_head.weight.detach().cpu(), sd_o["is_pad_head.weight"])
