@@ -15,8 +15,9 @@
 // layout they already have, with no transpose pass.  Shared-memory layouts are the canonical UMMA
 // SWIZZLE_128B layouts (K-major: 8-row x 128 B atoms, SBO = 1024 B; MN-major: 64-element x 8-row
 // atoms, SBO = 1024 B, LBO = BLOCK_K * 128 B) which are exactly what a SWIZZLE_128B TMA box writes.
-// One output tile per CTA; 3-stage ring (96 KB) so that two CTAs share an SM and one CTA's
-// epilogue overlaps the other's main loop.
+// Persistent: one CTA per SM walks output tiles; a 6-stage ring (192 KB) keeps TMA ahead of the
+// MMA warp across tile boundaries and two TMEM accumulators overlap a tile's epilogue with the
+// next tile's main loop.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -28,7 +29,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 6;   // 6 x 32 KB ring; one persistent CTA per SM
 constexpr int NUM_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,7 +113,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 struct GemmParams {
     int M, N, K;             // per-batch problem size
     int k_blocks_per_split;  // split-K: slice ks covers [ks * kbps, min((ks+1) * kbps, kblocks))
-    int split_k;             // blockIdx.z = batch * split_k + ks
+    int split_k, batch;      // tile index enumerates (batch, k-slice, m-block, n-block)
     // batching: operand row offset per batch, in rows of the operand's 2-D tensor (for an
     // MN-major operand the rows are the K dimension)
     long long a_batch_rows, b_batch_rows;
@@ -131,14 +132,22 @@ struct GemmParams {
     float alpha;  // C = alpha * acc (+ bias)
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// Tile order: n fastest, then m, then (batch, k-slice) -- CTAs running at the same time share the
+// A row-block and the whole (small) B operand through L2.  Two TMEM accumulators (2 x BLOCK_N
+// columns) let the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
 template <int BLOCK_N, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                   const __grid_constant__ CUtensorMap tmap_b,
-                                                                   const GemmParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                      const __grid_constant__ CUtensorMap tmap_b,
+                                                                      const GemmParams p) {
     constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 or 256: power of two >= 32
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=BF16
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -147,23 +156,21 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
     const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int zb = blockIdx.z / p.split_k;  // batch index
-    const int kb0 = (blockIdx.z - zb * p.split_k) * p.k_blocks_per_split;
-    const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
-    const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
-    const int nkb = kb1 - kb0;
+    const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles_mn = ((p.M + BLOCK_M - 1) / BLOCK_M) * tiles_n;
+    const int total_tiles = tiles_mn * p.split_k * p.batch;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -175,131 +182,156 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tcgen05_kernel(const __grid_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* sa = tiles + s * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                const int k0 = (kb0 + i) * BLOCK_K;
-                if (!A_MN) {
-                    tma_load_2d(sa, &tmap_a, &full_bar[s], k0, a_off + m_blk * BLOCK_M);
-                } else {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int zs = t / tiles_mn, r = t - zs * tiles_mn;
+                const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+                const int zb = zs / p.split_k, ks = zs - zb * p.split_k;
+                const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
+                const int kb0 = ks * p.k_blocks_per_split;
+                const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = tiles + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    const int k0 = kb * BLOCK_K;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[s], k0, a_off + m_blk * BLOCK_M);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_M / 64; ++c)
-                        tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, a_off + k0);
-                }
-                if (!B_MN) {
-                    tma_load_2d(sb, &tmap_b, &full_bar[s], k0, b_off + n_blk * BLOCK_N);
-                } else {
+                        for (int c = 0; c < BLOCK_M / 64; ++c)
+                            tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, a_off + k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[s], k0, b_off + n_blk * BLOCK_N);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 64; ++c)
-                        tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, b_off + k0);
+                        for (int c = 0; c < BLOCK_N / 64; ++c)
+                            tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, b_off + k0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0;
+            int i = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+                const int zs = t / tiles_mn;
+                const int ks = zs % p.split_k;
+                const int kb0 = ks * p.k_blocks_per_split;
+                const int nkb = min(kblocks_total, kb0 + p.k_blocks_per_split) - kb0;
+                const int acc = i & 1;
+                mbar_wait(&tmem_empty_bar[acc], (((uint32_t)i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 rows of 128 B
-                    const uint64_t da = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                             : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-                    const uint64_t db = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                             : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-                    umma_f16(tmem_base, da, db, IDESC, (i | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 rows of 128 B
+                        const uint64_t da = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                                 : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                                 : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                        umma_f16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                umma_commit(&tmem_full_bar[acc]);  // accumulator complete
             }
-            umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else {
         // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
-        const int row = m_blk * BLOCK_M + quad * 32 + lane;  // row inside this batch's M
-        if (nkb > 0) {
-            mbar_wait(tmem_full_bar, 0);
+        int i = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            const int zs = t / tiles_mn, r = t - zs * tiles_mn;
+            const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+            const int zb = zs / p.split_k;
+            const int acc = i & 1;
+            const int row = m_blk * BLOCK_M + quad * 32 + lane;  // row inside this batch's M
+            mbar_wait(&tmem_full_bar[acc], ((uint32_t)i >> 1) & 1);
             tc_fence_after();
-        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t v[32];
-            if (nkb > 0) {
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
                 tmem_ld_wait();
-            } else {
+                const int col0 = n_blk * BLOCK_N + c0;
+                if (row < p.M && col0 < p.N) {
+                    float f[32];
+                    // destination of this thread's 32-column strip (see GemmParams::c_mode)
+                    size_t dst;
+                    if (p.c_mode == 0) {
+                        dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
+                    } else if (p.c_mode == 1) {
+                        const int l = row / p.hs_B, b = row - l * p.hs_B;
+                        const int h = col0 >> 6, d = col0 & 63;
+                        dst = ((size_t)(b * p.hs_nh + h) * p.hs_L + l) * 64 + d;
+                    } else {
+                        const int b = zb / p.hs_nh, h = zb - b * p.hs_nh;
+                        dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0;
+                    }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            const int col0 = n_blk * BLOCK_N + c0;
-            if (row < p.M && col0 < p.N) {
-                float f[32];
-                // destination of this thread's 32-column strip (see GemmParams::c_mode)
-                size_t dst;
-                if (p.c_mode == 0) {
-                    dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
-                } else if (p.c_mode == 1) {
-                    const int l = row / p.hs_B, b = row - l * p.hs_B;
-                    const int h = col0 >> 6, d = col0 & 63;
-                    dst = ((size_t)(b * p.hs_nh + h) * p.hs_L + l) * 64 + d;
-                } else {
-                    const int b = zb / p.hs_nh, h = zb - b * p.hs_nh;
-                    dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0;
-                }
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]) * p.alpha;
+                        if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        f[j] = x;
+                    }
+                    const bool full = (col0 + 32 <= p.N);
+                    if (p.atomic) {
+                        float* crow = reinterpret_cast<float*>(p.C) + dst;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) * p.alpha;
-                    if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    f[j] = x;
-                }
-                const bool full = (col0 + 32 <= p.N);
-                if (p.atomic) {
-                    float* crow = reinterpret_cast<float*>(p.C) + dst;
+                        for (int j = 0; j < 32; ++j)
+                            if (full || col0 + j < p.N) atomicAdd(crow + j, f[j]);
+                    } else if (p.c_bf16) {
+                        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + dst;
+                        if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full || col0 + j < p.N) atomicAdd(crow + j, f[j]);
-                } else if (p.c_bf16) {
-                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + dst;
-                    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
+                                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                                *reinterpret_cast<uint4*>(crow + j) = pk;
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
-                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                            *reinterpret_cast<uint4*>(crow + j) = pk;
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
                         }
                     } else {
+                        float* crow = reinterpret_cast<float*>(p.C) + dst;
+                        if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
-                    }
-                } else {
-                    float* crow = reinterpret_cast<float*>(p.C) + dst;
-                    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) crow[j] = f[j];
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) crow[j] = f[j];
+                        }
                     }
                 }
             }
+            // this warp has read its accumulator quadrant: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
     tc_fence_before();
@@ -381,7 +413,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, (p.N + BLOCK_N - 1) / BLOCK_N, split_k * batch);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const long tiles = (long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * split_k * batch;
+    const int grid = (int)(tiles < num_sms ? tiles : num_sms);
     gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
     return pcm_launch_status();
 }
@@ -412,12 +452,13 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     p.k_blocks_per_split = (kblocks + split_k - 1) / split_k;
     split_k = (kblocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
     p.split_k = split_k;
+    p.batch = batch;
     p.a_batch_rows = a_batch_rows; p.b_batch_rows = b_batch_rows;
     p.C = C; p.ldc = ldc; p.c_mode = c_mode; p.c_batch_rows = c_batch_rows;
     p.hs_B = hs_B; p.hs_nh = hs_nh; p.hs_L = hs_L;
     p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16; p.alpha = alpha;
     p.atomic = (accumulate || split_k > 1) ? 1 : 0;
-    const int BN = 128;
+    const int BN = (N <= 64) ? 64 : 128;
     CUtensorMap ta, tb;
     int r;
     if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_M, &ta);
@@ -427,6 +468,12 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     else r = get_tensor_map(B, (uint64_t)N, (uint64_t)b_rows_total, (uint64_t)ldb, 64, BLOCK_K, &tb);
     if (r) return r;
     cudaStream_t st = pcm_cu_stream(stream);
+    if (BN == 64) {
+        if (!a_mn && !b_mn) return launch<64, false, false>(ta, tb, p, split_k, batch, st);
+        if (!a_mn && b_mn) return launch<64, false, true>(ta, tb, p, split_k, batch, st);
+        if (a_mn && !b_mn) return launch<64, true, false>(ta, tb, p, split_k, batch, st);
+        return launch<64, true, true>(ta, tb, p, split_k, batch, st);
+    }
     if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, batch, st);
     if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, batch, st);
     if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, p, split_k, batch, st);
