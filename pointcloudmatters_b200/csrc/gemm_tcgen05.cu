@@ -29,7 +29,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;   // 6 x 32 KB ring; one persistent CTA per SM
+template <int BLOCK_N> struct StagesFor { static constexpr int value = BLOCK_N == 256 ? 4 : 6; };  // <= 192 KB ring
 constexpr int NUM_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 or 256: power of two >= 32
+    constexpr int STAGES = StagesFor<BLOCK_N>::value;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128, 256 or 512: power of two >= 32
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=BF16
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -405,7 +406,7 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
-    constexpr size_t SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+    constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>,
@@ -458,7 +459,8 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     p.hs_B = hs_B; p.hs_nh = hs_nh; p.hs_L = hs_L;
     p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16; p.alpha = alpha;
     p.atomic = (accumulate || split_k > 1) ? 1 : 0;
-    const int BN = (N <= 64) ? 64 : 128;
+    // wide tiles cut L2->smem operand traffic per FLOP (ncu: 128x128 SS tiles are smem/L2 bound)
+    const int BN = (N <= 64) ? 64 : ((N >= 256 && ((N + 255) / 256 * 256 - N) < 128) ? 256 : 128);
     CUtensorMap ta, tb;
     int r;
     if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_M, &ta);
@@ -473,6 +475,12 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
         if (!a_mn && b_mn) return launch<64, false, true>(ta, tb, p, split_k, batch, st);
         if (a_mn && !b_mn) return launch<64, true, false>(ta, tb, p, split_k, batch, st);
         return launch<64, true, true>(ta, tb, p, split_k, batch, st);
+    }
+    if (BN == 256) {
+        if (!a_mn && !b_mn) return launch<256, false, false>(ta, tb, p, split_k, batch, st);
+        if (!a_mn && b_mn) return launch<256, false, true>(ta, tb, p, split_k, batch, st);
+        if (a_mn && !b_mn) return launch<256, true, false>(ta, tb, p, split_k, batch, st);
+        return launch<256, true, true>(ta, tb, p, split_k, batch, st);
     }
     if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, batch, st);
     if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, batch, st);

@@ -1,0 +1,31 @@
+"""Tiny ncu target: a few launches of one kernel family at a BASELINE cfg-2 shape.
+usage: python tools/ncu_target.py gemm|gemm_bf16out|fps|knn|sa"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+if which.startswith("gemm"):
+    from pointcloudmatters_b200.kernels import gemm_bf16
+
+    M, N, K = 32960, 1024, 512
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if which == "gemm_bf16out" else torch.float32)
+    for _ in range(4):
+        gemm_bf16(a, b, out=out)
+else:
+    import numpy as np
+
+    from pointcloudmatters_b200 import pointops as P
+    from tests._data import clouds
+
+    xyz, off, noff = clouds(64, 1024, 512, seed=1)
+    t_xyz, t_off, t_noff = [torch.from_numpy(x).cuda() for x in (xyz, off, noff)]
+    for _ in range(4):
+        fps = P.farthest_point_sampling(t_xyz, t_off, t_noff, n_max=1024, m_total=64 * 512)
+        q = t_xyz[fps.long()].contiguous()
+        P.knn_query(16, t_xyz, t_off, q, t_noff)
+torch.cuda.synchronize()
