@@ -9,7 +9,8 @@
 //     with the fp32 accumulator in TENSOR MEMORY, releases ring slots with tcgen05.commit;
 //     the same warp owns tcgen05.alloc / dealloc;
 //   * warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / cast ->
-//     128-byte-per-thread global stores, or red.global.add.f32 for split-K accumulation.
+//     swizzled shared-memory strip -> fully coalesced 128-byte row-segment stores (or coalesced
+//     red.global.add.f32 for split-K / gradient accumulation).
 // Both operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
 // second form lets the backward GEMMs (dX = dY W, dW = dY^T X) read activations / weights in the
 // layout they already have, with no transpose pass.  Shared-memory layouts are the canonical UMMA
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint8_t* epi_stage = tiles + STAGES * STAGE_BYTES + 256;  // 4 warps x 4 KB, 128-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -253,81 +255,108 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
     } else {
         // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
+        // Each warp drains its own 32 accumulator rows in strips of 128 bytes per row (32 fp32 or
+        // 64 bf16 columns): TMEM -> registers -> (alpha, bias, ReLU, cast) -> a private 4 KB
+        // shared-memory strip written with the 128B XOR swizzle -> read back transposed so that
+        // every global store instruction covers 4 complete 128-byte row segments (a row-per-lane
+        // store would touch 32 cache lines per instruction and make the kernel epilogue-bound).
         const int quad = warp & 3;
+        uint8_t* stage = epi_stage + (warp - 2) * 4096;
+        const int CW = p.c_bf16 ? 64 : 32;  // columns per strip
         int i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
             const int zs = t / tiles_mn, r = t - zs * tiles_mn;
             const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
             const int zb = zs / p.split_k;
             const int acc = i & 1;
-            const int row = m_blk * BLOCK_M + quad * 32 + lane;  // row inside this batch's M
+            const int row_base = m_blk * BLOCK_M + quad * 32;  // first row of this warp inside the batch's M
             mbar_wait(&tmem_full_bar[acc], ((uint32_t)i >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-                tmem_ld_wait();
+            for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
                 const int col0 = n_blk * BLOCK_N + c0;
-                if (row < p.M && col0 < p.N) {
+                if (col0 >= p.N) break;  // warp-uniform
+                // ---- TMEM -> registers -> swizzled smem strip (lane = row) ----
+#pragma unroll 1
+                for (int half = 0; half < (p.c_bf16 ? 2 : 1); ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0 + half * 32), v);
+                    tmem_ld_wait();
                     float f[32];
-                    // destination of this thread's 32-column strip (see GemmParams::c_mode)
-                    size_t dst;
-                    if (p.c_mode == 0) {
-                        dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
-                    } else if (p.c_mode == 1) {
-                        const int l = row / p.hs_B, b = row - l * p.hs_B;
-                        const int h = col0 >> 6, d = col0 & 63;
-                        dst = ((size_t)(b * p.hs_nh + h) * p.hs_L + l) * 64 + d;
-                    } else {
-                        const int b = zb / p.hs_nh, h = zb - b * p.hs_nh;
-                        dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0;
-                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + half * 32 + j;
                         float x = __uint_as_float(v[j]) * p.alpha;
-                        if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                        if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
                         if (p.relu) x = fmaxf(x, 0.f);
                         f[j] = x;
                     }
-                    const bool full = (col0 + 32 <= p.N);
-                    if (p.atomic) {
-                        float* crow = reinterpret_cast<float*>(p.C) + dst;
+                    if (p.c_bf16) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (full || col0 + j < p.N) atomicAdd(crow + j, f[j]);
-                    } else if (p.c_bf16) {
-                        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + dst;
-                        if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 pk;
-                                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
-                                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                                *reinterpret_cast<uint4*>(crow + j) = pk;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
+                        for (int c = 0; c < 4; ++c) {  // 4 x 16 B = 32 bf16 of this half
+                            uint4 pk;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
+                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]);
+                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                            const int chunk = half * 4 + c;
+                            *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
                         }
                     } else {
-                        float* crow = reinterpret_cast<float*>(p.C) + dst;
-                        if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<float4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                                make_float4(f[c * 4 + 0], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+                    }
+                }
+                __syncwarp();
+                // ---- smem strip -> global, 4 rows x 128 B per instruction ----
+                const int esz = p.c_bf16 ? 2 : 4;
+                if (p.atomic) {
+#pragma unroll 1
+                    for (int rl = 0; rl < 32; ++rl) {
+                        const int row = row_base + rl;
+                        if (row >= p.M) break;
+                        const float x = *reinterpret_cast<const float*>(stage + rl * 128 + (((lane >> 2) ^ (rl & 7)) << 4) + ((lane & 3) << 2));
+                        if (col0 + lane < p.N) {
+                            size_t dst;
+                            if (p.c_mode == 0) dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
+                            else if (p.c_mode == 1) { const int l = row / p.hs_B, b = row - l * p.hs_B; dst = ((size_t)(b * p.hs_nh + (col0 >> 6)) * p.hs_L + l) * 64 + (col0 & 63); }
+                            else { const int b = zb / p.hs_nh, h = zb - b * p.hs_nh; dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0; }
+                            atomicAdd(reinterpret_cast<float*>(p.C) + dst + lane, x);
+                        }
+                    }
+                } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) crow[j] = f[j];
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        const int rl = it8 * 4 + (lane >> 3);
+                        const int chunk = lane & 7;
+                        const int row = row_base + rl;
+                        const uint4 pk = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                        const int ecol = col0 + chunk * (16 / esz);  // first element column of this 16-byte piece
+                        if (row < p.M && ecol < p.N) {
+                            size_t dst;
+                            if (p.c_mode == 0) dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + ecol;
+                            else if (p.c_mode == 1) { const int l = row / p.hs_B, b = row - l * p.hs_B; dst = ((size_t)(b * p.hs_nh + (ecol >> 6)) * p.hs_L + l) * 64 + (ecol & 63); }
+                            else { const int b = zb / p.hs_nh, h = zb - b * p.hs_nh; dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + ecol; }
+                            uint8_t* g = reinterpret_cast<uint8_t*>(p.C) + dst * esz;
+                            if (ecol + 16 / esz <= p.N && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+                                *reinterpret_cast<uint4*>(g) = pk;
+                            } else if (p.c_bf16) {
+                                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&pk);
+                                for (int q = 0; q < 8; ++q)
+                                    if (ecol + q < p.N) reinterpret_cast<__nv_bfloat16*>(g)[q] = e[q];
+                            } else {
+                                const float* e = reinterpret_cast<const float*>(&pk);
+                                for (int q = 0; q < 4; ++q)
+                                    if (ecol + q < p.N) reinterpret_cast<float*>(g)[q] = e[q];
+                            }
                         }
                     }
                 }
+                __syncwarp();
             }
             // this warp has read its accumulator quadrant: hand the buffer back to the MMA warp
             tc_fence_before();
@@ -406,7 +435,7 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
-    constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+    constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256 + 4 * 4096;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>,
