@@ -96,7 +96,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld carries the destination registers as in/out operands: a true data dependency, so the
+// compiler cannot schedule any use of the loaded values above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), sm_100 version field = 1.
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
@@ -141,7 +150,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Tile order: n fastest, then m, then (batch, k-slice) -- CTAs running at the same time share the
 // A row-block and the whole (small) B operand through L2.  Two TMEM accumulators (2 x BLOCK_N
 // columns) let the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
-template <int BLOCK_N, bool A_MN, bool B_MN>
+enum { EPI_F32 = 0, EPI_BF16 = 1, EPI_ATOMIC = 2 };
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                       const __grid_constant__ CUtensorMap tmap_b,
                                                                       const GemmParams p) {
@@ -255,14 +266,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
     } else {
         // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
-        // Each warp drains its own 32 accumulator rows in strips of 128 bytes per row (32 fp32 or
-        // 64 bf16 columns): TMEM -> registers -> (alpha, bias, ReLU, cast) -> a private 4 KB
-        // shared-memory strip written with the 128B XOR swizzle -> read back transposed so that
-        // every global store instruction covers 4 complete 128-byte row segments (a row-per-lane
-        // store would touch 32 cache lines per instruction and make the kernel epilogue-bound).
+        // Each warp drains its own 32 accumulator rows in 32-column strips.  The TMEM loads are
+        // software-pipelined (strip q+1 is in flight while strip q is processed: with one epilogue
+        // warp per SM sub-partition nothing else hides the tcgen05.ld latency).  A strip goes
+        // registers -> (alpha, bias, ReLU, cast) -> a private swizzled 4 KB shared-memory strip ->
+        // read back transposed, so every global store instruction covers complete 128-byte row
+        // segments instead of 32 different cache lines.
         const int quad = warp & 3;
         uint8_t* stage = epi_stage + (warp - 2) * 4096;
-        const int CW = p.c_bf16 ? 64 : 32;  // columns per strip
+        constexpr int NLD = BLOCK_N / 32;
+        constexpr int ESZ = EPI == EPI_BF16 ? 2 : 4;
         int i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
             const int zs = t / tiles_mn, r = t - zs * tiles_mn;
@@ -270,62 +283,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int zb = zs / p.split_k;
             const int acc = i & 1;
             const int row_base = m_blk * BLOCK_M + quad * 32;  // first row of this warp inside the batch's M
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            // per-row destination offsets (elements) of this warp's 32 rows, lane rl holds row rl
+            size_t row_dst;
+            {
+                const int row = row_base + lane;
+                if (p.c_mode == 0) row_dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc;
+                else if (p.c_mode == 1) { const int l = row / p.hs_B, b = row - l * p.hs_B; row_dst = ((size_t)b * p.hs_nh * p.hs_L + l) * 64; }
+                else { const int b = zb / p.hs_nh, h = zb - b * p.hs_nh; row_dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64; }
+            }
             mbar_wait(&tmem_full_bar[acc], ((uint32_t)i >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
-                const int col0 = n_blk * BLOCK_N + c0;
-                if (col0 >= p.N) break;  // warp-uniform
-                // ---- TMEM -> registers -> swizzled smem strip (lane = row) ----
-#pragma unroll 1
-                for (int half = 0; half < (p.c_bf16 ? 2 : 1); ++half) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0 + half * 32), v);
-                    tmem_ld_wait();
-                    float f[32];
+
+            auto process = [&](uint32_t (&v)[32], int q) {
+                const int col0 = n_blk * BLOCK_N + q * 32;
+                if (col0 >= p.N) return;  // warp-uniform
+                float bl = 0.f;
+                if (p.bias != nullptr && col0 + lane < p.N) bl = __ldg(p.bias + col0 + lane);
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + half * 32 + j;
-                        float x = __uint_as_float(v[j]) * p.alpha;
-                        if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        f[j] = x;
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]) * p.alpha + __shfl_sync(PCM_FULL_MASK, bl, j);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                if (EPI == EPI_BF16) {
+                    // two consecutive loads (64 columns) share one 128-byte-per-row strip
+                    const int half = q & 1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 pk;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
+                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]);
+                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                        const int chunk = half * 4 + c;
+                        *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
                     }
-                    if (p.c_bf16) {
+                    if (half == 0 && col0 + 32 < p.N && q + 1 < NLD) return;  // wait for the second half of the strip
+                } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {  // 4 x 16 B = 32 bf16 of this half
-                            uint4 pk;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
-                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]);
-                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                            const int chunk = half * 4 + c;
-                            *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<float4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                                make_float4(f[c * 4 + 0], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
-                    }
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                            make_float4(f[c * 4 + 0], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
                 }
                 __syncwarp();
-                // ---- smem strip -> global, 4 rows x 128 B per instruction ----
-                const int esz = p.c_bf16 ? 2 : 4;
-                if (p.atomic) {
-#pragma unroll 1
+                const int scol0 = EPI == EPI_BF16 ? (n_blk * BLOCK_N + (q & ~1) * 32) : col0;  // first column of the strip
+                if (EPI == EPI_ATOMIC) {
+#pragma unroll 4
                     for (int rl = 0; rl < 32; ++rl) {
-                        const int row = row_base + rl;
-                        if (row >= p.M) break;
+                        const size_t rd = __shfl_sync(PCM_FULL_MASK, row_dst, rl);
                         const float x = *reinterpret_cast<const float*>(stage + rl * 128 + (((lane >> 2) ^ (rl & 7)) << 4) + ((lane & 3) << 2));
-                        if (col0 + lane < p.N) {
-                            size_t dst;
-                            if (p.c_mode == 0) dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + col0;
-                            else if (p.c_mode == 1) { const int l = row / p.hs_B, b = row - l * p.hs_B; dst = ((size_t)(b * p.hs_nh + (col0 >> 6)) * p.hs_L + l) * 64 + (col0 & 63); }
-                            else { const int b = zb / p.hs_nh, h = zb - b * p.hs_nh; dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + col0; }
-                            atomicAdd(reinterpret_cast<float*>(p.C) + dst + lane, x);
+                        if (row_base + rl < p.M && scol0 + lane < p.N) {
+                            const size_t dst = p.c_mode == 1 ? rd + (size_t)((scol0 + lane) >> 6) * p.hs_L * 64 + ((scol0 + lane) & 63)
+                                                             : rd + scol0 + lane;
+                            atomicAdd(reinterpret_cast<float*>(p.C) + dst, x);
                         }
                     }
                 } else {
@@ -333,30 +347,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     for (int it8 = 0; it8 < 8; ++it8) {
                         const int rl = it8 * 4 + (lane >> 3);
                         const int chunk = lane & 7;
-                        const int row = row_base + rl;
+                        const size_t rd = __shfl_sync(PCM_FULL_MASK, row_dst, rl);
                         const uint4 pk = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((chunk ^ (rl & 7)) << 4));
-                        const int ecol = col0 + chunk * (16 / esz);  // first element column of this 16-byte piece
-                        if (row < p.M && ecol < p.N) {
-                            size_t dst;
-                            if (p.c_mode == 0) dst = (size_t)(zb * p.c_batch_rows + row) * p.ldc + ecol;
-                            else if (p.c_mode == 1) { const int l = row / p.hs_B, b = row - l * p.hs_B; dst = ((size_t)(b * p.hs_nh + (ecol >> 6)) * p.hs_L + l) * 64 + (ecol & 63); }
-                            else { const int b = zb / p.hs_nh, h = zb - b * p.hs_nh; dst = ((size_t)row * p.hs_B + b) * p.ldc + h * 64 + ecol; }
-                            uint8_t* g = reinterpret_cast<uint8_t*>(p.C) + dst * esz;
-                            if (ecol + 16 / esz <= p.N && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+                        const int ecol = scol0 + chunk * (16 / ESZ);  // first element column of this 16-byte piece
+                        if (row_base + rl < p.M && ecol < p.N) {
+                            const size_t dst = p.c_mode == 1 ? rd + (size_t)(ecol >> 6) * p.hs_L * 64 + (ecol & 63) : rd + ecol;
+                            uint8_t* g = reinterpret_cast<uint8_t*>(p.C) + dst * ESZ;
+                            if (ecol + 16 / ESZ <= p.N && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
                                 *reinterpret_cast<uint4*>(g) = pk;
-                            } else if (p.c_bf16) {
+                            } else if (EPI == EPI_BF16) {
                                 const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&pk);
-                                for (int q = 0; q < 8; ++q)
-                                    if (ecol + q < p.N) reinterpret_cast<__nv_bfloat16*>(g)[q] = e[q];
+                                for (int qq = 0; qq < 8; ++qq)
+                                    if (ecol + qq < p.N) reinterpret_cast<__nv_bfloat16*>(g)[qq] = e[qq];
                             } else {
                                 const float* e = reinterpret_cast<const float*>(&pk);
-                                for (int q = 0; q < 4; ++q)
-                                    if (ecol + q < p.N) reinterpret_cast<float*>(g)[q] = e[q];
+                                for (int qq = 0; qq < 4; ++qq)
+                                    if (ecol + qq < p.N) reinterpret_cast<float*>(g)[qq] = e[qq];
                             }
                         }
                     }
                 }
                 __syncwarp();
+            };
+
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll 1
+            for (int q = 0; q < NLD; q += 2) {
+                tmem_ld_wait(va);
+                tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 1) * 32), vb);  // NLD is even: always valid
+                process(va, q);
+                tmem_ld_wait(vb);
+                if (q + 2 < NLD) tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 2) * 32), va);
+                process(vb, q + 1);
             }
             // this warp has read its accumulator quadrant: hand the buffer back to the MMA warp
             tc_fence_before();
@@ -433,12 +456,12 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
     return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
     constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256 + 4 * 4096;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
@@ -452,8 +475,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     }
     const long tiles = (long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * split_k * batch;
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
+    gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
     return pcm_launch_status();
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
+    if (p.atomic) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_ATOMIC>(ta, tb, p, split_k, batch, st);
+    if (p.c_bf16) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_BF16>(ta, tb, p, split_k, batch, st);
+    return launch_epi<BLOCK_N, A_MN, B_MN, EPI_F32>(ta, tb, p, split_k, batch, st);
 }
 
 }  // namespace
