@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (default: BASELINE cfg-2)")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (debug / profiling)")
     ap.add_argument("--skip-dead-decoder-layers", action="store_true",
                     help="reported separately: stop the decoder after layer 0 (only [0] is consumed)")
     return ap.parse_args()
@@ -184,7 +185,7 @@ def b200_arm(args):
     policy = build_policy(CFG2).to(dev).train()
     policy.transformer.decoder.skip_dead_layers = bool(args.skip_dead_decoder_layers)
     total_steps = max(1000, args.steps + args.warmup + 8)
-    module = ACTBCModule(policy, total_steps=total_steps)
+    module = ACTBCModule(policy, total_steps=total_steps, use_cuda_graph=not args.no_cuda_graph)
     module.configure_optimizers()
 
     # per-rank shard of the global batch: distinct synthetic batches, pinned on the host
@@ -224,22 +225,35 @@ def b200_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), (loss_host if from_host else float(loss))
 
-    # warm-up (also builds the flat parameter / gradient buffers on the first step)
-    run(resident, max(3, args.warmup), False)
+    # warm-up (builds the flat parameter / gradient buffers on the first step, captures the
+    # forward+backward CUDA graph on the third)
+    run(resident, max(3, args.warmup) + 2, False)
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    PF.KERNEL_TIMER.enable()
     lib_l0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
     sec, last_loss = run(resident, args.steps, False)
     t_wall1 = time.perf_counter()
-    launches = _lib.launch_count() - lib_l0
+    launches_outside_graph = _lib.launch_count() - lib_l0
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    # kernels of libpcm_b200.so launched per step: counted on one EAGER step (inside a CUDA-graph
+    # replay the library is not re-entered, the captured launches are replayed by the driver), and
+    # the dominant kernel families are timed there with CUDA events on the launch stream.
+    trainer = module._trainer
+    graph_was = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    run(resident, 1, False)
+    PF.KERNEL_TIMER.enable()
+    lib_e0 = _lib.launch_count()
+    run(resident, 3, False)
+    launches_per_step = (_lib.launch_count() - lib_e0) // 3
     kstats = PF.KERNEL_TIMER.summary()
     PF.KERNEL_TIMER.disable()
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    trainer.use_cuda_graph = graph_was
+    launches = launches_per_step * args.steps if graph_was else launches_outside_graph
 
     run(host, 2, True)
     sec_e2e, loss_e2e = run(host, args.steps, True)
@@ -269,6 +283,8 @@ def b200_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": 1e3 * sec_e2e / args.steps, "last_loss": loss_e2e},
         "gpu_launches": int(launches),
+        "gpu_launches_per_step": int(launches_per_step),
+        "cuda_graph": bool(graph_was),
         "clocks": clk,
         "roofline": roofline,
         "kernel_ms_per_step": {k: v["ms_per_step"] for k, v in kstats.items()},

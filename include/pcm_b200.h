@@ -179,12 +179,16 @@ int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void *A, int lda, int
  * softmax / dropout of nn.MultiheadAttention's math path, transformer.py:246-248).  Buffers are
  * [Z = B*nh, Lp, Sp] with zero padding.  fwd: S fp32 raw scores -> Y = softmax(scale*S + mask)
  * (bf16), Zd = dropout(Y) (bf16; pass Zd == Y when p_drop == 0); kpm (B, Sk) bytes, non-zero =
- * masked key, may be NULL.  bwd (in place on dZ): dS = scale * Y * (dY - <dY, Y>). */
+ * masked key, may be NULL.  bwd (in place on dZ): dS = scale * Y * (dY - <dY, Y>).  The dropout
+ * seed is *seed_base (device memory, may be NULL = 0; lets a CUDA-graph replay draw fresh masks
+ * every step) + seed_offset (distinguishes call sites). */
 int pcm_attn_softmax_fwd(int Z, int L, int Lp, int Sk, int Sp, int nh, const float *S,
                          const unsigned char *kpm, float scale, float p_drop,
-                         unsigned long long seed, void *Y, void *Zd, pcm_stream_t stream);
+                         const unsigned long long *seed_base, unsigned long long seed_offset, void *Y,
+                         void *Zd, pcm_stream_t stream);
 int pcm_attn_softmax_bwd(int Z, int L, int Lp, int Sk, int Sp, const void *Y, void *dZ, float scale,
-                         float p_drop, unsigned long long seed, pcm_stream_t stream);
+                         float p_drop, const unsigned long long *seed_base,
+                         unsigned long long seed_offset, pcm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused set-abstraction head.  Replaces, for ACTPCD.pcd_sampling (src/models/components/act/
@@ -216,6 +220,17 @@ int pcm_sa_bwd_coef(int H, const double *gstats, const double *fstats, const dou
 int pcm_sa_bwd_dense(int n, int H, const float *Pf, const float *xyz, const float *cnt,
                      const float *sq, const float *W, int ldw, const float *ab, const float *dPf,
                      void *dPf_bf16, pcm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused clip-by-global-norm + AdamW over flat fp32 buffers.
+ * Replaces torch.nn.utils.clip_grad_norm_ (Lightning gradient_clip_val, configs/trainer/
+ * ddp.yaml:12) + torch.optim.AdamW (src/utils/optimizer.py:33-72; configs/model/
+ * maniskill2_act_pcd_model.yaml:11-14).  hyper (device, 9 floats) = [lr, beta1, beta2, eps,
+ * weight_decay, bias_correction1, bias_correction2, clip_norm, grad_scale]; grad is scaled by
+ * grad_scale (1/world after a SUM all-reduce) and the clip coefficient in place.  n % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int pcm_clip_adamw_step(long long n, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                        const float *hyper, double *sumsq, float *norm_out, pcm_stream_t stream);
 
 #ifdef __cplusplus
 }

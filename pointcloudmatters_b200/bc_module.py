@@ -21,12 +21,13 @@ from .trainer import BCTrainer
 
 class ACTBCModule(nn.Module):
     def __init__(self, policy, optimizer: dict | None = None, lr_scheduler: dict | None = None,
-                 gradient_clip_val: float = 0.5, total_steps: int = 100000, **kwargs):
+                 gradient_clip_val: float = 0.5, total_steps: int = 100000, use_cuda_graph: bool = False, **kwargs):
         super().__init__()
         self.policy = policy
         # defaults = configs/model/maniskill2_act_pcd_model.yaml:11-25, configs/trainer/ddp.yaml:12
         self.hparams = dict(optimizer=dict(type="AdamW", lr=5e-5, weight_decay=0.05) | (optimizer or {}),
-                            lr_scheduler=lr_scheduler, gradient_clip_val=gradient_clip_val, total_steps=total_steps)
+                            lr_scheduler=lr_scheduler, gradient_clip_val=gradient_clip_val, total_steps=total_steps,
+                            use_cuda_graph=use_cuda_graph)
         self._trainer: BCTrainer | None = None
         self.logged: dict[str, Any] = {}
 
@@ -44,7 +45,7 @@ class ACTBCModule(nn.Module):
         sch = {k: v for k, v in sch.items() if k in ("pct_start", "div_factor", "final_div_factor")}
         self._trainer = BCTrainer(self.policy, lr=opt["lr"], weight_decay=opt.get("weight_decay", 0.01),
                                   clip_norm=self.hparams["gradient_clip_val"], total_steps=self.hparams["total_steps"],
-                                  scheduler=sch)
+                                  scheduler=sch, use_cuda_graph=self.hparams["use_cuda_graph"])
         return self._trainer
 
     def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:

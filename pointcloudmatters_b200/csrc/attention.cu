@@ -25,8 +25,9 @@ __device__ __forceinline__ uint32_t dropout_bits(unsigned long long seed, unsign
 
 __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
     const float* __restrict__ S, long rows_total, int L, int Lp, int Sk, int Sp, int nh,
-    const unsigned char* __restrict__ kpm, float scale, float p_drop, unsigned long long seed,
-    __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ Zd) {
+    const unsigned char* __restrict__ kpm, float scale, float p_drop, const unsigned long long* __restrict__ seed_base,
+    unsigned long long seed_offset, __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ Zd) {
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
 
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
     const __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ dZ, long rows_total, int L, int Lp, int Sk,
-    int Sp, float scale, float p_drop, unsigned long long seed) {
+    int Sp, float scale, float p_drop, const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset) {
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -103,26 +105,28 @@ inline int rows_grid(long rows) {
 // S: fp32 [Z, Lp, Sp] raw scores (Z = B * nh); kpm: (B, Sk) bytes, non-zero = masked key (may be NULL).
 // Y: bf16 softmax probabilities; Zd: bf16 dropped probabilities (pass Zd == Y when p_drop == 0).
 PCM_API int pcm_attn_softmax_fwd(int Z, int L, int Lp, int Sk, int Sp, int nh, const float* S,
-                                 const unsigned char* kpm, float scale, float p_drop, unsigned long long seed,
-                                 void* Y, void* Zd, pcm_stream_t stream) {
+                                 const unsigned char* kpm, float scale, float p_drop,
+                                 const unsigned long long* seed_base, unsigned long long seed_offset, void* Y,
+                                 void* Zd, pcm_stream_t stream) {
     const long rows = (long)Z * L;
     if (rows <= 0 || Sk <= 0) return PCM_OK;
     if (!S || !Y || !Zd || nh <= 0 || Lp < L || Sp < Sk) return PCM_EINVAL;
     if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && Zd == Y)) return PCM_EINVAL;
     attn_softmax_fwd_kernel<<<rows_grid(rows), 256, 0, pcm_cu_stream(stream)>>>(
-        S, rows, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed, reinterpret_cast<__nv_bfloat16*>(Y),
+        S, rows, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed_base, seed_offset, reinterpret_cast<__nv_bfloat16*>(Y),
         reinterpret_cast<__nv_bfloat16*>(Zd));
     return pcm_launch_status();
 }
 
 // dZ (in) = dO V^T in bf16; dZ (out) = dS = scale * y * (dy - <dy, y>), dy = dropout-backward(dZ).
 PCM_API int pcm_attn_softmax_bwd(int Z, int L, int Lp, int Sk, int Sp, const void* Y, void* dZ, float scale,
-                                 float p_drop, unsigned long long seed, pcm_stream_t stream) {
+                                 float p_drop, const unsigned long long* seed_base, unsigned long long seed_offset,
+                                 pcm_stream_t stream) {
     const long rows = (long)Z * L;
     if (rows <= 0 || Sk <= 0) return PCM_OK;
     if (!Y || !dZ || Lp < L || Sp < Sk || p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
     attn_softmax_bwd_kernel<<<rows_grid(rows), 256, 0, pcm_cu_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(dZ), rows, L, Lp, Sk, Sp, scale,
-        p_drop, seed);
+        p_drop, seed_base, seed_offset);
     return pcm_launch_status();
 }

@@ -26,8 +26,10 @@ def _need_cuda(t):
 
 def _split_k_for(m_tiles, n_tiles, kblocks):
     """Enough CTAs for ~2 waves of the 148 SMs when the output is small and K is long (dW GEMMs)."""
-    want = max(1, (2 * 148 + m_tiles * n_tiles - 1) // (m_tiles * n_tiles))
-    return max(1, min(want, kblocks))
+    # one wave of the 148 SMs, and at least 8 k-blocks per slice: every extra slice costs a full
+    # tile of fp32 atomics in the epilogue (profile: atomics, not MMAs, dominated 37-way splits)
+    want = max(1, 148 // max(1, m_tiles * n_tiles))
+    return max(1, min(want, max(1, kblocks // 8)))
 
 
 class _LinearTC(torch.autograd.Function):
@@ -103,6 +105,35 @@ def attention(q, k, v, key_padding_mask=None, dropout_p=0.0, training=False):
 _WORKSPACE = {}
 
 
+class _DropoutRNG:
+    """Seeds for the in-kernel dropout masks without host synchronisation: a device-resident
+    64-bit base (advanced once per training step by the trainer -- also under CUDA-graph replay)
+    plus a per-call-site offset that restarts at every step."""
+
+    def __init__(self):
+        self.base = {}
+        self.offset = 0
+
+    def base_for(self, device):
+        key = str(device)
+        if key not in self.base:
+            self.base[key] = torch.randint(1, 2 ** 62, (1,), dtype=torch.int64).to(device)
+        return self.base[key]
+
+    def next_offset(self):
+        self.offset += 1
+        return self.offset * 0x100000001B3
+
+    def new_step(self):
+        """Call once per training step (outside any graph capture the increment is a tiny kernel)."""
+        for t in self.base.values():
+            t.add_(1)
+        self.offset = 0
+
+
+DROPOUT_RNG = _DropoutRNG()
+
+
 def _workspace(name, shape, dtype, device, zero=False):
     """Cached scratch tensor.  `zero=True` buffers are zero-filled once; their users only ever write
     the valid (unpadded) region, so the padding stays zero across reuses."""
@@ -151,13 +182,15 @@ class _MHA(torch.autograd.Function):
         K.gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=Lp, ldc=Sp)
         Y = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev)
         Zd = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev) if p_drop > 0 else Y
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+        seed_base = DROPOUT_RNG.base_for(dev) if p_drop > 0 else None
+        seed = DROPOUT_RNG.next_offset() if p_drop > 0 else 0
         kpm_u8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
-        K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed)
+        K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed_base, seed)
         O_tok = torch.empty((L * B, E), dtype=bf, device=dev)
         K.gemm_ex(L, 64, S, Z, Zd, False, Lp, Vh, True, S, O_tok, c_mode=2, hs=(B, nh, L), ldc=E)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
         ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
+        ctx.seed_base = seed_base
         ctx.dims = (L, S, B, E, nh, Lp, Sp, scale, p_drop, seed, same_qk)
         return out.view(L, B, E)
 
@@ -180,7 +213,7 @@ class _MHA(torch.autograd.Function):
         # softmax backward
         dP = _workspace("attn_dP", (Z * Lp, Sp), bf, dev, zero=True)
         K.gemm_ex(L, S, 64, Z, dOh, False, L, Vh, False, S, dP, c_mode=0, c_batch_rows=Lp, ldc=Sp)
-        K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, seed)
+        K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, ctx.seed_base, seed)
         dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
         dK_tok = torch.empty((S * B, E), dtype=bf, device=dev)
         dV_tok = torch.empty((S * B, E), dtype=bf, device=dev)
@@ -332,22 +365,12 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
                                  knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training)
 
 
-def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, *, step, lr, beta1, beta2, eps, weight_decay, clip_norm):
-    """Fused clip-by-global-norm + AdamW over flat fp32 buffers (in place); returns the pre-clip
-    gradient norm as a 0-dim device tensor (no host sync).  Same arithmetic as
-    torch.nn.utils.clip_grad_norm_ followed by torch.optim.AdamW (decoupled weight decay)."""
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
+    """Fused clip-by-global-norm + AdamW over flat fp32 buffers, in place (csrc/optimizer.cu).
+    `hyper` = device tensor [lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2, clip_norm, grad_scale]."""
     _need_cuda(param)
-    norm = torch.linalg.vector_norm(grad)
-    if clip_norm is not None and clip_norm > 0:
-        grad.mul_(torch.clamp(clip_norm / (norm + 1e-6), max=1.0))
-    param.mul_(1.0 - lr * weight_decay)
-    exp_avg.lerp_(grad, 1.0 - beta1)
-    exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1.0 - beta2)
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
-    denom = (exp_avg_sq.sqrt() / math.sqrt(bc2)).add_(eps)
-    param.addcdiv_(exp_avg, denom, value=-lr / bc1)
-    return norm
+    K.clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out)
+    return norm_out
 
 
 # ------------------------------------------------------------------------------------------------

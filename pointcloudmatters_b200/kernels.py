@@ -48,11 +48,18 @@ def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, 
     return out
 
 
-def attn_softmax_fwd(S, Y, Zd, Z, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed):
-    check(lib.pcm_attn_softmax_fwd(Z, L, Lp, Sk, Sp, nh, ptr(S), ptr(kpm), float(scale), float(p_drop), int(seed),
-                                   ptr(Y), ptr(Zd), current_stream()), "pcm_attn_softmax_fwd")
+def attn_softmax_fwd(S, Y, Zd, Z, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed_base, seed_offset):
+    check(lib.pcm_attn_softmax_fwd(Z, L, Lp, Sk, Sp, nh, ptr(S), ptr(kpm), float(scale), float(p_drop), ptr(seed_base),
+                                   int(seed_offset), ptr(Y), ptr(Zd), current_stream()), "pcm_attn_softmax_fwd")
 
 
-def attn_softmax_bwd(Y, dZ, Z, L, Lp, Sk, Sp, scale, p_drop, seed):
-    check(lib.pcm_attn_softmax_bwd(Z, L, Lp, Sk, Sp, ptr(Y), ptr(dZ), float(scale), float(p_drop), int(seed),
-                                   current_stream()), "pcm_attn_softmax_bwd")
+def attn_softmax_bwd(Y, dZ, Z, L, Lp, Sk, Sp, scale, p_drop, seed_base, seed_offset):
+    check(lib.pcm_attn_softmax_bwd(Z, L, Lp, Sk, Sp, ptr(Y), ptr(dZ), float(scale), float(p_drop), ptr(seed_base),
+                                   int(seed_offset), current_stream()), "pcm_attn_softmax_bwd")
+
+
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
+    """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step); hyper is a 9-float device tensor."""
+    require_cuda(param, grad, exp_avg, exp_avg_sq, hyper, sumsq)
+    check(lib.pcm_clip_adamw_step(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
+                                  ptr(sumsq), ptr(norm_out), current_stream()), "pcm_clip_adamw_step")

@@ -85,8 +85,11 @@ class FlatState:
 
 
 class BCTrainer:
+    """forward + backward (+ CUDA graph) -> one all-reduce -> fused clip + AdamW -> LR step."""
+
     def __init__(self, policy: nn.Module, lr=5e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
-                 clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None):
+                 clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None,
+                 use_cuda_graph: bool = False):
         self.policy = policy
         self.lr, self.weight_decay, self.betas, self.eps, self.clip_norm = lr, weight_decay, betas, eps, clip_norm
         sch = dict(pct_start=0.1, div_factor=100.0, final_div_factor=1000.0)
@@ -97,39 +100,106 @@ class BCTrainer:
         self.flat: FlatState | None = None
         self.step_num = 0
         self.last_grad_norm = None
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}  # shape signature -> (graph, static batch, static outputs)
+        self._eager_steps = 0
 
     # -- gradient exchange: ONE collective over the flat buffer -----------------------------------
     def reduce_gradients(self):
+        """SUM all-reduce of the flat gradient; the 1/world average is folded into the optimizer kernel."""
         if self.world > 1:
-            g = self.flat.grad[: self.flat.n_active]
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-            g.mul_(1.0 / self.world)
+            dist.all_reduce(self.flat.grad[: self.flat.n_active], op=dist.ReduceOp.SUM, group=self.pg)
 
     def _build_flat(self):
         inactive = [p for p in self.policy.parameters() if p.requires_grad and p.grad is None]
         self.flat = FlatState(self.policy.parameters(), inactive)
+        dev = self.flat.param.device
+        self._hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(9)
+        self._hyper = torch.zeros(9, dtype=torch.float32, device=dev)
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def hyper_values(self, step_num: int):
+        lr, beta1 = self.schedule.at(min(step_num, self.schedule.total_steps - 1))
+        t = step_num + 1
+        return [lr, beta1, self.betas[1], self.eps, self.weight_decay, 1.0 - beta1 ** t, 1.0 - self.betas[1] ** t,
+                self.clip_norm if self.clip_norm else 0.0, 1.0 / self.world]
 
     def optimizer_step(self):
         from . import functional as PF
 
-        lr, beta1 = self.schedule.at(min(self.step_num, self.schedule.total_steps - 1))
         f = self.flat
-        self.last_grad_norm = PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq,
-                                                 step=self.step_num + 1, lr=lr, beta1=beta1, beta2=self.betas[1],
-                                                 eps=self.eps, weight_decay=self.weight_decay, clip_norm=self.clip_norm)
+        self._hyper_host.copy_(torch.tensor(self.hyper_values(self.step_num), dtype=torch.float32))
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq, self._hyper,
+                           self._sumsq, self._norm)
+        self.last_grad_norm = self._norm
         self.step_num += 1
 
-    def training_step(self, batch):
-        """One full step on this rank's shard; returns the (detached) loss dict."""
+    # -- forward + backward -----------------------------------------------------------------------
+    def _forward_backward(self, batch):
         if self.flat is not None:
             self.flat.zero_grad()
         out = self.policy(batch)
         out["loss"].backward()
-        if self.flat is None:  # first step: discover never-used parameters, then go flat
-            self._build_flat()
+        return {k: out[k].detach() for k in ("loss", "action_loss", "kl_loss")}
+
+    @staticmethod
+    def _signature(batch):
+        sig = []
+        for k in sorted(batch):
+            v = batch[k]
+            if isinstance(v, dict):
+                sig.append((k, BCTrainer._signature(v)))
+            elif torch.is_tensor(v):
+                sig.append((k, tuple(v.shape), str(v.dtype)))
+            else:
+                sig.append((k, v))
+        return tuple(sig)
+
+    @staticmethod
+    def _copy_into(static, batch):
+        for k, v in batch.items():
+            if isinstance(v, dict):
+                BCTrainer._copy_into(static[k], v)
+            elif torch.is_tensor(v):
+                static[k].copy_(v, non_blocking=True)
+
+    def _graphed_forward_backward(self, batch):
+        """Replay (capturing on first use per batch-shape signature) the forward+backward graph.
+        ~2000 kernel launches per step become one cudaGraphLaunch; inputs are copied into static
+        buffers, dropout seeds come from device memory so every replay draws fresh masks."""
+        sig = self._signature(batch)
+        entry = self._graphs.get(sig)
+        if entry is None:
+            static = {k: ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict)
+                          else (v.clone() if torch.is_tensor(v) else v)) for k, v in batch.items()}
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._forward_backward(static)
+            entry = (graph, static, outs)
+            self._graphs[sig] = entry
+        graph, static, outs = entry
+        self._copy_into(static, batch)
+        graph.replay()
+        return outs
+
+    def training_step(self, batch):
+        """One full step on this rank's shard; returns the (detached) loss dict."""
+        from . import functional as PF
+
+        PF.DROPOUT_RNG.new_step()
+        if self.use_cuda_graph and self.flat is not None and self._eager_steps >= 2:
+            losses = self._graphed_forward_backward(batch)
+        else:
+            losses = self._forward_backward(batch)
+            self._eager_steps += 1
+            if self.flat is None:  # first step: discover never-used parameters, then go flat
+                self._build_flat()
         self.reduce_gradients()
         self.optimizer_step()
-        return {k: out[k].detach() for k in ("loss", "action_loss", "kl_loss")}
+        return losses
 
 
 def shard_batch(batch: dict, rank: int, world: int) -> dict:

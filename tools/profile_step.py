@@ -33,3 +33,18 @@ out = ROOT / "gpurun_out" / "profile_step.txt"
 out.parent.mkdir(exist_ok=True)
 out.write_text(tab)
 print(tab[-9000:])
+
+# wall vs GPU-busy
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for i in range(steps):
+    module.training_step(b, i)
+t_cpu_issue = time.perf_counter() - t0
+torch.cuda.synchronize(); t1 = time.perf_counter() - t0
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+gpu_ms = sum(e.cuda_time for e in evs) / 1e3 if evs else float("nan")
+ka = prof.key_averages()
+self_cuda = sum(getattr(k, "self_device_time_total", getattr(k, "self_cuda_time_total", 0)) for k in ka) / 1e3
+summary = f"steps={steps} wall_ms_per_step={t1/steps*1e3:.2f} cpu_issue_ms_per_step={t_cpu_issue/steps*1e3:.2f} gpu_kernel_ms_per_step={self_cuda/steps:.2f} kernels_per_step={sum(k.count for k in ka if k.device_type == torch.autograd.DeviceType.CUDA)/steps:.0f}"
+print(summary)
+(out.parent / "profile_summary.txt").write_text(summary + "\n")
