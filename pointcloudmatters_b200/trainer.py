@@ -137,10 +137,18 @@ class BCTrainer:
         self.step_num += 1
 
     # -- forward + backward -----------------------------------------------------------------------
+    INPUT_KEYS = ("pcds", "qpos", "actions", "is_pad", "goal_cond", "env_state", "_eps")
+
+    @classmethod
+    def _inputs_only(cls, batch):
+        """The policy's forward writes its intermediates into the dict it is given (reference
+        behaviour, act.py:137-309); work on a shallow copy restricted to the batch-contract keys."""
+        return {k: (dict(batch[k]) if isinstance(batch[k], dict) else batch[k]) for k in cls.INPUT_KEYS if k in batch}
+
     def _forward_backward(self, batch):
         if self.flat is not None:
             self.flat.zero_grad()
-        out = self.policy(batch)
+        out = self.policy(self._inputs_only(batch))
         out["loss"].backward()
         return {k: out[k].detach() for k in ("loss", "action_loss", "kl_loss")}
 
@@ -169,6 +177,7 @@ class BCTrainer:
         """Replay (capturing on first use per batch-shape signature) the forward+backward graph.
         ~2000 kernel launches per step become one cudaGraphLaunch; inputs are copied into static
         buffers, dropout seeds come from device memory so every replay draws fresh masks."""
+        batch = self._inputs_only(batch)
         sig = self._signature(batch)
         entry = self._graphs.get(sig)
         if entry is None:
