@@ -222,6 +222,26 @@ int pcm_sa_bwd_dense(int n, int H, const float *Pf, const float *xyz, const floa
                      void *dPf_bf16, pcm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused residual + dropout + LayerNorm: y = LayerNorm(res + dropout(x)) -- the epilogue of every
+ * transformer sub-block of the reference (`src = self.norm1(src + self.dropout1(src2))`,
+ * src/models/components/act/transformer.py:249-253,333-345; ATen dropout / add / layer_norm
+ * kernels there).  C in {128, 256, 512, 1024}; x may be NULL (plain LayerNorm).  Optional outputs
+ * y_bf16, h = res + dropout(x), mean, rstd.  Backward accumulates dgamma / dbeta (caller
+ * zero-fills) and writes dres (and dx = dropout-backward(dres) when dx != dres).
+ * pcm_colsum: out[c] += sum_r src[r, c] (bias gradients of nn.Linear / in_proj / out_proj).
+ * ------------------------------------------------------------------------------------------ */
+int pcm_add_dropout_ln_fwd(long long rows, int C, const float *x, const float *res, const float *gamma,
+                           const float *beta, float eps, float p_drop,
+                           const unsigned long long *seed_base, unsigned long long seed_offset, float *y,
+                           void *y_bf16, float *h, float *mean, float *rstd, pcm_stream_t stream);
+int pcm_add_dropout_ln_bwd(long long rows, int C, const float *dy, const float *h, const float *mean,
+                           const float *rstd, const float *gamma, float p_drop,
+                           const unsigned long long *seed_base, unsigned long long seed_offset,
+                           float *dres, float *dx, float *dgamma, float *dbeta, pcm_stream_t stream);
+int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
+               pcm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused clip-by-global-norm + AdamW over flat fp32 buffers.
  * Replaces torch.nn.utils.clip_grad_norm_ (Lightning gradient_clip_val, configs/trainer/
  * ddp.yaml:12) + torch.optim.AdamW (src/utils/optimizer.py:33-72; configs/model/

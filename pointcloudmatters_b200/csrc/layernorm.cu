@@ -1,0 +1,250 @@
+// layernorm.cu -- fused residual + dropout + LayerNorm (forward / backward) and column sums, sm_100a.
+//
+// Every transformer sub-block of the reference ends with `norm(x_res + dropout(sublayer))`
+// (transformer.py:249-253,333-345): three ATen kernels forward and four backward (whose
+// gamma/beta reduction alone was 10% of the step in the ncu launch list).  Here:
+//   forward : h = res + dropout(x);  y = (h - mean) * rstd * gamma + beta   -> y (fp32), h, mean, rstd
+//   backward: dh = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;
+//             dx = dropout-backward(dh); dgamma += dy * xhat; dbeta += dy
+// One warp owns one row (C = 128 * V floats, V float4 per lane, fully coalesced 128-bit accesses),
+// row statistics by warp shuffles, dgamma / dbeta accumulated in registers across the rows a warp
+// visits and flushed with one fp32 atomic per column per CTA.  HBM-bound: 12-16 B per element.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t ln_dropout_bits(unsigned long long seed, unsigned long long idx) {
+    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return (uint32_t)(x >> 32);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PCM_FULL_MASK, v, o);
+    return v;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, long rows, float eps, float p_drop, const unsigned long long* __restrict__ seed_base,
+    unsigned long long seed_offset, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ h_out,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    constexpr int C = 128 * V;
+    const int lane = threadIdx.x & 31;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
+    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
+    const float ks = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    float4 g4[V], b4[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        g4[v] = reinterpret_cast<const float4*>(gamma)[v * 32 + lane];
+        b4[v] = reinterpret_cast<const float4*>(beta)[v * 32 + lane];
+    }
+    for (long r = wid; r < rows; r += nwarps) {
+        float4 h[V];
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
+            float4 xv = x ? *reinterpret_cast<const float4*>(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p_drop > 0.f) {
+                xv.x = ln_dropout_bits(seed, e + 0) >= thresh ? xv.x * ks : 0.f;
+                xv.y = ln_dropout_bits(seed, e + 1) >= thresh ? xv.y * ks : 0.f;
+                xv.z = ln_dropout_bits(seed, e + 2) >= thresh ? xv.z * ks : 0.f;
+                xv.w = ln_dropout_bits(seed, e + 3) >= thresh ? xv.w * ks : 0.f;
+            }
+            const float4 rv = *reinterpret_cast<const float4*>(res + e);
+            h[v] = make_float4(rv.x + xv.x, rv.y + xv.y, rv.z + xv.z, rv.w + xv.w);
+            s += (h[v].x + h[v].y) + (h[v].z + h[v].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float a = h[v].x - mean, b = h[v].y - mean, c = h[v].z - mean, d = h[v].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
+            float4 o;
+            o.x = (h[v].x - mean) * rstd * g4[v].x + b4[v].x;
+            o.y = (h[v].y - mean) * rstd * g4[v].y + b4[v].y;
+            o.z = (h[v].z - mean) * rstd * g4[v].z + b4[v].z;
+            o.w = (h[v].w - mean) * rstd * g4[v].w + b4[v].w;
+            *reinterpret_cast<float4*>(y + e) = o;
+            if (y_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(y_bf16 + e) = pk;
+            }
+            if (h_out) *reinterpret_cast<float4*>(h_out + e) = h[v];
+        }
+        if (lane == 0) {
+            if (mean_out) mean_out[r] = mean;
+            if (rstd_out) rstd_out[r] = rstd;
+        }
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
+    const float* __restrict__ dy, const float* __restrict__ h, const float* __restrict__ mean_in,
+    const float* __restrict__ rstd_in, const float* __restrict__ gamma, long rows, float p_drop,
+    const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset, float* __restrict__ dres,
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    constexpr int C = 128 * V;
+    __shared__ float sg[C], sb[C];
+    const int lane = threadIdx.x & 31;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
+    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
+    const float ks = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    float4 g4[V], ag[V], abt[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        g4[v] = reinterpret_cast<const float4*>(gamma)[v * 32 + lane];
+        ag[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        abt[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long r = wid; r < rows; r += nwarps) {
+        const float mean = mean_in[r], rstd = rstd_in[r];
+        float4 gy[V], xh[V];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
+            const float4 d = *reinterpret_cast<const float4*>(dy + e);
+            const float4 hv = *reinterpret_cast<const float4*>(h + e);
+            xh[v] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
+            gy[v] = make_float4(d.x * g4[v].x, d.y * g4[v].y, d.z * g4[v].z, d.w * g4[v].w);
+            s1 += (gy[v].x + gy[v].y) + (gy[v].z + gy[v].w);
+            s2 += (gy[v].x * xh[v].x + gy[v].y * xh[v].y) + (gy[v].z * xh[v].z + gy[v].w * xh[v].w);
+            ag[v].x += d.x * xh[v].x; ag[v].y += d.y * xh[v].y; ag[v].z += d.z * xh[v].z; ag[v].w += d.w * xh[v].w;
+            abt[v].x += d.x; abt[v].y += d.y; abt[v].z += d.z; abt[v].w += d.w;
+        }
+        const float c1 = warp_sum(s1) * (1.0f / C), c2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
+            float4 dh;
+            dh.x = rstd * (gy[v].x - c1 - xh[v].x * c2);
+            dh.y = rstd * (gy[v].y - c1 - xh[v].y * c2);
+            dh.z = rstd * (gy[v].z - c1 - xh[v].z * c2);
+            dh.w = rstd * (gy[v].w - c1 - xh[v].w * c2);
+            if (dres) *reinterpret_cast<float4*>(dres + e) = dh;
+            if (dx && dx != dres) {
+                float4 o = dh;
+                if (p_drop > 0.f) {
+                    o.x = ln_dropout_bits(seed, e + 0) >= thresh ? dh.x * ks : 0.f;
+                    o.y = ln_dropout_bits(seed, e + 1) >= thresh ? dh.y * ks : 0.f;
+                    o.z = ln_dropout_bits(seed, e + 2) >= thresh ? dh.z * ks : 0.f;
+                    o.w = ln_dropout_bits(seed, e + 3) >= thresh ? dh.w * ks : 0.f;
+                }
+                *reinterpret_cast<float4*>(dx + e) = o;
+            }
+        }
+    }
+    // flush per-warp partials: shared-memory atomics per CTA, then one global atomic per column
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        atomicAdd(&sg[c + 0], ag[v].x); atomicAdd(&sg[c + 1], ag[v].y); atomicAdd(&sg[c + 2], ag[v].z); atomicAdd(&sg[c + 3], ag[v].w);
+        atomicAdd(&sb[c + 0], abt[v].x); atomicAdd(&sb[c + 1], abt[v].y); atomicAdd(&sb[c + 2], abt[v].z); atomicAdd(&sb[c + 3], abt[v].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(dgamma + i, sg[i]);
+        atomicAdd(dbeta + i, sb[i]);
+    }
+}
+
+// out[c] += sum_r src[r, c]; src fp32 or bf16 with row pitch ld.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, long rows, int C, long ld, int rows_per_cta,
+                                                     float* __restrict__ out) {
+    const long r0 = (long)blockIdx.x * rows_per_cta;
+    const long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (long r = r0; r < r1; ++r) acc += (float)src[r * ld + c];
+        atomicAdd(out + c, acc);
+    }
+}
+
+inline int ln_grid(long rows) {
+    long blocks = (rows + 7) / 8;
+    const long cap = 148L * 8;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+#define LN_DISPATCH(V, KERNEL, ...)                                   \
+    switch (V) {                                                      \
+        case 1: KERNEL<1><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
+        case 2: KERNEL<2><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
+        case 4: KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
+        case 8: KERNEL<8><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
+        default: return PCM_EUNSUPPORTED;                             \
+    }
+
+// y = LayerNorm(res + dropout(x)) (x may be NULL = plain LayerNorm(res)); C in {128, 256, 512, 1024}.
+// Optional outputs: y_bf16 (operand of the next GEMM), h (= res + dropout(x), saved for backward),
+// mean / rstd (rows).
+PCM_API int pcm_add_dropout_ln_fwd(long long rows, int C, const float* x, const float* res, const float* gamma,
+                                   const float* beta, float eps, float p_drop, const unsigned long long* seed_base,
+                                   unsigned long long seed_offset, float* y, void* y_bf16, float* h, float* mean,
+                                   float* rstd, pcm_stream_t stream) {
+    if (rows <= 0) return PCM_OK;
+    if (!res || !gamma || !beta || !y || (C % 128)) return (C % 128) ? PCM_EUNSUPPORTED : PCM_EINVAL;
+    cudaStream_t st = pcm_cu_stream(stream);
+    const int grid = ln_grid(rows);
+    LN_DISPATCH(C / 128, add_dropout_ln_fwd_kernel, x, res, gamma, beta, rows, eps, p_drop, seed_base, seed_offset, y,
+                reinterpret_cast<__nv_bfloat16*>(y_bf16), h, mean, rstd)
+    return pcm_launch_status();
+}
+
+// dres = dLN/dh; dx = dropout-backward(dres) (pass dx == dres or NULL when not needed);
+// dgamma / dbeta are ACCUMULATED (caller zero-fills).
+PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const float* h, const float* mean,
+                                   const float* rstd, const float* gamma, float p_drop,
+                                   const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
+                                   float* dx, float* dgamma, float* dbeta, pcm_stream_t stream) {
+    if (rows <= 0) return PCM_OK;
+    if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
+    if (C % 128) return PCM_EUNSUPPORTED;
+    cudaStream_t st = pcm_cu_stream(stream);
+    const int grid = ln_grid(rows);
+    LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
+                dx, dgamma, dbeta)
+    return pcm_launch_status();
+}
+
+// out[c] += sum over rows of src[r, c] (bias gradients); src_bf16 selects the element type.
+PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int src_bf16, float* out,
+                       pcm_stream_t stream) {
+    if (rows <= 0 || C <= 0) return PCM_OK;
+    if (!src || !out) return PCM_EINVAL;
+    int rows_per_cta = (int)((rows + 148L * 4 - 1) / (148L * 4));
+    if (rows_per_cta < 16) rows_per_cta = 16;
+    const int grid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
+    if (src_bf16)
+        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, pcm_cu_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld,
+                                                                               rows_per_cta, out);
+    else
+        colsum_kernel<float><<<grid, 256, 0, pcm_cu_stream(stream)>>>(reinterpret_cast<const float*>(src), rows, C, ld,
+                                                                       rows_per_cta, out);
+    return pcm_launch_status();
+}

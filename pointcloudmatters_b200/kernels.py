@@ -63,3 +63,39 @@ def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
     require_cuda(param, grad, exp_avg, exp_avg_sq, hyper, sumsq)
     check(lib.pcm_clip_adamw_step(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
                                   ptr(sumsq), ptr(norm_out), current_stream()), "pcm_clip_adamw_step")
+
+
+def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, want_bf16=False):
+    rows, C = res.shape
+    y = torch.empty_like(res)
+    h = torch.empty_like(res)
+    mean = torch.empty(rows, dtype=torch.float32, device=res.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=res.device)
+    yb = torch.empty(res.shape, dtype=torch.bfloat16, device=res.device) if want_bf16 else None
+    check(lib.pcm_add_dropout_ln_fwd(rows, C, ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), float(p_drop),
+                                     ptr(seed_base), int(seed_offset), ptr(y), ptr(yb), ptr(h), ptr(mean), ptr(rstd),
+                                     current_stream()), "pcm_add_dropout_ln_fwd")
+    return y, yb, h, mean, rstd
+
+
+def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx):
+    rows, C = h.shape
+    dres = torch.empty_like(h)
+    dx = (torch.empty_like(h) if p_drop > 0 else dres) if need_dx else None
+    dgamma = torch.zeros(C, dtype=torch.float32, device=h.device)
+    dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
+    check(lib.pcm_add_dropout_ln_bwd(rows, C, ptr(dy), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
+                                     ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                     current_stream()), "pcm_add_dropout_ln_bwd")
+    return dres, dx, dgamma, dbeta
+
+
+def colsum(src, out=None):
+    """out[c] (+)= sum_r src[r, c] for a 2-D fp32 / bf16 tensor with contiguous columns."""
+    rows, C = src.shape
+    assert src.stride(1) == 1
+    if out is None:
+        out = torch.zeros(C, dtype=torch.float32, device=src.device)
+    check(lib.pcm_colsum(rows, C, ptr(src), src.stride(0), int(src.dtype == torch.bfloat16), ptr(out), current_stream()),
+          "pcm_colsum")
+    return out

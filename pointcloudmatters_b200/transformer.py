@@ -45,10 +45,10 @@ class TransformerEncoderLayer(nn.Module):
         assert src_mask is None, "attn_mask is never used by the reference ACT path"
         tr = self.training
         if self.normalize_before:
-            s2 = PF.add_dropout_layernorm(torch.zeros_like(src), src, self.norm1, 0.0, False)
+            s2 = PF.add_dropout_layernorm(None, src, self.norm1, 0.0, False)
             qk = s2 if pos is None else s2 + pos
             src = src + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, s2, src_key_padding_mask, tr), self.p, tr)
-            s2 = PF.add_dropout_layernorm(torch.zeros_like(src), src, self.norm2, 0.0, False)
+            s2 = PF.add_dropout_layernorm(None, src, self.norm2, 0.0, False)
             return src + PF.dropout(self._ffn(s2), self.p, tr)
         qk = src if pos is None else src + pos
         a = PF.multi_head_attention(self.self_attn, qk, qk, src, src_key_padding_mask, tr)
@@ -72,7 +72,7 @@ class TransformerEncoder(nn.Module):
         for layer in self.layers:
             out = layer(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
         if self.norm is not None:
-            out = PF.add_dropout_layernorm(torch.zeros_like(out), out, self.norm, 0.0, False)
+            out = PF.add_dropout_layernorm(None, out, self.norm, 0.0, False)
         return out
 
 
@@ -107,7 +107,7 @@ class TransformerDecoderLayer(nn.Module):
         wq = (lambda t: t if query_pos is None else t + query_pos)
         mem_k = memory if pos is None else memory + pos
         if self.normalize_before:
-            ln = (lambda x, n: PF.add_dropout_layernorm(torch.zeros_like(x), x, n, 0.0, False))
+            ln = (lambda x, n: PF.add_dropout_layernorm(None, x, n, 0.0, False))
             t2 = ln(tgt, self.norm1)
             qk = wq(t2)
             tgt = tgt + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, t2, None, tr), self.p, tr)
@@ -141,7 +141,7 @@ class TransformerDecoder(nn.Module):
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, query_pos=None):
         out, inter = tgt, []
-        ln = (lambda x: PF.add_dropout_layernorm(torch.zeros_like(x), x, self.norm, 0.0, False))
+        ln = (lambda x: PF.add_dropout_layernorm(None, x, self.norm, 0.0, False))
         for li, layer in enumerate(self.layers):
             out = layer(out, memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos)
             if self.return_intermediate:

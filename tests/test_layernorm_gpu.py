@@ -1,0 +1,78 @@
+"""Fused residual + dropout + LayerNorm kernels and the column-sum kernel against plain PyTorch fp32
+references of the same ops (fp32 arithmetic on both sides: rtol/atol 2e-5 forward, 1e-4 backward;
+the column-wise gamma / beta / bias gradients are fp32 sums in a different order: 2e-4)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,C", [(1, 128), (1000, 512), (33000, 512), (77, 1024), (515, 256)])
+@pytest.mark.parametrize("with_x", [True, False])
+def test_add_dropout_ln_matches_torch(rows, C, with_x):
+    from pointcloudmatters_b200 import functional as PF
+
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    norm = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.2 * torch.randn(C, device="cuda", generator=g))
+        norm.bias.copy_(0.1 * torch.randn(C, device="cuda", generator=g))
+    x0 = torch.randn(rows, C, device="cuda", generator=g) if with_x else None
+    r0 = torch.randn(rows, C, device="cuda", generator=g) * 2 + 0.3
+    dy = torch.randn(rows, C, device="cuda", generator=g)
+    outs = []
+    for ours in (False, True):
+        x = x0.clone().requires_grad_(True) if with_x else None
+        r = r0.clone().requires_grad_(True)
+        norm.zero_grad()
+        if ours:
+            y = PF.add_dropout_layernorm(x, r, norm, 0.1, training=False)
+        else:
+            y = F.layer_norm(r + x if with_x else r, (C,), norm.weight, norm.bias, norm.eps)
+        y.backward(dy)
+        outs.append((y.detach(), r.grad, x.grad if with_x else None, norm.weight.grad.clone(), norm.bias.grad.clone()))
+    ref, got = outs
+    torch.testing.assert_close(got[0], ref[0], rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(got[1], ref[1], rtol=1e-4, atol=1e-4)
+    if with_x:
+        torch.testing.assert_close(got[2], ref[2], rtol=1e-4, atol=1e-4)
+    scale = max(1.0, (rows ** 0.5))
+    torch.testing.assert_close(got[3], ref[3], rtol=2e-4, atol=2e-4 * scale)
+    torch.testing.assert_close(got[4], ref[4], rtol=2e-4, atol=2e-4 * scale)
+
+
+def test_add_dropout_ln_dropout_mask_is_consistent():
+    from pointcloudmatters_b200 import functional as PF
+
+    rows, C, p = 4000, 512, 0.1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    norm = torch.nn.LayerNorm(C).cuda()
+    x = (torch.randn(rows, C, device="cuda", generator=g) + 3.0).requires_grad_(True)  # no exact zeros
+    r = torch.randn(rows, C, device="cuda", generator=g).requires_grad_(True)
+    y = PF.add_dropout_layernorm(x, r, norm, p, training=True)
+    h = y.grad_fn.saved_tensors[0]
+    kept = (h - r.detach()) != 0
+    frac = 1 - kept.float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+    torch.testing.assert_close((h - r.detach())[kept], (x.detach() / (1 - p))[kept], rtol=1e-5, atol=1e-5)
+    ref = F.layer_norm(r.detach() + x.detach() * kept / (1 - p), (C,), norm.weight, norm.bias, norm.eps)
+    torch.testing.assert_close(y.detach(), ref, rtol=2e-5, atol=2e-5)
+    dy = torch.randn(rows, C, device="cuda", generator=g)
+    y.backward(dy)
+    assert float(x.grad[~kept].abs().max()) == 0.0  # dropped elements get no gradient
+    torch.testing.assert_close(x.grad[kept], (r.grad / (1 - p))[kept], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum(dtype):
+    from pointcloudmatters_b200.kernels import colsum
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    src = torch.randn(32960, 1024, device="cuda", generator=g).to(dtype)
+    view = src[:, 256:768]
+    got = colsum(view)
+    torch.testing.assert_close(got, view.float().sum(0), rtol=1e-4, atol=2e-2)
+    out = torch.ones(512, device="cuda")
+    colsum(view, out)
+    torch.testing.assert_close(out, 1 + view.float().sum(0), rtol=1e-4, atol=2e-2)
