@@ -97,7 +97,7 @@ def test_gradient_allreduce_world2_gloo():
     [p.join(60) for p in procs]
     (r0, g0, na0, nt0, sc0), (r1, g1, na1, nt1, sc1) = res
     assert torch.equal(g0, g1) and na0 == na1 and sc0 == 0.5
-    assert nt0 - na0 == 12  # the unused Linear(3,3): 9 + 3 parameters parked in the inactive tail
+    assert nt0 - na0 == 16  # the unused Linear(3,3): 9 -> 12 and 3 -> 4 padded floats parked in the inactive tail
     # equals the single-process gradient of the mean loss over the GLOBAL batch
     torch.manual_seed(0)
     model = nn.Sequential(nn.Linear(4, 8), nn.ReLU(), nn.Linear(8, 2))
