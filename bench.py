@@ -263,8 +263,10 @@ def b200_arm(args):
             dist.destroy_process_group()
         return 0
 
-    value = args.steps * 1.0 / sec  # global steps/s: every rank advances the same global step
-    e2e_value = args.steps * 1.0 / sec_e2e
+    # whole-job aggregate: every rank processes one cfg-2 step-unit (64 samples) per iteration, so
+    # the job processes `world` units per global iteration (weak scaling)
+    value = world * args.steps * 1.0 / sec
+    e2e_value = world * args.steps * 1.0 / sec_e2e
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -279,7 +281,11 @@ def b200_arm(args):
                    "l2": "per-step working set (activations + 385 MB parameter/optimizer state) exceeds the 126 MB L2; "
                          "4 distinct input batches cycled; no explicit flush",
                    "dropout": CFG2["dropout"], "decoder_layers_computed": 1 if args.skip_dead_decoder_layers else CFG2["dec_layers"],
-                   "samples_per_sec": value * args.batch * world, "last_loss": last_loss},
+                   "unit_definition": "one step = fwd+bwd+allreduce+clip+AdamW on one 64-sample cfg-2 batch; value = "
+                                      "step-units completed per second summed over ranks (N ranks finish N units per "
+                                      "global iteration)",
+                   "global_iterations_per_sec": args.steps / sec,
+                   "samples_per_sec": value * args.batch, "last_loss": last_loss},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": 1e3 * sec_e2e / args.steps, "last_loss": loss_e2e},
         "gpu_launches": int(launches),
