@@ -240,6 +240,10 @@ int pcm_add_dropout_ln_bwd(long long rows, int C, const float *dy, const float *
                            float *dres, float *dx, float *dgamma, float *dbeta, pcm_stream_t stream);
 int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
                pcm_stream_t stream);
+/* out = bf16(a + b): `with_pos_embed` (transformer.py:235-236) fused with the operand cast of the
+ * Q/K projections.  b may be NULL; b_row_div > 1 broadcasts b's rows over the batch. */
+int pcm_add_cast_bf16(long long rows, int C, const float *a, const float *b, int b_row_div, void *out,
+                      pcm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused clip-by-global-norm + AdamW over flat fp32 buffers.

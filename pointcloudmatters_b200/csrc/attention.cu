@@ -8,8 +8,8 @@
 //   backward: dy = dz * keep / (1 - p);  ds = scale * y * (dy - sum_j dy_j y_j)    (in place, bf16)
 // Replaces the (B*h, L, S) fp32 score / softmax / dropout tensors that nn.MultiheadAttention's
 // math path materialises in the reference (transformer.py:246-248; need_weights=True default).
-// Buffers are [Z, Lp, Sp] with zero padding (rows L..Lp, columns S..Sp) that these kernels never
-// write, so the padded K tails of the GEMMs meet exact zeros.
+// Buffers are [Z, Lp, Sp] with zero padding (rows L..Lp, columns S..Sp) that these kernels write
+// themselves (no memsets), so the padded K tails of the GEMMs meet exact zeros.
 #include "common.cuh"
 
 namespace {
@@ -23,6 +23,11 @@ __device__ __forceinline__ uint32_t dropout_bits(unsigned long long seed, unsign
     return (uint32_t)(x >> 32);
 }
 
+// One warp per row, the whole row in registers: lane owns float4 chunks c = lane, lane+32, ...
+// (NV chunks, Sp <= 128*NV columns): one 128-bit read per chunk, one exp per element, 64-bit bf16
+// stores.  Columns Sk..Sp of every row and rows L..Lp of every (batch, head) are written as zeros
+// here, so the buffers never need a memset.
+template <int NV>
 __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
     const float* __restrict__ S, long rows_total, int L, int Lp, int Sk, int Sp, int nh,
     const unsigned char* __restrict__ kpm, float scale, float p_drop, const unsigned long long* __restrict__ seed_base,
@@ -33,39 +38,71 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
     const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const int nchunk = Sp >> 2;
+    // rows_total counts PADDED rows (Z * Lp): pad rows are zero-filled
     for (long r = wid; r < rows_total; r += nwarps) {
-        const long z = r / L;
-        const int l = (int)(r - z * L);
+        const long z = r / Lp;
+        const int l = (int)(r - z * Lp);
+        const size_t base = (size_t)r * Sp;
+        if (l >= L) {
+            for (int c = lane; c < nchunk; c += 32) {
+                *reinterpret_cast<uint2*>(Y + base + 4 * c) = make_uint2(0u, 0u);
+                if (Zd != Y) *reinterpret_cast<uint2*>(Zd + base + 4 * c) = make_uint2(0u, 0u);
+            }
+            continue;
+        }
         const int b = (int)(z / nh);
-        const size_t base = ((size_t)z * Lp + l) * Sp;
-        const float* s = S + base;
         const unsigned char* mrow = kpm ? kpm + (size_t)b * Sk : nullptr;
+        float v[NV][4];
         float mx = -INFINITY;
-        for (int j = lane; j < Sk; j += 32) {
-            const float v = (mrow && mrow[j]) ? -INFINITY : s[j] * scale;
-            mx = fmaxf(mx, v);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (c < nchunk) t = *reinterpret_cast<const float4*>(S + base + 4 * c);
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * c + e;
+                const bool valid = c < nchunk && j < Sk && !(mrow && mrow[j]);
+                v[i][e] = valid ? tv[e] * scale : -INFINITY;
+                mx = fmaxf(mx, v[i][e]);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PCM_FULL_MASK, mx, o));
         if (mx == -INFINITY) mx = 0.f;  // fully masked row (never happens on the ACT path): all zeros
         float sum = 0.f;
-        for (int j = lane; j < Sk; j += 32) {
-            const float v = (mrow && mrow[j]) ? -INFINITY : s[j] * scale;
-            sum += __expf(v - mx);
-        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[i][e] = __expf(v[i][e] - mx); sum += v[i][e]; }
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(PCM_FULL_MASK, sum, o);
         const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-        for (int j = lane; j < Sk; j += 32) {
-            const float v = (mrow && mrow[j]) ? -INFINITY : s[j] * scale;
-            const float y = __expf(v - mx) * inv;
-            Y[base + j] = __float2bfloat16_rn(y);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c >= nchunk) continue;
+            float y[4], zd[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                y[e] = v[i][e] * inv;  // exactly 0 for masked / padded columns
+                zd[e] = y[e];
+                if (Zd != Y) {
+                    const bool keep = dropout_bits(seed, (unsigned long long)base + 4 * c + e) >= thresh;
+                    zd[e] = keep ? y[e] * keep_scale : 0.f;
+                }
+            }
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);
+            *reinterpret_cast<uint2*>(Y + base + 4 * c) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
             if (Zd != Y) {
-                const bool keep = dropout_bits(seed, (unsigned long long)base + j) >= thresh;
-                Zd[base + j] = __float2bfloat16_rn(keep ? y * keep_scale : 0.f);
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(zd[0], zd[1]), b1 = __floats2bfloat162_rn(zd[2], zd[3]);
+                *reinterpret_cast<uint2*>(Zd + base + 4 * c) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
             }
         }
     }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
     const __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ dZ, long rows_total, int L, int Lp, int Sk,
     int Sp, float scale, float p_drop, const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset) {
@@ -75,21 +112,50 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
     const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const int nchunk = Sp >> 2;
     for (long r = wid; r < rows_total; r += nwarps) {
-        const long z = r / L;
-        const int l = (int)(r - z * L);
-        const size_t base = ((size_t)z * Lp + l) * Sp;
+        const long z = r / Lp;
+        const int l = (int)(r - z * Lp);
+        const size_t base = (size_t)r * Sp;
+        if (l >= L) {  // pad rows of dS must be exact zeros (K tail of the dK GEMM)
+            for (int c = lane; c < nchunk; c += 32) *reinterpret_cast<uint2*>(dZ + base + 4 * c) = make_uint2(0u, 0u);
+            continue;
+        }
+        float y[NV][4], dy[NV][4];
         float dot = 0.f;
-        for (int j = lane; j < Sk; j += 32) {
-            float dy = __bfloat162float(dZ[base + j]);
-            if (p_drop > 0.f) dy = dropout_bits(seed, (unsigned long long)base + j) >= thresh ? dy * keep_scale : 0.f;
-            dot = fmaf(dy, __bfloat162float(Y[base + j]), dot);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            uint2 yr = make_uint2(0u, 0u), dr = make_uint2(0u, 0u);
+            if (c < nchunk) {
+                yr = *reinterpret_cast<const uint2*>(Y + base + 4 * c);
+                dr = *reinterpret_cast<const uint2*>(dZ + base + 4 * c);
+            }
+            const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&yr);
+            const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&dr);
+            const float2 y01 = __bfloat1622float2(yp[0]), y23 = __bfloat1622float2(yp[1]);
+            const float2 d01 = __bfloat1622float2(dp[0]), d23 = __bfloat1622float2(dp[1]);
+            y[i][0] = y01.x; y[i][1] = y01.y; y[i][2] = y23.x; y[i][3] = y23.y;
+            dy[i][0] = d01.x; dy[i][1] = d01.y; dy[i][2] = d23.x; dy[i][3] = d23.y;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * c + e;
+                if (c >= nchunk || j >= Sk) { dy[i][e] = 0.f; y[i][e] = 0.f; }
+                else if (p_drop > 0.f)
+                    dy[i][e] = dropout_bits(seed, (unsigned long long)base + j) >= thresh ? dy[i][e] * keep_scale : 0.f;
+                dot = fmaf(dy[i][e], y[i][e], dot);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(PCM_FULL_MASK, dot, o);
-        for (int j = lane; j < Sk; j += 32) {
-            float dy = __bfloat162float(dZ[base + j]);
-            if (p_drop > 0.f) dy = dropout_bits(seed, (unsigned long long)base + j) >= thresh ? dy * keep_scale : 0.f;
-            dZ[base + j] = __float2bfloat16_rn(scale * __bfloat162float(Y[base + j]) * (dy - dot));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c >= nchunk) continue;
+            float ds[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ds[e] = scale * y[i][e] * (dy[i][e] - dot);  // 0 for padded columns (y = 0)
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(ds[0], ds[1]), a1 = __floats2bfloat162_rn(ds[2], ds[3]);
+            *reinterpret_cast<uint2*>(dZ + base + 4 * c) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
         }
     }
 }
@@ -108,13 +174,19 @@ PCM_API int pcm_attn_softmax_fwd(int Z, int L, int Lp, int Sk, int Sp, int nh, c
                                  const unsigned char* kpm, float scale, float p_drop,
                                  const unsigned long long* seed_base, unsigned long long seed_offset, void* Y,
                                  void* Zd, pcm_stream_t stream) {
-    const long rows = (long)Z * L;
+    const long rows = (long)Z * Lp;  // padded rows are zero-filled by the kernel
     if (rows <= 0 || Sk <= 0) return PCM_OK;
     if (!S || !Y || !Zd || nh <= 0 || Lp < L || Sp < Sk) return PCM_EINVAL;
     if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && Zd == Y)) return PCM_EINVAL;
-    attn_softmax_fwd_kernel<<<rows_grid(rows), 256, 0, pcm_cu_stream(stream)>>>(
-        S, rows, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed_base, seed_offset, reinterpret_cast<__nv_bfloat16*>(Y),
-        reinterpret_cast<__nv_bfloat16*>(Zd));
+    if (Sp % 4 || Sp > 4096) return PCM_EUNSUPPORTED;
+    cudaStream_t st = pcm_cu_stream(stream);
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(Y);
+    __nv_bfloat16* zd = reinterpret_cast<__nv_bfloat16*>(Zd);
+    const int g = rows_grid(rows);
+#define FWD(NV) attn_softmax_fwd_kernel<NV><<<g, 256, 0, st>>>(S, rows, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed_base, seed_offset, y, zd)
+    if (Sp <= 128) FWD(1); else if (Sp <= 256) FWD(2); else if (Sp <= 512) FWD(4); else if (Sp <= 1024) FWD(8);
+    else if (Sp <= 2048) FWD(16); else FWD(32);
+#undef FWD
     return pcm_launch_status();
 }
 
@@ -122,11 +194,17 @@ PCM_API int pcm_attn_softmax_fwd(int Z, int L, int Lp, int Sk, int Sp, int nh, c
 PCM_API int pcm_attn_softmax_bwd(int Z, int L, int Lp, int Sk, int Sp, const void* Y, void* dZ, float scale,
                                  float p_drop, const unsigned long long* seed_base, unsigned long long seed_offset,
                                  pcm_stream_t stream) {
-    const long rows = (long)Z * L;
+    const long rows = (long)Z * Lp;
     if (rows <= 0 || Sk <= 0) return PCM_OK;
     if (!Y || !dZ || Lp < L || Sp < Sk || p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
-    attn_softmax_bwd_kernel<<<rows_grid(rows), 256, 0, pcm_cu_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(dZ), rows, L, Lp, Sk, Sp, scale,
-        p_drop, seed_base, seed_offset);
+    if (Sp % 4 || Sp > 4096) return PCM_EUNSUPPORTED;
+    cudaStream_t st = pcm_cu_stream(stream);
+    const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(Y);
+    __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(dZ);
+    const int g = rows_grid(rows);
+#define BWD(NV) attn_softmax_bwd_kernel<NV><<<g, 256, 0, st>>>(y, dz, rows, L, Lp, Sk, Sp, scale, p_drop, seed_base, seed_offset)
+    if (Sp <= 128) BWD(1); else if (Sp <= 256) BWD(2); else if (Sp <= 512) BWD(4); else if (Sp <= 1024) BWD(8);
+    else if (Sp <= 2048) BWD(16); else BWD(32);
+#undef BWD
     return pcm_launch_status();
 }

@@ -183,6 +183,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
     }
 }
 
+// out_bf16[r, c] = bf16(a[r, c] + b[r / b_row_div, c])  (b may be NULL; b_row_div > 1 broadcasts a
+// (L, 1, C) positional table over the batch of token-major (L*B, C) activations)
+__global__ void __launch_bounds__(256) add_cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            long n4, int C4, int b_row_div, __nv_bfloat16* __restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(a)[i];
+        if (b) {
+            long bi = i;
+            if (b_row_div > 1) { const long r = i / C4; bi = (r / b_row_div) * C4 + (i - r * C4); }
+            const float4 w = reinterpret_cast<const float4*>(b)[bi];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+}
+
 inline int ln_grid(long rows) {
     long blocks = (rows + 7) / 8;
     const long cap = 148L * 8;
@@ -246,5 +263,20 @@ PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int
     else
         colsum_kernel<float><<<grid, 256, 0, pcm_cu_stream(stream)>>>(reinterpret_cast<const float*>(src), rows, C, ld,
                                                                        rows_per_cta, out);
+    return pcm_launch_status();
+}
+
+// out = bf16(a + b) -- the fused `with_pos_embed` + operand cast in front of the Q/K projections
+// (reference transformer.py:235-236,243).  C % 4 == 0; b may be NULL (plain cast).
+PCM_API int pcm_add_cast_bf16(long long rows, int C, const float* a, const float* b, int b_row_div, void* out,
+                              pcm_stream_t stream) {
+    if (rows <= 0 || C <= 0) return PCM_OK;
+    if (!a || !out) return PCM_EINVAL;
+    if (C % 4) return PCM_EUNSUPPORTED;
+    const long n4 = rows * (C / 4);
+    long blocks = (n4 + 255) / 256;
+    const int grid = (int)(blocks < 148L * 16 ? blocks : 148L * 16);
+    add_cast_bf16_kernel<<<grid, 256, 0, pcm_cu_stream(stream)>>>(a, b, n4, C / 4, b_row_div < 1 ? 1 : b_row_div,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out));
     return pcm_launch_status();
 }

@@ -149,24 +149,131 @@ def _ceil64(x):
     return (x + 63) // 64 * 64
 
 
-class _MHA(torch.autograd.Function):
-    """nn.MultiheadAttention (head_dim 64) as a chain of tcgen05 GEMMs + row-wise softmax kernels:
+def _tok_bf16(x, pos, L, B, E):
+    """bf16 token-major (L*B, E) operand of a projection GEMM: x (+ pos), pos (L, B, E) or (L, 1, E)."""
+    x2 = x.reshape(L * B, E)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    if pos is None:
+        return K.add_cast_bf16(x2)
+    if pos.shape[1] == B:
+        p2 = pos.reshape(L * B, E)
+        return K.add_cast_bf16(x2, p2 if p2.is_contiguous() else p2.contiguous())
+    return K.add_cast_bf16(x2, pos.reshape(L, E).contiguous(), b_row_div=B)
+
+
+def _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev):
+    """softmax(Q K^T / 8 + mask) V for head_dim 64 on (B*nh)-batched tcgen05 GEMMs; returns the
+    token-major bf16 output and what backward needs."""
+    bf = torch.bfloat16
+    Z = B * nh
+    E = nh * 64
+    Lp, Sp = _ceil64(L), _ceil64(S)
+    scale = 0.125
+    Sbuf = _workspace("attn_scores", (Z * Lp, Sp), torch.float32, dev)
+    K.gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=Lp, ldc=Sp)
+    Y = torch.empty((Z * Lp, Sp), dtype=bf, device=dev)  # padding is zero-filled by the softmax kernel
+    Zd = torch.empty((Z * Lp, Sp), dtype=bf, device=dev) if p_drop > 0 else Y
+    seed_base = DROPOUT_RNG.base_for(dev) if p_drop > 0 else None
+    seed = DROPOUT_RNG.next_offset() if p_drop > 0 else 0
+    kpm_u8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
+    K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed_base, seed)
+    O_tok = torch.empty((L * B, E), dtype=bf, device=dev)
+    K.gemm_ex(L, 64, S, Z, Zd, False, Lp, Vh, True, S, O_tok, c_mode=2, hs=(B, nh, L), ldc=E)
+    return O_tok, Y, Zd, (Lp, Sp, scale, seed_base, seed)
+
+
+def _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, S, B, nh, aux, p_drop, dQ_out, dK_out, dV_out, ld_q, ld_kv):
+    """Backward of _attn_core_fwd: writes token-major bf16 dQ / dK / dV (head-merge epilogue) into
+    the given (possibly column-sliced) destinations."""
+    Lp, Sp, scale, seed_base, seed = aux
+    Z = B * nh
+    dP = _workspace("attn_dP", (Z * Lp, Sp), torch.bfloat16, dOh.device, zero=True)
+    K.gemm_ex(L, S, 64, Z, dOh, False, L, Vh, False, S, dP, c_mode=0, c_batch_rows=Lp, ldc=Sp)
+    K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, seed_base, seed)
+    K.gemm_ex(L, 64, S, Z, dP, False, Lp, Kh, True, S, dQ_out, c_mode=2, hs=(B, nh, L), ldc=ld_q)
+    K.gemm_ex(S, 64, L, Z, dP, True, Lp, Qh, True, L, dK_out, c_mode=2, hs=(B, nh, S), ldc=ld_kv)
+    K.gemm_ex(S, 64, L, Z, Zd, True, Lp, dOh, True, L, dV_out, c_mode=2, hs=(B, nh, S), ldc=ld_kv)
+
+
+def _dw(dtok, xb, out):
+    rows = dtok.shape[0]
+    K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=out, accumulate=True,
+                split_k=_split_k_for((out.shape[0] + 127) // 128, (out.shape[1] + 255) // 256, (rows + 63) // 64))
+
+
+class _MHASelf(torch.autograd.Function):
+    """Self-attention block of nn.MultiheadAttention (q = k = x + pos, v = x; head_dim 64):
     in-proj GEMMs write Q/K/V straight into (B, h, L, 64) (head-split epilogue), S = QK^T and
-    O = PV are batched GEMMs, O lands token-major (head-merge epilogue) for the out-proj GEMM.
-    Backward mirrors it with the MN-major operand forms; nothing is transposed or permuted."""
+    O = PV are batched tcgen05 GEMMs, O lands token-major (head-merge) for the out-proj GEMM.
+    Backward: the attention GEMMs write dQ|dK|dV side by side into ONE (rows, 3E) buffer, so
+    d(x + pos) is a single K = 2E GEMM and dW_in three in-place-layout GEMMs; nothing is permuted."""
 
     @staticmethod
-    def forward(ctx, xq, xk, xv, w_in, b_in, w_out, b_out, nh, kpm, p_drop, same_qk):
-        L, B, E = xq.shape
-        S = xk.shape[0]
-        d = E // nh
-        dev = xq.device
+    def forward(ctx, x, pos, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+        L, B, E = x.shape
+        dev = x.device
         bf = torch.bfloat16
-        xq_b = xq.reshape(L * B, E).to(bf)
-        xk_b = xq_b if same_qk else xk.reshape(S * B, E).to(bf)
-        xv_b = xv.reshape(S * B, E).to(bf)
-        wb = w_in.to(bf)
-        wo_b = w_out.to(bf)
+        xqk_b = _tok_bf16(x, pos, L, B, E)
+        xv_b = _tok_bf16(x, None, L, B, E) if pos is not None else xqk_b
+        wb, wo_b = w_in.to(bf), w_out.to(bf)
+        Z = B * nh
+        Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        Kh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        Vh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        for dst, src, j in ((Qh, xqk_b, 0), (Kh, xqk_b, 1), (Vh, xv_b, 2)):
+            K.gemm_ex(L * B, E, E, 1, src, False, 0, wb[j * E:(j + 1) * E], False, 0, dst, c_mode=1, hs=(B, nh, L), ldc=64,
+                      bias=b_in[j * E:(j + 1) * E])
+        O_tok, Y, Zd, aux = _attn_core_fwd(Qh, Kh, Vh, L, L, B, nh, kpm, p_drop, dev)
+        out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
+        ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
+        ctx.aux, ctx.dims = aux, (L, B, E, nh, p_drop, pos is not None, None if pos is None else tuple(pos.shape))
+        return out.view(L, B, E)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok = ctx.saved_tensors
+        L, B, E, nh, p_drop, has_pos, pos_shape = ctx.dims
+        dev, bf = dout.device, torch.bfloat16
+        Z = B * nh
+        dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
+        dWo = torch.zeros((E, E), dtype=torch.float32, device=dev)
+        _dw(dout_b, O_tok, dWo)
+        dbo = K.colsum(dout_b)
+        dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
+        buf = torch.empty((L * B, 3 * E), dtype=bf, device=dev)  # [dQ | dK | dV], token-major
+        _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, L, B, nh, ctx.aux, p_drop, buf[:, :E], buf[:, E:2 * E], buf[:, 2 * E:],
+                       3 * E, 3 * E)
+        dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
+        _dw(buf[:, :2 * E], xqk_b, dW_in[:2 * E])
+        _dw(buf[:, 2 * E:], xv_b, dW_in[2 * E:])
+        db_in = K.colsum(buf)
+        dpos = None
+        if has_pos:
+            d_qk = K.gemm_bf16(buf[:, :2 * E], wb[:2 * E], b_mn=True)          # d(x + pos), K = 2E
+            dx = d_qk + K.gemm_bf16(buf[:, 2 * E:], wb[2 * E:], b_mn=True)
+            if ctx.needs_input_grad[1]:
+                dpos = d_qk.view(L, B, E)
+                if pos_shape[1] != B:
+                    dpos = dpos.sum(1, keepdim=True)
+        else:
+            dx = K.gemm_bf16(buf, wb, b_mn=True)                                # single K = 3E GEMM
+        return dx.view(L, B, E), dpos, dW_in, db_in, dWo, dbo, None, None, None
+
+
+class _MHACross(torch.autograd.Function):
+    """Cross-attention block (q = x + qpos, k = mem + mpos, v = mem; head_dim 64), same machinery."""
+
+    @staticmethod
+    def forward(ctx, x, qpos, mem, mpos, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+        L, B, E = x.shape
+        S = mem.shape[0]
+        dev, bf = x.device, torch.bfloat16
+        xq_b = _tok_bf16(x, qpos, L, B, E)
+        xk_b = _tok_bf16(mem, mpos, S, B, E)
+        xv_b = _tok_bf16(mem, None, S, B, E) if mpos is not None else xk_b
+        wb, wo_b = w_in.to(bf), w_out.to(bf)
         Z = B * nh
         Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         Kh = torch.empty((Z * S, 64), dtype=bf, device=dev)
@@ -176,82 +283,75 @@ class _MHA(torch.autograd.Function):
                   bias=b_in[E:2 * E])
         K.gemm_ex(S * B, E, E, 1, xv_b, False, 0, wb[2 * E:], False, 0, Vh, c_mode=1, hs=(B, nh, S), ldc=64,
                   bias=b_in[2 * E:])
-        Lp, Sp = _ceil64(L), _ceil64(S)
-        scale = 1.0 / math.sqrt(d)
-        Sbuf = _workspace("attn_scores", (Z * Lp, Sp), torch.float32, dev)
-        K.gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=Lp, ldc=Sp)
-        Y = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev)
-        Zd = torch.zeros((Z * Lp, Sp), dtype=bf, device=dev) if p_drop > 0 else Y
-        seed_base = DROPOUT_RNG.base_for(dev) if p_drop > 0 else None
-        seed = DROPOUT_RNG.next_offset() if p_drop > 0 else 0
-        kpm_u8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
-        K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed_base, seed)
-        O_tok = torch.empty((L * B, E), dtype=bf, device=dev)
-        K.gemm_ex(L, 64, S, Z, Zd, False, Lp, Vh, True, S, O_tok, c_mode=2, hs=(B, nh, L), ldc=E)
+        O_tok, Y, Zd, aux = _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
         ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
-        ctx.seed_base = seed_base
-        ctx.dims = (L, S, B, E, nh, Lp, Sp, scale, p_drop, seed, same_qk)
+        ctx.aux = aux
+        ctx.dims = (L, S, B, E, nh, p_drop, None if qpos is None else tuple(qpos.shape), None if mpos is None else tuple(mpos.shape))
         return out.view(L, B, E)
 
     @staticmethod
     def backward(ctx, dout):
         xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok = ctx.saved_tensors
-        L, S, B, E, nh, Lp, Sp, scale, p_drop, seed, same_qk = ctx.dims
-        dev = dout.device
-        bf = torch.bfloat16
+        L, S, B, E, nh, p_drop, qpos_shape, mpos_shape = ctx.dims
+        dev, bf = dout.device, torch.bfloat16
         Z = B * nh
-        dout2 = dout.reshape(L * B, E)
-        dout_b = dout2.to(bf)
-        # out-proj
+        dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
         dWo = torch.zeros((E, E), dtype=torch.float32, device=dev)
-        K.gemm_bf16(dout_b, O_tok, a_mn=True, b_mn=True, out=dWo, accumulate=True,
-                    split_k=_split_k_for(E // 128, E // 128, (L * B + 63) // 64))
+        _dw(dout_b, O_tok, dWo)
         dbo = K.colsum(dout_b)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
-        # softmax backward
-        dP = _workspace("attn_dP", (Z * Lp, Sp), bf, dev, zero=True)
-        K.gemm_ex(L, S, 64, Z, dOh, False, L, Vh, False, S, dP, c_mode=0, c_batch_rows=Lp, ldc=Sp)
-        K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, ctx.seed_base, seed)
         dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
-        dK_tok = torch.empty((S * B, E), dtype=bf, device=dev)
-        dV_tok = torch.empty((S * B, E), dtype=bf, device=dev)
-        K.gemm_ex(L, 64, S, Z, dP, False, Lp, Kh, True, S, dQ_tok, c_mode=2, hs=(B, nh, L), ldc=E)
-        K.gemm_ex(S, 64, L, Z, dP, True, Lp, Qh, True, L, dK_tok, c_mode=2, hs=(B, nh, S), ldc=E)
-        K.gemm_ex(S, 64, L, Z, Zd, True, Lp, dOh, True, L, dV_tok, c_mode=2, hs=(B, nh, S), ldc=E)
-        # in-proj
+        kv = torch.empty((S * B, 2 * E), dtype=bf, device=dev)  # [dK | dV]
+        _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, S, B, nh, ctx.aux, p_drop, dQ_tok, kv[:, :E], kv[:, E:], E, 2 * E)
         dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
-        grads_x = []
-        for j, (dtok, xb) in enumerate(((dQ_tok, xq_b), (dK_tok, xk_b), (dV_tok, xv_b))):
-            rows = dtok.shape[0]
-            K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=dW_in[j * E:(j + 1) * E], accumulate=True,
-                        split_k=_split_k_for(E // 128, E // 128, (rows + 63) // 64))
-            grads_x.append(K.gemm_bf16(dtok, wb[j * E:(j + 1) * E], b_mn=True))
+        _dw(dQ_tok, xq_b, dW_in[:E])
+        _dw(kv[:, :E], xk_b, dW_in[E:2 * E])
+        _dw(kv[:, E:], xv_b, dW_in[2 * E:])
         db_in = torch.zeros(3 * E, dtype=torch.float32, device=dev)
-        K.colsum(dQ_tok, db_in[:E]); K.colsum(dK_tok, db_in[E:2 * E]); K.colsum(dV_tok, db_in[2 * E:])
-        dxq, dxk, dxv = grads_x
-        if same_qk:
-            dxq = dxq + dxk
-            dxk = None
-        else:
-            dxk = dxk.view(S, B, E)
-        return (dxq.view(L, B, E), dxk, dxv.view(S, B, E), dW_in, db_in, dWo, dbo, None, None, None, None)
+        K.colsum(dQ_tok, db_in[:E])
+        K.colsum(kv, db_in[E:])
+        dx = K.gemm_bf16(dQ_tok, wb[:E], b_mn=True)
+        dqpos = None
+        if qpos_shape is not None and ctx.needs_input_grad[1]:
+            dqpos = dx.view(L, B, E) if qpos_shape[1] == B else dx.view(L, B, E).sum(1, keepdim=True)
+        dmem = dmpos = None
+        if mpos_shape is not None:
+            d_k = K.gemm_bf16(kv[:, :E], wb[E:2 * E], b_mn=True)
+            if ctx.needs_input_grad[2]:
+                dmem = (d_k + K.gemm_bf16(kv[:, E:], wb[2 * E:], b_mn=True)).view(S, B, E)
+            if ctx.needs_input_grad[3]:
+                dmpos = d_k.view(S, B, E) if mpos_shape[1] == B else d_k.view(S, B, E).sum(1, keepdim=True)
+        elif ctx.needs_input_grad[2]:
+            dmem = K.gemm_bf16(kv, wb[E:], b_mn=True).view(S, B, E)              # single K = 2E GEMM
+        return dx.view(L, B, E), dqpos, dmem, dmpos, dW_in, db_in, dWo, dbo, None, None, None
 
 
-def multi_head_attention(mha, query, key, value, key_padding_mask=None, training=False):
-    """nn.MultiheadAttention semantics (seq-first (L, B, E) inputs, returns the attended output only;
-    the reference discards the averaged weights it asks for, transformer.py:246-248)."""
-    L, B, E = query.shape
-    S = key.shape[0]
+def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=None, training=False):
+    """nn.MultiheadAttention semantics of the reference's call sites (seq-first (L, B, E) tensors;
+    only the attended output is returned -- the reference discards the averaged weights it asks
+    for, transformer.py:246-248):
+        self-attention :  q = k = x + pos,          v = x      (mem is None)
+        cross-attention:  q = x + pos, k = mem + mem_pos, v = mem
+    """
+    L, B, E = x.shape
     h = mha.num_heads
     d = E // h
+    p = mha.dropout if training else 0.0
     if d == 64 and E % 128 == 0:
-        p = mha.dropout if training else 0.0
-        return _MHA.apply(query.contiguous(), key.contiguous(), value.contiguous(), mha.in_proj_weight,
-                          mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p,
-                          query is key)
+        if mem is None:
+            return _MHASelf.apply(x, pos, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias,
+                                  h, key_padding_mask, p)
+        return _MHACross.apply(x, pos, mem, mem_pos, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
+                               mha.out_proj.bias, h, key_padding_mask, p)
     # head sizes other than 64 (test fixtures only): composed from the same linear() + library bmm
+    query = x if pos is None else x + pos
+    if mem is None:
+        key, value = query, x
+    else:
+        key, value = (mem if mem_pos is None else mem + mem_pos), mem
+    S = key.shape[0]
     w, b = mha.in_proj_weight, mha.in_proj_bias
     q = linear(query, w[:E], b[:E])
     k = linear(key, w[E: 2 * E], b[E: 2 * E])

@@ -99,3 +99,11 @@ def colsum(src, out=None):
     check(lib.pcm_colsum(rows, C, ptr(src), src.stride(0), int(src.dtype == torch.bfloat16), ptr(out), current_stream()),
           "pcm_colsum")
     return out
+
+
+def add_cast_bf16(a, b=None, b_row_div=1):
+    """bf16(a + b) for token-major (rows, C) fp32 activations; b may be None or row-broadcast."""
+    rows, C = a.shape
+    out = torch.empty((rows, C), dtype=torch.bfloat16, device=a.device)
+    check(lib.pcm_add_cast_bf16(rows, C, ptr(a), ptr(b), int(b_row_div), ptr(out), current_stream()), "pcm_add_cast_bf16")
+    return out

@@ -46,12 +46,10 @@ class TransformerEncoderLayer(nn.Module):
         tr = self.training
         if self.normalize_before:
             s2 = PF.add_dropout_layernorm(None, src, self.norm1, 0.0, False)
-            qk = s2 if pos is None else s2 + pos
-            src = src + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, s2, src_key_padding_mask, tr), self.p, tr)
+            src = src + PF.dropout(PF.multi_head_attention(self.self_attn, s2, pos, None, None, src_key_padding_mask, tr), self.p, tr)
             s2 = PF.add_dropout_layernorm(None, src, self.norm2, 0.0, False)
             return src + PF.dropout(self._ffn(s2), self.p, tr)
-        qk = src if pos is None else src + pos
-        a = PF.multi_head_attention(self.self_attn, qk, qk, src, src_key_padding_mask, tr)
+        a = PF.multi_head_attention(self.self_attn, src, pos, None, None, src_key_padding_mask, tr)
         src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr)
         return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr)
 
@@ -104,22 +102,18 @@ class TransformerDecoderLayer(nn.Module):
                 memory_key_padding_mask=None, pos=None, query_pos=None):
         assert tgt_mask is None and memory_mask is None and tgt_key_padding_mask is None
         tr = self.training
-        wq = (lambda t: t if query_pos is None else t + query_pos)
-        mem_k = memory if pos is None else memory + pos
         if self.normalize_before:
             ln = (lambda x, n: PF.add_dropout_layernorm(None, x, n, 0.0, False))
             t2 = ln(tgt, self.norm1)
-            qk = wq(t2)
-            tgt = tgt + PF.dropout(PF.multi_head_attention(self.self_attn, qk, qk, t2, None, tr), self.p, tr)
+            tgt = tgt + PF.dropout(PF.multi_head_attention(self.self_attn, t2, query_pos, None, None, None, tr), self.p, tr)
             t2 = ln(tgt, self.norm2)
-            tgt = tgt + PF.dropout(PF.multi_head_attention(self.multihead_attn, wq(t2), mem_k, memory,
+            tgt = tgt + PF.dropout(PF.multi_head_attention(self.multihead_attn, t2, query_pos, memory, pos,
                                                            memory_key_padding_mask, tr), self.p, tr)
             t2 = ln(tgt, self.norm3)
             return tgt + PF.dropout(self._ffn(t2), self.p, tr)
-        qk = wq(tgt)
-        a = PF.multi_head_attention(self.self_attn, qk, qk, tgt, None, tr)
+        a = PF.multi_head_attention(self.self_attn, tgt, query_pos, None, None, None, tr)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr)
-        a = PF.multi_head_attention(self.multihead_attn, wq(tgt), mem_k, memory, memory_key_padding_mask, tr)
+        a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr)
         return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr)
 

@@ -43,17 +43,13 @@ def test_mha_matches_torch(L, S, B, E, nh, mask, self_attn):
     for ours in (False, True):
         xs = x.clone().requires_grad_(True)
         ms = xs if self_attn else mem.clone().requires_grad_(True)
-        qk = (xs + pos).bfloat16().float() if False else xs + pos
         mha.zero_grad()
-        if self_attn:
-            q_in = k_in = qk
-            v_in = xs
-        else:
-            q_in, k_in, v_in = qk, ms, ms
         if ours:
-            out = PF.multi_head_attention(mha, q_in, k_in, v_in, kpm, training=False)
+            out = (PF.multi_head_attention(mha, xs, pos, None, None, kpm, training=False) if self_attn
+                   else PF.multi_head_attention(mha, xs, pos, ms, None, kpm, training=False))
         else:
-            out = mha(q_in, k_in, v_in, key_padding_mask=kpm)[0]
+            qk = xs + pos
+            out = mha(qk, qk if self_attn else ms, xs if self_attn else ms, key_padding_mask=kpm)[0]
         out.backward(dout)
         res.append((out.detach(), xs.grad.clone(), None if self_attn else ms.grad.clone(),
                     mha.in_proj_weight.grad.clone(), mha.in_proj_bias.grad.clone(), mha.out_proj.weight.grad.clone(),
@@ -76,9 +72,9 @@ def test_mha_dropout_is_consistent():
     mha = _mk(E, nh, p=p)
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn(L, B, E, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
-    out = PF.multi_head_attention(mha, x, x, x, None, training=True)
+    out = PF.multi_head_attention(mha, x, None, None, None, None, training=True)
     fn = out.grad_fn
-    Y, Zd = fn.saved_tensors[8], fn.saved_tensors[9]
+    Y, Zd = fn.saved_tensors[7], fn.saved_tensors[8]
     Lp = Sp = 128
     Yv = Y.view(B * nh, Lp, Sp)[:, :L, :L].float()
     Zv = Zd.view(B * nh, Lp, Sp)[:, :L, :L].float()
