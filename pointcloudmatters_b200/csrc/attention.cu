@@ -14,15 +14,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t dropout_bits(unsigned long long seed, unsigned long long idx) {
-    // splitmix64 finaliser over (seed, element index): stateless, reproducible in backward
-    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    x ^= x >> 31;
-    return (uint32_t)(x >> 32);
-}
-
 // One warp per row, the whole row in registers: lane owns float4 chunks c = lane, lane+32, ...
 // (NV chunks, Sp <= 128*NV columns): one 128-bit read per chunk, one exp per element, 64-bit bf16
 // stores.  Columns Sk..Sp of every row and rows L..Lp of every (batch, head) are written as zeros
@@ -36,8 +27,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
-    const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float keep_scale = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
     const int nchunk = Sp >> 2;
     // rows_total counts PADDED rows (Z * Lp): pad rows are zero-filled
     for (long r = wid; r < rows_total; r += nwarps) {
@@ -53,6 +44,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
         }
         const int b = (int)(z / nh);
         const unsigned char* mrow = kpm ? kpm + (size_t)b * Sk : nullptr;
+        const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)base);
         float v[NV][4];
         float mx = -INFINITY;
 #pragma unroll
@@ -84,13 +76,13 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
             if (c >= nchunk) continue;
             float y[4], zd[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                y[e] = v[i][e] * inv;  // exactly 0 for masked / padded columns
-                zd[e] = y[e];
-                if (Zd != Y) {
-                    const bool keep = dropout_bits(seed, (unsigned long long)base + 4 * c + e) >= thresh;
-                    zd[e] = keep ? y[e] * keep_scale : 0.f;
-                }
+            for (int e = 0; e < 4; ++e) { y[e] = v[i][e] * inv; zd[e] = y[e]; }  // exactly 0 for masked / padded columns
+            if (Zd != Y) {
+                const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
+                zd[0] = (h0 & 0xFFFFu) >= thr16 ? y[0] * keep_scale : 0.f;
+                zd[1] = (h0 >> 16) >= thr16 ? y[1] * keep_scale : 0.f;
+                zd[2] = (h1 & 0xFFFFu) >= thr16 ? y[2] * keep_scale : 0.f;
+                zd[3] = (h1 >> 16) >= thr16 ? y[3] * keep_scale : 0.f;
             }
             __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);
             *reinterpret_cast<uint2*>(Y + base + 4 * c) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
@@ -110,13 +102,14 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
-    const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float keep_scale = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
     const int nchunk = Sp >> 2;
     for (long r = wid; r < rows_total; r += nwarps) {
         const long z = r / Lp;
         const int l = (int)(r - z * Lp);
         const size_t base = (size_t)r * Sp;
+        const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)base);
         if (l >= L) {  // pad rows of dS must be exact zeros (K tail of the dK GEMM)
             for (int c = lane; c < nchunk; c += 32) *reinterpret_cast<uint2*>(dZ + base + 4 * c) = make_uint2(0u, 0u);
             continue;
@@ -137,12 +130,17 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
             const float2 d01 = __bfloat1622float2(dp[0]), d23 = __bfloat1622float2(dp[1]);
             y[i][0] = y01.x; y[i][1] = y01.y; y[i][2] = y23.x; y[i][3] = y23.y;
             dy[i][0] = d01.x; dy[i][1] = d01.y; dy[i][2] = d23.x; dy[i][3] = d23.y;
+            if (p_drop > 0.f) {
+                const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
+                dy[i][0] = (h0 & 0xFFFFu) >= thr16 ? dy[i][0] * keep_scale : 0.f;
+                dy[i][1] = (h0 >> 16) >= thr16 ? dy[i][1] * keep_scale : 0.f;
+                dy[i][2] = (h1 & 0xFFFFu) >= thr16 ? dy[i][2] * keep_scale : 0.f;
+                dy[i][3] = (h1 >> 16) >= thr16 ? dy[i][3] * keep_scale : 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = 4 * c + e;
                 if (c >= nchunk || j >= Sk) { dy[i][e] = 0.f; y[i][e] = 0.f; }
-                else if (p_drop > 0.f)
-                    dy[i][e] = dropout_bits(seed, (unsigned long long)base + j) >= thresh ? dy[i][e] * keep_scale : 0.f;
                 dot = fmaf(dy[i][e], y[i][e], dot);
             }
         }

@@ -38,3 +38,25 @@ __device__ __forceinline__ int pcm_cloud_of(int i, const int* __restrict__ offse
     }
     return lo;
 }
+
+// ---- counter-based dropout RNG shared by the attention / LayerNorm kernels --------------------
+// A 64-bit splitmix mix per ROW (seed, row base index) and one cheap 32-bit hash ("lowbias32") per
+// PAIR of elements: low / high 16 bits decide the two elements.  The drop probability actually
+// realised is thr16 / 65536; kernels scale survivors by 65536 / (65536 - thr16), so the estimator
+// is exactly unbiased.  Stateless: the backward kernels regenerate the identical mask.
+__device__ __forceinline__ uint32_t pcm_row_seed(unsigned long long seed, unsigned long long row_base) {
+    unsigned long long x = seed + row_base * 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return (uint32_t)(x >> 32) ^ (uint32_t)x;
+}
+__device__ __forceinline__ uint32_t pcm_pair_bits(uint32_t row_seed, uint32_t pair) {
+    uint32_t x = row_seed ^ (pair * 0x9E3779B9u);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t pcm_drop_thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+__device__ __forceinline__ float pcm_keep_scale(uint32_t thr16) { return 65536.0f / (65536.0f - (float)thr16); }

@@ -13,14 +13,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t ln_dropout_bits(unsigned long long seed, unsigned long long idx) {
-    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    x ^= x >> 31;
-    return (uint32_t)(x >> 32);
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PCM_FULL_MASK, v, o);
     return v;
@@ -37,8 +29,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
-    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
-    const float ks = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float ks = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
     float4 g4[V], b4[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -48,15 +40,18 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     for (long r = wid; r < rows; r += nwarps) {
         float4 h[V];
         float s = 0.f;
+        const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)r * C);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
             float4 xv = x ? *reinterpret_cast<const float4*>(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (p_drop > 0.f) {
-                xv.x = ln_dropout_bits(seed, e + 0) >= thresh ? xv.x * ks : 0.f;
-                xv.y = ln_dropout_bits(seed, e + 1) >= thresh ? xv.y * ks : 0.f;
-                xv.z = ln_dropout_bits(seed, e + 2) >= thresh ? xv.z * ks : 0.f;
-                xv.w = ln_dropout_bits(seed, e + 3) >= thresh ? xv.w * ks : 0.f;
+                const uint32_t c = (uint32_t)(v * 32 + lane);
+                const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
+                xv.x = (h0 & 0xFFFFu) >= thr16 ? xv.x * ks : 0.f;
+                xv.y = (h0 >> 16) >= thr16 ? xv.y * ks : 0.f;
+                xv.z = (h1 & 0xFFFFu) >= thr16 ? xv.z * ks : 0.f;
+                xv.w = (h1 >> 16) >= thr16 ? xv.w * ks : 0.f;
             }
             const float4 rv = *reinterpret_cast<const float4*>(res + e);
             h[v] = make_float4(rv.x + xv.x, rv.y + xv.y, rv.z + xv.z, rv.w + xv.w);
@@ -107,8 +102,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
-    const uint32_t thresh = (uint32_t)fminf(p_drop * 4294967296.0f, 4294967295.0f);
-    const float ks = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float ks = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
     for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
     __syncthreads();
     float4 g4[V], ag[V], abt[V];
@@ -120,6 +115,7 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     }
     for (long r = wid; r < rows; r += nwarps) {
         const float mean = mean_in[r], rstd = rstd_in[r];
+        const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)r * C);
         float4 gy[V], xh[V];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -147,10 +143,12 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
             if (dx && dx != dres) {
                 float4 o = dh;
                 if (p_drop > 0.f) {
-                    o.x = ln_dropout_bits(seed, e + 0) >= thresh ? dh.x * ks : 0.f;
-                    o.y = ln_dropout_bits(seed, e + 1) >= thresh ? dh.y * ks : 0.f;
-                    o.z = ln_dropout_bits(seed, e + 2) >= thresh ? dh.z * ks : 0.f;
-                    o.w = ln_dropout_bits(seed, e + 3) >= thresh ? dh.w * ks : 0.f;
+                    const uint32_t c = (uint32_t)(v * 32 + lane);
+                    const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
+                    o.x = (h0 & 0xFFFFu) >= thr16 ? dh.x * ks : 0.f;
+                    o.y = (h0 >> 16) >= thr16 ? dh.y * ks : 0.f;
+                    o.z = (h1 & 0xFFFFu) >= thr16 ? dh.z * ks : 0.f;
+                    o.w = (h1 >> 16) >= thr16 ? dh.w * ks : 0.f;
                 }
                 *reinterpret_cast<float4*>(dx + e) = o;
             }
