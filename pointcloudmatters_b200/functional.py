@@ -512,61 +512,27 @@ def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
 
 
 # ------------------------------------------------------------------------------------------------
-# live kernel timing for bench.py's roofline (CUDA events on the launching stream)
+# live kernel timing for bench.py's roofline (CUDA events on the launching stream, kernels.TIMER)
 # ------------------------------------------------------------------------------------------------
-class _KernelTimer:
-    def __init__(self):
-        self.enabled = False
-        self.events = {}
-
-    def enable(self):
-        self.enabled, self.events = True, {}
-
-    def disable(self):
-        self.enabled = False
-
-    class _Region:
-        def __init__(self, timer, name):
-            self.t, self.name = timer, name
-
-        def __enter__(self):
-            if self.t.enabled:
-                self.e0 = torch.cuda.Event(enable_timing=True)
-                self.e0.record()
-            return self
-
-        def __exit__(self, *exc):
-            if self.t.enabled:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                self.t.events.setdefault(self.name, []).append((self.e0, e1))
-            return False
-
-    def region(self, name):
-        return self._Region(self, name)
-
-    def summary(self):
-        torch.cuda.synchronize()
-        out = {}
-        for name, evs in self.events.items():
-            ms = [a.elapsed_time(b) for a, b in evs]
-            out[name] = {"launches": len(ms), "avg_ms": sum(ms) / len(ms), "total_ms": sum(ms)}
-        steps = max((v["launches"] for v in out.values()), default=1)
-        for name, v in out.items():
-            v["ms_per_step"] = v["total_ms"] / max(1, min(steps, v["launches"]))
-        return out
+KERNEL_TIMER = K.TIMER
 
 
-KERNEL_TIMER = _KernelTimer()
-
-
-def roofline_for(kstats, peaks, batch, n_points, cfg):
-    """Roofline object for the dominant timed kernel family of the step (bench.py)."""
-    if not kstats:
+def roofline_for(kstats, peaks, steps):
+    """Roofline object for the dominant timed kernel family of the step (bench.py): the tcgen05 GEMM.
+    achieved = algorithmic FLOPs (2*M*N*K per launch, summed) / CUDA-event time of those launches."""
+    if not kstats or "gemm_tcgen05" not in kstats:
         return None
-    name = max(kstats, key=lambda k: kstats[k]["total_ms"])
-    st = kstats[name]
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    return {"kernel": name, "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
-            "traffic": None, "avg_launch_ms": st["avg_ms"], "launches_timed": st["launches"], "peak_source": which}
+    st = kstats["gemm_tcgen05"]
+    have = "bf16_tflops_sustained" in peaks
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = st["flops"] / (st["total_ms"] * 1e-3) / 1e12
+    return {"kernel": "gemm_tcgen05_kernel (all projection / attention / weight-gradient GEMMs of the step)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured"
+                            if have else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback"),
+            "launches_per_step": st["launches"] / steps, "ms_per_step": st["total_ms"] / steps,
+            "algorithmic_gflop_per_step": st["flops"] / steps / 1e9,
+            "algorithmic_gbytes_per_step": st["bytes"] / steps / 1e9,
+            "note": "timed with CUDA events around every launch on an eager (non-graph) replica of the step; "
+                    "traffic (dram bytes per launch from ncu --set full) is in profiles/ for the dominant shape"}

@@ -8,6 +8,47 @@ import torch
 from ._lib import check, current_stream, lib, ptr, require_cuda
 
 
+class _Timer:
+    """Optional live timing of one kernel family with CUDA events on the launching stream
+    (bench.py's `roofline`): records (events, algorithmic flops, algorithmic bytes) per launch."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = {}
+
+    def start(self):
+        self.enabled, self.records = True, {}
+
+    def stop(self):
+        self.enabled = False
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, name, flops, nbytes):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.setdefault(name, []).append((e0, e1, flops, nbytes))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _, _ in recs]
+            out[name] = {"launches": len(recs), "total_ms": sum(ms), "avg_ms": sum(ms) / len(ms),
+                         "flops": float(sum(r[2] for r in recs)), "bytes": float(sum(r[3] for r in recs))}
+        return out
+
+
+TIMER = _Timer()
+
+
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32, bias=None, relu=False,
               accumulate=False, split_k=1):
     """C[m,n] (+)= sum_k A(m,k) B(n,k) (+bias) (ReLU) on tcgen05 (pcm_gemm_bf16).
@@ -26,9 +67,11 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32
     assert out.shape == (M, N) and out.stride(1) == 1
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    t0 = TIMER.begin()
     check(lib.pcm_gemm_bf16(M, N, K, ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out),
                             out.stride(0), int(out.dtype == torch.bfloat16), ptr(bias), int(relu), int(accumulate),
                             int(split_k), current_stream()), "pcm_gemm_bf16")
+    TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
     return out
 
 
@@ -40,11 +83,14 @@ def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, 
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
     if ldc is None:
         ldc = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
+    t0 = TIMER.begin()
     check(lib.pcm_gemm_bf16_ex(M, N, Kd, batch, ptr(a), a.stride(0), int(a_mn), a.shape[0], a_batch_rows,
                                ptr(b), b.stride(0), int(b_mn), b.shape[0], b_batch_rows, ptr(out), ldc,
                                int(out.dtype == torch.bfloat16), c_mode, c_batch_rows, hs[0], hs[1], hs[2],
                                float(alpha), ptr(bias), int(relu), int(accumulate), int(split_k), current_stream()),
           "pcm_gemm_bf16_ex")
+    TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * Kd * batch,
+              batch * (2.0 * (M * Kd + N * Kd) + M * N * out.element_size()))
     return out
 
 
