@@ -29,20 +29,26 @@ class _Timer:
         e.record()
         return e
 
-    def end(self, e0, name, flops, nbytes):
+    def end(self, e0, name, flops, nbytes, tag=None):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.records.setdefault(name, []).append((e0, e1, flops, nbytes))
+        self.records.setdefault(name, []).append((e0, e1, flops, nbytes, tag))
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
         for name, recs in self.records.items():
-            ms = [a.elapsed_time(b) for a, b, _, _ in recs]
+            ms = [r[0].elapsed_time(r[1]) for r in recs]
+            shapes = {}
+            for r, t in zip(recs, ms):
+                d = shapes.setdefault(r[4], [0, 0.0, 0.0])
+                d[0] += 1; d[1] += t; d[2] += r[2]
             out[name] = {"launches": len(recs), "total_ms": sum(ms), "avg_ms": sum(ms) / len(ms),
-                         "flops": float(sum(r[2] for r in recs)), "bytes": float(sum(r[3] for r in recs))}
+                         "flops": float(sum(r[2] for r in recs)), "bytes": float(sum(r[3] for r in recs)),
+                         "by_shape": {str(k): {"launches": v[0], "total_ms": v[1], "tflops": v[2] / max(v[1], 1e-9) / 1e9}
+                                      for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}}
         return out
 
 
@@ -71,7 +77,8 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32
     check(lib.pcm_gemm_bf16(M, N, K, ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out),
                             out.stride(0), int(out.dtype == torch.bfloat16), ptr(bias), int(relu), int(accumulate),
                             int(split_k), current_stream()), "pcm_gemm_bf16")
-    TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
+    TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size(),
+              (M, N, K, 1, int(a_mn), int(b_mn), str(out.dtype)[6:], int(split_k)))
     return out
 
 
@@ -90,7 +97,8 @@ def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, 
                                float(alpha), ptr(bias), int(relu), int(accumulate), int(split_k), current_stream()),
           "pcm_gemm_bf16_ex")
     TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * Kd * batch,
-              batch * (2.0 * (M * Kd + N * Kd) + M * N * out.element_size()))
+              batch * (2.0 * (M * Kd + N * Kd) + M * N * out.element_size()),
+              (M, N, Kd, batch, int(a_mn), int(b_mn), str(out.dtype)[6:], int(split_k)))
     return out
 
 
