@@ -8,7 +8,8 @@
 //   * warp 1 (one elected lane): issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BLOCK_N x 16)
 //     with the fp32 accumulator in TENSOR MEMORY, releases ring slots with tcgen05.commit;
 //     the same warp owns tcgen05.alloc / dealloc;
-//   * warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / cast ->
+//   * warps 2-9: epilogue (two warps per TMEM lane quadrant, each draining half of the tile's
+//     columns: short-K GEMMs are epilogue-latency-bound) -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / cast ->
 //     swizzled shared-memory strip -> fully coalesced 128-byte row-segment stores (or coalesced
 //     red.global.add.f32 for split-K / gradient accumulation).
 // Both operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
@@ -31,7 +32,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 template <int BLOCK_N> struct StagesFor { static constexpr int value = BLOCK_N == 256 ? 4 : 6; };  // <= 192 KB ring
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
+constexpr int NUM_EPI_WARPS = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    uint8_t* epi_stage = tiles + STAGES * STAGE_BYTES + 256;  // 4 warps x 4 KB, 128-byte aligned
+    uint8_t* epi_stage = tiles + STAGES * STAGE_BYTES + 256;  // 8 warps x 4 KB, 128-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -272,9 +274,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         // registers -> (alpha, bias, ReLU, cast) -> a private swizzled 4 KB shared-memory strip ->
         // read back transposed, so every global store instruction covers complete 128-byte row
         // segments instead of 32 different cache lines.
-        const int quad = warp & 3;
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int chalf = (warp - 2) >> 2;         // which half of the tile's columns it drains
         uint8_t* stage = epi_stage + (warp - 2) * 4096;
-        constexpr int NLD = BLOCK_N / 32;
+        constexpr int NLD = BLOCK_N / 64;          // 32-column loads per warp
         constexpr int ESZ = EPI == EPI_BF16 ? 2 : 4;
         int i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
@@ -283,7 +286,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int zb = zs / p.split_k;
             const int acc = i & 1;
             const int row_base = m_blk * BLOCK_M + quad * 32;  // first row of this warp inside the batch's M
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const int cbase = chalf * (BLOCK_N / 2);  // first tile column of this warp
+            const int col_lim = min(p.N, n_blk * BLOCK_N + cbase + BLOCK_N / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + cbase);
             // per-row destination offsets (elements) of this warp's 32 rows, lane rl holds row rl
             size_t row_dst;
             {
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             tc_fence_after();
 
             auto process = [&](uint32_t (&v)[32], int q) {
-                const int col0 = n_blk * BLOCK_N + q * 32;
+                const int col0 = n_blk * BLOCK_N + cbase + q * 32;
                 if (col0 >= p.N) return;  // warp-uniform
                 float bl = 0.f;
                 if (p.bias != nullptr && col0 + lane < p.N) bl = __ldg(p.bias + col0 + lane);
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         const int chunk = half * 4 + c;
                         *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
                     }
-                    if (half == 0 && col0 + 32 < p.N && q + 1 < NLD) return;  // wait for the second half of the strip
+                    if (half == 0 && col0 + 32 < col_lim && q + 1 < NLD) return;  // wait for the second half of the strip
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -330,13 +335,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                             make_float4(f[c * 4 + 0], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
                 }
                 __syncwarp();
-                const int scol0 = EPI == EPI_BF16 ? (n_blk * BLOCK_N + (q & ~1) * 32) : col0;  // first column of the strip
+                const int scol0 = EPI == EPI_BF16 ? (n_blk * BLOCK_N + cbase + (q & ~1) * 32) : col0;  // first column of the strip
                 if (EPI == EPI_ATOMIC) {
 #pragma unroll 4
                     for (int rl = 0; rl < 32; ++rl) {
                         const size_t rd = __shfl_sync(PCM_FULL_MASK, row_dst, rl);
                         const float x = *reinterpret_cast<const float*>(stage + rl * 128 + (((lane >> 2) ^ (rl & 7)) << 4) + ((lane & 3) << 2));
-                        if (row_base + rl < p.M && scol0 + lane < p.N) {
+                        if (row_base + rl < p.M && scol0 + lane < col_lim) {
                             const size_t dst = p.c_mode == 1 ? rd + (size_t)((scol0 + lane) >> 6) * p.hs_L * 64 + ((scol0 + lane) & 63)
                                                              : rd + scol0 + lane;
                             atomicAdd(reinterpret_cast<float*>(p.C) + dst, x);
@@ -350,19 +355,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         const size_t rd = __shfl_sync(PCM_FULL_MASK, row_dst, rl);
                         const uint4 pk = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((chunk ^ (rl & 7)) << 4));
                         const int ecol = scol0 + chunk * (16 / ESZ);  // first element column of this 16-byte piece
-                        if (row_base + rl < p.M && ecol < p.N) {
+                        if (row_base + rl < p.M && ecol < col_lim) {
                             const size_t dst = p.c_mode == 1 ? rd + (size_t)(ecol >> 6) * p.hs_L * 64 + (ecol & 63) : rd + ecol;
                             uint8_t* g = reinterpret_cast<uint8_t*>(p.C) + dst * ESZ;
-                            if (ecol + 16 / ESZ <= p.N && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+                            if (ecol + 16 / ESZ <= col_lim && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
                                 *reinterpret_cast<uint4*>(g) = pk;
                             } else if (EPI == EPI_BF16) {
                                 const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&pk);
                                 for (int qq = 0; qq < 8; ++qq)
-                                    if (ecol + qq < p.N) reinterpret_cast<__nv_bfloat16*>(g)[qq] = e[qq];
+                                    if (ecol + qq < col_lim) reinterpret_cast<__nv_bfloat16*>(g)[qq] = e[qq];
                             } else {
                                 const float* e = reinterpret_cast<const float*>(&pk);
                                 for (int qq = 0; qq < 4; ++qq)
-                                    if (ecol + qq < p.N) reinterpret_cast<float*>(g)[qq] = e[qq];
+                                    if (ecol + qq < col_lim) reinterpret_cast<float*>(g)[qq] = e[qq];
                             }
                         }
                     }
@@ -375,11 +380,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 #pragma unroll 1
             for (int q = 0; q < NLD; q += 2) {
                 tmem_ld_wait(va);
-                tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 1) * 32), vb);  // NLD is even: always valid
+                if (q + 1 < NLD) tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 1) * 32), vb);
                 process(va, q);
-                tmem_ld_wait(vb);
-                if (q + 2 < NLD) tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 2) * 32), va);
-                process(vb, q + 1);
+                if (q + 1 < NLD) {
+                    tmem_ld_wait(vb);
+                    if (q + 2 < NLD) tmem_ld_32x32b_x32(taddr + (uint32_t)((q + 2) * 32), va);
+                    process(vb, q + 1);
+                }
             }
             // this warp has read its accumulator quadrant: hand the buffer back to the MMA warp
             tc_fence_before();
@@ -458,7 +465,7 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
-    constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256 + 4 * 4096;
+    constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * 4096;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>,

@@ -7,7 +7,9 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-if which.startswith("gemm"):
+if which == "attn_s":
+    pass
+elif which.startswith("gemm"):
     from pointcloudmatters_b200.kernels import gemm_bf16
 
     M, N, K = 32960, 1024, 512
@@ -29,3 +31,12 @@ else:
         q = t_xyz[fps.long()].contiguous()
         P.knn_query(16, t_xyz, t_off, q, t_noff)
 torch.cuda.synchronize()
+if which == "attn_s":
+    from pointcloudmatters_b200.kernels import gemm_ex
+    Z, L, S = 512, 515, 515
+    Qh = torch.randn(Z * L, 64, device="cuda").bfloat16()
+    Kh = torch.randn(Z * S, 64, device="cuda").bfloat16()
+    Sbuf = torch.empty(Z * 576, 576, device="cuda")
+    for _ in range(4):
+        gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=576, ldc=576)
+    torch.cuda.synchronize()
