@@ -125,11 +125,19 @@ class ACTPCD(nn.Module):
     def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None):
         p, x, o = pxo
         b = o.shape[0]
-        n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
-        o32 = o.int() if o.dtype != torch.int32 else o
-        idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=n_max, m_total=b * self.pcd_npoints)
-        n_p = p[idx.long(), :].contiguous()
-        knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
+        pre = getattr(self, "_presampled", None)
+        if pre is not None:
+            side, n_o, o32, idx, n_p, knn_idx = pre
+            torch.cuda.current_stream().wait_stream(side)  # join
+            for t in (n_o, idx, n_p, knn_idx):
+                t.record_stream(torch.cuda.current_stream())
+            self._presampled = None
+        else:
+            n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
+            o32 = o.int() if o.dtype != torch.int32 else o
+            idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=n_max, m_total=b * self.pcd_npoints)
+            n_p = p[idx.long(), :].contiguous()
+            knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
         x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
         if return_index:
             return [n_p, x, n_o, idx]
@@ -195,7 +203,32 @@ class ACTPCD(nn.Module):
         data_dict["loss"] = action_loss + total_kld * self.kl_weight
         return data_dict
 
+    def _presample(self, data_dict):
+        """FPS + kNN depend only on the input coordinates and are latency-bound (a chain of M-1
+        dependent rounds on 64 of the 148 SMs): run them on a side stream while the CVAE encoder
+        occupies the main stream.  Under CUDA-graph capture this becomes a fork/join in the graph."""
+        pcd = data_dict["pcds"]
+        p, o = pcd["coord"], pcd["offset"]
+        if not p.is_cuda:
+            return
+        b = o.shape[0]
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
+            o32 = o.int() if o.dtype != torch.int32 else o
+            idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=pcd.get("n_max", None), m_total=b * self.pcd_npoints)
+            n_p = p[idx.long(), :].contiguous()
+            knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
+        self._presampled = (side, n_o, o32, idx, n_p, knn_idx)
+
     def forward(self, data_dict):
+        self._presampled = None
+        if data_dict["pcds"].get("n_max", None) is not None:  # sync-free path only
+            self._presample(data_dict)
         data_dict = self.forward_encoder(data_dict)
         data_dict = self.forward_obs_embed(data_dict)
         data_dict = self.forward_decoder(data_dict)

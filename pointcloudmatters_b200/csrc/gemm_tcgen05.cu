@@ -303,14 +303,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             auto process = [&](uint32_t (&v)[32], int q) {
                 const int col0 = n_blk * BLOCK_N + cbase + q * 32;
                 if (col0 >= p.N) return;  // warp-uniform
-                float bl = 0.f;
-                if (p.bias != nullptr && col0 + lane < p.N) bl = __ldg(p.bias + col0 + lane);
                 float f[32];
+                if (p.bias != nullptr) {  // one coalesced load per strip, broadcast by shuffles
+                    const float bl = col0 + lane < p.N ? __ldg(p.bias + col0 + lane) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) * p.alpha + __shfl_sync(PCM_FULL_MASK, bl, j);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    f[j] = x;
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha + __shfl_sync(PCM_FULL_MASK, bl, j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
                 if (EPI == EPI_BF16) {
                     // two consecutive loads (64 columns) share one 128-byte-per-row strip
