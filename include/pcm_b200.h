@@ -190,6 +190,29 @@ int pcm_attn_softmax_bwd(int Z, int L, int Lp, int Sk, int Sp, const void *Y, vo
                          float p_drop, const unsigned long long *seed_base,
                          unsigned long long seed_offset, pcm_stream_t stream);
 
+/* Fused multi-head attention for head_dim 64 (tcgen05 / TMEM / TMA; csrc/flash_attn.cu): replaces
+ * the whole score -> softmax -> dropout -> value chain of nn.MultiheadAttention's math path
+ * (transformer.py:246-248 self-attention, :329-340 cross-attention; torch's
+ * multi_head_attention_forward) without materialising the (B*nh, L, S) tensors.
+ *   Q (B*nh, L, 64), K, V (B*nh, S, 64): bf16 "head-split" (pcm_gemm_bf16_ex c_mode 1);
+ *   kpm (B, S) bytes, non-zero = masked key, may be NULL; scale = 1/sqrt(64) at the call sites;
+ *   dropout on the probabilities with the counter-based mask of (*seed_base, seed_offset);
+ *   O: bf16 token-major (row l*B + b, column h*64 + d), pitch ldo;
+ *   lse (B*nh, L) fp32: log2-domain log-sum-exp per query row (saved for backward).
+ * Backward recomputes the probabilities from lse: dO (B*nh, L, 64) bf16 head-split in;
+ * dQ (pitch ldq), dK, dV (pitch ldkv) bf16 token-major out; delta (B*nh*L floats) and dQacc
+ * (B*nh*L*64 floats) are caller-owned workspaces (dQacc is cleared by the call). */
+int pcm_flash_attn_fwd(int B, int nh, int L, int S, const void *Q, const void *K, const void *V,
+                       const unsigned char *kpm, float scale, float p_drop,
+                       const unsigned long long *seed_base, unsigned long long seed_offset, void *O,
+                       int ldo, float *lse, pcm_stream_t stream);
+int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void *Q, const void *K, const void *V,
+                       const void *O, int ldo, const void *dO, const float *lse,
+                       const unsigned char *kpm, float scale, float p_drop,
+                       const unsigned long long *seed_base, unsigned long long seed_offset,
+                       float *delta, float *dQacc, void *dQ, int ldq, void *dK, void *dV, int ldkv,
+                       pcm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused set-abstraction head.  Replaces, for ACTPCD.pcd_sampling (src/models/components/act/
  * act.py:446-460) and PCDObsEncoder.pcd_sampling (.../vision/pcd_obs_encoder.py:179-193), the

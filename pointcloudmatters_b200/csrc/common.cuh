@@ -58,5 +58,5 @@ __device__ __forceinline__ uint32_t pcm_pair_bits(uint32_t row_seed, uint32_t pa
     x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ uint32_t pcm_drop_thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
-__device__ __forceinline__ float pcm_keep_scale(uint32_t thr16) { return 65536.0f / (65536.0f - (float)thr16); }
+__host__ __device__ __forceinline__ uint32_t pcm_drop_thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+__host__ __device__ __forceinline__ float pcm_keep_scale(uint32_t thr16) { return 65536.0f / (65536.0f - (float)thr16); }

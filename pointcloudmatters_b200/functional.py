@@ -163,37 +163,22 @@ def _tok_bf16(x, pos, L, B, E):
 
 
 def _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev):
-    """softmax(Q K^T / 8 + mask) V for head_dim 64 on (B*nh)-batched tcgen05 GEMMs; returns the
-    token-major bf16 output and what backward needs."""
-    bf = torch.bfloat16
-    Z = B * nh
-    E = nh * 64
-    Lp, Sp = _ceil64(L), _ceil64(S)
-    scale = 0.125
-    Sbuf = _workspace("attn_scores", (Z * Lp, Sp), torch.float32, dev)
-    K.gemm_ex(L, S, 64, Z, Qh, False, L, Kh, False, S, Sbuf, c_mode=0, c_batch_rows=Lp, ldc=Sp)
-    Y = torch.empty((Z * Lp, Sp), dtype=bf, device=dev)  # padding is zero-filled by the softmax kernel
-    Zd = torch.empty((Z * Lp, Sp), dtype=bf, device=dev) if p_drop > 0 else Y
+    """dropout(softmax(Q K^T / 8 + mask)) V for head_dim 64 in ONE fused tcgen05 kernel
+    (csrc/flash_attn.cu): returns the token-major bf16 output and what backward needs (the
+    log-sum-exp per row; probabilities are recomputed, never stored)."""
     seed_base = DROPOUT_RNG.base_for(dev) if p_drop > 0 else None
     seed = DROPOUT_RNG.next_offset() if p_drop > 0 else 0
     kpm_u8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
-    K.attn_softmax_fwd(Sbuf, Y, Zd, Z, L, Lp, S, Sp, nh, kpm_u8, scale, p_drop, seed_base, seed)
-    O_tok = torch.empty((L * B, E), dtype=bf, device=dev)
-    K.gemm_ex(L, 64, S, Z, Zd, False, Lp, Vh, True, S, O_tok, c_mode=2, hs=(B, nh, L), ldc=E)
-    return O_tok, Y, Zd, (Lp, Sp, scale, seed_base, seed)
+    O_tok, lse = K.flash_attn_fwd(Qh, Kh, Vh, B, nh, L, S, kpm_u8, 0.125, p_drop, seed_base, seed)
+    return O_tok, lse, kpm_u8, (seed_base, seed)
 
 
-def _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, S, B, nh, aux, p_drop, dQ_out, dK_out, dV_out, ld_q, ld_kv):
-    """Backward of _attn_core_fwd: writes token-major bf16 dQ / dK / dV (head-merge epilogue) into
-    the given (possibly column-sliced) destinations."""
-    Lp, Sp, scale, seed_base, seed = aux
-    Z = B * nh
-    dP = _workspace("attn_dP", (Z * Lp, Sp), torch.bfloat16, dOh.device, zero=True)
-    K.gemm_ex(L, S, 64, Z, dOh, False, L, Vh, False, S, dP, c_mode=0, c_batch_rows=Lp, ldc=Sp)
-    K.attn_softmax_bwd(Y, dP, Z, L, Lp, S, Sp, scale, p_drop, seed_base, seed)
-    K.gemm_ex(L, 64, S, Z, dP, False, Lp, Kh, True, S, dQ_out, c_mode=2, hs=(B, nh, L), ldc=ld_q)
-    K.gemm_ex(S, 64, L, Z, dP, True, Lp, Qh, True, L, dK_out, c_mode=2, hs=(B, nh, S), ldc=ld_kv)
-    K.gemm_ex(S, 64, L, Z, Zd, True, Lp, dOh, True, L, dV_out, c_mode=2, hs=(B, nh, S), ldc=ld_kv)
+def _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, S, B, nh, aux, p_drop, dQ_out, dK_out, dV_out):
+    """Backward of _attn_core_fwd: writes token-major bf16 dQ / dK / dV into the given (possibly
+    column-sliced) destinations."""
+    seed_base, seed = aux
+    K.flash_attn_bwd(Qh, Kh, Vh, O_tok, dOh, lse, B, nh, L, S, kpm_u8, 0.125, p_drop, seed_base, seed,
+                     dQ_out, dK_out, dV_out)
 
 
 def _dw(dtok, xb, out):
@@ -224,15 +209,15 @@ class _MHASelf(torch.autograd.Function):
         for dst, src, j in ((Qh, xqk_b, 0), (Kh, xqk_b, 1), (Vh, xv_b, 2)):
             K.gemm_ex(L * B, E, E, 1, src, False, 0, wb[j * E:(j + 1) * E], False, 0, dst, c_mode=1, hs=(B, nh, L), ldc=64,
                       bias=b_in[j * E:(j + 1) * E])
-        O_tok, Y, Zd, aux = _attn_core_fwd(Qh, Kh, Vh, L, L, B, nh, kpm, p_drop, dev)
+        O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, L, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
-        ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
+        ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok)
         ctx.aux, ctx.dims = aux, (L, B, E, nh, p_drop, pos is not None, None if pos is None else tuple(pos.shape))
         return out.view(L, B, E)
 
     @staticmethod
     def backward(ctx, dout):
-        xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok = ctx.saved_tensors
+        xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok = ctx.saved_tensors
         L, B, E, nh, p_drop, has_pos, pos_shape = ctx.dims
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
@@ -243,8 +228,8 @@ class _MHASelf(torch.autograd.Function):
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         buf = torch.empty((L * B, 3 * E), dtype=bf, device=dev)  # [dQ | dK | dV], token-major
-        _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, L, B, nh, ctx.aux, p_drop, buf[:, :E], buf[:, E:2 * E], buf[:, 2 * E:],
-                       3 * E, 3 * E)
+        _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, L, B, nh, ctx.aux, p_drop, buf[:, :E], buf[:, E:2 * E],
+                       buf[:, 2 * E:])
         dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
         _dw(buf[:, :2 * E], xqk_b, dW_in[:2 * E])
         _dw(buf[:, 2 * E:], xv_b, dW_in[2 * E:])
@@ -283,16 +268,16 @@ class _MHACross(torch.autograd.Function):
                   bias=b_in[E:2 * E])
         K.gemm_ex(S * B, E, E, 1, xv_b, False, 0, wb[2 * E:], False, 0, Vh, c_mode=1, hs=(B, nh, S), ldc=64,
                   bias=b_in[2 * E:])
-        O_tok, Y, Zd, aux = _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev)
+        O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
-        ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok)
+        ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok)
         ctx.aux = aux
         ctx.dims = (L, S, B, E, nh, p_drop, None if qpos is None else tuple(qpos.shape), None if mpos is None else tuple(mpos.shape))
         return out.view(L, B, E)
 
     @staticmethod
     def backward(ctx, dout):
-        xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, Y, Zd, O_tok = ctx.saved_tensors
+        xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok = ctx.saved_tensors
         L, S, B, E, nh, p_drop, qpos_shape, mpos_shape = ctx.dims
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
@@ -304,7 +289,7 @@ class _MHACross(torch.autograd.Function):
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
         kv = torch.empty((S * B, 2 * E), dtype=bf, device=dev)  # [dK | dV]
-        _attn_core_bwd(dOh, Qh, Kh, Vh, Y, Zd, L, S, B, nh, ctx.aux, p_drop, dQ_tok, kv[:, :E], kv[:, E:], E, 2 * E)
+        _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, S, B, nh, ctx.aux, p_drop, dQ_tok, kv[:, :E], kv[:, E:])
         dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
         _dw(dQ_tok, xq_b, dW_in[:E])
         _dw(kv[:, :E], xk_b, dW_in[E:2 * E])

@@ -112,6 +112,39 @@ def attn_softmax_bwd(Y, dZ, Z, L, Lp, Sk, Sp, scale, p_drop, seed_base, seed_off
                                    int(seed_offset), current_stream()), "pcm_attn_softmax_bwd")
 
 
+def flash_attn_fwd(Qh, Kh, Vh, B, nh, L, S, kpm, scale, p_drop, seed_base, seed_offset, out=None):
+    """Fused attention forward (pcm_flash_attn_fwd): head-split bf16 Q (B*nh*L, 64), K / V
+    (B*nh*S, 64) -> token-major bf16 O (L*B, nh*64) and the log2-domain log-sum-exp (B*nh, L)."""
+    require_cuda(Qh, Kh, Vh)
+    E = nh * 64
+    if out is None:
+        out = torch.empty((L * B, E), dtype=torch.bfloat16, device=Qh.device)
+    lse = torch.empty((B * nh, L), dtype=torch.float32, device=Qh.device)
+    t0 = TIMER.begin()
+    check(lib.pcm_flash_attn_fwd(B, nh, L, S, ptr(Qh), ptr(Kh), ptr(Vh), ptr(kpm), float(scale), float(p_drop),
+                                 ptr(seed_base), int(seed_offset), ptr(out), out.stride(0), ptr(lse), current_stream()),
+          "pcm_flash_attn_fwd")
+    Z = B * nh
+    TIMER.end(t0, "flash_attn_fwd", 4.0 * Z * L * S * 64, 2.0 * Z * (2 * L + 2 * S) * 64, (Z, L, S))
+    return out, lse
+
+
+def flash_attn_bwd(Qh, Kh, Vh, O_tok, dOh, lse, B, nh, L, S, kpm, scale, p_drop, seed_base, seed_offset, dQ, dK, dV):
+    """Fused attention backward (pcm_flash_attn_bwd); dQ / dK / dV are token-major bf16 destinations
+    (possibly column slices of a wider buffer: the row pitch is taken from their stride)."""
+    require_cuda(Qh, Kh, Vh, O_tok, dOh, lse, dQ, dK, dV)
+    Z = B * nh
+    delta = torch.empty((Z, L), dtype=torch.float32, device=Qh.device)
+    dq_acc = torch.empty((Z * L, 64), dtype=torch.float32, device=Qh.device)
+    assert dK.stride(0) == dV.stride(0)
+    t0 = TIMER.begin()
+    check(lib.pcm_flash_attn_bwd(B, nh, L, S, ptr(Qh), ptr(Kh), ptr(Vh), ptr(O_tok), O_tok.stride(0), ptr(dOh), ptr(lse),
+                                 ptr(kpm), float(scale), float(p_drop), ptr(seed_base), int(seed_offset), ptr(delta),
+                                 ptr(dq_acc), ptr(dQ), dQ.stride(0), ptr(dK), ptr(dV), dK.stride(0), current_stream()),
+          "pcm_flash_attn_bwd")
+    TIMER.end(t0, "flash_attn_bwd", 10.0 * Z * L * S * 64, 2.0 * Z * (4 * L + 4 * S) * 64 + 8.0 * Z * L * 64, (Z, L, S))
+
+
 def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
     """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step); hyper is a 9-float device tensor."""
     require_cuda(param, grad, exp_avg, exp_avg_sq, hyper, sumsq)
