@@ -278,6 +278,12 @@ int pcm_add_cast_bf16(long long rows, int C, const float *a, const float *b, int
  * ------------------------------------------------------------------------------------------ */
 int pcm_clip_adamw_step(long long n, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                         const float *hyper, double *sumsq, float *norm_out, pcm_stream_t stream);
+/* Same, and additionally writes bf16(param) to param_bf16 (n elements, 8-byte aligned; may be
+ * NULL): the operand copy the tensor-core GEMMs of the next step read, so no fp32 -> bf16 weight
+ * conversion kernels run inside the step. */
+int pcm_clip_adamw_step_bf16(long long n, float *param, float *grad, float *exp_avg,
+                             float *exp_avg_sq, const float *hyper, double *sumsq, float *norm_out,
+                             void *param_bf16, pcm_stream_t stream);
 
 #ifdef __cplusplus
 }

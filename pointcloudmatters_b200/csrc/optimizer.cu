@@ -8,7 +8,7 @@
 //   pass 2: p, m, v update with the clip coefficient computed ON DEVICE from that scalar and
 //           lr / beta1 / bias corrections read from a small device-resident `hyper` vector, so
 //           the step has no host synchronisation and can live inside a CUDA graph.
-// HBM-bound: 16 B read + 12 B written per parameter (+4 B read in pass 1): 128-bit accesses,
+// HBM-bound: 16 B read + 12 B (+2 B bf16 operand copy) written per parameter (+4 B read in pass 1): 128-bit accesses,
 // grid = a multiple of the SM count with a grid-stride loop.
 #include "common.cuh"
 
@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 // hyper = [lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, clip_norm, grad_scale]
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long n4, const float* __restrict__ hyper,
-                                                    const double* __restrict__ sumsq, float* __restrict__ norm_out) {
+                                                    const double* __restrict__ sumsq, float* __restrict__ norm_out,
+                                                    __nv_bfloat16* __restrict__ p_bf16) {
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
     const float bc1 = hyper[5], bc2 = hyper[6], clip = hyper[7], gscale = hyper[8];
     const float norm = (float)sqrt(*sumsq) * gscale;
@@ -60,6 +61,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
             P[k] = P[k] * decay - step * (M[k] / denom);             // p.mul_(1 - lr wd); p.addcdiv_(m, denom, -lr/bc1)
         }
         reinterpret_cast<float4*>(p)[i] = pp;
+        if (p_bf16 != nullptr) {  // bf16 operand copy read by the tensor-core GEMMs of the next step
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            reinterpret_cast<uint2*>(p_bf16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
         reinterpret_cast<float4*>(g)[i] = gg;
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
@@ -70,8 +75,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 
 // n must be a multiple of 4 and the buffers 16-byte aligned (FlatState pads every tensor to 4).
 // sumsq: one zero-initialised fp64 scratch scalar (re-zeroed by this call for the next step).
-PCM_API int pcm_clip_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
-                                const float* hyper, double* sumsq, float* norm_out, pcm_stream_t stream) {
+PCM_API int pcm_clip_adamw_step_bf16(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                     const float* hyper, double* sumsq, float* norm_out, void* param_bf16,
+                                     pcm_stream_t stream) {
     if (n <= 0) return PCM_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !sumsq) return PCM_EINVAL;
     if (n % 4) return PCM_EUNSUPPORTED;
@@ -84,6 +90,12 @@ PCM_API int pcm_clip_adamw_step(long long n, float* param, float* grad, float* e
     sumsq_kernel<<<grid, 256, 0, st>>>(grad, n4, sumsq);
     int r = pcm_launch_status();
     if (r) return r;
-    adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4, hyper, sumsq, norm_out);
+    adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4, hyper, sumsq, norm_out,
+                                       reinterpret_cast<__nv_bfloat16*>(param_bf16));
     return pcm_launch_status();
+}
+
+PCM_API int pcm_clip_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                const float* hyper, double* sumsq, float* norm_out, pcm_stream_t stream) {
+    return pcm_clip_adamw_step_bf16(n, param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, nullptr, stream);
 }

@@ -32,6 +32,47 @@ def _split_k_for(m_tiles, n_tiles, kblocks):
     return max(1, min(want, max(1, kblocks // 8)))
 
 
+class _Bf16Shadow:
+    """bf16 copy of the trainer's flat fp32 parameter buffer (trainer.FlatState.param_bf16), kept in
+    sync by the fused AdamW kernel: GEMM weight operands are views into it, so no per-use fp32 ->
+    bf16 conversion kernels run inside the step.  Outside a trainer (unit tests, inference on a
+    plain module) weights are converted on the fly -- same kernels, same numerics."""
+
+    def __init__(self):
+        self.base_ptr, self.nbytes, self.bf16 = 0, 0, None
+
+    def register(self, param_flat, bf16_flat):
+        self.base_ptr, self.nbytes, self.bf16 = param_flat.data_ptr(), param_flat.numel() * 4, bf16_flat
+
+    def clear(self):
+        self.base_ptr, self.nbytes, self.bf16 = 0, 0, None
+
+    def view(self, w):
+        if self.bf16 is not None and w.dtype == torch.float32 and w.is_contiguous():
+            off = w.data_ptr() - self.base_ptr
+            if 0 <= off < self.nbytes and w.device == self.bf16.device:
+                return self.bf16[off // 4: off // 4 + w.numel()].view(w.shape)
+        return w.to(torch.bfloat16)
+
+
+BF16_SHADOW = _Bf16Shadow()
+
+
+def _wb(w):
+    """bf16 operand form of an fp32 master weight."""
+    return BF16_SHADOW.view(w)
+
+
+def _grad_slot(p):
+    """The fp32 gradient buffer a parameter already owns (the trainer's flat-gradient view, or a
+    .grad left by an earlier backward): weight-gradient kernels accumulate straight into it and the
+    backward returns None for that input, so autograd launches no zero-fill / add kernels."""
+    g = getattr(p, "grad", None)
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape and g.device == p.device:
+        return g
+    return None
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T (+b) (ReLU) on the tcgen05 GEMM; backward dX = dY W and dW = dY^T X read dY, W, X in
     place through the MN-major operand forms of the same kernel (no transposes)."""
@@ -39,9 +80,10 @@ class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, weight, bias, relu, out_bf16):
         xb = x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16)
-        wb = weight.to(torch.bfloat16)
+        wb = _wb(weight)
         y = K.gemm_bf16(xb, wb, bias=bias, relu=relu, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
         ctx.relu, ctx.has_bias, ctx.x_dtype = relu, bias is not None, x2.dtype
+        ctx.params = (weight, bias)
         ctx.save_for_backward(xb, wb, y if relu else None)
         return y
 
@@ -58,12 +100,19 @@ class _LinearTC(torch.autograd.Function):
             dx = K.gemm_bf16(dyb, wb, b_mn=True)  # (M, N) x W(N, Kin) -> (M, Kin)
             if ctx.x_dtype == torch.bfloat16:
                 dx = dx.to(torch.bfloat16)
+        weight, bias = ctx.params
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((N, Kin), dtype=torch.float32, device=dyb.device)
+            slot = _grad_slot(weight)
+            dw = slot if slot is not None else torch.zeros((N, Kin), dtype=torch.float32, device=dyb.device)
             sk = _split_k_for((N + 127) // 128, (Kin + 127) // 128, (M + 63) // 64)
             K.gemm_bf16(dyb, xb, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=sk)
+            if slot is not None:
+                dw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dyb)
+            slot = _grad_slot(bias)
+            db = K.colsum(dyb, slot)
+            if slot is not None:
+                db = None
         return dx, dw, db, None, None
 
 
@@ -187,21 +236,42 @@ def _dw(dtok, xb, out):
                 split_k=_split_k_for((out.shape[0] + 127) // 128, (out.shape[1] + 255) // 256, (rows + 63) // 64))
 
 
+def _param_grads(ctx_params, E, dev):
+    """(dW_in, db_in, dWo, dbo) accumulation targets: the parameters' own gradient buffers when they
+    exist (trainer flat views), else fresh zero tensors that are returned to autograd."""
+    w_in, b_in, w_out, b_out = ctx_params
+    slots = [_grad_slot(w_in), _grad_slot(b_in), _grad_slot(w_out), _grad_slot(b_out)]
+    shapes = [(3 * E, E), (3 * E,), (E, E), (E,)]
+    bufs = [sl if sl is not None else torch.zeros(sh, dtype=torch.float32, device=dev) for sl, sh in zip(slots, shapes)]
+    rets = [None if sl is not None else bf_ for sl, bf_ in zip(slots, bufs)]
+    return bufs, rets
+
+
+def _pos_head_grad(d_full, head, L, B, E):
+    """Gradient of the learned leading rows of a positional tensor (the rest are constants)."""
+    n = head.shape[0]
+    g = d_full.view(L, B, E)[:n]
+    return g.sum(1, keepdim=True) if head.shape[1] != B else g.clone()
+
+
 class _MHASelf(torch.autograd.Function):
     """Self-attention block of nn.MultiheadAttention (q = k = x + pos, v = x; head_dim 64):
-    in-proj GEMMs write Q/K/V straight into (B, h, L, 64) (head-split epilogue), S = QK^T and
-    O = PV are batched tcgen05 GEMMs, O lands token-major (head-merge) for the out-proj GEMM.
-    Backward: the attention GEMMs write dQ|dK|dV side by side into ONE (rows, 3E) buffer, so
-    d(x + pos) is a single K = 2E GEMM and dW_in three in-place-layout GEMMs; nothing is permuted."""
+    in-proj GEMMs write Q/K/V straight into (B, h, L, 64) (head-split epilogue), the whole
+    score/softmax/dropout/value chain is ONE fused tcgen05 kernel, O lands token-major (head-merge)
+    for the out-proj GEMM.  Backward: the fused attention backward writes dQ|dK|dV side by side
+    into ONE (rows, 3E) buffer, so d(x + pos) is a single K = 2E GEMM and dW_in in-place-layout
+    GEMMs that accumulate straight into the parameters' gradient buffers; nothing is permuted.
+    `pos` is used as a constant; `pos_head` (n, B|1, E), if given, is the learned tensor whose
+    values are the first n rows of `pos` and receives their gradient."""
 
     @staticmethod
-    def forward(ctx, x, pos, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+    def forward(ctx, x, pos, pos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
         L, B, E = x.shape
         dev = x.device
         bf = torch.bfloat16
         xqk_b = _tok_bf16(x, pos, L, B, E)
         xv_b = _tok_bf16(x, None, L, B, E) if pos is not None else xqk_b
-        wb, wo_b = w_in.to(bf), w_out.to(bf)
+        wb, wo_b = _wb(w_in), _wb(w_out)
         Z = B * nh
         Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         Kh = torch.empty((Z * L, 64), dtype=bf, device=dev)
@@ -211,54 +281,62 @@ class _MHASelf(torch.autograd.Function):
                       bias=b_in[j * E:(j + 1) * E])
         O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, L, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
-        ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok)
+        ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok, pos_head)
         ctx.aux, ctx.dims = aux, (L, B, E, nh, p_drop, pos is not None, None if pos is None else tuple(pos.shape))
+        ctx.params = (w_in, b_in, w_out, b_out)
         return out.view(L, B, E)
 
     @staticmethod
     def backward(ctx, dout):
-        xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok = ctx.saved_tensors
+        xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok, pos_head = ctx.saved_tensors
         L, B, E, nh, p_drop, has_pos, pos_shape = ctx.dims
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
+        (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
         dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
-        dWo = torch.zeros((E, E), dtype=torch.float32, device=dev)
         _dw(dout_b, O_tok, dWo)
-        dbo = K.colsum(dout_b)
+        K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         buf = torch.empty((L * B, 3 * E), dtype=bf, device=dev)  # [dQ | dK | dV], token-major
         _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, L, B, nh, ctx.aux, p_drop, buf[:, :E], buf[:, E:2 * E],
                        buf[:, 2 * E:])
-        dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
         _dw(buf[:, :2 * E], xqk_b, dW_in[:2 * E])
         _dw(buf[:, 2 * E:], xv_b, dW_in[2 * E:])
-        db_in = K.colsum(buf)
-        dpos = None
-        if has_pos:
+        K.colsum(buf, db_in)
+        dpos = dhead = None
+        need_pos = has_pos and ctx.needs_input_grad[1]
+        need_head = pos_head is not None and ctx.needs_input_grad[2]
+        if need_pos:
             d_qk = K.gemm_bf16(buf[:, :2 * E], wb[:2 * E], b_mn=True)          # d(x + pos), K = 2E
-            dx = d_qk + K.gemm_bf16(buf[:, 2 * E:], wb[2 * E:], b_mn=True)
-            if ctx.needs_input_grad[1]:
-                dpos = d_qk.view(L, B, E)
-                if pos_shape[1] != B:
-                    dpos = dpos.sum(1, keepdim=True)
+            dx = K.gemm_bf16(buf[:, 2 * E:], wb[2 * E:], b_mn=True)
+            if need_head:
+                dhead = _pos_head_grad(d_qk, pos_head, L, B, E)
+            dx += d_qk
+            dpos = d_qk.view(L, B, E)
+            if pos_shape[1] != B:
+                dpos = dpos.sum(1, keepdim=True)
         else:
             dx = K.gemm_bf16(buf, wb, b_mn=True)                                # single K = 3E GEMM
-        return dx.view(L, B, E), dpos, dW_in, db_in, dWo, dbo, None, None, None
+            if need_head:  # d(x + pos) restricted to the learned leading rows: a tiny GEMM
+                n = pos_head.shape[0]
+                dhead = _pos_head_grad(K.gemm_bf16(buf[: n * B, :2 * E], wb[:2 * E], b_mn=True), pos_head, n, B, E)
+        return (dx.view(L, B, E), dpos, dhead, *rets, None, None, None)
 
 
 class _MHACross(torch.autograd.Function):
-    """Cross-attention block (q = x + qpos, k = mem + mpos, v = mem; head_dim 64), same machinery."""
+    """Cross-attention block (q = x + qpos, k = mem + mpos, v = mem; head_dim 64), same machinery;
+    `mpos_head`: learned leading rows of the constant `mpos` (see _MHASelf)."""
 
     @staticmethod
-    def forward(ctx, x, qpos, mem, mpos, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+    def forward(ctx, x, qpos, mem, mpos, mpos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
         L, B, E = x.shape
         S = mem.shape[0]
         dev, bf = x.device, torch.bfloat16
         xq_b = _tok_bf16(x, qpos, L, B, E)
         xk_b = _tok_bf16(mem, mpos, S, B, E)
         xv_b = _tok_bf16(mem, None, S, B, E) if mpos is not None else xk_b
-        wb, wo_b = w_in.to(bf), w_out.to(bf)
+        wb, wo_b = _wb(w_in), _wb(w_out)
         Z = B * nh
         Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         Kh = torch.empty((Z * S, 64), dtype=bf, device=dev)
@@ -270,66 +348,81 @@ class _MHACross(torch.autograd.Function):
                   bias=b_in[2 * E:])
         O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
-        ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok)
+        ctx.save_for_backward(xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok, mpos_head)
         ctx.aux = aux
         ctx.dims = (L, S, B, E, nh, p_drop, None if qpos is None else tuple(qpos.shape), None if mpos is None else tuple(mpos.shape))
+        ctx.params = (w_in, b_in, w_out, b_out)
         return out.view(L, B, E)
 
     @staticmethod
     def backward(ctx, dout):
-        xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok = ctx.saved_tensors
+        xq_b, xk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok, mpos_head = ctx.saved_tensors
         L, S, B, E, nh, p_drop, qpos_shape, mpos_shape = ctx.dims
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
+        (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
         dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
-        dWo = torch.zeros((E, E), dtype=torch.float32, device=dev)
         _dw(dout_b, O_tok, dWo)
-        dbo = K.colsum(dout_b)
+        K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
         kv = torch.empty((S * B, 2 * E), dtype=bf, device=dev)  # [dK | dV]
         _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, S, B, nh, ctx.aux, p_drop, dQ_tok, kv[:, :E], kv[:, E:])
-        dW_in = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
         _dw(dQ_tok, xq_b, dW_in[:E])
         _dw(kv[:, :E], xk_b, dW_in[E:2 * E])
         _dw(kv[:, E:], xv_b, dW_in[2 * E:])
-        db_in = torch.zeros(3 * E, dtype=torch.float32, device=dev)
         K.colsum(dQ_tok, db_in[:E])
         K.colsum(kv, db_in[E:])
         dx = K.gemm_bf16(dQ_tok, wb[:E], b_mn=True)
         dqpos = None
         if qpos_shape is not None and ctx.needs_input_grad[1]:
             dqpos = dx.view(L, B, E) if qpos_shape[1] == B else dx.view(L, B, E).sum(1, keepdim=True)
-        dmem = dmpos = None
-        if mpos_shape is not None:
+        dmem = dmpos = dhead = None
+        need_mpos = mpos_shape is not None and ctx.needs_input_grad[3]
+        need_head = mpos_head is not None and ctx.needs_input_grad[4]
+        if need_mpos:
             d_k = K.gemm_bf16(kv[:, :E], wb[E:2 * E], b_mn=True)
+            if need_head:
+                dhead = _pos_head_grad(d_k, mpos_head, S, B, E)
             if ctx.needs_input_grad[2]:
                 dmem = (d_k + K.gemm_bf16(kv[:, E:], wb[2 * E:], b_mn=True)).view(S, B, E)
-            if ctx.needs_input_grad[3]:
-                dmpos = d_k.view(S, B, E) if mpos_shape[1] == B else d_k.view(S, B, E).sum(1, keepdim=True)
-        elif ctx.needs_input_grad[2]:
-            dmem = K.gemm_bf16(kv, wb[E:], b_mn=True).view(S, B, E)              # single K = 2E GEMM
-        return dx.view(L, B, E), dqpos, dmem, dmpos, dW_in, db_in, dWo, dbo, None, None, None
+            dmpos = d_k.view(S, B, E) if mpos_shape[1] == B else d_k.view(S, B, E).sum(1, keepdim=True)
+        else:
+            if ctx.needs_input_grad[2]:
+                dmem = K.gemm_bf16(kv, wb[E:], b_mn=True).view(S, B, E)          # single K = 2E GEMM
+            if need_head:  # d(mem + mpos) restricted to the learned leading rows: a tiny GEMM
+                n = mpos_head.shape[0]
+                d_k = K.gemm_bf16(kv[: n * B, :E], wb[E:2 * E], b_mn=True)
+                dhead = _pos_head_grad(d_k, mpos_head, n, B, E)
+        return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None)
 
 
-def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=None, training=False):
+def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=None, training=False, pos_head=None,
+                         mem_pos_head=None):
     """nn.MultiheadAttention semantics of the reference's call sites (seq-first (L, B, E) tensors;
     only the attended output is returned -- the reference discards the averaged weights it asks
     for, transformer.py:246-248):
         self-attention :  q = k = x + pos,          v = x      (mem is None)
         cross-attention:  q = x + pos, k = mem + mem_pos, v = mem
-    """
+    `pos_head` / `mem_pos_head` (n, B, E): when the positional tensor is [learned rows ; constant
+    rows] (Transformer.forward concatenates additional_pos_embed with the sine embedding), pass the
+    detached concatenation as `pos` / `mem_pos` and the learned rows here: only their gradient is
+    formed instead of a full (S, B, E) tensor per layer."""
     L, B, E = x.shape
     h = mha.num_heads
     d = E // h
     p = mha.dropout if training else 0.0
     if d == 64 and E % 128 == 0:
         if mem is None:
-            return _MHASelf.apply(x, pos, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias,
-                                  h, key_padding_mask, p)
-        return _MHACross.apply(x, pos, mem, mem_pos, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
-                               mha.out_proj.bias, h, key_padding_mask, p)
+            return _MHASelf.apply(x, pos, pos_head, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
+                                  mha.out_proj.bias, h, key_padding_mask, p)
+        return _MHACross.apply(x, pos, mem, mem_pos, mem_pos_head, mha.in_proj_weight, mha.in_proj_bias,
+                               mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p)
+    if pos_head is not None:  # restore the differentiable concatenation for the composed path
+        pos = torch.cat([pos_head.expand(-1, B, -1), pos[pos_head.shape[0]:]], dim=0)
+    if mem_pos_head is not None:
+        mem_pos = torch.cat([mem_pos_head.expand(-1, B, -1), mem_pos[mem_pos_head.shape[0]:]], dim=0)
     # head sizes other than 64 (test fixtures only): composed from the same linear() + library bmm
     query = x if pos is None else x + pos
     if mem is None:
@@ -363,6 +456,7 @@ class _AddDropoutLN(torch.autograd.Function):
         y, _, h, mean, rstd = K.add_dropout_ln_fwd(x2, res2, gamma, beta, eps, p_drop, seed_base, seed)
         ctx.save_for_backward(h, mean, rstd, gamma)
         ctx.cfg = (p_drop, seed_base, seed, x is not None, shape)
+        ctx.params = (gamma, beta)
         return y.view(shape)
 
     @staticmethod
@@ -372,8 +466,11 @@ class _AddDropoutLN(torch.autograd.Function):
         dy2 = dy.reshape(h.shape)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dres, dx, dgamma, dbeta = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x)
-        return (dx.view(shape) if has_x else None), dres.view(shape), dgamma, dbeta, None, None
+        g_slot, b_slot = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
+        dres, dx, dgamma, dbeta = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
+                                                       dgamma=g_slot, dbeta=b_slot)
+        return ((dx.view(shape) if has_x else None), dres.view(shape), None if g_slot is not None else dgamma,
+                None if b_slot is not None else dbeta, None, None)
 
 
 def add_dropout_layernorm(x, residual, norm, p, training):
@@ -488,11 +585,11 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
                                  knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training)
 
 
-def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):
     """Fused clip-by-global-norm + AdamW over flat fp32 buffers, in place (csrc/optimizer.cu).
     `hyper` = device tensor [lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2, clip_norm, grad_scale]."""
     _need_cuda(param)
-    K.clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out)
+    K.clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16)
     return norm_out
 
 

@@ -145,11 +145,13 @@ def flash_attn_bwd(Qh, Kh, Vh, O_tok, dOh, lse, B, nh, L, S, kpm, scale, p_drop,
     TIMER.end(t0, "flash_attn_bwd", 10.0 * Z * L * S * 64, 2.0 * Z * (4 * L + 4 * S) * 64 + 8.0 * Z * L * 64, (Z, L, S))
 
 
-def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out):
-    """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step); hyper is a 9-float device tensor."""
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):
+    """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step_bf16); hyper is a 9-float device
+    tensor; `param_bf16` (optional) receives the bf16 copy of the updated parameters."""
     require_cuda(param, grad, exp_avg, exp_avg_sq, hyper, sumsq)
-    check(lib.pcm_clip_adamw_step(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
-                                  ptr(sumsq), ptr(norm_out), current_stream()), "pcm_clip_adamw_step")
+    check(lib.pcm_clip_adamw_step_bf16(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
+                                       ptr(sumsq), ptr(norm_out), ptr(param_bf16), current_stream()),
+          "pcm_clip_adamw_step_bf16")
 
 
 def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, want_bf16=False):
@@ -165,12 +167,15 @@ def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset,
     return y, yb, h, mean, rstd
 
 
-def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx):
+def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None):
+    """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics)."""
     rows, C = h.shape
     dres = torch.empty_like(h)
     dx = (torch.empty_like(h) if p_drop > 0 else dres) if need_dx else None
-    dgamma = torch.zeros(C, dtype=torch.float32, device=h.device)
-    dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
+    if dgamma is None:
+        dgamma = torch.zeros(C, dtype=torch.float32, device=h.device)
+    if dbeta is None:
+        dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
     check(lib.pcm_add_dropout_ln_bwd(rows, C, ptr(dy), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
                                      ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
                                      current_stream()), "pcm_add_dropout_ln_bwd")

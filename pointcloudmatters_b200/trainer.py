@@ -69,6 +69,8 @@ class FlatState:
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(self.n_active, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n_active, dtype=torch.float32, device=dev)
+        # bf16 operand copy of the parameters (kept current by the fused AdamW kernel)
+        self.param_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         off = 0
         for p in ordered:
             n = p.numel()
@@ -79,6 +81,16 @@ class FlatState:
             if old is not None:
                 p.grad.copy_(old)
             off += pad4(n)
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        """Refresh the bf16 operand copy from the fp32 masters (after construction or after weights
+        were changed behind the optimizer's back, e.g. load_state_dict) and publish it to the ops."""
+        from . import functional as PF
+
+        self.param_bf16.copy_(self.param)
+        if self.param.is_cuda:
+            PF.BF16_SHADOW.register(self.param, self.param_bf16)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -132,7 +144,7 @@ class BCTrainer:
         self._hyper_host.copy_(torch.tensor(self.hyper_values(self.step_num), dtype=torch.float32))
         self._hyper.copy_(self._hyper_host, non_blocking=True)
         PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq, self._hyper,
-                           self._sumsq, self._norm)
+                           self._sumsq, self._norm, f.param_bf16[: f.n_active])
         self.last_grad_norm = self._norm
         self.step_num += 1
 

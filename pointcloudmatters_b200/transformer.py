@@ -41,15 +41,18 @@ class TransformerEncoderLayer(nn.Module):
         return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
 
     def forward(self, src, src_mask: Optional[Tensor] = None, src_key_padding_mask: Optional[Tensor] = None,
-                pos: Optional[Tensor] = None):
+                pos: Optional[Tensor] = None, pos_head: Optional[Tensor] = None):
+        """`pos_head` (extension, see functional.multi_head_attention): learned leading rows of a
+        detached `pos`."""
         assert src_mask is None, "attn_mask is never used by the reference ACT path"
         tr = self.training
         if self.normalize_before:
             s2 = PF.add_dropout_layernorm(None, src, self.norm1, 0.0, False)
-            src = src + PF.dropout(PF.multi_head_attention(self.self_attn, s2, pos, None, None, src_key_padding_mask, tr), self.p, tr)
+            src = src + PF.dropout(PF.multi_head_attention(self.self_attn, s2, pos, None, None, src_key_padding_mask, tr,
+                                                           pos_head=pos_head), self.p, tr)
             s2 = PF.add_dropout_layernorm(None, src, self.norm2, 0.0, False)
             return src + PF.dropout(self._ffn(s2), self.p, tr)
-        a = PF.multi_head_attention(self.self_attn, src, pos, None, None, src_key_padding_mask, tr)
+        a = PF.multi_head_attention(self.self_attn, src, pos, None, None, src_key_padding_mask, tr, pos_head=pos_head)
         src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr)
         return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr)
 
@@ -65,10 +68,10 @@ class TransformerEncoder(nn.Module):
         self.num_layers = num_layers
         self.norm = nn.LayerNorm(d_model) if normalize_before else None
 
-    def forward(self, src, mask=None, src_key_padding_mask=None, pos=None):
+    def forward(self, src, mask=None, src_key_padding_mask=None, pos=None, pos_head=None):
         out = src
         for layer in self.layers:
-            out = layer(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+            out = layer(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos, pos_head=pos_head)
         if self.norm is not None:
             out = PF.add_dropout_layernorm(None, out, self.norm, 0.0, False)
         return out
@@ -99,7 +102,7 @@ class TransformerDecoderLayer(nn.Module):
         return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
-                memory_key_padding_mask=None, pos=None, query_pos=None):
+                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):
         assert tgt_mask is None and memory_mask is None and tgt_key_padding_mask is None
         tr = self.training
         if self.normalize_before:
@@ -108,12 +111,13 @@ class TransformerDecoderLayer(nn.Module):
             tgt = tgt + PF.dropout(PF.multi_head_attention(self.self_attn, t2, query_pos, None, None, None, tr), self.p, tr)
             t2 = ln(tgt, self.norm2)
             tgt = tgt + PF.dropout(PF.multi_head_attention(self.multihead_attn, t2, query_pos, memory, pos,
-                                                           memory_key_padding_mask, tr), self.p, tr)
+                                                           memory_key_padding_mask, tr, mem_pos_head=pos_head), self.p, tr)
             t2 = ln(tgt, self.norm3)
             return tgt + PF.dropout(self._ffn(t2), self.p, tr)
         a = PF.multi_head_attention(self.self_attn, tgt, query_pos, None, None, None, tr)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr)
-        a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr)
+        a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr,
+                                    mem_pos_head=pos_head)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr)
         return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr)
 
@@ -133,11 +137,12 @@ class TransformerDecoder(nn.Module):
         self.skip_dead_layers = False
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
-                memory_key_padding_mask=None, pos=None, query_pos=None):
+                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):
         out, inter = tgt, []
         ln = (lambda x: PF.add_dropout_layernorm(None, x, self.norm, 0.0, False))
         for li, layer in enumerate(self.layers):
-            out = layer(out, memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos)
+            out = layer(out, memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos,
+                        pos_head=pos_head)
             if self.return_intermediate:
                 inter.append(ln(out))
                 if self.skip_dead_layers and li == 0:
@@ -180,14 +185,22 @@ class Transformer(nn.Module):
         if pos_embed.shape[1] == 1:
             pos_embed = pos_embed.repeat(1, bs, 1)
         query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
-        additional_pos_embed = additional_pos_embed.unsqueeze(1).repeat(1, bs, 1)
-        pos_embed = torch.cat([additional_pos_embed, pos_embed], dim=0)
+        # [learned rows ; sine embedding]: when the sine part is a constant (it always is on the
+        # reference path: a function of the input coordinates) only the learned rows need a
+        # gradient -- hand them over separately instead of differentiating through the concatenation
+        pos_head = None
+        if pos_embed.requires_grad or not additional_pos_embed.requires_grad:
+            pos_embed = torch.cat([additional_pos_embed.unsqueeze(1).repeat(1, bs, 1), pos_embed], dim=0)
+        else:
+            pos_head = additional_pos_embed.unsqueeze(1)  # (n_add, 1, E), broadcast over the batch
+            pos_embed = torch.cat([additional_pos_embed.detach().unsqueeze(1).repeat(1, bs, 1), pos_embed], dim=0)
         if latent_input.dim() == 2:
             addition_input = torch.stack([latent_input, proprio_input], dim=0)
         else:
             addition_input = torch.cat([latent_input, proprio_input], dim=0)
         src = torch.cat([addition_input, src], dim=0)
         tgt = torch.zeros_like(query_embed)
-        memory = self.encoder(src, src_key_padding_mask=mask, pos=pos_embed)
-        hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed)
+        memory = self.encoder(src, src_key_padding_mask=mask, pos=pos_embed, pos_head=pos_head)
+        hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed,
+                          pos_head=pos_head)
         return hs.transpose(1, 2)

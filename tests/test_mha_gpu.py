@@ -94,3 +94,46 @@ def test_mha_dropout_is_consistent():
     assert _rel(out.detach(), o.detach()) <= 1.5e-2
     o.backward(dout)
     assert _rel(gx, x2.grad) <= 4e-2
+
+
+def test_weight_grads_accumulate_in_place_into_existing_buffers():
+    """Second backward with populated .grad buffers takes the direct-accumulation path (kernels add
+    into the parameters' own gradient memory, autograd receives None): gradients exactly double up
+    to fp32 atomics ordering, and the buffers are not re-allocated.  Also covers the learned
+    positional head (gradient only for the leading rows of a detached positional tensor)."""
+    from pointcloudmatters_b200 import functional as PF
+
+    E, nh, L, S, B = 128, 2, 70, 133, 3
+    mha = _mk(E, nh)
+    ln = torch.nn.LayerNorm(E).cuda()
+    lin = torch.nn.Linear(E, 64).cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(L, B, E, device="cuda", generator=g).bfloat16().float()
+    mem = torch.randn(S, B, E, device="cuda", generator=g).bfloat16().float()
+    head = torch.nn.Parameter(torch.randn(2, 1, E, device="cuda", generator=g).bfloat16().float())
+    sine = torch.randn(S - 2, B, E, device="cuda", generator=g).bfloat16().float()
+    params = list(mha.parameters()) + list(ln.parameters()) + list(lin.parameters()) + [head]
+
+    def run(use_head):
+        if use_head:
+            mpos = torch.cat([head.detach().repeat(1, B, 1), sine], 0)
+            a = PF.multi_head_attention(mha, x, None, mem, mpos, None, training=False, mem_pos_head=head)
+        else:
+            mpos = torch.cat([head.repeat(1, B, 1), sine], 0)
+            a = PF.multi_head_attention(mha, x, None, mem, mpos, None, training=False)
+        y = PF.add_dropout_layernorm(a, x, ln, 0.0, False)
+        return PF.linear(y, lin.weight, lin.bias).square().mean()
+
+    run(False).backward()
+    ref = [p.grad.clone() for p in params]
+    ptrs = [p.grad.data_ptr() for p in params]
+    for p in params:
+        p.grad = None
+    run(True).backward()
+    for p, r in zip(params, ref):
+        assert _rel(p.grad, r) <= 1e-3, _rel(p.grad, r)
+    ptrs = [p.grad.data_ptr() for p in params]
+    run(True).backward()  # accumulates in place
+    for p, r, q in zip(params, ref, ptrs):
+        assert p.grad.data_ptr() == q
+        assert _rel(p.grad, 2 * r) <= 1e-3, _rel(p.grad, 2 * r)

@@ -1,5 +1,5 @@
 """Tiny ncu target: a few launches of one kernel family at a BASELINE cfg-2 shape.
-usage: python tools/ncu_target.py gemm|gemm_bf16out|fps|knn|sa"""
+usage: python tools/ncu_target.py gemm|gemm_bf16out|fps|knn|sa|flash"""
 import sys
 from pathlib import Path
 
@@ -9,6 +9,20 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
 if which == "attn_s":
     pass
+elif which == "flash":
+    from pointcloudmatters_b200 import kernels as K
+
+    B, nh, L, S = 64, 8, 515, 515
+    Z, E = B * nh, nh * 64
+    q = torch.randn(Z * L, 64, device="cuda").bfloat16()
+    k = torch.randn(Z * S, 64, device="cuda").bfloat16()
+    v = torch.randn(Z * S, 64, device="cuda").bfloat16()
+    do = torch.randn(Z * L, 64, device="cuda").bfloat16()
+    sb = torch.tensor([1234567], dtype=torch.int64, device="cuda")
+    buf = torch.empty(L * B, 3 * E, dtype=torch.bfloat16, device="cuda")
+    for _ in range(2):
+        O, lse = K.flash_attn_fwd(q, k, v, B, nh, L, S, None, 0.125, 0.1, sb, 77)
+        K.flash_attn_bwd(q, k, v, O, do, lse, B, nh, L, S, None, 0.125, 0.1, sb, 77, buf[:, :E], buf[:, E:2 * E], buf[:, 2 * E:])
 elif which.startswith("gemm"):
     from pointcloudmatters_b200.kernels import gemm_bf16
 
