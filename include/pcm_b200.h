@@ -213,6 +213,10 @@ int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void *Q, const void *K
                        float *delta, float *dQacc, void *dQ, int ldq, void *dK, void *dV, int ldkv,
                        pcm_stream_t stream);
 
+/* Debug aid: the first n_ctas CTAs of subsequent pcm_flash_attn_* launches write 64 clock64()
+ * stamps each (role phase boundaries) to buf (device, n_ctas * 64 int64); NULL = off. */
+int pcm_flash_attn_debug_trace(long long *buf, int n_ctas);
+
 /* ------------------------------------------------------------------------------------------
  * Fused set-abstraction head.  Replaces, for ACTPCD.pcd_sampling (src/models/components/act/
  * act.py:446-460) and PCDObsEncoder.pcd_sampling (.../vision/pcd_obs_encoder.py:179-193), the

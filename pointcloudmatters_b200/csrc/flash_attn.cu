@@ -32,6 +32,8 @@ namespace {
 
 using namespace pcm_tc;
 
+#define MBWAIT(bar, parity) mbar_wait_backoff(bar, parity, 32)
+
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // one [128 rows x 64] bf16 operand tile = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int MAX_KEYS = 8192;
@@ -54,7 +56,15 @@ struct FlashParams {
     __nv_bfloat16* dK;
     __nv_bfloat16* dV;
     int ldkv;
+    long long* trace;  // debug: 64 clock64() stamps per CTA for the first trace_ctas CTAs (NULL = off)
+    int trace_ctas;
 };
+
+#define TRACE(slot)                                                                                    \
+    do {                                                                                               \
+        if (p.trace != nullptr && (int)blockIdx.x < p.trace_ctas && (slot) < 64)                       \
+            p.trace[(size_t)blockIdx.x * 64 + (slot)] = clock64();                                     \
+    } while (0)
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -69,6 +79,17 @@ __device__ __forceinline__ uint32_t sw128_off(int blk, int row, int piece) {
 
 __device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+
+// Warp-private 4 KB staging tile (32 rows x 128 B, 16-byte pieces XOR-swizzled by row): a thread
+// that owns one accumulator row parks it here, and the warp reads it back with lanes running
+// along the row, so that every global store / reduction instruction touches 4 complete 128-byte
+// lines instead of 32 different ones.
+__device__ __forceinline__ void stage_put(uint8_t* stage, int lane, int piece, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((piece ^ (lane & 7)) << 4)) = make_uint4(a, b, c, d);
+}
+__device__ __forceinline__ uint4 stage_get(const uint8_t* stage, int rl, int piece) {
+    return *reinterpret_cast<const uint4*>(stage + rl * 128 + ((piece ^ (rl & 7)) << 4));
 }
 
 // valid-key bit mask of the CTA's key range: word w covers keys key0 + 32 w .. + 31
@@ -89,6 +110,7 @@ constexpr int FWD_THREADS = 192;
 constexpr uint32_t FWD_SMEM_TILES = 6 * TILE_BYTES;  // Q, K0, K1, V, P (2 blocks)
 constexpr uint32_t FWD_SMEM = FWD_SMEM_TILES + 256 + MAX_KEYS / 8 + 1024;
 
+template <bool DROPOUT>
 __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_constant__ CUtensorMap tq,
                                                                     const __grid_constant__ CUtensorMap tk,
                                                                     const __grid_constant__ CUtensorMap tv,
@@ -118,6 +140,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
     const int b = z / p.nh, h = z - b * p.nh;
     const int n_kv = (p.S + 127) >> 7;
 
+    if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv);
         mbar_init(q_full, 1);
@@ -133,92 +156,126 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S = 0, TM_PV = 128;
+    if (threadIdx.x == 0) TRACE(1);
 
     if (warp == 0) {
-        if (lane == 0) {
+        // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
+        if (elect_one_sync()) {
             mbar_expect_tx(q_full, TILE_BYTES);
             tma_load_3d(sQ, &tq, q_full, 0, q0, z);
-            for (int j = 0; j < n_kv; ++j) {
-                const int st = j & 1;
-                mbar_wait(&k_empty[st], (((uint32_t)j >> 1) & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+            const int st = j & 1;
+            MBWAIT(&k_empty[st], (((uint32_t)j >> 1) & 1) ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&k_full[st], TILE_BYTES);
                 tma_load_3d(sK + st * TILE_BYTES, &tk, &k_full[st], 0, j << 7, z);
-                mbar_wait(v_empty, ((uint32_t)j & 1) ^ 1);
+            }
+            __syncwarp();
+            MBWAIT(v_empty, ((uint32_t)j & 1) ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(v_full, TILE_BYTES);
                 tma_load_3d(sV, &tv, v_full, 0, j << 7, z);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-            auto issue_s = [&](int j) {
-                const int st = j & 1;
-                const int nkv16 = (min(128, p.S - (j << 7)) + 15) & ~15;
-                mbar_wait(&k_full[st], ((uint32_t)j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t idesc = make_idesc_bf16(128, nkv16, false, false);
+        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+        auto issue_s = [&](int j) {
+            const int st = j & 1;
+            const int nkv16 = (min(128, p.S - (j << 7)) + 15) & ~15;
+            MBWAIT(&k_full[st], ((uint32_t)j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_bf16(128, nkv16, false, false);
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tmem_base + TM_S, make_smem_desc(aQ + k * 32, 16, 1024),
                              make_smem_desc(aK + st * TILE_BYTES + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
                 umma_commit(s_full);
                 umma_commit(&k_empty[st]);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(p_full, (uint32_t)j & 1);  // P_j in smem; S_j and PV_{j-1} have been read out of TMEM
-                tc_fence_after();
-                if (j + 1 < n_kv) issue_s(j + 1);
-                mbar_wait(v_full, (uint32_t)j & 1);
-                tc_fence_after();
-                const int ksteps = ((min(128, p.S - (j << 7)) + 15) & ~15) >> 4;
+                TRACE(8 + 2 * j);
+            }
+            __syncwarp();
+        };
+        MBWAIT(q_full, 0);
+        issue_s(0);
+        const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+        for (int j = 0; j < n_kv; ++j) {
+            MBWAIT(p_full, (uint32_t)j & 1);  // P_j in smem; S_j and PV_{j-1} have been read out of TMEM
+            tc_fence_after();
+            if (j + 1 < n_kv) issue_s(j + 1);
+            MBWAIT(v_full, (uint32_t)j & 1);
+            tc_fence_after();
+            const int ksteps = ((min(128, p.S - (j << 7)) + 15) & ~15) >> 4;
+            if (elect_one_sync()) {
                 for (int ks = 0; ks < ksteps; ++ks)
                     umma_f16(tmem_base + TM_PV, make_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                              make_smem_desc(aV + ks * 2048, 16384, 1024), idesc_pv, ks != 0 ? 1u : 0u);
                 umma_commit(pv_full);
                 umma_commit(v_empty);
+                TRACE(9 + 2 * j);
             }
+            __syncwarp();
         }
     } else {
         // ===== softmax warps: thread = query row =====
+        // Straight-line, branch-free inner code (dropout is a template parameter; the key mask
+        // costs a warp-uniform test per 32-column chunk) staged over whole chunks so that the 32
+        // exp2 / 16 hash chains of a chunk are independent instruction streams; the hashes are
+        // computed while the chunk's tcgen05.ld is in flight.
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int l = q0 + row;
         const bool warp_active = q0 + quad * 32 < p.L;  // warp-uniform
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const unsigned long long seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
-        const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
-        const uint32_t thr16 = p.thr16;
+        const float sl2 = p.scale_log2;
+        const uint32_t thr_hi = p.thr16 << 16;
+        uint32_t rseed = 0;
+        if (DROPOUT) {
+            const unsigned long long seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
+            rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
+        }
         float o[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) o[e] = 0.f;
-        float m = -INFINITY, lsum = 0.f;
+        float m = -INFINITY;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t v[32];
+        const bool tr = warp == 2 && lane == 0;
         for (int j = 0; j < n_kv; ++j) {
             const int nkv = min(128, p.S - (j << 7));
-            mbar_wait(s_full, (uint32_t)j & 1);
+            MBWAIT(s_full, (uint32_t)j & 1);
             tc_fence_after();
+            if (tr) TRACE(24 + 5 * j);
             float alpha = 1.f, m_use = 0.f, m_new = m;
             if (warp_active) {
-                float mx = -INFINITY;
+                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     if (c * 32 >= nkv) break;
                     tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                    tmem_ld_wait(v);
                     const uint32_t bits = kbits[j * 4 + c];
+                    tmem_ld_wait(v);
+                    if (bits == 0xFFFFFFFFu) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        mx = fmaxf(mx, ((bits >> e) & 1u) ? __uint_as_float(v[e]) * p.scale_log2 : -INFINITY);
+                        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(v[e]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            mx[e & 3] = fmaxf(mx[e & 3], ((bits >> e) & 1u) ? __uint_as_float(v[e]) : -INFINITY);
+                    }
                 }
-                m_new = fmaxf(m, mx);
+                // the scale is positive: max(scale * s) = scale * max(s)
+                m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
                 m_use = m_new == -INFINITY ? 0.f : m_new;
                 alpha = fast_exp2(m - m_use);
             }
+            if (tr) TRACE(25 + 5 * j);
             if (j > 0) {
-                mbar_wait(pv_full, ((uint32_t)j - 1) & 1);
+                MBWAIT(pv_full, ((uint32_t)j - 1) & 1);
                 tc_fence_after();
                 if (warp_active) {
 #pragma unroll
@@ -226,47 +283,62 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                         tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
                         tmem_ld_wait(v);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                        for (int e = 0; e < 32; ++e) o[c * 32 + e] = (o[c * 32 + e] + __uint_as_float(v[e])) * alpha;
                     }
                 }
             }
+            if (tr) TRACE(26 + 5 * j);
             if (warp_active) {
 #pragma unroll
-                for (int e = 0; e < 64; ++e) o[e] *= alpha;
-                lsum *= alpha;
+                for (int q = 0; q < 4; ++q) ls[q] *= alpha;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     if (c * 32 >= nkv) break;
                     tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                    tmem_ld_wait(v);
                     const uint32_t bits = kbits[j * 4 + c];
-                    const uint32_t pair0 = (uint32_t)((j << 7) + c * 32) >> 1;
-                    uint32_t pk[16];
+                    uint32_t hb[4];
+                    if (DROPOUT) {
+                        const uint32_t grp0 = (uint32_t)((j << 7) + c * 32) >> 3;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float p0 = ((bits >> e) & 1u) ? fast_exp2(__uint_as_float(v[e]) * p.scale_log2 - m_use) : 0.f;
-                        float p1 = ((bits >> (e + 1)) & 1u) ? fast_exp2(__uint_as_float(v[e + 1]) * p.scale_log2 - m_use) : 0.f;
-                        lsum += p0 + p1;
-                        if (thr16 != 0) {
-                            const uint32_t hb = pcm_pair_bits(rseed, pair0 + (e >> 1));
-                            p0 = (hb & 0xFFFFu) >= thr16 ? p0 : 0.f;
-                            p1 = (hb >> 16) >= thr16 ? p1 : 0.f;
+                        for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
+                    }
+                    tmem_ld_wait(v);
+                    float pr[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_use));
+                    if (bits != 0xFFFFFFFFu) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) ls[e & 3] += pr[e];
+                    if (DROPOUT) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t x = hb[q];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                pr[8 * q + k] = x >= thr_hi ? pr[8 * q + k] : 0.f;
+                                x = pcm_lcg_next(x);
+                            }
                         }
-                        pk[e >> 1] = pack_bf16(p0, p1);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        st_shared_v4(sP + sw128_off(c >> 1, row, (c & 1) * 4 + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2],
-                                     pk[4 * i + 3]);
+                        st_shared_v4(sP + sw128_off(c >> 1, row, (c & 1) * 4 + i), pack_bf16(pr[8 * i], pr[8 * i + 1]),
+                                     pack_bf16(pr[8 * i + 2], pr[8 * i + 3]), pack_bf16(pr[8 * i + 4], pr[8 * i + 5]),
+                                     pack_bf16(pr[8 * i + 6], pr[8 * i + 7]));
                 }
                 m = m_new;
             }
+            if (tr) TRACE(27 + 5 * j);
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            if (tr) TRACE(28 + 5 * j);
         }
-        mbar_wait(pv_full, ((uint32_t)n_kv - 1) & 1);
+        MBWAIT(pv_full, ((uint32_t)n_kv - 1) & 1);
         tc_fence_after();
         if (warp_active) {
 #pragma unroll
@@ -276,20 +348,29 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
 #pragma unroll
                 for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
             }
-            if (l < p.L) {
-                const float inv = lsum > 0.f ? p.keep_scale / lsum : 0.f;
-                uint4* dst = reinterpret_cast<uint4*>(p.O + ((size_t)l * p.B + b) * p.ldo + h * 64);
+            const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            const float inv = lsum > 0.f ? p.keep_scale / lsum : 0.f;
+            uint8_t* stage = sP + (warp - 2) * 4096;  // P tile is free: the last PV MMA has completed
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    dst[i] = make_uint4(pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                                        pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
-                p.lse[(size_t)z * p.L + l] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
+            for (int i = 0; i < 8; ++i)
+                stage_put(stage, lane, i, pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                          pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
+                const int lr = q0 + quad * 32 + rl;
+                if (lr < p.L)
+                    *reinterpret_cast<uint4*>(p.O + ((size_t)lr * p.B + b) * p.ldo + h * 64 + piece * 8) = stage_get(stage, rl, piece);
             }
+            if (l < p.L) p.lse[(size_t)z * p.L + l] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
         }
+        if (tr) TRACE(62);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (threadIdx.x == 0) TRACE(63);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -328,9 +409,10 @@ __global__ void __launch_bounds__(256) flash_dq_store_kernel(const float* __rest
 }
 
 constexpr int BWD_THREADS = 320;
-constexpr uint32_t BWD_SMEM_TILES = 10 * TILE_BYTES;  // K, V, Q[2], dO[2], Pd (2 blocks), dS (2 blocks)
+constexpr uint32_t BWD_SMEM_TILES = 12 * TILE_BYTES;  // K, V, Q[2], dO[2], Pd (2 blocks), dS (2 blocks), dQ staging
 constexpr uint32_t BWD_SMEM = BWD_SMEM_TILES + 256 + 1024;
 
+template <bool DROPOUT>
 __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_constant__ CUtensorMap tq,
                                                                     const __grid_constant__ CUtensorMap tk,
                                                                     const __grid_constant__ CUtensorMap tv,
@@ -344,6 +426,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
     uint8_t* sdO = sm + 4 * TILE_BYTES;  // 2 stages
     uint8_t* sPd = sm + 6 * TILE_BYTES;  // [128 q x 128 kv] bf16
     uint8_t* sdS = sm + 8 * TILE_BYTES;
+    uint8_t* sStage = sm + 10 * TILE_BYTES;  // 8 warps x 4 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BWD_SMEM_TILES);
     uint64_t* kv_full = bars + 0;
     uint64_t* qdo_full = bars + 1;   // [2]
@@ -364,6 +447,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
     const int nkv = min(128, p.S - kv0);
     const int nkv16 = (nkv + 15) & ~15;
 
+    if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv); prefetch_tmap(&tdo);
         mbar_init(kv_full, 1);
@@ -378,31 +462,38 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+    if (threadIdx.x == 0) TRACE(1);
 
     if (warp == 0) {
-        if (lane == 0) {
+        // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
+        if (elect_one_sync()) {
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             tma_load_3d(sK, &tk, kv_full, 0, kv0, z);
             tma_load_3d(sV, &tv, kv_full, 0, kv0, z);
-            for (int i = 0; i < nq_tiles; ++i) {
-                const int st = i & 1;
-                mbar_wait(&qdo_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int i = 0; i < nq_tiles; ++i) {
+            const int st = i & 1;
+            MBWAIT(&qdo_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
                 tma_load_3d(sQ + st * TILE_BYTES, &tq, &qdo_full[st], 0, i << 7, z);
                 tma_load_3d(sdO + st * TILE_BYTES, &tdo, &qdo_full[st], 0, i << 7, z);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
-            const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
-            const uint32_t idesc_s = make_idesc_bf16(128, nkv16, false, false);
-            const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);    // dV, dK: A and B MN-major
-            const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
-            auto issue_sdp = [&](int i) {
-                const int st = i & 1;
-                mbar_wait(&qdo_full[st], ((uint32_t)i >> 1) & 1);
-                tc_fence_after();
+        // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+        const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
+        const uint32_t idesc_s = make_idesc_bf16(128, nkv16, false, false);
+        const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);    // dV, dK: A and B MN-major
+        const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
+        auto issue_sdp = [&](int i) {
+            const int st = i & 1;
+            MBWAIT(&qdo_full[st], ((uint32_t)i >> 1) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tmem_base + TM_S, make_smem_desc(aQ + st * TILE_BYTES + k * 32, 16, 1024),
@@ -412,28 +503,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                     umma_f16(tmem_base + TM_DP, make_smem_desc(adO + st * TILE_BYTES + k * 32, 16, 1024),
                              make_smem_desc(aV + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(sdp_full);
-            };
-            mbar_wait(kv_full, 0);
-            issue_sdp(0);
-            for (int i = 0; i < nq_tiles; ++i) {
-                const int st = i & 1;
-                mbar_wait(pds_full, (uint32_t)i & 1);  // Pd_i, dS_i in smem; S_i, dP_i, dQ_{i-1} read out of TMEM
-                tc_fence_after();
-                if (i + 1 < nq_tiles) issue_sdp(i + 1);
-                const int qsteps = ((min(128, p.L - (i << 7)) + 15) & ~15) >> 4;  // query rows are the K dimension
+                TRACE(8 + 2 * i);
+            }
+            __syncwarp();
+        };
+        MBWAIT(kv_full, 0);
+        issue_sdp(0);
+        for (int i = 0; i < nq_tiles; ++i) {
+            const int st = i & 1;
+            MBWAIT(pds_full, (uint32_t)i & 1);  // Pd_i, dS_i in smem; S_i, dP_i, dQ_{i-1} read out of TMEM
+            tc_fence_after();
+            if (i + 1 < nq_tiles) issue_sdp(i + 1);
+            const int qsteps = ((min(128, p.L - (i << 7)) + 15) & ~15) >> 4;  // query rows are the K dimension
+            const int ksteps = nkv16 >> 4;
+            if (elect_one_sync()) {
                 for (int ks = 0; ks < qsteps; ++ks)
                     umma_f16(tmem_base + TM_DV, make_smem_desc(aPd + ks * 2048, 16384, 1024),
                              make_smem_desc(adO + st * TILE_BYTES + ks * 2048, 16384, 1024), idesc_t, (i | ks) != 0 ? 1u : 0u);
                 for (int ks = 0; ks < qsteps; ++ks)
                     umma_f16(tmem_base + TM_DK, make_smem_desc(adS + ks * 2048, 16384, 1024),
                              make_smem_desc(aQ + st * TILE_BYTES + ks * 2048, 16384, 1024), idesc_t, (i | ks) != 0 ? 1u : 0u);
-                const int ksteps = nkv16 >> 4;
                 for (int ks = 0; ks < ksteps; ++ks)
                     umma_f16(tmem_base + TM_DQ, make_smem_desc(adS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                              make_smem_desc(aK + ks * 2048, 16384, 1024), idesc_dq, ks != 0 ? 1u : 0u);
                 umma_commit(dq_full);
                 umma_commit(&qdo_empty[st]);
+                TRACE(9 + 2 * i);
             }
+            __syncwarp();
         }
     } else {
         // ===== softmax / gradient warps: thread = (query row, 64-key half) =====
@@ -441,39 +538,59 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
         const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const unsigned long long seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
-        const uint32_t thr16 = p.thr16;
+        const float sl2 = p.scale_log2, sc = p.scale;
+        const uint32_t thr_hi = p.thr16 << 16;
         const float keep_scale = p.keep_scale;
+        unsigned long long seed = 0;
+        if (DROPOUT) seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
         uint32_t v[32], w[32];
+        const bool tr = warp == 2 && lane == 0;
 
-        auto flush_dq = [&](int i_prev) {
-            // dQ_{i_prev} columns [half*32, +32) of this thread's row -> global fp32 accumulator
+        // dQ_{i_prev} columns [half*32, +32) of this thread's row: TMEM -> registers -> (scaled)
+        // 16-byte reductions into the global fp32 accumulator
+        auto flush_dq = [&]() {
             tmem_ld_32x32b_x32(t_row + TM_DQ + half * 32, v);
             tmem_ld_wait(v);
         };
+        uint8_t* stage = sStage + (warp - 2) * 4096;
         auto red_dq = [&](int i_prev) {
-            const int lq = (i_prev << 7) + row;
-            if (lq < p.L) {
-                float* dst = p.dQacc + ((size_t)z * p.L + lq) * 64 + half * 32;
+            __syncwarp();
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                               __uint_as_float(v[e + 3]));
+            for (int c = 0; c < 8; ++c) stage_put(stage, lane, c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
+                const int lq = (i_prev << 7) + quad * 32 + rl;
+                if (lq < p.L) {
+                    const uint4 x = stage_get(stage, rl, piece);
+                    red_add_v4(p.dQacc + ((size_t)z * p.L + lq) * 64 + half * 32 + piece * 4, __uint_as_float(x.x) * sc,
+                               __uint_as_float(x.y) * sc, __uint_as_float(x.z) * sc, __uint_as_float(x.w) * sc);
+                }
             }
         };
 
+        // per-row statistics of the NEXT tile are fetched one iteration ahead
+        float lse_n = row < p.L ? p.lse[(size_t)z * p.L + row] : INFINITY;
+        float delta_n = row < p.L ? p.delta[(size_t)z * p.L + row] : 0.f;
         for (int i = 0; i < nq_tiles; ++i) {
             const int nq = min(128, p.L - (i << 7));
             const int nq16 = (nq + 15) & ~15;
             const bool warp_active = quad * 32 < nq16;  // warp-uniform: rows this warp owns are read by the MMAs
             const int l = (i << 7) + row;
             const bool row_valid = row < nq;
-            const float lse_r = row_valid ? p.lse[(size_t)z * p.L + l] : INFINITY;
-            const float delta_r = row_valid ? p.delta[(size_t)z * p.L + l] : 0.f;
-            const uint32_t rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
+            const float lse_r = lse_n, delta_r = delta_n;
+            if (i + 1 < nq_tiles) {
+                const int l2 = l + 128;
+                lse_n = l2 < p.L ? p.lse[(size_t)z * p.L + l2] : INFINITY;
+                delta_n = l2 < p.L ? p.delta[(size_t)z * p.L + l2] : 0.f;
+            }
+            uint32_t rseed = 0;
+            if (DROPOUT) rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
             uint32_t pd_pk[32], ds_pk[32];
-            mbar_wait(sdp_full, (uint32_t)i & 1);
+            MBWAIT(sdp_full, (uint32_t)i & 1);
             tc_fence_after();
+            if (tr) TRACE(24 + 5 * i);
             if (warp_active) {
 #pragma unroll
                 for (int c2 = 0; c2 < 2; ++c2) {
@@ -481,35 +598,65 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                     if (c * 32 < nkv16) {
                         tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
                         tmem_ld_32x32b_x32(t_row + TM_DP + c * 32, w);
+                        const uint32_t bits = row_valid ? kbits[c] : 0u;
+                        uint32_t hb[4];
+                        if (DROPOUT) {
+                            const uint32_t grp0 = (uint32_t)(kv0 + c * 32) >> 3;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
+                        }
                         tmem_ld_wait(v);
                         tmem_ld_wait(w);
-                        const uint32_t bits = row_valid ? kbits[c] : 0u;
-                        const uint32_t pair0 = (uint32_t)(kv0 + c * 32) >> 1;
+                        float pr[32], g[32];
 #pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float p0 = ((bits >> e) & 1u) ? fast_exp2(__uint_as_float(v[e]) * p.scale_log2 - lse_r) : 0.f;
-                            const float p1 = ((bits >> (e + 1)) & 1u) ? fast_exp2(__uint_as_float(v[e + 1]) * p.scale_log2 - lse_r) : 0.f;
-                            float pd0 = p0, pd1 = p1;
-                            float g0 = __uint_as_float(w[e]), g1 = __uint_as_float(w[e + 1]);
-                            if (thr16 != 0) {
-                                const uint32_t hb = pcm_pair_bits(rseed, pair0 + (e >> 1));
-                                const bool k0 = (hb & 0xFFFFu) >= thr16, k1 = (hb >> 16) >= thr16;
-                                pd0 = k0 ? p0 * keep_scale : 0.f; g0 = k0 ? g0 * keep_scale : 0.f;
-                                pd1 = k1 ? p1 * keep_scale : 0.f; g1 = k1 ? g1 * keep_scale : 0.f;
+                        for (int e = 0; e < 32; ++e) {
+                            pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -lse_r));
+                            g[e] = __uint_as_float(w[e]);
+                        }
+                        if (bits != 0xFFFFFFFFu) {  // masked keys, rows past L, columns past nkv16 (uninitialised TMEM)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
+                                g[e] = ((bits >> e) & 1u) ? g[e] : 0.f;
                             }
-                            // select (not multiply by zero): columns past nkv16 hold uninitialised TMEM
-                            const float s0 = ((bits >> e) & 1u) ? p0 * (g0 - delta_r) * p.scale : 0.f;
-                            const float s1 = ((bits >> (e + 1)) & 1u) ? p1 * (g1 - delta_r) * p.scale : 0.f;
-                            pd_pk[c2 * 16 + (e >> 1)] = pack_bf16(pd0, pd1);
-                            ds_pk[c2 * 16 + (e >> 1)] = pack_bf16(s0, s1);
+                        }
+                        // dropout: Pd = keep ? P : 0 and dS = P * (keep ? keep_scale * dP : 0 - delta); the
+                        // keep_scale of Pd and the softmax scale of dS are folded into the epilogues
+                        if (DROPOUT) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t x = hb[q];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const bool keep = x >= thr_hi;
+                                    x = pcm_lcg_next(x);
+                                    g[8 * q + k] = keep ? g[8 * q + k] : 0.f;
+                                    w[8 * q + k] = __float_as_uint(keep ? pr[8 * q + k] : 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                pd_pk[c2 * 16 + q] = pack_bf16(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                ds_pk[c2 * 16 + q] = pack_bf16(pr[2 * q] * fmaf(g[2 * q], keep_scale, -delta_r),
+                                                               pr[2 * q + 1] * fmaf(g[2 * q + 1], keep_scale, -delta_r));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) pd_pk[c2 * 16 + q] = pack_bf16(pr[2 * q], pr[2 * q + 1]);
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                ds_pk[c2 * 16 + q] = pack_bf16(pr[2 * q] * (g[2 * q] - delta_r), pr[2 * q + 1] * (g[2 * q + 1] - delta_r));
                         }
                     }
                 }
             }
+            if (tr) TRACE(25 + 5 * i);
             if (i > 0) {
-                mbar_wait(dq_full, ((uint32_t)i - 1) & 1);  // tile i-1's MMAs are done: Pd / dS smem free, dQ_{i-1} ready
+                MBWAIT(dq_full, ((uint32_t)i - 1) & 1);  // tile i-1's MMAs are done: Pd / dS smem free, dQ_{i-1} ready
                 tc_fence_after();
             }
+            if (tr) TRACE(26 + 5 * i);
             if (warp_active) {
 #pragma unroll
                 for (int c2 = 0; c2 < 2; ++c2) {
@@ -527,43 +674,59 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                 }
             }
             fence_proxy_async();
-            if (i > 0) flush_dq(i - 1);
+            if (i > 0) flush_dq();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
+            if (tr) TRACE(27 + 5 * i);
             if (i > 0) red_dq(i - 1);
+            if (tr) TRACE(28 + 5 * i);
         }
-        mbar_wait(dq_full, ((uint32_t)nq_tiles - 1) & 1);
+        MBWAIT(dq_full, ((uint32_t)nq_tiles - 1) & 1);
         tc_fence_after();
-        flush_dq(nq_tiles - 1);
+        if (tr) TRACE(60);
+        flush_dq();
         red_dq(nq_tiles - 1);
-        // dV, dK: this thread's key row, columns [half*32, +32)
-        const int s_row = kv0 + row;
+        if (tr) TRACE(61);
+        // dV, dK: this thread's key row, columns [half*32, +32); dK carries the softmax scale
         tmem_ld_32x32b_x32(t_row + TM_DV + half * 32, v);
         tmem_ld_32x32b_x32(t_row + TM_DK + half * 32, w);
         tmem_ld_wait(v);
         tmem_ld_wait(w);
-        if (s_row < p.S) {
-            const size_t off = ((size_t)s_row * p.B + b) * p.ldkv + h * 64 + half * 32;
-            uint4* dv = reinterpret_cast<uint4*>(p.dV + off);
-            uint4* dk = reinterpret_cast<uint4*>(p.dK + off);
+        {
+            uint8_t* st2 = sPd + (warp - 2) * 4096;  // Pd tile is free: the last MMAs have completed
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                dv[q] = make_uint4(pack_bf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])),
-                                   pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-                                   pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-                                   pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
-                dk[q] = make_uint4(pack_bf16(__uint_as_float(w[8 * q]), __uint_as_float(w[8 * q + 1])),
-                                   pack_bf16(__uint_as_float(w[8 * q + 2]), __uint_as_float(w[8 * q + 3])),
-                                   pack_bf16(__uint_as_float(w[8 * q + 4]), __uint_as_float(w[8 * q + 5])),
-                                   pack_bf16(__uint_as_float(w[8 * q + 6]), __uint_as_float(w[8 * q + 7])));
+                stage_put(st2, lane, q, pack_bf16(__uint_as_float(v[8 * q]) * keep_scale, __uint_as_float(v[8 * q + 1]) * keep_scale),
+                          pack_bf16(__uint_as_float(v[8 * q + 2]) * keep_scale, __uint_as_float(v[8 * q + 3]) * keep_scale),
+                          pack_bf16(__uint_as_float(v[8 * q + 4]) * keep_scale, __uint_as_float(v[8 * q + 5]) * keep_scale),
+                          pack_bf16(__uint_as_float(v[8 * q + 6]) * keep_scale, __uint_as_float(v[8 * q + 7]) * keep_scale));
+                stage_put(st2, lane, 4 + q, pack_bf16(__uint_as_float(w[8 * q]) * sc, __uint_as_float(w[8 * q + 1]) * sc),
+                          pack_bf16(__uint_as_float(w[8 * q + 2]) * sc, __uint_as_float(w[8 * q + 3]) * sc),
+                          pack_bf16(__uint_as_float(w[8 * q + 4]) * sc, __uint_as_float(w[8 * q + 5]) * sc),
+                          pack_bf16(__uint_as_float(w[8 * q + 6]) * sc, __uint_as_float(w[8 * q + 7]) * sc));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
+                const int sr = kv0 + quad * 32 + rl;
+                if (sr < p.S) {
+                    const size_t off = ((size_t)sr * p.B + b) * p.ldkv + h * 64 + half * 32 + (piece & 3) * 8;
+                    *reinterpret_cast<uint4*>((piece < 4 ? p.dV : p.dK) + off) = stage_get(st2, rl, piece);
+                }
             }
         }
     }
+    if (warp == 2 && lane == 0) TRACE(62);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) TRACE(63);
 }
+
+long long* g_trace_buf = nullptr;
+int g_trace_ctas = 0;
 
 int head_split_map(const void* ptr, int Z, int rows, CUtensorMap* out) {
     const uint64_t dims[3] = {64, (uint64_t)rows, (uint64_t)Z};
@@ -574,7 +737,7 @@ int head_split_map(const void* ptr, int Z, int rows, CUtensorMap* out) {
 
 int fill_common(FlashParams& p, int B, int nh, int L, int S, const unsigned char* kpm, float scale, float p_drop,
                 const unsigned long long* seed_base, unsigned long long seed_offset) {
-    if (B <= 0 || nh <= 0 || L <= 0 || S <= 0) return PCM_EINVAL;
+    if (B <= 0 || nh <= 0 || L <= 0 || S <= 0 || !(scale > 0.f)) return PCM_EINVAL;
     if (p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
     if (S > MAX_KEYS) return PCM_EUNSUPPORTED;
     p.B = B; p.nh = nh; p.L = L; p.S = S; p.kpm = kpm;
@@ -582,6 +745,7 @@ int fill_common(FlashParams& p, int B, int nh, int L, int S, const unsigned char
     p.thr16 = p_drop > 0.f ? pcm_drop_thr16(p_drop) : 0u;
     p.keep_scale = p.thr16 ? pcm_keep_scale(p.thr16) : 1.0f;
     p.seed_base = seed_base; p.seed_offset = seed_offset;
+    p.trace = g_trace_buf; p.trace_ctas = g_trace_ctas;
     return PCM_OK;
 }
 
@@ -606,12 +770,17 @@ PCM_API int pcm_flash_attn_fwd(int B, int nh, int L, int S, const void* Q, const
     if ((r = head_split_map(V, Z, S, &tv))) return r;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(flash_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     const long grid = (long)Z * ((L + 127) / 128);
-    flash_fwd_kernel<<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
+    if (p.thr16)
+        flash_fwd_kernel<true><<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
+    else
+        flash_fwd_kernel<false><<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
     return pcm_launch_status();
 }
 
@@ -637,7 +806,9 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     if ((r = head_split_map(dO, Z, L, &tdo))) return r;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(flash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -650,8 +821,20 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
                                           ldo, B, nh, L, rows, delta);
     if ((r = pcm_launch_status())) return r;
     const long grid = (long)Z * ((S + 127) / 128);
-    flash_bwd_kernel<<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+    if (p.thr16)
+        flash_bwd_kernel<true><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+    else
+        flash_bwd_kernel<false><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
     if ((r = pcm_launch_status())) return r;
     flash_dq_store_kernel<<<g, 256, 0, st>>>(dQacc, B, nh, L, rows, reinterpret_cast<__nv_bfloat16*>(dQ), ldq);
     return pcm_launch_status();
+}
+
+// Debug aid (tools/flash_trace.py): the first n_ctas CTAs of subsequent attention launches write 64
+// clock64() stamps each (phase boundaries of the producer / MMA / softmax roles) to `buf`
+// (device memory, n_ctas * 64 int64).  buf = NULL switches tracing off.
+PCM_API int pcm_flash_attn_debug_trace(long long* buf, int n_ctas) {
+    g_trace_buf = buf;
+    g_trace_ctas = buf ? n_ctas : 0;
+    return PCM_OK;
 }

@@ -108,20 +108,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int zs = t / tiles_mn, r = t - zs * tiles_mn;
-                const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
-                const int zb = zs / p.split_k, ks = zs - zb * p.split_k;
-                const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
-                const int kb0 = ks * p.k_blocks_per_split;
-                const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+        // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int zs = t / tiles_mn, r = t - zs * tiles_mn;
+            const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+            const int zb = zs / p.split_k, ks = zs - zb * p.split_k;
+            const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
+            const int kb0 = ks * p.k_blocks_per_split;
+            const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (elect_one_sync()) {
                     uint8_t* sa = tiles + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -141,29 +141,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                             tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], n_blk * BLOCK_N + c * 64, b_off + k0);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            int i = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-                const int zs = t / tiles_mn;
-                const int ks = zs % p.split_k;
-                const int kb0 = ks * p.k_blocks_per_split;
-                const int nkb = min(kblocks_total, kb0 + p.k_blocks_per_split) - kb0;
-                const int acc = i & 1;
-                mbar_wait(&tmem_empty_bar[acc], (((uint32_t)i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues.
+        // With an `if (lane == 0)` region the compiler wraps every UTCHMMA in a per-thread waterfall
+        // loop (R2UR + ELECT + BRA.U.ANY, ~20 instructions); warp-uniform descriptors stay in uniform
+        // registers and the MMAs of a k-block issue back to back.
+        uint32_t it = 0;
+        int i = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            const int zs = t / tiles_mn;
+            const int ks = zs % p.split_k;
+            const int kb0 = ks * p.k_blocks_per_split;
+            const int nkb = min(kblocks_total, kb0 + p.k_blocks_per_split) - kb0;
+            const int acc = i & 1;
+            mbar_wait(&tmem_empty_bar[acc], (((uint32_t)i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 rows of 128 B
@@ -174,8 +178,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         umma_f16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                    if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
                 }
-                umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+                __syncwarp();
             }
         }
     } else {

@@ -169,6 +169,47 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
 }
 
 // out[c] += sum_r src[r, c]; src fp32 or bf16 with row pitch ld.
+// Vector form (C % VEC == 0, 16-byte aligned rows): a thread owns VEC consecutive columns and
+// walks rows with 16-byte loads, several row groups per CTA in flight; partial sums meet in
+// shared memory and leave as one atomic per column per CTA.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ src, long rows, int C, long ld,
+                                                         int rows_per_cta, float* __restrict__ out) {
+    extern __shared__ float part[];  // [groups][C]
+    const int tpr = C / VEC;                      // threads per row
+    const int groups = max(1, 256 / tpr);          // row groups per CTA
+    const int rg = threadIdx.x / tpr, tc = threadIdx.x - rg * tpr;
+    const long r0 = (long)blockIdx.x * rows_per_cta;
+    const long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    if (rg < groups) {
+        const int c0 = tc * VEC;  // tpr * VEC == C: one column chunk per thread
+#pragma unroll 4
+        for (long r = r0 + rg; r < r1; r += groups) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+            if (sizeof(T) == 2) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            } else {
+                const float* f = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] += f[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) part[rg * C + c0 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int g = 0; g < groups; ++g) t += part[g * C + c];
+        atomicAdd(out + c, t);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, long rows, int C, long ld, int rows_per_cta,
                                                      float* __restrict__ out) {
@@ -255,12 +296,22 @@ PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int
     int rows_per_cta = (int)((rows + 148L * 4 - 1) / (148L * 4));
     if (rows_per_cta < 16) rows_per_cta = 16;
     const int grid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-    if (src_bf16)
-        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, pcm_cu_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld,
-                                                                               rows_per_cta, out);
-    else
-        colsum_kernel<float><<<grid, 256, 0, pcm_cu_stream(stream)>>>(reinterpret_cast<const float*>(src), rows, C, ld,
-                                                                       rows_per_cta, out);
+    cudaStream_t st = pcm_cu_stream(stream);
+    const int vec = src_bf16 ? 8 : 4;
+    const bool vec_ok = (C % vec) == 0 && C / vec <= 256 && (ld % vec) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    if (vec_ok) {
+        const int groups = 256 / (C / vec) > 0 ? 256 / (C / vec) : 1;
+        const size_t smem = (size_t)groups * C * sizeof(float);
+        if (src_bf16)
+            colsum_vec_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld,
+                                                                         rows_per_cta, out);
+        else
+            colsum_vec_kernel<float, 4><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(src), rows, C, ld, rows_per_cta, out);
+    } else if (src_bf16) {
+        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld, rows_per_cta, out);
+    } else {
+        colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), rows, C, ld, rows_per_cta, out);
+    }
     return pcm_launch_status();
 }
 

@@ -27,6 +27,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Polling wait with back-off: on sm_100 try_wait returns within a few cycles when the phase is
+// still pending, so a bare loop burns the issue slots of the warps that share the scheduler
+// (ncu: 43% of all executed instructions of the first attention kernel were TRYWAIT/BRA/YIELD).
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -115,6 +131,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // 16-byte vector reduction into global fp32 memory (sm_90+)
 __device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// One lane of a fully converged warp (elect.sync): MMA-issue loops run warp-uniform and predicate
+// only the tcgen05 instructions on this, so descriptors stay in uniform registers (an `if (lane
+// == 0)` region makes the compiler wrap every UTCHMMA in a per-thread waterfall loop).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // D = F32, A = B = BF16 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor):

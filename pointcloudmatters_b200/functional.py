@@ -33,25 +33,32 @@ def _split_k_for(m_tiles, n_tiles, kblocks):
 
 
 class _Bf16Shadow:
-    """bf16 copy of the trainer's flat fp32 parameter buffer (trainer.FlatState.param_bf16), kept in
-    sync by the fused AdamW kernel: GEMM weight operands are views into it, so no per-use fp32 ->
+    """bf16 copies of trainers' flat fp32 parameter buffers (trainer.FlatState.param_bf16), kept in
+    sync by the fused AdamW kernel: GEMM weight operands are views into them, so no per-use fp32 ->
     bf16 conversion kernels run inside the step.  Outside a trainer (unit tests, inference on a
-    plain module) weights are converted on the fly -- same kernels, same numerics."""
+    plain module) weights are converted on the fly -- same kernels, same numerics.
+    Registrations are weak: an entry disappears with its FlatState, so a later allocation that
+    reuses the freed address range can never alias a stale copy."""
 
     def __init__(self):
-        self.base_ptr, self.nbytes, self.bf16 = 0, 0, None
+        self.entries = {}  # id -> (weakref to FlatState, base_ptr, nbytes)
 
-    def register(self, param_flat, bf16_flat):
-        self.base_ptr, self.nbytes, self.bf16 = param_flat.data_ptr(), param_flat.numel() * 4, bf16_flat
+    def register(self, flat_state):
+        import weakref
 
-    def clear(self):
-        self.base_ptr, self.nbytes, self.bf16 = 0, 0, None
+        key = id(flat_state)
+        ref = weakref.ref(flat_state, lambda _r, k=key: self.entries.pop(k, None))
+        self.entries[key] = (ref, flat_state.param.data_ptr(), flat_state.param.numel() * 4)
 
     def view(self, w):
-        if self.bf16 is not None and w.dtype == torch.float32 and w.is_contiguous():
-            off = w.data_ptr() - self.base_ptr
-            if 0 <= off < self.nbytes and w.device == self.bf16.device:
-                return self.bf16[off // 4: off // 4 + w.numel()].view(w.shape)
+        if self.entries and w.dtype == torch.float32 and w.is_contiguous():
+            ptr_ = w.data_ptr()
+            for ref, base, nbytes in self.entries.values():
+                off = ptr_ - base
+                if 0 <= off < nbytes:
+                    fs = ref()
+                    if fs is not None and fs.param_bf16.device == w.device:
+                        return fs.param_bf16[off // 4: off // 4 + w.numel()].view(w.shape)
         return w.to(torch.bfloat16)
 
 
@@ -67,7 +74,7 @@ def _grad_slot(p):
     """The fp32 gradient buffer a parameter already owns (the trainer's flat-gradient view, or a
     .grad left by an earlier backward): weight-gradient kernels accumulate straight into it and the
     backward returns None for that input, so autograd launches no zero-fill / add kernels."""
-    g = getattr(p, "grad", None)
+    g = p.grad if (p is not None and p.is_leaf) else None
     if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape and g.device == p.device:
         return g
     return None

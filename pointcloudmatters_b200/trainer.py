@@ -62,9 +62,11 @@ class FlatState:
         self.inactive = [p for p in params if id(p) in inactive_ids]
         ordered = self.active + self.inactive
         dev = ordered[0].device
-        pad4 = lambda n: (n + 3) // 4 * 4  # keep every view 16-byte aligned for 128-bit accesses
-        self.n_active = sum(pad4(p.numel()) for p in self.active)
-        total = self.n_active + sum(pad4(p.numel()) for p in self.inactive)
+        # every view starts on a multiple of 8 elements: 16-byte aligned in the bf16 operand copy too
+        # (TMA base alignment), 32-byte aligned in fp32
+        pad8 = lambda n: (n + 7) // 8 * 8
+        self.n_active = sum(pad8(p.numel()) for p in self.active)
+        total = self.n_active + sum(pad8(p.numel()) for p in self.inactive)
         self.param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(self.n_active, dtype=torch.float32, device=dev)
@@ -80,7 +82,7 @@ class FlatState:
             p.grad = self.grad[off:off + n].view_as(p)
             if old is not None:
                 p.grad.copy_(old)
-            off += pad4(n)
+            off += pad8(n)
         self.sync_shadow()
 
     def sync_shadow(self):
@@ -90,7 +92,7 @@ class FlatState:
 
         self.param_bf16.copy_(self.param)
         if self.param.is_cuda:
-            PF.BF16_SHADOW.register(self.param, self.param_bf16)
+            PF.BF16_SHADOW.register(self)
 
     def zero_grad(self):
         self.grad.zero_()

@@ -36,7 +36,7 @@ def test_flat_state_views_and_inactive_tail():
     m[0](torch.randn(2, 5)).sum().backward()  # only layer 0 receives a gradient
     inactive = [p for p in m.parameters() if p.grad is None]
     fs = FlatState(m.parameters(), inactive)
-    assert fs.n_active == 36 + 8 and fs.param.numel() % 4 == 0  # (35->36) + (7->8), padded to 4
+    assert fs.n_active == 40 + 8 and fs.param.numel() % 8 == 0  # (35->40) + (7->8), padded to 8
     for k, v in m.state_dict().items():
         assert torch.equal(v, before[k])
     assert all(p.data.data_ptr() >= fs.param.data_ptr() for p in m.parameters())
@@ -97,11 +97,11 @@ def test_gradient_allreduce_world2_gloo():
     [p.join(60) for p in procs]
     (r0, g0, na0, nt0, sc0), (r1, g1, na1, nt1, sc1) = res
     assert torch.equal(g0, g1) and na0 == na1 and sc0 == 0.5
-    assert nt0 - na0 == 16  # the unused Linear(3,3): 9 -> 12 and 3 -> 4 padded floats parked in the inactive tail
+    assert nt0 - na0 == 24  # the unused Linear(3,3): 9 -> 16 and 3 -> 8 padded floats parked in the inactive tail
     # equals the single-process gradient of the mean loss over the GLOBAL batch
     torch.manual_seed(0)
     model = nn.Sequential(nn.Linear(4, 8), nn.ReLU(), nn.Linear(8, 2))
     x = torch.randn(8, 4, generator=torch.Generator().manual_seed(7))
     (model(x).pow(2).sum() / 8).backward()
-    ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 4)) for p in model.parameters()])
+    ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 8)) for p in model.parameters()])
     torch.testing.assert_close(g0 * 2, ref, rtol=1e-5, atol=1e-6)  # each rank held half the samples of a /8 loss
