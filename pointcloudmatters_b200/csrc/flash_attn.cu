@@ -36,7 +36,6 @@ using namespace pcm_tc;
 
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // one [128 rows x 64] bf16 operand tile = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr int MAX_KEYS = 8192;
 
 struct FlashParams {
     int B, nh, L, S;
@@ -107,9 +106,14 @@ __device__ __forceinline__ void build_key_bits(uint32_t* kbits, int nwords, int 
 // forward
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_THREADS = 192;
-constexpr uint32_t FWD_SMEM_TILES = 6 * TILE_BYTES;  // Q, K0, K1, V, P (2 blocks)
-constexpr uint32_t FWD_SMEM = FWD_SMEM_TILES + 256 + MAX_KEYS / 8 + 1024;
+constexpr uint32_t FWD_SMEM_TILES = 5 * TILE_BYTES;   // Q, K, V, P (2 blocks)
+constexpr uint32_t FWD_STAGE_BYTES = 4 * 4096;        // 4 softmax warps x 4 KB output staging
+constexpr uint32_t FWD_SMEM = FWD_SMEM_TILES + FWD_STAGE_BYTES + 256 + 1024;
 
+// Persistent: grid = min(#items, 2 x #SMs), two CTAs resident per SM; a CTA walks work items
+// (batch*head z, 128-query tile) and all pipelines run across item boundaries: the next item's Q and
+// first K / V tiles are loaded, and its first score tile is issued, while the softmax warps still
+// normalise and store the current item's output.
 template <bool DROPOUT>
 __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_constant__ CUtensorMap tq,
                                                                     const __grid_constant__ CUtensorMap tk,
@@ -118,39 +122,37 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = sm;
-    uint8_t* sK = sm + TILE_BYTES;      // 2 stages
-    uint8_t* sV = sm + 3 * TILE_BYTES;  // 1 stage
-    uint8_t* sP = sm + 4 * TILE_BYTES;  // [128 x 128] bf16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FWD_SMEM_TILES);
+    uint8_t* sK = sm + TILE_BYTES;
+    uint8_t* sV = sm + 2 * TILE_BYTES;
+    uint8_t* sP = sm + 3 * TILE_BYTES;  // [128 x 128] bf16
+    uint8_t* sStage = sm + FWD_SMEM_TILES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FWD_SMEM_TILES + FWD_STAGE_BYTES);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;   // [2]
-    uint64_t* k_empty = bars + 3;  // [2]
-    uint64_t* v_full = bars + 5;
-    uint64_t* v_empty = bars + 6;
-    uint64_t* s_full = bars + 7;
-    uint64_t* p_full = bars + 8;
-    uint64_t* pv_full = bars + 9;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* k_full = bars + 2;
+    uint64_t* k_empty = bars + 3;
+    uint64_t* v_full = bars + 4;
+    uint64_t* v_empty = bars + 5;
+    uint64_t* s_full = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* pv_full = bars + 8;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
-    uint32_t* kbits = reinterpret_cast<uint32_t*>(sm + FWD_SMEM_TILES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nq_tiles = (p.L + 127) >> 7;
-    const int z = blockIdx.x / nq_tiles;
-    const int q0 = (blockIdx.x - z * nq_tiles) << 7;
-    const int b = z / p.nh, h = z - b * p.nh;
     const int n_kv = (p.S + 127) >> 7;
+    const int n_items = p.B * p.nh * nq_tiles;
 
     if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        mbar_init(k_full, 1); mbar_init(k_empty, 1);
         mbar_init(v_full, 1); mbar_init(v_empty, 1);
         mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(pv_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, 256);
-    build_key_bits(kbits, n_kv * 4, 0, p, b, warp, FWD_THREADS / 32, lane);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -160,210 +162,239 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
-        if (elect_one_sync()) {
-            mbar_expect_tx(q_full, TILE_BYTES);
-            tma_load_3d(sQ, &tq, q_full, 0, q0, z);
-        }
-        __syncwarp();
-        for (int j = 0; j < n_kv; ++j) {
-            const int st = j & 1;
-            MBWAIT(&k_empty[st], (((uint32_t)j >> 1) & 1) ^ 1);
+        uint32_t t = 0, n = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n) {
+            const int z = w / nq_tiles, q0 = (w - z * nq_tiles) << 7;
+            MBWAIT(q_empty, (n & 1) ^ 1);
             if (elect_one_sync()) {
-                mbar_expect_tx(&k_full[st], TILE_BYTES);
-                tma_load_3d(sK + st * TILE_BYTES, &tk, &k_full[st], 0, j << 7, z);
+                mbar_expect_tx(q_full, TILE_BYTES);
+                tma_load_3d(sQ, &tq, q_full, 0, q0, z);
             }
             __syncwarp();
-            MBWAIT(v_empty, ((uint32_t)j & 1) ^ 1);
-            if (elect_one_sync()) {
-                mbar_expect_tx(v_full, TILE_BYTES);
-                tma_load_3d(sV, &tv, v_full, 0, j << 7, z);
+            for (int j = 0; j < n_kv; ++j, ++t) {
+                MBWAIT(k_empty, (t & 1) ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(k_full, TILE_BYTES);
+                    tma_load_3d(sK, &tk, k_full, 0, j << 7, z);
+                }
+                __syncwarp();
+                MBWAIT(v_empty, (t & 1) ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(v_full, TILE_BYTES);
+                    tma_load_3d(sV, &tv, v_full, 0, j << 7, z);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
         const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-        auto issue_s = [&](int j) {
-            const int st = j & 1;
+        const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+        // S = Q K_j^T of global tile tt (key tile j of the item whose Q is resident)
+        auto issue_s = [&](uint32_t tt, int j) {
             const int nkv16 = (min(128, p.S - (j << 7)) + 15) & ~15;
-            MBWAIT(&k_full[st], ((uint32_t)j >> 1) & 1);
+            MBWAIT(k_full, tt & 1);
             tc_fence_after();
             const uint32_t idesc = make_idesc_bf16(128, nkv16, false, false);
             if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_f16(tmem_base + TM_S, make_smem_desc(aQ + k * 32, 16, 1024),
-                             make_smem_desc(aK + st * TILE_BYTES + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+                    umma_f16(tmem_base + TM_S, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc,
+                             k != 0 ? 1u : 0u);
                 umma_commit(s_full);
-                umma_commit(&k_empty[st]);
-                TRACE(8 + 2 * j);
+                umma_commit(k_empty);
+                if (j == n_kv - 1) umma_commit(q_empty);  // last score tile of the item: Q may be replaced
+                TRACE(tt < 8 ? 8 + 2 * (int)tt : 64);
             }
             __syncwarp();
         };
-        MBWAIT(q_full, 0);
-        issue_s(0);
-        const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
-        for (int j = 0; j < n_kv; ++j) {
-            MBWAIT(p_full, (uint32_t)j & 1);  // P_j in smem; S_j and PV_{j-1} have been read out of TMEM
-            tc_fence_after();
-            if (j + 1 < n_kv) issue_s(j + 1);
-            MBWAIT(v_full, (uint32_t)j & 1);
-            tc_fence_after();
-            const int ksteps = ((min(128, p.S - (j << 7)) + 15) & ~15) >> 4;
-            if (elect_one_sync()) {
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma_f16(tmem_base + TM_PV, make_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                             make_smem_desc(aV + ks * 2048, 16384, 1024), idesc_pv, ks != 0 ? 1u : 0u);
-                umma_commit(pv_full);
-                umma_commit(v_empty);
-                TRACE(9 + 2 * j);
+        uint32_t t = 0, n = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n) {
+            if (n == 0) {
+                MBWAIT(q_full, 0);
+                issue_s(0, 0);
             }
-            __syncwarp();
+            for (int j = 0; j < n_kv; ++j, ++t) {
+                MBWAIT(p_full, t & 1);  // P_t in smem; S_t and PV_{t-1} have been read out of TMEM
+                tc_fence_after();
+                if (j + 1 < n_kv) {
+                    issue_s(t + 1, j + 1);
+                } else if (w + (int)gridDim.x < n_items) {
+                    MBWAIT(q_full, (n + 1) & 1);
+                    issue_s(t + 1, 0);
+                }
+                MBWAIT(v_full, t & 1);
+                tc_fence_after();
+                const int ksteps = ((min(128, p.S - (j << 7)) + 15) & ~15) >> 4;
+                if (elect_one_sync()) {
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_f16(tmem_base + TM_PV, make_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                                 make_smem_desc(aV + ks * 2048, 16384, 1024), idesc_pv, ks != 0 ? 1u : 0u);
+                    umma_commit(pv_full);
+                    umma_commit(v_empty);
+                    TRACE(t < 8 ? 9 + 2 * (int)t : 64);
+                }
+                __syncwarp();
+            }
         }
     } else {
         // ===== softmax warps: thread = query row =====
         // Straight-line, branch-free inner code (dropout is a template parameter; the key mask
         // costs a warp-uniform test per 32-column chunk) staged over whole chunks so that the 32
-        // exp2 / 16 hash chains of a chunk are independent instruction streams; the hashes are
-        // computed while the chunk's tcgen05.ld is in flight.
+        // exp2 chains of a chunk are independent instruction streams.
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int l = q0 + row;
-        const bool warp_active = q0 + quad * 32 < p.L;  // warp-uniform
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
         const float sl2 = p.scale_log2;
         const uint32_t thr_hi = p.thr16 << 16;
-        uint32_t rseed = 0;
-        if (DROPOUT) {
-            const unsigned long long seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
-            rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
-        }
-        float o[64];
-#pragma unroll
-        for (int e = 0; e < 64; ++e) o[e] = 0.f;
-        float m = -INFINITY;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t v[32];
+        unsigned long long seed = 0;
+        if (DROPOUT) seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
+        uint8_t* stage = sStage + (warp - 2) * 4096;
         const bool tr = warp == 2 && lane == 0;
-        for (int j = 0; j < n_kv; ++j) {
-            const int nkv = min(128, p.S - (j << 7));
-            MBWAIT(s_full, (uint32_t)j & 1);
-            tc_fence_after();
-            if (tr) TRACE(24 + 5 * j);
-            float alpha = 1.f, m_use = 0.f, m_new = m;
-            if (warp_active) {
-                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 >= nkv) break;
-                    tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                    const uint32_t bits = kbits[j * 4 + c];
-                    tmem_ld_wait(v);
-                    if (bits == 0xFFFFFFFFu) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(v[e]));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            mx[e & 3] = fmaxf(mx[e & 3], ((bits >> e) & 1u) ? __uint_as_float(v[e]) : -INFINITY);
-                    }
+        uint32_t v[32];
+        uint32_t t = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int z = w / nq_tiles, q0 = (w - z * nq_tiles) << 7;
+            const int b = z / p.nh, h = z - b * p.nh;
+            const int l = q0 + row;
+            const bool warp_active = q0 + quad * 32 < p.L;  // warp-uniform
+            // valid-key bits of the 32 keys starting at col0 (warp-uniform value)
+            auto key_bits = [&](int col0) -> uint32_t {
+                if (p.kpm == nullptr) {
+                    const int r = p.S - col0;
+                    return r >= 32 ? 0xFFFFFFFFu : (r <= 0 ? 0u : ((1u << r) - 1u));
                 }
-                // the scale is positive: max(scale * s) = scale * max(s)
-                m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
-                m_use = m_new == -INFINITY ? 0.f : m_new;
-                alpha = fast_exp2(m - m_use);
-            }
-            if (tr) TRACE(25 + 5 * j);
-            if (j > 0) {
-                MBWAIT(pv_full, ((uint32_t)j - 1) & 1);
+                const int col = col0 + lane;
+                return __ballot_sync(PCM_FULL_MASK, col < p.S && p.kpm[(size_t)b * p.S + col] == 0);
+            };
+            uint32_t rseed = 0;
+            if (DROPOUT) rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
+            float o[64];
+#pragma unroll
+            for (int e = 0; e < 64; ++e) o[e] = 0.f;
+            float m = -INFINITY;
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < n_kv; ++j, ++t) {
+                const int nkv = min(128, p.S - (j << 7));
+                MBWAIT(s_full, t & 1);
                 tc_fence_after();
+                if (tr) TRACE(t < 7 ? 24 + 5 * (int)t : 64);
+                float alpha = 1.f, m_use = 0.f, m_new = m;
                 if (warp_active) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
-                        tmem_ld_wait(v);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) o[c * 32 + e] = (o[c * 32 + e] + __uint_as_float(v[e])) * alpha;
-                    }
-                }
-            }
-            if (tr) TRACE(26 + 5 * j);
-            if (warp_active) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ls[q] *= alpha;
+                    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 >= nkv) break;
-                    tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                    const uint32_t bits = kbits[j * 4 + c];
-                    uint32_t hb[4];
-                    if (DROPOUT) {
-                        const uint32_t grp0 = (uint32_t)((j << 7) + c * 32) >> 3;
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 >= nkv) break;
+                        tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
+                        const uint32_t bits = key_bits((j << 7) + c * 32);
+                        tmem_ld_wait(v);
+                        if (bits == 0xFFFFFFFFu) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
-                    }
-                    tmem_ld_wait(v);
-                    float pr[32];
+                            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(v[e]));
+                        } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_use));
-                    if (bits != 0xFFFFFFFFu) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) ls[e & 3] += pr[e];
-                    if (DROPOUT) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t x = hb[q];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                pr[8 * q + k] = x >= thr_hi ? pr[8 * q + k] : 0.f;
-                                x = pcm_lcg_next(x);
-                            }
+                            for (int e = 0; e < 32; ++e)
+                                mx[e & 3] = fmaxf(mx[e & 3], ((bits >> e) & 1u) ? __uint_as_float(v[e]) : -INFINITY);
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        st_shared_v4(sP + sw128_off(c >> 1, row, (c & 1) * 4 + i), pack_bf16(pr[8 * i], pr[8 * i + 1]),
-                                     pack_bf16(pr[8 * i + 2], pr[8 * i + 3]), pack_bf16(pr[8 * i + 4], pr[8 * i + 5]),
-                                     pack_bf16(pr[8 * i + 6], pr[8 * i + 7]));
+                    // the scale is positive: max(scale * s) = scale * max(s)
+                    m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
+                    m_use = m_new == -INFINITY ? 0.f : m_new;
+                    alpha = fast_exp2(m - m_use);
                 }
-                m = m_new;
+                if (tr) TRACE(t < 7 ? 25 + 5 * (int)t : 64);
+                if (j > 0) {
+                    MBWAIT(pv_full, (t - 1) & 1);
+                    tc_fence_after();
+                    if (warp_active) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
+                            tmem_ld_wait(v);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[c * 32 + e] = (o[c * 32 + e] + __uint_as_float(v[e])) * alpha;
+                        }
+                    }
+                }
+                if (tr) TRACE(t < 7 ? 26 + 5 * (int)t : 64);
+                if (warp_active) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ls[q] *= alpha;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 >= nkv) break;
+                        tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
+                        const uint32_t bits = key_bits((j << 7) + c * 32);
+                        uint32_t hb[4];
+                        if (DROPOUT) {
+                            const uint32_t grp0 = (uint32_t)((j << 7) + c * 32) >> 3;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
+                        }
+                        tmem_ld_wait(v);
+                        float pr[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_use));
+                        if (bits != 0xFFFFFFFFu) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ls[e & 3] += pr[e];
+                        if (DROPOUT) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t x = hb[q];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    pr[8 * q + k] = x >= thr_hi ? pr[8 * q + k] : 0.f;
+                                    x = pcm_lcg_next(x);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            st_shared_v4(sP + sw128_off(c >> 1, row, (c & 1) * 4 + i), pack_bf16(pr[8 * i], pr[8 * i + 1]),
+                                         pack_bf16(pr[8 * i + 2], pr[8 * i + 3]), pack_bf16(pr[8 * i + 4], pr[8 * i + 5]),
+                                         pack_bf16(pr[8 * i + 6], pr[8 * i + 7]));
+                    }
+                    m = m_new;
+                }
+                if (tr) TRACE(t < 7 ? 27 + 5 * (int)t : 64);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                if (tr) TRACE(t < 7 ? 28 + 5 * (int)t : 64);
             }
-            if (tr) TRACE(27 + 5 * j);
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-            if (tr) TRACE(28 + 5 * j);
-        }
-        MBWAIT(pv_full, ((uint32_t)n_kv - 1) & 1);
-        tc_fence_after();
-        if (warp_active) {
+            // ---- item epilogue: last PV tile, normalise, store (the MMA warp is already on the next item) ----
+            MBWAIT(pv_full, (t - 1) & 1);
+            tc_fence_after();
+            if (warp_active) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
-                tmem_ld_wait(v);
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
+                    tmem_ld_wait(v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                    for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                }
+                const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+                const float inv = lsum > 0.f ? p.keep_scale / lsum : 0.f;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    stage_put(stage, lane, i, pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                              pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rl = it * 4 + (lane >> 3), piece = lane & 7;
+                    const int lr = q0 + quad * 32 + rl;
+                    if (lr < p.L)
+                        *reinterpret_cast<uint4*>(p.O + ((size_t)lr * p.B + b) * p.ldo + h * 64 + piece * 8) = stage_get(stage, rl, piece);
+                }
+                if (l < p.L) p.lse[(size_t)z * p.L + l] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
             }
-            const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-            const float inv = lsum > 0.f ? p.keep_scale / lsum : 0.f;
-            uint8_t* stage = sP + (warp - 2) * 4096;  // P tile is free: the last PV MMA has completed
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                stage_put(stage, lane, i, pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                          pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
-                const int lr = q0 + quad * 32 + rl;
-                if (lr < p.L)
-                    *reinterpret_cast<uint4*>(p.O + ((size_t)lr * p.B + b) * p.ldo + h * 64 + piece * 8) = stage_get(stage, rl, piece);
-            }
-            if (l < p.L) p.lse[(size_t)z * p.L + l] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
         }
         if (tr) TRACE(62);
     }
@@ -409,9 +440,17 @@ __global__ void __launch_bounds__(256) flash_dq_store_kernel(const float* __rest
 }
 
 constexpr int BWD_THREADS = 320;
-constexpr uint32_t BWD_SMEM_TILES = 12 * TILE_BYTES;  // K, V, Q[2], dO[2], Pd (2 blocks), dS (2 blocks), dQ staging
-constexpr uint32_t BWD_SMEM = BWD_SMEM_TILES + 256 + 1024;
+constexpr uint32_t BWD_SMEM_TILES = 12 * TILE_BYTES;  // K[2], V[2], Q[2], dO[2], Pd (2 blocks), dS (2 blocks)
+constexpr uint32_t BWD_STAGE_BYTES = 8 * 4096;        // 8 warps x 4 KB epilogue staging
+constexpr uint32_t BWD_SMEM = BWD_SMEM_TILES + BWD_STAGE_BYTES + 256 + 1024;
 
+// Persistent: grid = min(#items, #SMs); a CTA walks work items (batch*head z, 128-key tile jt) and,
+// inside an item, the query tiles.  All pipelines run ACROSS item boundaries -- the producer
+// prefetches the next item's K / V (2 stages) and Q / dO tiles while the current one computes, the
+// MMA warp issues the next item's S / dP as soon as the last score tile of this one has been
+// consumed, and the dK / dV / dQ epilogue of an item overlaps the tensor work of the next -- so
+// TMEM allocation, barrier set-up and the first-load latency are paid once per CTA, not once per
+// key tile (they were 25-50% of a CTA's life with one item per CTA).
 template <bool DROPOUT>
 __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_constant__ CUtensorMap tq,
                                                                     const __grid_constant__ CUtensorMap tk,
@@ -420,43 +459,40 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                                                                     const FlashParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sK = sm;
-    uint8_t* sV = sm + TILE_BYTES;
-    uint8_t* sQ = sm + 2 * TILE_BYTES;   // 2 stages
-    uint8_t* sdO = sm + 4 * TILE_BYTES;  // 2 stages
-    uint8_t* sPd = sm + 6 * TILE_BYTES;  // [128 q x 128 kv] bf16
-    uint8_t* sdS = sm + 8 * TILE_BYTES;
-    uint8_t* sStage = sm + 10 * TILE_BYTES;  // 8 warps x 4 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BWD_SMEM_TILES);
-    uint64_t* kv_full = bars + 0;
-    uint64_t* qdo_full = bars + 1;   // [2]
-    uint64_t* qdo_empty = bars + 3;  // [2]
-    uint64_t* sdp_full = bars + 5;
-    uint64_t* pds_full = bars + 6;
-    uint64_t* dq_full = bars + 7;
+    uint8_t* sK = sm;                     // 2 stages
+    uint8_t* sV = sm + 2 * TILE_BYTES;    // 2 stages
+    uint8_t* sQ = sm + 4 * TILE_BYTES;    // 2 stages
+    uint8_t* sdO = sm + 6 * TILE_BYTES;   // 2 stages
+    uint8_t* sPd = sm + 8 * TILE_BYTES;   // [128 q x 128 kv] bf16
+    uint8_t* sdS = sm + 10 * TILE_BYTES;
+    uint8_t* sStage = sm + BWD_SMEM_TILES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BWD_SMEM_TILES + BWD_STAGE_BYTES);
+    uint64_t* kv_full = bars + 0;    // [2]
+    uint64_t* kv_empty = bars + 2;   // [2]
+    uint64_t* qdo_full = bars + 4;   // [2]
+    uint64_t* qdo_empty = bars + 6;  // [2]
+    uint64_t* sdp_full = bars + 8;
+    uint64_t* pds_full = bars + 9;
+    uint64_t* dq_full = bars + 10;
+    uint64_t* dkv_empty = bars + 11;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
-    uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 20);  // 4 words
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (p.S + 127) >> 7;
-    const int z = blockIdx.x / n_kv;
-    const int jt = blockIdx.x - z * n_kv;
-    const int kv0 = jt << 7;
-    const int b = z / p.nh, h = z - b * p.nh;
     const int nq_tiles = (p.L + 127) >> 7;
-    const int nkv = min(128, p.S - kv0);
-    const int nkv16 = (nkv + 15) & ~15;
+    const int n_items = p.B * p.nh * n_kv;
 
     if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv); prefetch_tmap(&tdo);
-        mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-        mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1);
+        }
+        mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(dkv_empty, 8);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
-    build_key_bits(kbits, 4, kv0, p, b, warp, BWD_THREADS / 32, lane);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -466,71 +502,114 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
-        if (elect_one_sync()) {
-            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-            tma_load_3d(sK, &tk, kv_full, 0, kv0, z);
-            tma_load_3d(sV, &tv, kv_full, 0, kv0, z);
-        }
-        __syncwarp();
-        for (int i = 0; i < nq_tiles; ++i) {
-            const int st = i & 1;
-            MBWAIT(&qdo_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
+        uint32_t t = 0, n = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n) {
+            const int z = w / n_kv, kv0 = (w - z * n_kv) << 7;
+            const uint32_t ks = n & 1;
+            MBWAIT(&kv_empty[ks], ((n >> 1) & 1) ^ 1);
             if (elect_one_sync()) {
-                mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
-                tma_load_3d(sQ + st * TILE_BYTES, &tq, &qdo_full[st], 0, i << 7, z);
-                tma_load_3d(sdO + st * TILE_BYTES, &tdo, &qdo_full[st], 0, i << 7, z);
+                mbar_expect_tx(&kv_full[ks], 2 * TILE_BYTES);
+                tma_load_3d(sK + ks * TILE_BYTES, &tk, &kv_full[ks], 0, kv0, z);
+                tma_load_3d(sV + ks * TILE_BYTES, &tv, &kv_full[ks], 0, kv0, z);
             }
             __syncwarp();
+            for (int i = 0; i < nq_tiles; ++i, ++t) {
+                const uint32_t st = t & 1;
+                MBWAIT(&qdo_empty[st], ((t >> 1) & 1) ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
+                    tma_load_3d(sQ + st * TILE_BYTES, &tq, &qdo_full[st], 0, i << 7, z);
+                    tma_load_3d(sdO + st * TILE_BYTES, &tdo, &qdo_full[st], 0, i << 7, z);
+                }
+                __syncwarp();
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
         const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
         const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
-        const uint32_t idesc_s = make_idesc_bf16(128, nkv16, false, false);
         const uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);    // dV, dK: A and B MN-major
         const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
-        auto issue_sdp = [&](int i) {
-            const int st = i & 1;
-            MBWAIT(&qdo_full[st], ((uint32_t)i >> 1) & 1);
+        // S = Q K^T and dP = dO V^T of global tile tt, which belongs to the item with key stage ks / width nkv16
+        auto issue_sdp = [&](uint32_t tt, uint32_t ks, int nkv16) {
+            const uint32_t st = tt & 1;
+            MBWAIT(&qdo_full[st], (tt >> 1) & 1);
             tc_fence_after();
+            const uint32_t idesc_s = make_idesc_bf16(128, nkv16, false, false);
             if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tmem_base + TM_S, make_smem_desc(aQ + st * TILE_BYTES + k * 32, 16, 1024),
-                             make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                             make_smem_desc(aK + ks * TILE_BYTES + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tmem_base + TM_DP, make_smem_desc(adO + st * TILE_BYTES + k * 32, 16, 1024),
-                             make_smem_desc(aV + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                             make_smem_desc(aV + ks * TILE_BYTES + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(sdp_full);
-                TRACE(8 + 2 * i);
+                TRACE(tt < 8 ? 8 + 2 * (int)tt : 64);
             }
             __syncwarp();
         };
-        MBWAIT(kv_full, 0);
-        issue_sdp(0);
-        for (int i = 0; i < nq_tiles; ++i) {
-            const int st = i & 1;
-            MBWAIT(pds_full, (uint32_t)i & 1);  // Pd_i, dS_i in smem; S_i, dP_i, dQ_{i-1} read out of TMEM
-            tc_fence_after();
-            if (i + 1 < nq_tiles) issue_sdp(i + 1);
-            const int qsteps = ((min(128, p.L - (i << 7)) + 15) & ~15) >> 4;  // query rows are the K dimension
-            const int ksteps = nkv16 >> 4;
-            if (elect_one_sync()) {
-                for (int ks = 0; ks < qsteps; ++ks)
-                    umma_f16(tmem_base + TM_DV, make_smem_desc(aPd + ks * 2048, 16384, 1024),
-                             make_smem_desc(adO + st * TILE_BYTES + ks * 2048, 16384, 1024), idesc_t, (i | ks) != 0 ? 1u : 0u);
-                for (int ks = 0; ks < qsteps; ++ks)
-                    umma_f16(tmem_base + TM_DK, make_smem_desc(adS + ks * 2048, 16384, 1024),
-                             make_smem_desc(aQ + st * TILE_BYTES + ks * 2048, 16384, 1024), idesc_t, (i | ks) != 0 ? 1u : 0u);
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma_f16(tmem_base + TM_DQ, make_smem_desc(adS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                             make_smem_desc(aK + ks * 2048, 16384, 1024), idesc_dq, ks != 0 ? 1u : 0u);
-                umma_commit(dq_full);
-                umma_commit(&qdo_empty[st]);
-                TRACE(9 + 2 * i);
+        uint32_t t = 0, n = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n) {
+            const int z = w / n_kv, kv0 = (w - z * n_kv) << 7;
+            const int nkv16 = (min(128, p.S - kv0) + 15) & ~15;
+            const uint32_t ks = n & 1;
+            if (n == 0) {
+                MBWAIT(&kv_full[0], 0);
+                issue_sdp(0, 0, nkv16);
             }
-            __syncwarp();
+            for (int i = 0; i < nq_tiles; ++i, ++t) {
+                const uint32_t st = t & 1;
+                MBWAIT(pds_full, t & 1);  // Pd_t, dS_t in smem; S_t, dP_t, dQ_{t-1} read out of TMEM
+                tc_fence_after();
+                // look ahead: scores of the next tile -- of this item or of the first tile of the next one.
+                // Preferred order is A(t+1) then B(t) (the softmax warps get their next tile sooner); if
+                // the next Q / dO tile has not landed yet, B(t) goes first instead of idling behind the load.
+                bool has_next = false;
+                uint32_t ks2 = ks;
+                int nkv16_2 = nkv16;
+                if (i + 1 < nq_tiles) {
+                    has_next = true;
+                } else if (w + (int)gridDim.x < n_items) {
+                    has_next = true;
+                    const int w2 = w + (int)gridDim.x;
+                    const int kv2 = (w2 - (w2 / n_kv) * n_kv) << 7;
+                    ks2 = ks ^ 1;
+                    nkv16_2 = (min(128, p.S - kv2) + 15) & ~15;
+                    MBWAIT(&kv_full[ks2], ((n + 1) >> 1) & 1);
+                }
+                bool next_ready = false;
+                if (has_next) {
+                    uint32_t ok = 0;
+                    if (lane == 0) ok = mbar_try_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1) ? 1u : 0u;
+                    next_ready = __shfl_sync(PCM_FULL_MASK, ok, 0) != 0;
+                    if (next_ready) issue_sdp(t + 1, ks2, nkv16_2);
+                }
+                if (i == 0 && n > 0) {  // the previous item's dV / dK accumulators have been drained
+                    MBWAIT(dkv_empty, (n - 1) & 1);
+                    tc_fence_after();
+                }
+                const int qsteps = ((min(128, p.L - (i << 7)) + 15) & ~15) >> 4;  // query rows are the K dimension
+                const int ksteps = nkv16 >> 4;
+                if (elect_one_sync()) {
+                    for (int q = 0; q < qsteps; ++q)
+                        umma_f16(tmem_base + TM_DV, make_smem_desc(aPd + q * 2048, 16384, 1024),
+                                 make_smem_desc(adO + st * TILE_BYTES + q * 2048, 16384, 1024), idesc_t, (i | q) != 0 ? 1u : 0u);
+                    for (int q = 0; q < qsteps; ++q)
+                        umma_f16(tmem_base + TM_DK, make_smem_desc(adS + q * 2048, 16384, 1024),
+                                 make_smem_desc(aQ + st * TILE_BYTES + q * 2048, 16384, 1024), idesc_t, (i | q) != 0 ? 1u : 0u);
+                    for (int q = 0; q < ksteps; ++q)
+                        umma_f16(tmem_base + TM_DQ, make_smem_desc(adS + (q >> 2) * 16384 + (q & 3) * 32, 16, 1024),
+                                 make_smem_desc(aK + ks * TILE_BYTES + q * 2048, 16384, 1024), idesc_dq, q != 0 ? 1u : 0u);
+                    umma_commit(dq_full);
+                    umma_commit(&qdo_empty[st]);
+                    if (i == nq_tiles - 1) umma_commit(&kv_empty[ks]);
+                    TRACE(t < 8 ? 9 + 2 * (int)t : 64);
+                }
+                __syncwarp();
+                if (has_next && !next_ready) issue_sdp(t + 1, ks2, nkv16_2);
+            }
         }
     } else {
         // ===== softmax / gradient warps: thread = (query row, 64-key half) =====
@@ -545,15 +624,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
         if (DROPOUT) seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
         uint32_t v[32], w[32];
         const bool tr = warp == 2 && lane == 0;
+        uint8_t* stage = sStage + (warp - 2) * 4096;
 
-        // dQ_{i_prev} columns [half*32, +32) of this thread's row: TMEM -> registers -> (scaled)
-        // 16-byte reductions into the global fp32 accumulator
-        auto flush_dq = [&]() {
+        // The TMEM results of tile t-1 (its dQ tile and, if it closed an item, that item's dV / dK) are
+        // drained while tile t's Pd / dS are already on their way to the MMA warp: the arithmetic of a
+        // tile never waits for the previous tile's (or item's) gradient MMAs.
+        int pz = 0, pkv0 = 0, pi = 0;  // previous tile: batch*head, key offset, query tile
+        bool have_prev = false, prev_last = false;
+        uint32_t dvp[16];
+        auto drain_load = [&]() {  // TMEM -> registers (must complete before the barrier arrive)
             tmem_ld_32x32b_x32(t_row + TM_DQ + half * 32, v);
             tmem_ld_wait(v);
+            if (prev_last) {
+                tmem_ld_32x32b_x32(t_row + TM_DV + half * 32, w);
+                tmem_ld_wait(w);
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    dvp[q] = pack_bf16(__uint_as_float(w[2 * q]) * keep_scale, __uint_as_float(w[2 * q + 1]) * keep_scale);
+                tmem_ld_32x32b_x32(t_row + TM_DK + half * 32, w);
+                tmem_ld_wait(w);
+            }
         };
-        uint8_t* stage = sStage + (warp - 2) * 4096;
-        auto red_dq = [&](int i_prev) {
+        auto drain_store = [&]() {  // registers -> staging -> global, lanes running along rows
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 8; ++c) stage_put(stage, lane, c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -561,164 +653,176 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rl = it * 4 + (lane >> 3), piece = lane & 7;
-                const int lq = (i_prev << 7) + quad * 32 + rl;
+                const int lq = (pi << 7) + quad * 32 + rl;
                 if (lq < p.L) {
                     const uint4 x = stage_get(stage, rl, piece);
-                    red_add_v4(p.dQacc + ((size_t)z * p.L + lq) * 64 + half * 32 + piece * 4, __uint_as_float(x.x) * sc,
+                    red_add_v4(p.dQacc + ((size_t)pz * p.L + lq) * 64 + half * 32 + piece * 4, __uint_as_float(x.x) * sc,
                                __uint_as_float(x.y) * sc, __uint_as_float(x.z) * sc, __uint_as_float(x.w) * sc);
+                }
+            }
+            if (prev_last) {
+                const int pb = pz / p.nh, ph = pz - pb * p.nh;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    stage_put(stage, lane, q, dvp[4 * q], dvp[4 * q + 1], dvp[4 * q + 2], dvp[4 * q + 3]);
+                    stage_put(stage, lane, 4 + q, pack_bf16(__uint_as_float(w[8 * q]) * sc, __uint_as_float(w[8 * q + 1]) * sc),
+                              pack_bf16(__uint_as_float(w[8 * q + 2]) * sc, __uint_as_float(w[8 * q + 3]) * sc),
+                              pack_bf16(__uint_as_float(w[8 * q + 4]) * sc, __uint_as_float(w[8 * q + 5]) * sc),
+                              pack_bf16(__uint_as_float(w[8 * q + 6]) * sc, __uint_as_float(w[8 * q + 7]) * sc));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rl = it * 4 + (lane >> 3), piece = lane & 7;
+                    const int sr = pkv0 + quad * 32 + rl;
+                    if (sr < p.S) {
+                        const size_t off = ((size_t)sr * p.B + pb) * p.ldkv + ph * 64 + half * 32 + (piece & 3) * 8;
+                        *reinterpret_cast<uint4*>((piece < 4 ? p.dV : p.dK) + off) = stage_get(stage, rl, piece);
+                    }
                 }
             }
         };
 
-        // per-row statistics of the NEXT tile are fetched one iteration ahead
-        float lse_n = row < p.L ? p.lse[(size_t)z * p.L + row] : INFINITY;
-        float delta_n = row < p.L ? p.delta[(size_t)z * p.L + row] : 0.f;
-        for (int i = 0; i < nq_tiles; ++i) {
-            const int nq = min(128, p.L - (i << 7));
-            const int nq16 = (nq + 15) & ~15;
-            const bool warp_active = quad * 32 < nq16;  // warp-uniform: rows this warp owns are read by the MMAs
-            const int l = (i << 7) + row;
-            const bool row_valid = row < nq;
-            const float lse_r = lse_n, delta_r = delta_n;
-            if (i + 1 < nq_tiles) {
-                const int l2 = l + 128;
-                lse_n = l2 < p.L ? p.lse[(size_t)z * p.L + l2] : INFINITY;
-                delta_n = l2 < p.L ? p.delta[(size_t)z * p.L + l2] : 0.f;
+        uint32_t t = 0, n = 0;
+        for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++n) {
+            const int z = wi / n_kv, kv0 = (wi - z * n_kv) << 7;
+            const int b = z / p.nh;
+            const int nkv16 = (min(128, p.S - kv0) + 15) & ~15;
+            // valid-key bits of this thread's two 32-key chunks
+            uint32_t kb[2];
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int col = kv0 + (half * 2 + c2) * 32 + lane;
+                const bool valid = col < p.S && !(p.kpm != nullptr && p.kpm[(size_t)b * p.S + col] != 0);
+                kb[c2] = __ballot_sync(PCM_FULL_MASK, valid);
             }
-            uint32_t rseed = 0;
-            if (DROPOUT) rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
-            uint32_t pd_pk[32], ds_pk[32];
-            MBWAIT(sdp_full, (uint32_t)i & 1);
-            tc_fence_after();
-            if (tr) TRACE(24 + 5 * i);
-            if (warp_active) {
+            // per-row statistics of the NEXT tile are fetched one iteration ahead
+            float lse_n = row < p.L ? p.lse[(size_t)z * p.L + row] : INFINITY;
+            float delta_n = row < p.L ? p.delta[(size_t)z * p.L + row] : 0.f;
+            for (int i = 0; i < nq_tiles; ++i, ++t) {
+                const int nq = min(128, p.L - (i << 7));
+                const int nq16 = (nq + 15) & ~15;
+                const bool warp_active = quad * 32 < nq16;  // warp-uniform: rows this warp owns are read by the MMAs
+                const int l = (i << 7) + row;
+                const bool row_valid = row < nq;
+                const float lse_r = lse_n, delta_r = delta_n;
+                if (i + 1 < nq_tiles) {
+                    const int l2 = l + 128;
+                    lse_n = l2 < p.L ? p.lse[(size_t)z * p.L + l2] : INFINITY;
+                    delta_n = l2 < p.L ? p.delta[(size_t)z * p.L + l2] : 0.f;
+                }
+                uint32_t rseed = 0;
+                if (DROPOUT) rseed = pcm_row_seed(seed, (unsigned long long)z * p.L + l);
+                // Pd / dS smem (and the TMEM results of tile t-1) become free when tile t-1's MMAs complete;
+                // that is waited for only in front of the first shared-memory store, i.e. after half of the
+                // tile's arithmetic
+                bool prev_done = !have_prev;
+                auto wait_prev = [&]() {
+                    if (!prev_done) {
+                        MBWAIT(dq_full, (t - 1) & 1);
+                        tc_fence_after();
+                        prev_done = true;
+                    }
+                };
+                MBWAIT(sdp_full, t & 1);
+                tc_fence_after();
+                if (tr) TRACE(t < 7 ? 24 + 5 * (int)t : 64);
+                if (warp_active) {
 #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int c = half * 2 + c2;
-                    if (c * 32 < nkv16) {
-                        tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                        tmem_ld_32x32b_x32(t_row + TM_DP + c * 32, w);
-                        const uint32_t bits = row_valid ? kbits[c] : 0u;
-                        uint32_t hb[4];
-                        if (DROPOUT) {
-                            const uint32_t grp0 = (uint32_t)(kv0 + c * 32) >> 3;
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int c = half * 2 + c2;
+                        if (c * 32 < nkv16) {
+                            tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
+                            tmem_ld_32x32b_x32(t_row + TM_DP + c * 32, w);
+                            const uint32_t bits = row_valid ? kb[c2] : 0u;
+                            uint32_t hb[4];
+                            if (DROPOUT) {
+                                const uint32_t grp0 = (uint32_t)(kv0 + c * 32) >> 3;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
-                        }
-                        tmem_ld_wait(v);
-                        tmem_ld_wait(w);
-                        float pr[32], g[32];
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -lse_r));
-                            g[e] = __uint_as_float(w[e]);
-                        }
-                        if (bits != 0xFFFFFFFFu) {  // masked keys, rows past L, columns past nkv16 (uninitialised TMEM)
+                                for (int q = 0; q < 4; ++q) hb[q] = pcm_pair_bits(rseed, grp0 + q);
+                            }
+                            tmem_ld_wait(v);
+                            tmem_ld_wait(w);
+                            float pr[32], g[32];
+                            uint32_t pd_pk[16], ds_pk[16];
 #pragma unroll
                             for (int e = 0; e < 32; ++e) {
-                                pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
-                                g[e] = ((bits >> e) & 1u) ? g[e] : 0.f;
+                                pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -lse_r));
+                                g[e] = __uint_as_float(w[e]);
                             }
-                        }
-                        // dropout: Pd = keep ? P : 0 and dS = P * (keep ? keep_scale * dP : 0 - delta); the
-                        // keep_scale of Pd and the softmax scale of dS are folded into the epilogues
-                        if (DROPOUT) {
+                            if (bits != 0xFFFFFFFFu) {  // masked keys, rows past L, columns past nkv16 (uninitialised TMEM)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t x = hb[q];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    const bool keep = x >= thr_hi;
-                                    x = pcm_lcg_next(x);
-                                    g[8 * q + k] = keep ? g[8 * q + k] : 0.f;
-                                    w[8 * q + k] = __float_as_uint(keep ? pr[8 * q + k] : 0.f);
+                                for (int e = 0; e < 32; ++e) {
+                                    pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
+                                    g[e] = ((bits >> e) & 1u) ? g[e] : 0.f;
                                 }
                             }
+                            // dropout: Pd = keep ? P : 0 and dS = P * (keep ? keep_scale * dP : 0 - delta); the
+                            // keep_scale of Pd and the softmax scale of dS are folded into the epilogues
+                            if (DROPOUT) {
 #pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                pd_pk[c2 * 16 + q] = pack_bf16(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
+                                for (int q = 0; q < 4; ++q) {
+                                    uint32_t x = hb[q];
 #pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                ds_pk[c2 * 16 + q] = pack_bf16(pr[2 * q] * fmaf(g[2 * q], keep_scale, -delta_r),
-                                                               pr[2 * q + 1] * fmaf(g[2 * q + 1], keep_scale, -delta_r));
-                        } else {
+                                    for (int k = 0; k < 8; ++k) {
+                                        const bool keep = x >= thr_hi;
+                                        x = pcm_lcg_next(x);
+                                        g[8 * q + k] = keep ? g[8 * q + k] : 0.f;
+                                        w[8 * q + k] = __float_as_uint(keep ? pr[8 * q + k] : 0.f);
+                                    }
+                                }
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) pd_pk[c2 * 16 + q] = pack_bf16(pr[2 * q], pr[2 * q + 1]);
+                                for (int q = 0; q < 16; ++q)
+                                    pd_pk[q] = pack_bf16(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
 #pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                ds_pk[c2 * 16 + q] = pack_bf16(pr[2 * q] * (g[2 * q] - delta_r), pr[2 * q + 1] * (g[2 * q + 1] - delta_r));
+                                for (int q = 0; q < 16; ++q)
+                                    ds_pk[q] = pack_bf16(pr[2 * q] * fmaf(g[2 * q], keep_scale, -delta_r),
+                                                         pr[2 * q + 1] * fmaf(g[2 * q + 1], keep_scale, -delta_r));
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) pd_pk[q] = pack_bf16(pr[2 * q], pr[2 * q + 1]);
+#pragma unroll
+                                for (int q = 0; q < 16; ++q)
+                                    ds_pk[q] = pack_bf16(pr[2 * q] * (g[2 * q] - delta_r), pr[2 * q + 1] * (g[2 * q + 1] - delta_r));
+                            }
+                            if (tr && c2 == 0) TRACE(t < 7 ? 25 + 5 * (int)t : 64);
+                            wait_prev();
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t off = sw128_off(c >> 1, row, (c & 1) * 4 + q);
+                                st_shared_v4(sPd + off, pd_pk[4 * q], pd_pk[4 * q + 1], pd_pk[4 * q + 2], pd_pk[4 * q + 3]);
+                                st_shared_v4(sdS + off, ds_pk[4 * q], ds_pk[4 * q + 1], ds_pk[4 * q + 2], ds_pk[4 * q + 3]);
+                            }
                         }
                     }
                 }
-            }
-            if (tr) TRACE(25 + 5 * i);
-            if (i > 0) {
-                MBWAIT(dq_full, ((uint32_t)i - 1) & 1);  // tile i-1's MMAs are done: Pd / dS smem free, dQ_{i-1} ready
-                tc_fence_after();
-            }
-            if (tr) TRACE(26 + 5 * i);
-            if (warp_active) {
-#pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int c = half * 2 + c2;
-                    if (c * 32 < nkv16) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t off = sw128_off(c >> 1, row, (c & 1) * 4 + q);
-                            st_shared_v4(sPd + off, pd_pk[c2 * 16 + 4 * q], pd_pk[c2 * 16 + 4 * q + 1], pd_pk[c2 * 16 + 4 * q + 2],
-                                         pd_pk[c2 * 16 + 4 * q + 3]);
-                            st_shared_v4(sdS + off, ds_pk[c2 * 16 + 4 * q], ds_pk[c2 * 16 + 4 * q + 1], ds_pk[c2 * 16 + 4 * q + 2],
-                                         ds_pk[c2 * 16 + 4 * q + 3]);
-                        }
-                    }
+                wait_prev();
+                if (tr) TRACE(t < 7 ? 26 + 5 * (int)t : 64);
+                fence_proxy_async();
+                if (have_prev) drain_load();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(pds_full);
+                    if (have_prev && prev_last) mbar_arrive(dkv_empty);  // the closed item's accumulators are drained
                 }
-            }
-            fence_proxy_async();
-            if (i > 0) flush_dq();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
-            if (tr) TRACE(27 + 5 * i);
-            if (i > 0) red_dq(i - 1);
-            if (tr) TRACE(28 + 5 * i);
-        }
-        MBWAIT(dq_full, ((uint32_t)nq_tiles - 1) & 1);
-        tc_fence_after();
-        if (tr) TRACE(60);
-        flush_dq();
-        red_dq(nq_tiles - 1);
-        if (tr) TRACE(61);
-        // dV, dK: this thread's key row, columns [half*32, +32); dK carries the softmax scale
-        tmem_ld_32x32b_x32(t_row + TM_DV + half * 32, v);
-        tmem_ld_32x32b_x32(t_row + TM_DK + half * 32, w);
-        tmem_ld_wait(v);
-        tmem_ld_wait(w);
-        {
-            uint8_t* st2 = sPd + (warp - 2) * 4096;  // Pd tile is free: the last MMAs have completed
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                stage_put(st2, lane, q, pack_bf16(__uint_as_float(v[8 * q]) * keep_scale, __uint_as_float(v[8 * q + 1]) * keep_scale),
-                          pack_bf16(__uint_as_float(v[8 * q + 2]) * keep_scale, __uint_as_float(v[8 * q + 3]) * keep_scale),
-                          pack_bf16(__uint_as_float(v[8 * q + 4]) * keep_scale, __uint_as_float(v[8 * q + 5]) * keep_scale),
-                          pack_bf16(__uint_as_float(v[8 * q + 6]) * keep_scale, __uint_as_float(v[8 * q + 7]) * keep_scale));
-                stage_put(st2, lane, 4 + q, pack_bf16(__uint_as_float(w[8 * q]) * sc, __uint_as_float(w[8 * q + 1]) * sc),
-                          pack_bf16(__uint_as_float(w[8 * q + 2]) * sc, __uint_as_float(w[8 * q + 3]) * sc),
-                          pack_bf16(__uint_as_float(w[8 * q + 4]) * sc, __uint_as_float(w[8 * q + 5]) * sc),
-                          pack_bf16(__uint_as_float(w[8 * q + 6]) * sc, __uint_as_float(w[8 * q + 7]) * sc));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
-                const int sr = kv0 + quad * 32 + rl;
-                if (sr < p.S) {
-                    const size_t off = ((size_t)sr * p.B + b) * p.ldkv + h * 64 + half * 32 + (piece & 3) * 8;
-                    *reinterpret_cast<uint4*>((piece < 4 ? p.dV : p.dK) + off) = stage_get(st2, rl, piece);
-                }
+                if (tr) TRACE(t < 7 ? 27 + 5 * (int)t : 64);
+                if (have_prev) drain_store();
+                if (tr) TRACE(t < 7 ? 28 + 5 * (int)t : 64);
+                pz = z; pkv0 = kv0; pi = i;
+                prev_last = (i == nq_tiles - 1);
+                have_prev = true;
             }
         }
+        if (have_prev) {  // the very last tile of this CTA
+            MBWAIT(dq_full, (t - 1) & 1);
+            tc_fence_after();
+            drain_load();
+            drain_store();
+        }
+        if (tr) TRACE(62);
     }
-    if (warp == 2 && lane == 0) TRACE(62);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -739,7 +843,6 @@ int fill_common(FlashParams& p, int B, int nh, int L, int S, const unsigned char
                 const unsigned long long* seed_base, unsigned long long seed_offset) {
     if (B <= 0 || nh <= 0 || L <= 0 || S <= 0 || !(scale > 0.f)) return PCM_EINVAL;
     if (p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
-    if (S > MAX_KEYS) return PCM_EUNSUPPORTED;
     p.B = B; p.nh = nh; p.L = L; p.S = S; p.kpm = kpm;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
     p.thr16 = p_drop > 0.f ? pcm_drop_thr16(p_drop) : 0u;
@@ -776,7 +879,15 @@ PCM_API int pcm_flash_attn_fwd(int B, int nh, int L, int S, const void* Q, const
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    const long grid = (long)Z * ((L + 127) / 128);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const long items = (long)Z * ((L + 127) / 128);
+    const long grid = items < 2L * num_sms ? items : 2L * num_sms;
     if (p.thr16)
         flash_fwd_kernel<true><<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
     else
@@ -820,7 +931,15 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     flash_delta_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dO), reinterpret_cast<const __nv_bfloat16*>(O),
                                           ldo, B, nh, L, rows, delta);
     if ((r = pcm_launch_status())) return r;
-    const long grid = (long)Z * ((S + 127) / 128);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const long items = (long)Z * ((S + 127) / 128);
+    const long grid = items < num_sms ? items : num_sms;
     if (p.thr16)
         flash_bwd_kernel<true><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
     else
