@@ -265,6 +265,20 @@ int pcm_add_dropout_ln_bwd(long long rows, int C, const float *dy, const float *
                            const float *rstd, const float *gamma, float p_drop,
                            const unsigned long long *seed_base, unsigned long long seed_offset,
                            float *dres, float *dx, float *dgamma, float *dbeta, pcm_stream_t stream);
+/* Extended forms: the forward can additionally emit ypos_bf16 = bf16(y + pos[r / pos_row_div]) --
+ * the `with_pos_embed` operand of the NEXT attention block (transformer.py:235-236), so no separate
+ * add + cast pass reads y again; the backward can emit dx_bf16 = bf16(dx), the operand of the
+ * sub-block's backward GEMMs. */
+int pcm_add_dropout_ln_fwd_ex(long long rows, int C, const float *x, const float *res,
+                              const float *gamma, const float *beta, float eps, float p_drop,
+                              const unsigned long long *seed_base, unsigned long long seed_offset,
+                              float *y, void *y_bf16, float *h, float *mean, float *rstd,
+                              const float *pos, int pos_row_div, void *ypos_bf16, pcm_stream_t stream);
+int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const float *h, const float *mean,
+                              const float *rstd, const float *gamma, float p_drop,
+                              const unsigned long long *seed_base, unsigned long long seed_offset,
+                              float *dres, float *dx, float *dgamma, float *dbeta, void *dx_bf16,
+                              pcm_stream_t stream);
 int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
                pcm_stream_t stream);
 /* out = bf16(a + b): `with_pos_embed` (transformer.py:235-236) fused with the operand cast of the

@@ -217,12 +217,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
             for (int j = 0; j < n_kv; ++j, ++t) {
                 MBWAIT(p_full, t & 1);  // P_t in smem; S_t and PV_{t-1} have been read out of TMEM
                 tc_fence_after();
-                if (j + 1 < n_kv) {
-                    issue_s(t + 1, j + 1);
-                } else if (w + (int)gridDim.x < n_items) {
-                    MBWAIT(q_full, (n + 1) & 1);
-                    issue_s(t + 1, 0);
-                }
+                // PV_t goes to the tensor pipe BEFORE S_{t+1}: the pipe executes in order, so when the
+                // softmax warps receive S_{t+1} the product they still have to collect (and the P tile
+                // they are about to overwrite) is already finished with -- no second wait per tile
                 MBWAIT(v_full, t & 1);
                 tc_fence_after();
                 const int ksteps = ((min(128, p.S - (j << 7)) + 15) & ~15) >> 4;
@@ -235,6 +232,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                     TRACE(t < 8 ? 9 + 2 * (int)t : 64);
                 }
                 __syncwarp();
+                if (j + 1 < n_kv) {
+                    issue_s(t + 1, j + 1);
+                } else if (w + (int)gridDim.x < n_items) {
+                    MBWAIT(q_full, (n + 1) & 1);
+                    issue_s(t + 1, 0);
+                }
             }
         }
     } else {
@@ -279,8 +282,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                 MBWAIT(s_full, t & 1);
                 tc_fence_after();
                 if (tr) TRACE(t < 7 ? 24 + 5 * (int)t : 64);
-                float alpha = 1.f, m_use = 0.f, m_new = m;
-                if (warp_active) {
+                // Lazy reference maximum: only the first key tile of an item pays the max pass.  Later
+                // tiles exponentiate against the reference m the row already has -- probabilities may
+                // then exceed 1, which is exact as long as nothing overflows (O, the row sum and the
+                // log-sum-exp all carry the same reference) -- and a warp falls back to the exact
+                // max + rescale path only if a row sum leaves the safe range (scores that grow by more
+                // than ~100 octaves between key tiles).
+                auto row_max = [&]() -> float {  // raw (unscaled) maximum over the valid keys of this tile
                     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
@@ -297,29 +305,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                                 mx[e & 3] = fmaxf(mx[e & 3], ((bits >> e) & 1u) ? __uint_as_float(v[e]) : -INFINITY);
                         }
                     }
-                    // the scale is positive: max(scale * s) = scale * max(s)
-                    m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
-                    m_use = m_new == -INFINITY ? 0.f : m_new;
-                    alpha = fast_exp2(m - m_use);
-                }
-                if (tr) TRACE(t < 7 ? 25 + 5 * (int)t : 64);
-                if (j > 0) {
-                    MBWAIT(pv_full, (t - 1) & 1);
-                    tc_fence_after();
-                    if (warp_active) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
-                            tmem_ld_wait(v);
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) o[c * 32 + e] = (o[c * 32 + e] + __uint_as_float(v[e])) * alpha;
-                        }
-                    }
-                }
-                if (tr) TRACE(t < 7 ? 26 + 5 * (int)t : 64);
-                if (warp_active) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ls[q] *= alpha;
+                    return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                };
+                auto emit_p = [&](float m_ref) {  // P = exp2(scale*s - m_ref) -> row sums, dropout, bf16 tile in smem
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 >= nkv) break;
@@ -334,7 +322,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                         tmem_ld_wait(v);
                         float pr[32];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_use));
+                        for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref));
                         if (bits != 0xFFFFFFFFu) {
 #pragma unroll
                             for (int e = 0; e < 32; ++e) pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
@@ -358,8 +346,60 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                                          pack_bf16(pr[8 * i + 2], pr[8 * i + 3]), pack_bf16(pr[8 * i + 4], pr[8 * i + 5]),
                                          pack_bf16(pr[8 * i + 6], pr[8 * i + 7]));
                     }
-                    m = m_new;
+                };
+                float m_ref = 0.f;
+                bool row_has_ref = true;
+                if (warp_active && j == 0) {  // exact: the scale is positive, max(scale * s) = scale * max(s)
+                    const float m0 = row_max() * sl2;
+                    row_has_ref = m0 != -INFINITY;
+                    m_ref = row_has_ref ? m0 : 0.f;
+                } else {
+                    row_has_ref = m != -INFINITY;
+                    m_ref = row_has_ref ? m : 0.f;
                 }
+                if (tr) TRACE(t < 7 ? 25 + 5 * (int)t : 64);
+                // O += P_{t-1} V_{t-1}: with a common reference there is no rescale between tiles, so the
+                // previous tile's product is collected AFTER this tile's probabilities are on their way
+                // (its MMA was issued behind S_t and is still in flight when S_t arrives)
+                bool pv_collected = (j == 0);
+                auto collect_pv = [&]() {
+                    if (!pv_collected) {
+                        MBWAIT(pv_full, (t - 1) & 1);
+                        tc_fence_after();
+                        if (warp_active) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
+                                tmem_ld_wait(v);
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                            }
+                        }
+                        pv_collected = true;
+                    }
+                };
+                if (warp_active) {
+                    const float lp0 = ls[0], lp1 = ls[1], lp2 = ls[2], lp3 = ls[3];
+                    emit_p(m_ref);
+                    const float tot = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+                    if (j > 0 && __any_sync(PCM_FULL_MASK, !(tot < 1.0e30f))) {
+                        // exact path: true maximum, rescale what the row has accumulated, redo the tile
+                        collect_pv();
+                        const float m_new = fmaxf(row_has_ref ? m_ref : -INFINITY, row_max() * sl2);
+                        const float m2 = m_new == -INFINITY ? 0.f : m_new;
+                        const float alpha = row_has_ref ? fast_exp2(m_ref - m2) : 0.f;
+#pragma unroll
+                        for (int e = 0; e < 64; ++e) o[e] *= alpha;
+                        ls[0] = lp0 * alpha; ls[1] = lp1 * alpha; ls[2] = lp2 * alpha; ls[3] = lp3 * alpha;
+                        row_has_ref = m_new != -INFINITY;
+                        m_ref = m2;
+                        emit_p(m_ref);
+                    }
+                    // the reference only counts once a valid key has been seen
+                    m = (row_has_ref || (ls[0] + ls[1]) + (ls[2] + ls[3]) > 0.f) ? m_ref : -INFINITY;
+                }
+                if (tr) TRACE(t < 7 ? 26 + 5 * (int)t : 64);
+                collect_pv();
                 if (tr) TRACE(t < 7 ? 27 + 5 * (int)t : 64);
                 tc_fence_before();
                 fence_proxy_async();
@@ -456,6 +496,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                                                                     const __grid_constant__ CUtensorMap tk,
                                                                     const __grid_constant__ CUtensorMap tv,
                                                                     const __grid_constant__ CUtensorMap tdo,
+                                                                    const __grid_constant__ CUtensorMap tdq,
+                                                                    const __grid_constant__ CUtensorMap tdk,
+                                                                    const __grid_constant__ CUtensorMap tdv,
                                                                     const FlashParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -485,6 +528,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
     if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv); prefetch_tmap(&tdo);
+        prefetch_tmap(&tdq); prefetch_tmap(&tdk); prefetch_tmap(&tdv);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
             mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1);
@@ -624,8 +668,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
         if (DROPOUT) seed = (p.seed_base ? *p.seed_base : 0ULL) * 0xD1342543DE82EF95ULL + p.seed_offset;
         uint32_t v[32], w[32];
         const bool tr = warp == 2 && lane == 0;
-        uint8_t* stage = sStage + (warp - 2) * 4096;
-
         // The TMEM results of tile t-1 (its dQ tile and, if it closed an item, that item's dV / dK) are
         // drained while tile t's Pd / dS are already on their way to the MMA warp: the arithmetic of a
         // tile never waits for the previous tile's (or item's) gradient MMAs.
@@ -645,41 +687,45 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                 tmem_ld_wait(w);
             }
         };
-        auto drain_store = [&]() {  // registers -> staging -> global, lanes running along rows
-            __syncwarp();
+        // registers -> SWIZZLE_128B staging tiles -> global through the TMA: the 128 x 64 fp32 dQ tile
+        // leaves as two bulk tensor REDUCTIONS (add), the bf16 dV / dK tiles of a finished item as two
+        // bulk tensor stores -- no red / st.global instruction streams in the softmax warps, rows past
+        // L / S are clipped by the tensor maps.  Staging is shared by the 8 warps (named barrier 1).
+        const bool issuer = (warp == 2 && lane == 0);
+        auto drain_store = [&]() {
+            if (issuer) bulk_wait_read_all();  // earlier bulk operations have finished reading the staging tiles
+            named_bar_sync(1, 256);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) stage_put(stage, lane, c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rl = it * 4 + (lane >> 3), piece = lane & 7;
-                const int lq = (pi << 7) + quad * 32 + rl;
-                if (lq < p.L) {
-                    const uint4 x = stage_get(stage, rl, piece);
-                    red_add_v4(p.dQacc + ((size_t)pz * p.L + lq) * 64 + half * 32 + piece * 4, __uint_as_float(x.x) * sc,
-                               __uint_as_float(x.y) * sc, __uint_as_float(x.z) * sc, __uint_as_float(x.w) * sc);
-                }
+            for (int c = 0; c < 8; ++c)
+                st_shared_v4(sStage + sw128_off(half, row, c), __float_as_uint(__uint_as_float(v[4 * c]) * sc),
+                             __float_as_uint(__uint_as_float(v[4 * c + 1]) * sc), __float_as_uint(__uint_as_float(v[4 * c + 2]) * sc),
+                             __float_as_uint(__uint_as_float(v[4 * c + 3]) * sc));
+            fence_proxy_async();
+            named_bar_sync(1, 256);
+            if (issuer) {
+                tma_reduce_add_3d(&tdq, sStage, 0, pi << 7, pz);
+                tma_reduce_add_3d(&tdq, sStage + 16384, 32, pi << 7, pz);
+                bulk_commit();
             }
             if (prev_last) {
-                const int pb = pz / p.nh, ph = pz - pb * p.nh;
-                __syncwarp();
+                if (issuer) bulk_wait_read_all();
+                named_bar_sync(1, 256);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    stage_put(stage, lane, q, dvp[4 * q], dvp[4 * q + 1], dvp[4 * q + 2], dvp[4 * q + 3]);
-                    stage_put(stage, lane, 4 + q, pack_bf16(__uint_as_float(w[8 * q]) * sc, __uint_as_float(w[8 * q + 1]) * sc),
-                              pack_bf16(__uint_as_float(w[8 * q + 2]) * sc, __uint_as_float(w[8 * q + 3]) * sc),
-                              pack_bf16(__uint_as_float(w[8 * q + 4]) * sc, __uint_as_float(w[8 * q + 5]) * sc),
-                              pack_bf16(__uint_as_float(w[8 * q + 6]) * sc, __uint_as_float(w[8 * q + 7]) * sc));
+                    st_shared_v4(sStage + sw128_off(0, row, half * 4 + q), dvp[4 * q], dvp[4 * q + 1], dvp[4 * q + 2], dvp[4 * q + 3]);
+                    st_shared_v4(sStage + sw128_off(1, row, half * 4 + q),
+                                 pack_bf16(__uint_as_float(w[8 * q]) * sc, __uint_as_float(w[8 * q + 1]) * sc),
+                                 pack_bf16(__uint_as_float(w[8 * q + 2]) * sc, __uint_as_float(w[8 * q + 3]) * sc),
+                                 pack_bf16(__uint_as_float(w[8 * q + 4]) * sc, __uint_as_float(w[8 * q + 5]) * sc),
+                                 pack_bf16(__uint_as_float(w[8 * q + 6]) * sc, __uint_as_float(w[8 * q + 7]) * sc));
                 }
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rl = it * 4 + (lane >> 3), piece = lane & 7;
-                    const int sr = pkv0 + quad * 32 + rl;
-                    if (sr < p.S) {
-                        const size_t off = ((size_t)sr * p.B + pb) * p.ldkv + ph * 64 + half * 32 + (piece & 3) * 8;
-                        *reinterpret_cast<uint4*>((piece < 4 ? p.dV : p.dK) + off) = stage_get(stage, rl, piece);
-                    }
+                fence_proxy_async();
+                named_bar_sync(1, 256);
+                if (issuer) {
+                    const int pb = pz / p.nh, ph = pz - pb * p.nh;
+                    tma_store_4d(&tdv, sStage, 0, ph, pb, pkv0);
+                    tma_store_4d(&tdk, sStage + 16384, 0, ph, pb, pkv0);
+                    bulk_commit();
                 }
             }
         };
@@ -821,6 +867,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
             drain_load();
             drain_store();
         }
+        if (issuer) bulk_wait_all();  // bulk reductions / stores complete before the CTA retires
         if (tr) TRACE(62);
     }
     tc_fence_before();
@@ -915,6 +962,20 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     if ((r = head_split_map(K, Z, S, &tk))) return r;
     if ((r = head_split_map(V, Z, S, &tv))) return r;
     if ((r = head_split_map(dO, Z, L, &tdo))) return r;
+    CUtensorMap tdq, tdk, tdv;
+    {   // fp32 dQ accumulator (Z, L, 64): boxes of 32 columns x 128 rows
+        const uint64_t dims[3] = {64, (uint64_t)L, (uint64_t)Z};
+        const uint64_t strides[2] = {256, (uint64_t)L * 256};
+        const uint32_t box[3] = {32, 128, 1};
+        if ((r = tensor_map(dQacc, true, 3, dims, strides, box, &tdq))) return r;
+    }
+    {   // token-major bf16 dK / dV: element (d, h, b, s) at ((s * B + b) * ldkv + h * 64 + d)
+        const uint64_t dims[4] = {64, (uint64_t)nh, (uint64_t)B, (uint64_t)S};
+        const uint64_t strides[3] = {128, (uint64_t)ldkv * 2, (uint64_t)B * ldkv * 2};
+        const uint32_t box[4] = {64, 1, 1, 128};
+        if ((r = tensor_map(dK, false, 4, dims, strides, box, &tdk))) return r;
+        if ((r = tensor_map(dV, false, 4, dims, strides, box, &tdv))) return r;
+    }
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
@@ -941,9 +1002,9 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     const long items = (long)Z * ((S + 127) / 128);
     const long grid = items < num_sms ? items : num_sms;
     if (p.thr16)
-        flash_bwd_kernel<true><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+        flash_bwd_kernel<true><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
     else
-        flash_bwd_kernel<false><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+        flash_bwd_kernel<false><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
     if ((r = pcm_launch_status())) return r;
     flash_dq_store_kernel<<<g, 256, 0, st>>>(dQacc, B, nh, L, rows, reinterpret_cast<__nv_bfloat16*>(dQ), ldq);
     return pcm_launch_status();

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, long rows, float eps, float p_drop, const unsigned long long* __restrict__ seed_base,
     unsigned long long seed_offset, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ h_out,
-    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ pos, int pos_row_div,
+    __nv_bfloat16* __restrict__ ypos_bf16) {
     constexpr int C = 128 * V;
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -81,6 +82,14 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
                 *reinterpret_cast<uint2*>(y_bf16 + e) = pk;
             }
+            if (ypos_bf16) {  // operand of the next attention block: bf16(y + pos), pos row-broadcast over the batch
+                const float4 pv = *reinterpret_cast<const float4*>(pos + (size_t)(r / pos_row_div) * C + (size_t)(v * 32 + lane) * 4);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x + pv.x, o.y + pv.y), hi = __floats2bfloat162_rn(o.z + pv.z, o.w + pv.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(ypos_bf16 + e) = pk;
+            }
             if (h_out) *reinterpret_cast<float4*>(h_out + e) = h[v];
         }
         if (lane == 0) {
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ h, const float* __restrict__ mean_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, long rows, float p_drop,
     const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset, float* __restrict__ dres,
-    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16) {
     constexpr int C = 128 * V;
     __shared__ float sg[C], sb[C];
     const int lane = threadIdx.x & 31;
@@ -140,8 +149,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
             dh.z = rstd * (gy[v].z - c1 - xh[v].z * c2);
             dh.w = rstd * (gy[v].w - c1 - xh[v].w * c2);
             if (dres) *reinterpret_cast<float4*>(dres + e) = dh;
+            float4 o = dh;
             if (dx && dx != dres) {
-                float4 o = dh;
                 if (p_drop > 0.f) {
                     const uint32_t c = (uint32_t)(v * 32 + lane);
                     const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
@@ -151,6 +160,13 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
                     o.w = (h1 >> 16) >= thr16 ? dh.w * ks : 0.f;
                 }
                 *reinterpret_cast<float4*>(dx + e) = o;
+            }
+            if (dx_bf16) {  // bf16 copy of dx: the operand of the sub-block's backward GEMMs
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dx_bf16 + e) = pk;
             }
         }
     }
@@ -259,33 +275,52 @@ inline int ln_grid(long rows) {
 // y = LayerNorm(res + dropout(x)) (x may be NULL = plain LayerNorm(res)); C in {128, 256, 512, 1024}.
 // Optional outputs: y_bf16 (operand of the next GEMM), h (= res + dropout(x), saved for backward),
 // mean / rstd (rows).
+PCM_API int pcm_add_dropout_ln_fwd_ex(long long rows, int C, const float* x, const float* res, const float* gamma,
+                                      const float* beta, float eps, float p_drop, const unsigned long long* seed_base,
+                                      unsigned long long seed_offset, float* y, void* y_bf16, float* h, float* mean,
+                                      float* rstd, const float* pos, int pos_row_div, void* ypos_bf16,
+                                      pcm_stream_t stream) {
+    if (rows <= 0) return PCM_OK;
+    if (!res || !gamma || !beta || !y || (C % 128)) return (C % 128) ? PCM_EUNSUPPORTED : PCM_EINVAL;
+    if (ypos_bf16 && (!pos || pos_row_div < 1)) return PCM_EINVAL;
+    cudaStream_t st = pcm_cu_stream(stream);
+    const int grid = ln_grid(rows);
+    LN_DISPATCH(C / 128, add_dropout_ln_fwd_kernel, x, res, gamma, beta, rows, eps, p_drop, seed_base, seed_offset, y,
+                reinterpret_cast<__nv_bfloat16*>(y_bf16), h, mean, rstd, pos, pos_row_div,
+                reinterpret_cast<__nv_bfloat16*>(ypos_bf16))
+    return pcm_launch_status();
+}
+
 PCM_API int pcm_add_dropout_ln_fwd(long long rows, int C, const float* x, const float* res, const float* gamma,
                                    const float* beta, float eps, float p_drop, const unsigned long long* seed_base,
                                    unsigned long long seed_offset, float* y, void* y_bf16, float* h, float* mean,
                                    float* rstd, pcm_stream_t stream) {
-    if (rows <= 0) return PCM_OK;
-    if (!res || !gamma || !beta || !y || (C % 128)) return (C % 128) ? PCM_EUNSUPPORTED : PCM_EINVAL;
-    cudaStream_t st = pcm_cu_stream(stream);
-    const int grid = ln_grid(rows);
-    LN_DISPATCH(C / 128, add_dropout_ln_fwd_kernel, x, res, gamma, beta, rows, eps, p_drop, seed_base, seed_offset, y,
-                reinterpret_cast<__nv_bfloat16*>(y_bf16), h, mean, rstd)
-    return pcm_launch_status();
+    return pcm_add_dropout_ln_fwd_ex(rows, C, x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, y, y_bf16, h, mean,
+                                     rstd, nullptr, 1, nullptr, stream);
 }
 
 // dres = dLN/dh; dx = dropout-backward(dres) (pass dx == dres or NULL when not needed);
-// dgamma / dbeta are ACCUMULATED (caller zero-fills).
-PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const float* h, const float* mean,
-                                   const float* rstd, const float* gamma, float p_drop,
-                                   const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
-                                   float* dx, float* dgamma, float* dbeta, pcm_stream_t stream) {
+// dgamma / dbeta are ACCUMULATED (caller zero-fills); dx_bf16 (optional) = bf16(dx).
+PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, const float* h, const float* mean,
+                                      const float* rstd, const float* gamma, float p_drop,
+                                      const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
+                                      float* dx, float* dgamma, float* dbeta, void* dx_bf16, pcm_stream_t stream) {
     if (rows <= 0) return PCM_OK;
     if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
     if (C % 128) return PCM_EUNSUPPORTED;
     cudaStream_t st = pcm_cu_stream(stream);
     const int grid = ln_grid(rows);
     LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
-                dx, dgamma, dbeta)
+                dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16))
     return pcm_launch_status();
+}
+
+PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const float* h, const float* mean,
+                                   const float* rstd, const float* gamma, float p_drop,
+                                   const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
+                                   float* dx, float* dgamma, float* dbeta, pcm_stream_t stream) {
+    return pcm_add_dropout_ln_bwd_ex(rows, C, dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, dres, dx, dgamma, dbeta,
+                                     nullptr, stream);
 }
 
 // out[c] += sum over rows of src[r, c] (bias gradients); src_bf16 selects the element type.

@@ -98,6 +98,23 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
                  :: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+// tcgen05.wait::ld waits for ALL of the thread's outstanding tensor-memory loads; the destination
+// registers are in/out operands so that no use can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), sm_100 version field = 1.
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version [46,48), layout_type [61,64).
@@ -147,6 +164,26 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// shared -> global bulk tensor copies (TMA stores): a staged SWIZZLE_128B tile leaves as ONE
+// asynchronous operation; out-of-range rows / columns of the box are clipped by the tensor map.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// the same with an element-wise ADD into global memory (fp32 map): a reduction tile without a
+// single red / atom instruction in the SM
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // D = F32, A = B = BF16 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor):
 // a_mn / b_mn = 1 selects the MN-major ("transposed") shared-memory form of that operand.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
@@ -183,31 +220,39 @@ inline EncodeTiledFnT encode_tiled_fn() {
 
 struct TmapKey {
     const void* ptr;
-    uint64_t d[3], s[2];
-    uint32_t b[3];
-    int rank;
+    uint64_t d[4], s[3];
+    uint32_t b[4];
+    int rank, dtype;
     bool operator==(const TmapKey& o) const {
-        return ptr == o.ptr && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && s[0] == o.s[0] &&
-               s[1] == o.s[1] && b[0] == o.b[0] && b[1] == o.b[1] && b[2] == o.b[2];
+        if (ptr != o.ptr || rank != o.rank || dtype != o.dtype) return false;
+        for (int i = 0; i < 4; ++i)
+            if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
+        for (int i = 0; i < 3; ++i)
+            if (s[i] != o.s[i]) return false;
+        return true;
     }
 };
 struct TmapKeyHash {
     size_t operator()(const TmapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-        for (int i = 0; i < 3; ++i) { mix(k.d[i]); mix(k.b[i]); }
-        mix(k.s[0]); mix(k.s[1]); mix((uint64_t)k.rank);
+        for (int i = 0; i < 4; ++i) { mix(k.d[i]); mix(k.b[i]); }
+        for (int i = 0; i < 3; ++i) mix(k.s[i]);
+        mix((uint64_t)k.rank * 16 + (uint64_t)k.dtype);
         return h;
     }
 };
 
-// dims / box in elements (innermost first), strides in BYTES for dimensions 1.. (rank - 1 values).
-inline int tensor_map_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, CUtensorMap* out) {
+// Cached tensor map of rank 2..4 over bf16 (f32 = false) or fp32 (f32 = true) elements: dims / box in
+// elements (innermost first), strides in BYTES for dimensions 1.. (rank - 1 values); SWIZZLE_128B
+// boxes (inner box extent = 128 bytes), zero fill / clipping out of bounds.
+inline int tensor_map(const void* ptr, bool f32, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, CUtensorMap* out) {
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     static std::mutex mu;
+    if (rank < 2 || rank > 4) return (int)cudaErrorInvalidValue;
     TmapKey key{};
-    key.ptr = ptr; key.rank = rank;
+    key.ptr = ptr; key.rank = rank; key.dtype = f32 ? 1 : 0;
     for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) key.s[i] = strides_bytes[i];
     std::lock_guard<std::mutex> lock(mu);
@@ -215,19 +260,24 @@ inline int tensor_map_bf16(const void* ptr, int rank, const uint64_t* dims, cons
     if (it != cache.end()) { *out = it->second; return 0; }
     EncodeTiledFnT enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
-    cuuint64_t gdim[3] = {1, 1, 1}, gstr[2] = {0, 0};
-    cuuint32_t bx[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
+    cuuint64_t gdim[4] = {1, 1, 1, 1}, gstr[3] = {0, 0, 0};
+    cuuint32_t bx[4] = {1, 1, 1, 1}, estr[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                     const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 700 + (int)r;
     if (cache.size() > 8192) cache.clear();
     cache.emplace(key, m);
     *out = m;
     return 0;
+}
+
+inline int tensor_map_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, CUtensorMap* out) {
+    return tensor_map(ptr, false, rank, dims, strides_bytes, box, out);
 }
 
 }  // namespace pcm_tc

@@ -80,13 +80,48 @@ def _grad_slot(p):
     return None
 
 
+# bf16 operand copies that a kernel produced as a by-product of the fp32 tensor it wrote:
+#  * forward: attached to the fp32 activation as attributes (`_pcm_bf16`, `_pcm_bf16_pos`) by
+#    add_dropout_layernorm(); the next projection GEMM picks them up instead of running a cast pass;
+#  * backward: bf16(dx) of the LayerNorm backward, keyed by the gradient tensor's address and consumed
+#    (popped) by the sub-block backward that receives that very tensor from autograd.  Entries hold
+#    a reference to the fp32 gradient (its memory cannot be recycled under a live key) and the table
+#    is emptied by the next LayerNorm backward, so a key can never outlive its tensor.
+_GRAD_BF16 = {}
+
+
+def _act_bf16(x, rows, C):
+    """bf16 (rows, C) copy attached to activation `x`, or None."""
+    t = getattr(x, "_pcm_bf16", None)
+    if t is not None and t.numel() == rows * C and t.device == x.device:
+        return t.view(rows, C)
+    return None
+
+
+def _act_pos_bf16(x, pos, rows, C):
+    """bf16(x + pos) attached to activation `x` for exactly this `pos` object, or None."""
+    e = getattr(x, "_pcm_bf16_pos", None)
+    if e is not None and e[0] is pos and e[1].numel() == rows * C:
+        return e[1].view(rows, C)
+    return None
+
+
+def _grad_bf16(g, rows, C):
+    """bf16 copy of incoming gradient `g` left by the kernel that produced it, else a cast pass."""
+    e = _GRAD_BF16.pop(g.data_ptr(), None)
+    if e is not None and e[1].data_ptr() == g.data_ptr() and e[1].numel() == g.numel() == rows * C and g.is_contiguous():
+        return e[0].view(rows, C)
+    g2 = g.reshape(rows, C)
+    return K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T (+b) (ReLU) on the tcgen05 GEMM; backward dX = dY W and dW = dY^T X read dY, W, X in
     place through the MN-major operand forms of the same kernel (no transposes)."""
 
     @staticmethod
-    def forward(ctx, x2, weight, bias, relu, out_bf16):
-        xb = x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16)
+    def forward(ctx, x2, weight, bias, relu, out_bf16, xb_hint=None):
+        xb = xb_hint if xb_hint is not None else (x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16))
         wb = _wb(weight)
         y = K.gemm_bf16(xb, wb, bias=bias, relu=relu, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
         ctx.relu, ctx.has_bias, ctx.x_dtype = relu, bias is not None, x2.dtype
@@ -99,7 +134,11 @@ class _LinearTC(torch.autograd.Function):
         xb, wb, y = ctx.saved_tensors
         if ctx.relu:
             dy = dy * (y > 0)
-        dyb = dy.contiguous() if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+            dyb = dy.contiguous() if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        elif dy.dtype == torch.bfloat16:
+            dyb = dy.contiguous()
+        else:
+            dyb = _grad_bf16(dy, dy.shape[0], dy.shape[1])
         M, N = dyb.shape
         Kin = xb.shape[1]
         dx = dw = db = None
@@ -120,7 +159,7 @@ class _LinearTC(torch.autograd.Function):
             db = K.colsum(dyb, slot)
             if slot is not None:
                 db = None
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 def linear(x, weight, bias=None, relu=False, out_bf16=False):
@@ -138,7 +177,7 @@ def linear(x, weight, bias=None, relu=False, out_bf16=False):
             x2 = x2.contiguous()
         if weight.stride(-1) != 1:
             weight = weight.contiguous()
-        y = _LinearTC.apply(x2, weight, bias, relu, out_bf16)
+        y = _LinearTC.apply(x2, weight, bias, relu, out_bf16, _act_bf16(x, x2.shape[0], Kin))
         return y.view(*lead, N)
     y = F.linear(x.float(), weight, bias)
     return F.relu(y) if relu else y
@@ -272,12 +311,12 @@ class _MHASelf(torch.autograd.Function):
     values are the first n rows of `pos` and receives their gradient."""
 
     @staticmethod
-    def forward(ctx, x, pos, pos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+    def forward(ctx, x, pos, pos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop, xqk_hint=None, xv_hint=None):
         L, B, E = x.shape
         dev = x.device
         bf = torch.bfloat16
-        xqk_b = _tok_bf16(x, pos, L, B, E)
-        xv_b = _tok_bf16(x, None, L, B, E) if pos is not None else xqk_b
+        xqk_b = xqk_hint if xqk_hint is not None else _tok_bf16(x, pos, L, B, E)
+        xv_b = (xv_hint if xv_hint is not None else _tok_bf16(x, None, L, B, E)) if pos is not None else xqk_b
         wb, wo_b = _wb(w_in), _wb(w_out)
         Z = B * nh
         Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
@@ -300,7 +339,7 @@ class _MHASelf(torch.autograd.Function):
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
         (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
-        dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
+        dout_b = _grad_bf16(dout, L * B, E)
         _dw(dout_b, O_tok, dWo)
         K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
@@ -328,7 +367,7 @@ class _MHASelf(torch.autograd.Function):
             if need_head:  # d(x + pos) restricted to the learned leading rows: a tiny GEMM
                 n = pos_head.shape[0]
                 dhead = _pos_head_grad(K.gemm_bf16(buf[: n * B, :2 * E], wb[:2 * E], b_mn=True), pos_head, n, B, E)
-        return (dx.view(L, B, E), dpos, dhead, *rets, None, None, None)
+        return (dx.view(L, B, E), dpos, dhead, *rets, None, None, None, None, None)
 
 
 class _MHACross(torch.autograd.Function):
@@ -336,13 +375,14 @@ class _MHACross(torch.autograd.Function):
     `mpos_head`: learned leading rows of the constant `mpos` (see _MHASelf)."""
 
     @staticmethod
-    def forward(ctx, x, qpos, mem, mpos, mpos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop):
+    def forward(ctx, x, qpos, mem, mpos, mpos_head, w_in, b_in, w_out, b_out, nh, kpm, p_drop, xq_hint=None, xk_hint=None,
+                xv_hint=None):
         L, B, E = x.shape
         S = mem.shape[0]
         dev, bf = x.device, torch.bfloat16
-        xq_b = _tok_bf16(x, qpos, L, B, E)
-        xk_b = _tok_bf16(mem, mpos, S, B, E)
-        xv_b = _tok_bf16(mem, None, S, B, E) if mpos is not None else xk_b
+        xq_b = xq_hint if xq_hint is not None else _tok_bf16(x, qpos, L, B, E)
+        xk_b = xk_hint if xk_hint is not None else _tok_bf16(mem, mpos, S, B, E)
+        xv_b = (xv_hint if xv_hint is not None else _tok_bf16(mem, None, S, B, E)) if mpos is not None else xk_b
         wb, wo_b = _wb(w_in), _wb(w_out)
         Z = B * nh
         Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
@@ -368,7 +408,7 @@ class _MHACross(torch.autograd.Function):
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
         (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
-        dout_b = K.add_cast_bf16(dout.reshape(L * B, E).contiguous())
+        dout_b = _grad_bf16(dout, L * B, E)
         _dw(dout_b, O_tok, dWo)
         K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
@@ -402,7 +442,7 @@ class _MHACross(torch.autograd.Function):
                 n = mpos_head.shape[0]
                 d_k = K.gemm_bf16(kv[: n * B, :E], wb[E:2 * E], b_mn=True)
                 dhead = _pos_head_grad(d_k, mpos_head, n, B, E)
-        return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None)
+        return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None, None, None, None)
 
 
 def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=None, training=False, pos_head=None,
@@ -421,11 +461,16 @@ def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=N
     d = E // h
     p = mha.dropout if training else 0.0
     if d == 64 and E % 128 == 0:
+        # bf16 operand copies left on the activations by the LayerNorm that produced them
+        xq_hint = _act_bf16(x, L * B, E) if pos is None else _act_pos_bf16(x, pos, L * B, E)
         if mem is None:
             return _MHASelf.apply(x, pos, pos_head, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
-                                  mha.out_proj.bias, h, key_padding_mask, p)
+                                  mha.out_proj.bias, h, key_padding_mask, p, xq_hint, _act_bf16(x, L * B, E))
+        S = mem.shape[0]
+        xk_hint = _act_bf16(mem, S * B, E) if mem_pos is None else _act_pos_bf16(mem, mem_pos, S * B, E)
         return _MHACross.apply(x, pos, mem, mem_pos, mem_pos_head, mha.in_proj_weight, mha.in_proj_bias,
-                               mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p)
+                               mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p, xq_hint, xk_hint,
+                               _act_bf16(mem, S * B, E))
     if pos_head is not None:  # restore the differentiable concatenation for the composed path
         pos = torch.cat([pos_head.expand(-1, B, -1), pos[pos_head.shape[0]:]], dim=0)
     if mem_pos_head is not None:
@@ -450,45 +495,71 @@ def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=N
 
 
 class _AddDropoutLN(torch.autograd.Function):
-    """y = LayerNorm(res + dropout(x)) in one kernel each way (csrc/layernorm.cu)."""
+    """y = LayerNorm(res + dropout(x)) in one kernel each way (csrc/layernorm.cu).  Optional
+    by-products (non-differentiable): bf16(y) and bf16(y + pos), the operands of the next sub-block's
+    GEMMs; the backward leaves bf16(dx) for the sub-block backward that consumes dx."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps, p_drop):
+    def forward(ctx, x, res, gamma, beta, eps, p_drop, want_bf16, pos):
         shape = res.shape
         C = shape[-1]
         res2 = res.reshape(-1, C)
         x2 = x.reshape(-1, C) if x is not None else None
         seed_base = DROPOUT_RNG.base_for(res.device) if p_drop > 0 else None
         seed = DROPOUT_RNG.next_offset() if p_drop > 0 else 0
-        y, _, h, mean, rstd = K.add_dropout_ln_fwd(x2, res2, gamma, beta, eps, p_drop, seed_base, seed)
+        pos2, div = None, 1
+        if pos is not None:  # (L, B, C) or (L, 1, C) row-broadcast over the batch of (L, B, C) activations
+            div = 1 if pos.shape[1] == shape[1] else shape[1]
+            pos2 = pos.reshape(-1, C)
+            pos2 = pos2 if pos2.is_contiguous() else pos2.contiguous()
+        y, yb, h, mean, rstd, ypb = K.add_dropout_ln_fwd(x2, res2, gamma, beta, eps, p_drop, seed_base, seed,
+                                                         want_bf16=want_bf16, pos=pos2, pos_row_div=div)
         ctx.save_for_backward(h, mean, rstd, gamma)
         ctx.cfg = (p_drop, seed_base, seed, x is not None, shape)
         ctx.params = (gamma, beta)
-        return y.view(shape)
+        outs = (y.view(shape), yb, ypb)
+        ctx.mark_non_differentiable(*[t for t in outs[1:] if t is not None])
+        return outs
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dyb=None, _dypb=None):
         h, mean, rstd, gamma = ctx.saved_tensors
         p_drop, seed_base, seed, has_x, shape = ctx.cfg
         dy2 = dy.reshape(h.shape)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         g_slot, b_slot = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
-        dres, dx, dgamma, dbeta = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
-                                                       dgamma=g_slot, dbeta=b_slot)
-        return ((dx.view(shape) if has_x else None), dres.view(shape), None if g_slot is not None else dgamma,
-                None if b_slot is not None else dbeta, None, None)
+        dres, dx, dgamma, dbeta, dxb = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
+                                                            dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x)
+        _GRAD_BF16.clear()
+        dx_out = None
+        if has_x:
+            dx_out = dx.view(shape)
+            _GRAD_BF16[dx_out.data_ptr()] = (dxb, dx_out)
+        return (dx_out, dres.view(shape), None if g_slot is not None else dgamma, None if b_slot is not None else dbeta,
+                None, None, None, None)
 
 
-def add_dropout_layernorm(x, residual, norm, p, training):
+def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=None):
     """LayerNorm(residual + dropout(x)) -- the post-LN epilogue of every transformer sub-block.
-    `x` may be None (plain LayerNorm of `residual`)."""
+    `x` may be None (plain LayerNorm of `residual`).  `cast` / `cast_pos`: also produce the bf16
+    operand copies bf16(y) / bf16(y + cast_pos) that the NEXT sub-block's GEMMs read (attached to the
+    returned tensor; see _act_bf16)."""
     _need_cuda(residual)
     C = residual.shape[-1]
     p_eff = p if (training and p > 0) else 0.0
     if C % 128 == 0 and C <= 1024 and residual.dtype == torch.float32:
         xr = x.contiguous() if x is not None else None
-        return _AddDropoutLN.apply(xr, residual.contiguous(), norm.weight, norm.bias, norm.eps, p_eff)
+        if cast_pos is not None and not (cast_pos.dim() == 3 and cast_pos.shape[0] == residual.shape[0] and residual.dim() == 3
+                                         and cast_pos.shape[2] == C and cast_pos.dtype == torch.float32):
+            cast_pos = None
+        y, yb, ypb = _AddDropoutLN.apply(xr, residual.contiguous(), norm.weight, norm.bias, norm.eps, p_eff, bool(cast),
+                                         None if cast_pos is None else cast_pos.detach())
+        if yb is not None:
+            y._pcm_bf16 = yb
+        if ypb is not None:
+            y._pcm_bf16_pos = (cast_pos, ypb)
+        return y
     # widths that are not a multiple of 128 (test fixtures only): ATen composition
     if x is not None:
         if p_eff > 0:

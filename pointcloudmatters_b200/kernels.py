@@ -154,21 +154,26 @@ def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, pa
           "pcm_clip_adamw_step_bf16")
 
 
-def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, want_bf16=False):
+def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, want_bf16=False, pos=None, pos_row_div=1):
+    """y = LayerNorm(res + dropout(x)); optional extra outputs yb = bf16(y) and ypb = bf16(y + pos[r // pos_row_div])
+    (operands of the next sub-block's GEMMs).  Returns (y, yb, h, mean, rstd, ypb)."""
     rows, C = res.shape
     y = torch.empty_like(res)
     h = torch.empty_like(res)
     mean = torch.empty(rows, dtype=torch.float32, device=res.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=res.device)
     yb = torch.empty(res.shape, dtype=torch.bfloat16, device=res.device) if want_bf16 else None
-    check(lib.pcm_add_dropout_ln_fwd(rows, C, ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), float(p_drop),
-                                     ptr(seed_base), int(seed_offset), ptr(y), ptr(yb), ptr(h), ptr(mean), ptr(rstd),
-                                     current_stream()), "pcm_add_dropout_ln_fwd")
-    return y, yb, h, mean, rstd
+    ypb = torch.empty(res.shape, dtype=torch.bfloat16, device=res.device) if pos is not None else None
+    check(lib.pcm_add_dropout_ln_fwd_ex(rows, C, ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), float(p_drop),
+                                        ptr(seed_base), int(seed_offset), ptr(y), ptr(yb), ptr(h), ptr(mean), ptr(rstd),
+                                        ptr(pos), int(pos_row_div), ptr(ypb), current_stream()), "pcm_add_dropout_ln_fwd_ex")
+    return y, yb, h, mean, rstd, ypb
 
 
-def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None):
-    """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics)."""
+def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None,
+                       want_dx_bf16=False):
+    """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics).
+    Returns (dres, dx, dgamma, dbeta, dx_bf16)."""
     rows, C = h.shape
     dres = torch.empty_like(h)
     dx = (torch.empty_like(h) if p_drop > 0 else dres) if need_dx else None
@@ -176,10 +181,11 @@ def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset,
         dgamma = torch.zeros(C, dtype=torch.float32, device=h.device)
     if dbeta is None:
         dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
-    check(lib.pcm_add_dropout_ln_bwd(rows, C, ptr(dy), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
-                                     ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
-                                     current_stream()), "pcm_add_dropout_ln_bwd")
-    return dres, dx, dgamma, dbeta
+    dxb = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device) if (want_dx_bf16 and need_dx) else None
+    check(lib.pcm_add_dropout_ln_bwd_ex(rows, C, ptr(dy), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
+                                        ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                        ptr(dxb), current_stream()), "pcm_add_dropout_ln_bwd_ex")
+    return dres, dx, dgamma, dbeta, dxb
 
 
 def colsum(src, out=None):

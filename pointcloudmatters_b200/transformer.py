@@ -53,8 +53,10 @@ class TransformerEncoderLayer(nn.Module):
             s2 = PF.add_dropout_layernorm(None, src, self.norm2, 0.0, False)
             return src + PF.dropout(self._ffn(s2), self.p, tr)
         a = PF.multi_head_attention(self.self_attn, src, pos, None, None, src_key_padding_mask, tr, pos_head=pos_head)
-        src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr)
-        return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr)
+        # norm1 feeds the FFN (bf16 copy), norm2 feeds the next layer's attention / the decoder's
+        # cross-attention (bf16(y) for values, bf16(y + pos) for queries and keys)
+        src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr, cast=True)
+        return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr, cast=True, cast_pos=pos)
 
 
 class TransformerEncoder(nn.Module):
@@ -115,11 +117,12 @@ class TransformerDecoderLayer(nn.Module):
             t2 = ln(tgt, self.norm3)
             return tgt + PF.dropout(self._ffn(t2), self.p, tr)
         a = PF.multi_head_attention(self.self_attn, tgt, query_pos, None, None, None, tr)
-        tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr)
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr, cast_pos=query_pos)  # -> cross-attention queries
         a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr,
                                     mem_pos_head=pos_head)
-        tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr)
-        return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr)
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr, cast=True)  # -> FFN
+        # -> next layer's self-attention
+        return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr, cast=True, cast_pos=query_pos)
 
 
 class TransformerDecoder(nn.Module):

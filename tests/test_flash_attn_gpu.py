@@ -95,3 +95,33 @@ def test_flash_attention_fully_masked_row_is_zero():
     O, lse = K.flash_attn_fwd(q, k, v, B, nh, L, S, kpm, 0.125, 0.0, None, 0)
     O = O.view(L, B, 64)
     assert torch.isfinite(O[:, 0]).all() and (O[:, 1] == 0).all()
+
+
+def test_flash_attention_growing_scores_take_exact_rescale_path():
+    """Later key tiles carry scores thousands of octaves above the first tile's maximum: the lazy
+    reference maximum of the forward kernel overflows there and the warp must fall back to the
+    exact max + rescale path (and the backward must stay finite with the saved log-sum-exp)."""
+    from pointcloudmatters_b200 import kernels as K
+
+    B, nh, L, S = 1, 2, 200, 400
+    Z, E = B * nh, nh * 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = (4 * torch.randn(Z, L, 64, device="cuda", generator=g)).bfloat16()
+    k = torch.randn(Z, S, 64, device="cuda", generator=g)
+    k[:, 128:] *= 200.0
+    k[:, 300:] *= 0.01  # and back down again: the reference must not be lowered
+    k = k.bfloat16()
+    v = torch.randn(Z, S, 64, device="cuda", generator=g).bfloat16()
+    O, lse = K.flash_attn_fwd(q.view(Z * L, 64), k.view(Z * S, 64), v.view(Z * S, 64), B, nh, L, S, None, 0.125, 0.0, None, 0)
+    s = q.float() @ k.float().transpose(1, 2) * 0.125
+    ref = torch.softmax(s, -1) @ v.float()
+    ref_tok = ref.view(B, nh, L, 64).permute(2, 0, 1, 3).reshape(L * B, E)
+    assert torch.isfinite(O.float()).all()
+    assert _rel(O.float(), ref_tok) <= 1e-2, _rel(O.float(), ref_tok)
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1) * 1.4426950408889634, rtol=1e-3, atol=5e-2)
+    do = torch.randn(Z * L, 64, device="cuda", generator=g).bfloat16()
+    dq = torch.empty(L * B, E, dtype=torch.bfloat16, device="cuda")
+    dkv = torch.empty(S * B, 2 * E, dtype=torch.bfloat16, device="cuda")
+    K.flash_attn_bwd(q.view(Z * L, 64), k.view(Z * S, 64), v.view(Z * S, 64), O, do, lse, B, nh, L, S, None, 0.125, 0.0, None, 0,
+                     dq, dkv[:, :E], dkv[:, E:])
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
