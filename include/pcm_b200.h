@@ -156,6 +156,7 @@ int pcm_attention_fusion_step_backward(int m, int g, int c, const float *weight,
  *                    dW = dY^T * X read tensors in place, without transposes.
  *   c_bf16: C is bf16 (else fp32), pitch ldc.  accumulate: atomically ADD into fp32 C
  *   (gradient accumulation; implied when split_k > 1).  bias / relu only with split_k == 1.
+ *   split_k == 0 (accumulate only): the launcher picks tile width and K split together.
  * Base pointers must be 16-byte aligned and lda / ldb multiples of 8 (TMA). */
 int pcm_gemm_bf16(int M, int N, int K, const void *A, int lda, int a_mn, const void *B, int ldb,
                   int b_mn, void *C, int ldc, int c_bf16, const float *bias, int relu,
@@ -174,6 +175,10 @@ int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void *A, int lda, int
                      long long b_rows_total, long long b_batch_rows, void *C, int ldc, int c_bf16,
                      int c_mode, long long c_batch_rows, int hs_B, int hs_nh, int hs_L, float alpha,
                      const float *bias, int relu, int accumulate, int split_k, pcm_stream_t stream);
+
+/* Debug aid for tile-shape sweeps (tools/bench_gemm.py): force the N extent of the output tile
+ * of subsequent GEMM launches (64 / 128 / 256; 0 = heuristic). */
+int pcm_gemm_debug_force_bn(int bn);
 
 /* Row-wise softmax stages of multi-head attention between the batched GEMMs (replaces the
  * softmax / dropout of nn.MultiheadAttention's math path, transformer.py:246-248).  Buffers are

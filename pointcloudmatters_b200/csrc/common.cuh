@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <utility>
 #include "../../include/pcm_b200.h"
 
 #define PCM_API extern "C" __attribute__((visibility("default")))
@@ -15,6 +16,33 @@ extern long long g_pcm_launch_count;
 static inline int pcm_launch_status() { ++g_pcm_launch_count; return (int)cudaPeekAtLastError(); }
 static inline cudaStream_t pcm_cu_stream(pcm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int pcm_divup(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The training step is ~1100 short kernels (average 14 us) replayed from a CUDA graph: launch
+// latency and per-kernel prologues (tensor-map fetch, barrier init, TMEM allocation) are a
+// double-digit share of it.  Kernels launched through pcm_launch() carry the
+// programmatic-stream-serialization attribute: their CTAs may become resident and run their
+// prologue while the preceding kernel is still draining; pcm_pdl_wait() -- executed before the first
+// global-memory access -- blocks until every prerequisite grid has completed and flushed, so memory
+// semantics are exactly those of ordinary stream order.  pcm_pdl_launch_dependents() lets the NEXT
+// kernel start its own prologue early.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pcm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pcm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pcm_pdl_enabled();  // PCM_PDL=1 in the environment switches the attribute on (A/B timing; measured neutral)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pcm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pcm_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Reference block-size rule (libs/pointops/src/cuda_utils.h:11-14): largest power of two
 // <= work_size, capped at 1024.  Host-side, same libm expression as the reference launcher.

@@ -159,6 +159,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S = 0, TM_PV = 128;
     if (threadIdx.x == 0) TRACE(1);
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -447,9 +450,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// delta[z, l] = sum_d dO[z, l, d] * O[l * B + b, h * 64 + d]      (one warp per row)
+// delta[z, l] = sum_d dO[z, l, d] * O[l * B + b, h * 64 + d]      (one warp per row); also zero-fills
+// the fp32 dQ accumulator the backward kernel reduces into
 __global__ void __launch_bounds__(256) flash_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
-                                                          int ldo, int B, int nh, int L, long rows, float* __restrict__ delta) {
+                                                          int ldo, int B, int nh, int L, long rows, float* __restrict__ delta,
+                                                          float* __restrict__ dq_acc) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -462,12 +469,15 @@ __global__ void __launch_bounds__(256) flash_delta_kernel(const __nv_bfloat16* _
         float s = af.x * cf.x + af.y * cf.y;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(PCM_FULL_MASK, s, o);
         if (lane == 0) delta[r] = s;
+        reinterpret_cast<float2*>(dq_acc + (size_t)r * 64)[lane] = make_float2(0.f, 0.f);  // clears the dQ accumulator row
     }
 }
 
 // dQ token-major bf16 <- fp32 (Z, L, 64) accumulator          (one warp per row, 8 bytes per lane)
 __global__ void __launch_bounds__(256) flash_dq_store_kernel(const float* __restrict__ acc, int B, int nh, int L, long rows,
                                                              __nv_bfloat16* __restrict__ dQ, int ldq) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -543,6 +553,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
     if (threadIdx.x == 0) TRACE(1);
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -935,10 +948,9 @@ PCM_API int pcm_flash_attn_fwd(int B, int nh, int L, int S, const void* Q, const
     }
     const long items = (long)Z * ((L + 127) / 128);
     const long grid = items < 2L * num_sms ? items : 2L * num_sms;
-    if (p.thr16)
-        flash_fwd_kernel<true><<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
-    else
-        flash_fwd_kernel<false><<<(unsigned)grid, FWD_THREADS, FWD_SMEM, pcm_cu_stream(stream)>>>(tq, tk, tv, p);
+    cudaError_t le = p.thr16 ? pcm_launch(flash_fwd_kernel<true>, dim3((unsigned)grid), dim3(FWD_THREADS), FWD_SMEM, pcm_cu_stream(stream), tq, tk, tv, p)
+                             : pcm_launch(flash_fwd_kernel<false>, dim3((unsigned)grid), dim3(FWD_THREADS), FWD_SMEM, pcm_cu_stream(stream), tq, tk, tv, p);
+    if (le != cudaSuccess) return (int)le;
     return pcm_launch_status();
 }
 
@@ -986,11 +998,10 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     }
     cudaStream_t st = pcm_cu_stream(stream);
     const long rows = (long)Z * L;
-    cudaError_t e = cudaMemsetAsync(dQacc, 0, (size_t)rows * 64 * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
     const int g = (int)((rows + 7) / 8 < 148L * 16 ? (rows + 7) / 8 : 148L * 16);
-    flash_delta_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dO), reinterpret_cast<const __nv_bfloat16*>(O),
-                                          ldo, B, nh, L, rows, delta);
+    cudaError_t le = pcm_launch(flash_delta_kernel, dim3(g), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(dO),
+                                reinterpret_cast<const __nv_bfloat16*>(O), ldo, B, nh, L, rows, delta, dQacc);
+    if (le != cudaSuccess) return (int)le;
     if ((r = pcm_launch_status())) return r;
     static int num_sms = 0;
     if (!num_sms) {
@@ -1001,12 +1012,13 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     }
     const long items = (long)Z * ((S + 127) / 128);
     const long grid = items < num_sms ? items : num_sms;
-    if (p.thr16)
-        flash_bwd_kernel<true><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
-    else
-        flash_bwd_kernel<false><<<(unsigned)grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+    le = p.thr16 ? pcm_launch(flash_bwd_kernel<true>, dim3((unsigned)grid), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, tdq, tdk, tdv, p)
+                 : pcm_launch(flash_bwd_kernel<false>, dim3((unsigned)grid), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, tdq, tdk, tdv, p);
+    if (le != cudaSuccess) return (int)le;
     if ((r = pcm_launch_status())) return r;
-    flash_dq_store_kernel<<<g, 256, 0, st>>>(dQacc, B, nh, L, rows, reinterpret_cast<__nv_bfloat16*>(dQ), ldq);
+    le = pcm_launch(flash_dq_store_kernel, dim3(g), dim3(256), 0, st, (const float*)dQacc, B, nh, L, rows,
+                    reinterpret_cast<__nv_bfloat16*>(dQ), ldq);
+    if (le != cudaSuccess) return (int)le;
     return pcm_launch_status();
 }
 

@@ -16,10 +16,20 @@
 // FPS is a chain of M-1 dependent block-wide reductions: it is latency-bound, never HBM-bound
 // (algorithmic traffic 12N+4M bytes per cloud).
 #include "common.cuh"
+#include <cstdlib>
 #include <math.h>
 
 long long g_pcm_launch_count = 0;
 PCM_API long long pcm_launch_count(void) { return g_pcm_launch_count; }
+
+bool pcm_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PCM_PDL");
+        on = (e && e[0] == '1') ? 1 : 0;  // measured neutral inside the CUDA-graph replay of the step: opt-in
+    }
+    return on == 1;
+}
 
 int pcm_ref_opt_n_threads(int work_size) {
     const int pow_2 = (int)(log((double)work_size) / log(2.0));

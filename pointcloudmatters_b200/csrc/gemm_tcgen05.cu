@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above touched only parameters, shared and tensor memory: let the next kernel start
+    // its own prologue, then wait for the producers of our operands (programmatic dependent launch)
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -403,7 +407,8 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
     }
     const long tiles = (long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * split_k * batch;
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI><<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
+    cudaError_t le = pcm_launch(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>, dim3(grid), dim3(NUM_THREADS), SMEM, st, ta, tb, p);
+    if (le != cudaSuccess) return (int)le;
     return pcm_launch_status();
 }
 
@@ -414,7 +419,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     return launch_epi<BLOCK_N, A_MN, B_MN, EPI_F32>(ta, tb, p, split_k, batch, st);
 }
 
+int g_force_bn = 0;
+
 }  // namespace
+
+// Debug aid for tile-shape sweeps (tools/bench_gemm.py): force the N extent of the output tile of
+// subsequent GEMM launches (64 / 128 / 256; 0 = heuristic).
+PCM_API int pcm_gemm_debug_force_bn(int bn) {
+    g_force_bn = bn;
+    return PCM_OK;
+}
 
 // Extended entry point: batched, scaled, with head-split / head-merge output addressing (used by
 // the attention GEMMs).  Operand tensor maps span `batch` stacked problems: a_rows_total /
@@ -428,12 +442,30 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     if (!A || !B || !C || K <= 0) return PCM_EINVAL;
     if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return PCM_EUNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
-    if (split_k < 1) split_k = 1;
     if ((split_k > 1 || accumulate) && c_bf16) return PCM_EINVAL;
     if (split_k > 1 && (bias || relu)) return PCM_EINVAL;
     if (c_mode < 0 || c_mode > 2 || (c_mode != 0 && (hs_B <= 0 || hs_nh <= 0))) return PCM_EINVAL;
     if (c_mode == 1 && (N % 64)) return PCM_EUNSUPPORTED;
     const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    // wide tiles cut L2->smem operand traffic per FLOP (ncu: 128x128 SS tiles are smem/L2 bound)
+    int BN = (N <= 64) ? 64 : ((N >= 256 && ((N + 255) / 256 * 256 - N) < 128) ? 256 : 128);
+    if (split_k <= 0) {
+        // auto (weight-gradient GEMMs: small output, long K): tile width and K split chosen together
+        // from the measured sweep (tools/bench_gemm_sweep.py): short K wants 64-wide tiles and few
+        // slices (every slice costs a tile of fp32 atomics), long K with one row of tiles wants
+        // 128-wide tiles, otherwise wide tiles; slices fill one wave of the SMs, >= 8 k-blocks each
+        if (!accumulate) return PCM_EINVAL;
+        const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+        if (kblocks <= 128) BN = 64;
+        else if (m_tiles == 1 && N >= 128) BN = 128;
+        const int tiles = m_tiles * ((N + BN - 1) / BN);
+        int want = 148 / (tiles > 0 ? tiles : 1);
+        if (want < 1) want = 1;
+        int cap = kblocks / 8;
+        if (cap < 1) cap = 1;
+        split_k = want < cap ? want : cap;
+    }
+    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) BN = g_force_bn;  // tools/bench_gemm_sweep.py
     if (split_k > kblocks) split_k = kblocks;
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
@@ -446,8 +478,6 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     p.hs_B = hs_B; p.hs_nh = hs_nh; p.hs_L = hs_L;
     p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16; p.alpha = alpha;
     p.atomic = (accumulate || split_k > 1) ? 1 : 0;
-    // wide tiles cut L2->smem operand traffic per FLOP (ncu: 128x128 SS tiles are smem/L2 bound)
-    const int BN = (N <= 64) ? 64 : ((N >= 256 && ((N + 255) / 256 * 256 - N) < 128) ? 256 : 128);
     CUtensorMap ta, tb;
     int r;
     if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_M, &ta);

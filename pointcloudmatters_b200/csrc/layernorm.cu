@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ pos, int pos_row_div,
     __nv_bfloat16* __restrict__ ypos_bf16) {
     constexpr int C = 128 * V;
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16) {
     constexpr int C = 128 * V;
     __shared__ float sg[C], sb[C];
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -192,6 +196,8 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ src, long rows, int C, long ld,
                                                          int rows_per_cta, float* __restrict__ out) {
     extern __shared__ float part[];  // [groups][C]
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const int tpr = C / VEC;                      // threads per row
     const int groups = max(1, 256 / tpr);          // row groups per CTA
     const int rg = threadIdx.x / tpr, tc = threadIdx.x - rg * tpr;
@@ -229,6 +235,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ s
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, long rows, int C, long ld, int rows_per_cta,
                                                      float* __restrict__ out) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     const long r0 = (long)blockIdx.x * rows_per_cta;
     const long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -242,6 +250,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
 // (L, 1, C) positional table over the batch of token-major (L*B, C) activations)
 __global__ void __launch_bounds__(256) add_cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             long n4, int C4, int b_row_div, __nv_bfloat16* __restrict__ out) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(a)[i];
         if (b) {
@@ -265,10 +275,10 @@ inline int ln_grid(long rows) {
 
 #define LN_DISPATCH(V, KERNEL, ...)                                   \
     switch (V) {                                                      \
-        case 1: KERNEL<1><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
-        case 2: KERNEL<2><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
-        case 4: KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
-        case 8: KERNEL<8><<<grid, 256, 0, st>>>(__VA_ARGS__); break;  \
+        case 1: pcm_launch(KERNEL<1>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 2: pcm_launch(KERNEL<2>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 4: pcm_launch(KERNEL<4>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 8: pcm_launch(KERNEL<8>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
         default: return PCM_EUNSUPPORTED;                             \
     }
 
@@ -338,14 +348,17 @@ PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int
         const int groups = 256 / (C / vec) > 0 ? 256 / (C / vec) : 1;
         const size_t smem = (size_t)groups * C * sizeof(float);
         if (src_bf16)
-            colsum_vec_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld,
-                                                                         rows_per_cta, out);
+            pcm_launch(colsum_vec_kernel<__nv_bfloat16, 8>, dim3(grid), dim3(256), smem, st, reinterpret_cast<const __nv_bfloat16*>(src),
+                       (long)rows, C, (long)ld, rows_per_cta, out);
         else
-            colsum_vec_kernel<float, 4><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(src), rows, C, ld, rows_per_cta, out);
+            pcm_launch(colsum_vec_kernel<float, 4>, dim3(grid), dim3(256), smem, st, reinterpret_cast<const float*>(src), (long)rows, C,
+                       (long)ld, rows_per_cta, out);
     } else if (src_bf16) {
-        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, C, ld, rows_per_cta, out);
+        pcm_launch(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), (long)rows, C,
+                   (long)ld, rows_per_cta, out);
     } else {
-        colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), rows, C, ld, rows_per_cta, out);
+        pcm_launch(colsum_kernel<float>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(src), (long)rows, C, (long)ld,
+                   rows_per_cta, out);
     }
     return pcm_launch_status();
 }
@@ -360,7 +373,7 @@ PCM_API int pcm_add_cast_bf16(long long rows, int C, const float* a, const float
     const long n4 = rows * (C / 4);
     long blocks = (n4 + 255) / 256;
     const int grid = (int)(blocks < 148L * 16 ? blocks : 148L * 16);
-    add_cast_bf16_kernel<<<grid, 256, 0, pcm_cu_stream(stream)>>>(a, b, n4, C / 4, b_row_div < 1 ? 1 : b_row_div,
-                                                                 reinterpret_cast<__nv_bfloat16*>(out));
+    pcm_launch(add_cast_bf16_kernel, dim3(grid), dim3(256), 0, pcm_cu_stream(stream), a, b, n4, C / 4, b_row_div < 1 ? 1 : b_row_div,
+               reinterpret_cast<__nv_bfloat16*>(out));
     return pcm_launch_status();
 }

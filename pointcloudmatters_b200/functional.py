@@ -24,14 +24,6 @@ def _need_cuda(t):
         raise PcmError("pointcloudmatters_b200 runs on CUDA tensors only (no CPU fallback)")
 
 
-def _split_k_for(m_tiles, n_tiles, kblocks):
-    """Enough CTAs for ~2 waves of the 148 SMs when the output is small and K is long (dW GEMMs)."""
-    # one wave of the 148 SMs, and at least 8 k-blocks per slice: every extra slice costs a full
-    # tile of fp32 atomics in the epilogue (profile: atomics, not MMAs, dominated 37-way splits)
-    want = max(1, 148 // max(1, m_tiles * n_tiles))
-    return max(1, min(want, max(1, kblocks // 8)))
-
-
 class _Bf16Shadow:
     """bf16 copies of trainers' flat fp32 parameter buffers (trainer.FlatState.param_bf16), kept in
     sync by the fused AdamW kernel: GEMM weight operands are views into them, so no per-use fp32 ->
@@ -150,8 +142,7 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             slot = _grad_slot(weight)
             dw = slot if slot is not None else torch.zeros((N, Kin), dtype=torch.float32, device=dyb.device)
-            sk = _split_k_for((N + 127) // 128, (Kin + 127) // 128, (M + 63) // 64)
-            K.gemm_bf16(dyb, xb, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=sk)
+            K.gemm_bf16(dyb, xb, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=0)  # 0: tile / split auto
             if slot is not None:
                 dw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -277,9 +268,9 @@ def _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, S, B, nh, aux, p_drop
 
 
 def _dw(dtok, xb, out):
-    rows = dtok.shape[0]
-    K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=out, accumulate=True,
-                split_k=_split_k_for((out.shape[0] + 127) // 128, (out.shape[1] + 255) // 256, (rows + 63) // 64))
+    """out (N, K) += dtok^T xb -- weight gradient in the tensors' own layouts (MN-major operands);
+    tile width and K split are chosen by the launcher (split_k = 0)."""
+    K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=0)
 
 
 def _param_grads(ctx_params, E, dev):
@@ -646,8 +637,7 @@ class _SetAbstraction(torch.autograd.Function):
         dfeat = None
         if ctx.needs_input_grad[0]:
             dfeat = K.gemm_bf16(dPfb, wfb, b_mn=True)  # (n, H) x Wf(H, C)
-        sk = _split_k_for((H + 127) // 128, (C + 127) // 128, (n + 63) // 64)
-        K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=sk)
+        K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=0)
         return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 

@@ -41,7 +41,7 @@ def test_gemm_bias_relu_bf16_out():
     assert got16.dtype == torch.bfloat16
 
 
-@pytest.mark.parametrize("split_k", [1, 4, 37])
+@pytest.mark.parametrize("split_k", [0, 1, 4, 37])
 def test_gemm_split_k_accumulate(split_k):
     """dW = dY^T X shape: tiny output, very long K, accumulated atomically into an existing buffer."""
     from pointcloudmatters_b200.kernels import gemm_bf16

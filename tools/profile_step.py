@@ -29,6 +29,17 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         module.training_step(b, i)
     torch.cuda.synchronize()
 tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+# every device kernel (name, launches / step, us / step), sorted by time
+kern = {}
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        d = kern.setdefault(e.name, [0, 0.0])
+        d[0] += 1
+        d[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+lines = [f"{v[1] / steps:10.1f} us/step {v[0] / steps:7.1f} launches/step  {k[:150]}" for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])]
+total = sum(v[1] for v in kern.values()) / steps
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "kernels_per_step.txt").write_text(f"# total {total:.1f} us/step over {sum(v[0] for v in kern.values()) / steps:.0f} launches/step (torch.profiler, eager step)\n" + "\n".join(lines) + "\n")
 out = ROOT / "gpurun_out" / "profile_step.txt"
 out.parent.mkdir(exist_ok=True)
 out.write_text(tab)
