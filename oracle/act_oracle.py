@@ -311,11 +311,12 @@ class OracleACTPCD(nn.Module):
                  pcd_npoints=1024, sampling="fps", heatmap_th=0.1, ignore_vae=False, use_mask=False,
                  bg_ratio=0.0, pre_sample=False, in_channels=6):
         super().__init__()
-        assert not use_mask and not pre_sample and sampling == "fps", "oracle covers the BASELINE configs only"
+        assert sampling == "fps"  # act.py:443-444 raises for anything else
         self.backbone, self.transformer, self.encoder = backbone, transformer, encoder
         self.hidden_dim, self.num_queries, self.action_dim, self.qpos_dim = hidden_dim, num_queries, action_dim, qpos_dim
         self.latent_dim, self.kl_weight, self.goal_cond_dim = latent_dim, kl_weight, goal_cond_dim
         self.pcd_nsample, self.pcd_npoints, self.ignore_vae = pcd_nsample, pcd_npoints, ignore_vae
+        self.pre_sample, self.use_mask, self.bg_ratio = pre_sample, use_mask, bg_ratio
         if freeze_backbone:
             for p in self.backbone.parameters():
                 p.requires_grad = False
@@ -334,9 +335,14 @@ class OracleACTPCD(nn.Module):
         self.query_embed = nn.Embedding(num_queries, hidden_dim)
         self.latent_out_proj = nn.Linear(latent_dim, hidden_dim)
         self.additional_pos_embed = nn.Embedding(2 + int(goal_cond_dim > 0), hidden_dim)
-        # set abstraction head (act.py:367-379)
-        self.linear = nn.Linear(3 + backbone.num_channels, hidden_dim, bias=False)
-        self.bn = nn.BatchNorm1d(hidden_dim)
+        # set abstraction head (act.py:367-379): on the backbone features, or -- pre_sample -- on the raw
+        # input channels in front of the backbone
+        if not pre_sample:
+            self.linear = nn.Linear(3 + backbone.num_channels, hidden_dim, bias=False)
+            self.bn = nn.BatchNorm1d(hidden_dim)
+        else:
+            self.linear = nn.Linear(3 + backbone.in_channels, backbone.in_channels, bias=False)
+            self.bn = nn.BatchNorm1d(backbone.in_channels)
 
     # act.py:137-188
     def forward_encoder(self, d):
@@ -363,21 +369,46 @@ class OracleACTPCD(nn.Module):
         return d
 
     # act.py:384-465
-    def pcd_sampling(self, p, x, o):
+    def pcd_sampling(self, p, x, o, mask=None):
         b = o.shape[0]
         n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
-        idx = oracle_fps(p, o, n_o)
+        if not self.use_mask or mask is None:
+            idx = oracle_fps(p, o, n_o)
+        else:
+            # act.py:396-442: FPS separately on the foreground (and, bg_ratio > 0, background) points of
+            # the boolean-compacted cloud.  Restated with the reference's quirks: the indices returned
+            # by FPS refer to the COMPACTED arrays and are used on the full cloud unchanged, and the
+            # background picks are appended after ALL foreground picks (not interleaved per cloud).
+            n_bg = int(self.pcd_npoints * self.bg_ratio)
+            ar = torch.arange(1, b + 1, dtype=torch.int32, device=o.device)
+            fg_n_o = ar * (self.pcd_npoints - n_bg) if self.bg_ratio > 0.0 else n_o
+            ends = o.long()
+            cm = torch.cumsum(mask.long(), 0)
+            fg_o = cm[ends - 1].int()
+            fg_idx = oracle_fps(p[mask].contiguous(), fg_o, fg_n_o)
+            if self.bg_ratio > 0.0:
+                cb = torch.cumsum((~mask).long(), 0)
+                bg_idx = oracle_fps(p[~mask].contiguous(), cb[ends - 1].int(), ar * n_bg)
+                idx = torch.cat([fg_idx, bg_idx], 0)
+            else:
+                idx = fg_idx
         n_p = p[idx.long(), :]
         kidx = oracle_knn(self.pcd_nsample, p, o, n_p, n_o)
         g = grouping_with_xyz(kidx, x, p, n_p)  # (m, ns, 3+c)
         y = F.relu(self.bn(self.linear(g).transpose(1, 2).contiguous()))  # (m, c, ns)
-        return n_p, y.max(dim=-1).values, n_o
+        return n_p, y.max(dim=-1).values, n_o, idx
 
     # act.py:508-598
     def forward_obs_embed(self, d):
         pcd = d["pcds"]
-        feats = self.backbone(pcd)
-        coord, feats, _ = self.pcd_sampling(pcd["coord"], feats, pcd["offset"])
+        mask = pcd.get("mask") if self.use_mask else None
+        if self.pre_sample:  # act.py:509-527: sample + group the raw channels first, backbone on the M-point cloud
+            coord, feats, off, idx = self.pcd_sampling(pcd["coord"], pcd["feat"], pcd["offset"], mask)
+            pcd = dict(pcd, coord=coord, feat=feats, offset=off, grid_coord=pcd["grid_coord"][idx.long()])
+            feats = self.backbone(pcd)
+        else:
+            feats = self.backbone(pcd)
+            coord, feats, _, _ = self.pcd_sampling(pcd["coord"], feats, pcd["offset"], mask)
         pos = coord_embedding_sine(coord, self.hidden_dim)
         bs = d["qpos"].shape[0]
         src = feats.view(bs, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)  # (b, c, 1, n)
@@ -445,7 +476,7 @@ class OracleACTRLBenchPCD(OracleACTPCD):
 def build_oracle_policy(cfg: dict, rlbench: bool = False):
     """cfg keys: hidden_dim, nhead, dim_feedforward, enc_layers, dec_layers, dropout, num_queries,
     action_dim, qpos_dim, goal_cond_dim, latent_dim, kl_weight, pcd_npoints, pcd_nsample, in_channels."""
-    backbone = OraclePointNet(cfg.get("in_channels", 6), 0)
+    backbone = OraclePointNet(cfg.get("in_channels", 6), int(cfg.get("backbone_classes", 0)))
     tr = OracleTransformer(cfg["hidden_dim"], cfg["nhead"], cfg["enc_layers"], cfg["dec_layers"],
                            cfg["dim_feedforward"], cfg["dropout"], "relu", False, True)
     enc = OracleTransformerEncoder(cfg["hidden_dim"], cfg["nhead"], cfg["dim_feedforward"], cfg["dropout"], "relu",
@@ -455,4 +486,5 @@ def build_oracle_policy(cfg: dict, rlbench: bool = False):
     return cls(backbone, tr, enc, cfg["hidden_dim"], cfg["num_queries"], 0, cfg["action_dim"], cfg["qpos_dim"],
                latent_dim=cfg.get("latent_dim", 32), kl_weight=cfg.get("kl_weight", 10.0),
                goal_cond_dim=cfg.get("goal_cond_dim", 0), pcd_nsample=cfg.get("pcd_nsample", 16),
-               pcd_npoints=cfg["pcd_npoints"], **extra)
+               pcd_npoints=cfg["pcd_npoints"], use_mask=bool(cfg.get("use_mask", False)),
+               bg_ratio=float(cfg.get("bg_ratio", 0.0)), pre_sample=bool(cfg.get("pre_sample", False)), **extra)

@@ -1,7 +1,7 @@
 """oracle/gen_golden_act.py -- TEST INFRASTRUCTURE.  Run in the BUILD CONTAINER only
 (needs /root/reference; the GPU box never sees it):
 
-    python -m oracle.gen_golden_act            # writes tests/golden/act_*.npz
+    python -m oracle.gen_golden_act [case ...]   # writes tests/golden/act_*.npz (all cases, or the named ones)
 
 Imports the REFERENCE's own modules read-only from /root/reference --
 `src/models/components/act/{act,transformer,utils}.py`, `src/models/components/loss/misc.py`,
@@ -110,6 +110,15 @@ CASES = {
                                  dropout=0.0, num_queries=6, action_dim=11, qpos_dim=4, goal_cond_dim=16,
                                  latent_dim=32, kl_weight=10.0, pcd_npoints=24, pcd_nsample=16, collision=True,
                                  position_loss_weight=3.0), 2, 70),
+    # SURVEY.md 8 a4': set-abstraction variants selected by config (act.py:366-376,396-442,509-527)
+    "maniskill_presample": (False, dict(hidden_dim=96, nhead=2, dim_feedforward=32, enc_layers=1, dec_layers=2,
+                                        dropout=0.0, num_queries=8, action_dim=7, qpos_dim=9, goal_cond_dim=3,
+                                        latent_dim=32, kl_weight=10.0, pcd_npoints=32, pcd_nsample=8, pre_sample=1,
+                                        backbone_classes=96), 3, 96),  # backbone must emit hidden_dim channels
+    "maniskill_mask": (False, dict(hidden_dim=96, nhead=2, dim_feedforward=32, enc_layers=1, dec_layers=2,
+                                   dropout=0.0, num_queries=8, action_dim=7, qpos_dim=9, goal_cond_dim=3,
+                                   latent_dim=32, kl_weight=10.0, pcd_npoints=32, pcd_nsample=8, use_mask=1,
+                                   bg_ratio=0.25), 3, 96),
 }
 
 
@@ -128,13 +137,17 @@ def synth_batch(cfg, b, n, seed, ragged=True):
         actions[..., -2:] = torch.rand(b, cfg["num_queries"], 2, generator=g)
     npad = torch.randint(0, cfg["num_queries"] // 2 + 1, (b,), generator=g)
     is_pad = torch.arange(cfg["num_queries"])[None, :] >= (cfg["num_queries"] - npad)[:, None]
-    return {
+    batch = {
         "pcds": {"coord": coord, "grid_coord": grid, "feat": torch.cat([color, coord], 1),
                  "offset": torch.cumsum(sizes, 0)},
         "qpos": torch.randn(b, cfg["qpos_dim"], generator=g),
         "actions": actions, "is_pad": is_pad,
         "goal_cond": torch.randn(b, cfg["goal_cond_dim"], generator=g),
     }
+    # foreground mask (use_mask data, rlbench_single_task_act.py:289-309): ~55% of every cloud, drawn
+    # LAST so that the other tensors of the older fixtures are unchanged
+    batch["pcds"]["mask"] = torch.rand(total, generator=g) < 0.55
+    return batch
 
 
 def clone_batch(batch):
@@ -146,9 +159,12 @@ def main():
 
     act, tr, loss = install_reference_shim()
     OUT.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases
     for name, (rlbench, cfg, b, n) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(2024)
-        backbone = OraclePointNet(6, 0)
+        backbone = OraclePointNet(6, int(cfg.get("backbone_classes", 0)))
         transformer = tr.Transformer(d_model=cfg["hidden_dim"], nhead=cfg["nhead"], num_encoder_layers=cfg["enc_layers"],
                                      num_decoder_layers=cfg["dec_layers"], dim_feedforward=cfg["dim_feedforward"],
                                      dropout=cfg["dropout"], normalize_before=False, return_intermediate_dec=True)
@@ -159,6 +175,9 @@ def main():
                   latent_dim=cfg["latent_dim"], action_loss=torch.nn.MSELoss(reduction="none"),
                   klloss=loss.KLDivergence(), kl_weight=cfg["kl_weight"], goal_cond_dim=cfg["goal_cond_dim"],
                   pcd_nsample=cfg["pcd_nsample"], pcd_npoints=cfg["pcd_npoints"])
+        if cfg.get("pre_sample", 0) or cfg.get("use_mask", 0):
+            kw.update(pre_sample=bool(cfg.get("pre_sample", 0)), use_mask=bool(cfg.get("use_mask", 0)),
+                      bg_ratio=float(cfg.get("bg_ratio", 0.0)))
         if rlbench:
             model = act.ACTRLBenchPCD(**kw, collision=cfg["collision"], position_loss_weight=cfg["position_loss_weight"])
         else:
@@ -196,7 +215,7 @@ def main():
             flat["grad/" + k] = v
         for k, v in post.items():
             flat["post/" + k] = v
-        for k in ("coord", "grid_coord", "feat", "offset"):
+        for k in ("coord", "grid_coord", "feat", "offset") + (("mask",) if cfg.get("use_mask", 0) else ()):
             flat["in/pcds/" + k] = batch["pcds"][k].numpy()
         for k in ("qpos", "actions", "is_pad", "goal_cond"):
             flat["in/" + k] = batch[k].numpy()

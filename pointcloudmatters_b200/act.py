@@ -52,9 +52,6 @@ class ACTPCD(nn.Module):
         super().__init__()
         if backbone is None:
             raise NotImplementedError("state-only ACT (backbone=None) is outside the point-cloud hot path")
-        if use_mask or pre_sample:
-            raise NotImplementedError("use_mask / pre_sample set-abstraction variants (SURVEY.md 8 a4') are not "
-                                      "built yet; all BASELINE configs run with both off")
         if "fps" not in sampling:
             raise NotImplementedError(sampling)  # same as the reference (act.py:443-444)
         self.backbone, self.transformer, self.encoder = backbone, transformer, encoder
@@ -86,8 +83,12 @@ class ACTPCD(nn.Module):
         self.input_proj = None
         # set-abstraction head (act.py:363-382)
         self.pcd_nsample, self.pcd_npoints, self.pre_sample = pcd_nsample, pcd_npoints, pre_sample
-        self.linear = nn.Linear(3 + self.backbone.num_channels, hidden_dim, bias=False)
-        self.bn = nn.BatchNorm1d(hidden_dim)
+        if not pre_sample:
+            self.linear = nn.Linear(3 + self.backbone.num_channels, hidden_dim, bias=False)
+            self.bn = nn.BatchNorm1d(hidden_dim)
+        else:  # act.py:371-375: the head runs on the raw input channels, in front of the backbone
+            self.linear = nn.Linear(3 + self.backbone.in_channels, self.backbone.in_channels, bias=False)
+            self.bn = nn.BatchNorm1d(self.backbone.in_channels)
         self.pool = nn.MaxPool1d(pcd_nsample)
         self.relu = nn.ReLU(inplace=True)
         self.sampling, self.use_mask, self.bg_ratio = sampling, use_mask, bg_ratio
@@ -122,7 +123,33 @@ class ACTPCD(nn.Module):
         return data_dict
 
     # ---- set abstraction (act.py:384-465) ----------------------------------------------------
-    def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None):
+    def _sample_indices(self, p, o32, n_o, mask, hints):
+        """FPS picks (act.py:393-442).  Plain: one FPS over the batch.  use_mask: FPS separately on the
+        foreground (and, bg_ratio > 0, background) points of the boolean-compacted clouds, with the
+        reference's quirks kept as they are: the indices FPS returns refer to the COMPACTED arrays and
+        are applied to the full cloud unchanged, and all background picks follow all foreground picks
+        (`torch.cat([fg_idx, bg_idx])`, not re-interleaved per cloud).
+
+        The compaction is a stable argsort instead of `p[mask]` (static shapes, no host sync; FPS reads
+        only the rows below its offsets) and the per-cloud counts are one cumsum instead of the
+        reference's O(B) `.sum().item()` loops (act.py:423-426,434-437)."""
+        b = o32.shape[0]
+        if not self.use_mask or mask is None:
+            return pointops.farthest_point_sampling(p, o32, n_o, n_max=hints.get("n_max"), m_total=b * self.pcd_npoints)
+        n_bg = int(self.pcd_npoints * self.bg_ratio) if self.bg_ratio > 0.0 else 0
+        ar = torch.arange(1, b + 1, dtype=torch.int32, device=p.device)
+        ends = o32.long() - 1
+        picks = []
+        for keep, per, hint in ((mask, self.pcd_npoints - n_bg, "fg_n_max"), (~mask, n_bg, "bg_n_max")):
+            if per == 0:
+                continue
+            order = torch.argsort(~keep, stable=True)  # kept rows first, original order preserved
+            sub_o = torch.cumsum(keep.int(), 0, dtype=torch.int32)[ends].contiguous()
+            picks.append(pointops.farthest_point_sampling(p[order].contiguous(), sub_o, ar * per,
+                                                          n_max=hints.get(hint), m_total=b * per))
+        return picks[0] if len(picks) == 1 else torch.cat(picks, 0)
+
+    def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None, hints=None):
         p, x, o = pxo
         b = o.shape[0]
         pre = getattr(self, "_presampled", None)
@@ -133,9 +160,11 @@ class ACTPCD(nn.Module):
                 t.record_stream(torch.cuda.current_stream())
             self._presampled = None
         else:
+            hints = dict(hints or {})
+            hints.setdefault("n_max", n_max)
             n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
             o32 = o.int() if o.dtype != torch.int32 else o
-            idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=n_max, m_total=b * self.pcd_npoints)
+            idx = self._sample_indices(p, o32, n_o, mask, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
         x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
@@ -157,9 +186,19 @@ class ACTPCD(nn.Module):
         return torch.cat((pos, torch.zeros_like(pos)[:, :pad]), dim=1)
 
     def forward_pcd_embed(self, pcd_dict):
-        features = self.backbone(pcd_dict)
-        coord, features, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]),
-                                               n_max=pcd_dict.get("n_max", None))
+        mask = pcd_dict.get("mask", None) if self.use_mask else None
+        hints = {k: pcd_dict.get(k, None) for k in ("n_max", "fg_n_max", "bg_n_max")}
+        if self.pre_sample:
+            # act.py:509-527: sample + group the RAW channels first (Linear(3+c -> c)), re-index the voxel
+            # coordinates, then run the backbone on the M-point cloud
+            coord, features, offset, idx = self.pcd_sampling((pcd_dict["coord"], pcd_dict["feat"], pcd_dict["offset"]),
+                                                             mask, return_index=True, hints=hints)
+            pcd_dict["coord"], pcd_dict["feat"], pcd_dict["offset"] = coord, features, offset
+            pcd_dict["grid_coord"] = pcd_dict["grid_coord"][idx.long()]
+            features = self.backbone(pcd_dict)
+        else:
+            features = self.backbone(pcd_dict)
+            coord, features, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]), mask, hints=hints)
         pcd_pos = self.coord_embedding_sine(coord)
         b = pcd_dict["offset"].shape[0]
         features = features.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)  # (b, c, 1, n)
@@ -220,14 +259,21 @@ class ACTPCD(nn.Module):
         with torch.cuda.stream(side):
             n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
             o32 = o.int() if o.dtype != torch.int32 else o
-            idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=pcd.get("n_max", None), m_total=b * self.pcd_npoints)
+            hints = {k: pcd.get(k, None) for k in ("n_max", "fg_n_max", "bg_n_max")}
+            idx = self._sample_indices(p, o32, n_o, pcd.get("mask", None) if self.use_mask else None, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
         self._presampled = (side, n_o, o32, idx, n_p, knn_idx)
 
+    def sync_free(self, pcds) -> bool:
+        """True when the host-known cloud-size hints make FPS run without a device->host read."""
+        need = ["n_max"] if not (self.use_mask and pcds.get("mask", None) is not None) else (
+            ["fg_n_max"] + (["bg_n_max"] if self.bg_ratio > 0.0 else []))
+        return all(pcds.get(k, None) is not None for k in need)
+
     def forward(self, data_dict):
         self._presampled = None
-        if data_dict["pcds"].get("n_max", None) is not None:  # sync-free path only
+        if self.sync_free(data_dict["pcds"]):
             self._presample(data_dict)
         data_dict = self.forward_encoder(data_dict)
         data_dict = self.forward_obs_embed(data_dict)
@@ -302,7 +348,7 @@ def build_policy(cfg: dict, rlbench: bool = False):
     from .pointnet import PointNet
     from .transformer import Transformer, TransformerEncoder
 
-    backbone = PointNet(cfg.get("in_channels", 6), 0)
+    backbone = PointNet(cfg.get("in_channels", 6), int(cfg.get("backbone_classes", 0)))
     tr = Transformer(d_model=cfg["hidden_dim"], nhead=cfg["nhead"], num_encoder_layers=cfg["enc_layers"],
                      num_decoder_layers=cfg["dec_layers"], dim_feedforward=cfg["dim_feedforward"],
                      dropout=cfg["dropout"], normalize_before=False, return_intermediate_dec=True)
@@ -312,7 +358,8 @@ def build_policy(cfg: dict, rlbench: bool = False):
               num_queries=cfg["num_queries"], num_cameras=1, action_dim=cfg["action_dim"], qpos_dim=cfg["qpos_dim"],
               latent_dim=cfg.get("latent_dim", 32), kl_weight=cfg.get("kl_weight", 10.0),
               goal_cond_dim=cfg.get("goal_cond_dim", 0), pcd_nsample=cfg.get("pcd_nsample", 16),
-              pcd_npoints=cfg["pcd_npoints"])
+              pcd_npoints=cfg["pcd_npoints"], use_mask=bool(cfg.get("use_mask", False)),
+              bg_ratio=float(cfg.get("bg_ratio", 0.0)), pre_sample=bool(cfg.get("pre_sample", False)))
     if rlbench:
         return ACTRLBenchPCD(**kw, collision=cfg.get("collision", False),
                              position_loss_weight=cfg.get("position_loss_weight", 1.0))

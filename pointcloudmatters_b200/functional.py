@@ -157,8 +157,9 @@ def linear(x, weight, bias=None, relu=False, out_bf16=False):
     """y = x @ weight^T (+ bias) (+ ReLU); x (..., K) fp32 or bf16, weight (N, K) fp32 master.
 
     Tensor-core path (pcm_gemm_bf16, tcgen05) whenever TMA's alignment rules allow (K, N multiples
-    of 8); the handful of tiny embedding / head linears with K or N in {1, 3, 6, 7, 9} are plain
-    fp32 library GEMMs (well under 0.1% of the step's FLOPs)."""
+    of 8; a narrow K over many rows is zero-padded to 16); the handful of tiny embedding / head
+    linears with K or N in {1, 3, 7, 9} on B or B*Q rows are plain fp32 library GEMMs (well under 0.1%
+    of the step's FLOPs)."""
     _need_cuda(x)
     N, Kin = weight.shape
     lead = x.shape[:-1]
@@ -170,6 +171,10 @@ def linear(x, weight, bias=None, relu=False, out_bf16=False):
             weight = weight.contiguous()
         y = _LinearTC.apply(x2, weight, bias, relu, out_bf16, _act_bf16(x, x2.shape[0], Kin))
         return y.view(*lead, N)
+    if Kin < 16 and N % 8 == 0 and x.numel() // max(Kin, 1) >= 4096 and x.dtype == torch.float32:
+        # narrow input layer over many rows (PointNet conv1: 6 channels x 65 536 points): zero-pad K
+        # to one UMMA step and use the tensor-core path instead of an fp32 SIMT library GEMM
+        return linear(F.pad(x, (0, 16 - Kin)), F.pad(weight, (0, 16 - Kin)), bias, relu, out_bf16)
     y = F.linear(x.float(), weight, bias)
     return F.relu(y) if relu else y
 
@@ -510,10 +515,13 @@ class _AddDropoutLN(torch.autograd.Function):
         ctx.params = (gamma, beta)
         outs = (y.view(shape), yb, ypb)
         ctx.mark_non_differentiable(*[t for t in outs[1:] if t is not None])
+        ctx.set_materialize_grads(False)  # no zero-filled "gradients" for the bf16 by-products
         return outs
 
     @staticmethod
     def backward(ctx, dy, _dyb=None, _dypb=None):
+        if dy is None:
+            return (None,) * 8
         h, mean, rstd, gamma = ctx.saved_tensors
         p_drop, seed_base, seed, has_x, shape = ctx.cfg
         dy2 = dy.reshape(h.shape)
@@ -649,6 +657,22 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     momentum = bn.momentum if bn.momentum is not None else 0.0
+    H, C = linear_weight.shape[0], feat.shape[1]
+    if C % 8 or H % 8:
+        # narrow head (pre_sample: Linear(3+6 -> 6), act.py:371-375): zero-pad channels to the TMA / float4
+        # granularity.  Padded outputs are identically 0 (y = 0 on every edge -> BN(0) with beta 0 -> 0) and
+        # receive zero gradient; autograd slices the real gradients back out of the padded tensors.
+        Cp, Hp = -(-C // 8) * 8, -(-H // 8) * 8
+        w = F.pad(linear_weight, (0, Cp - C, 0, Hp - H))
+        rm = F.pad(bn.running_mean, (0, Hp - H)) if bn.running_mean is not None else None
+        rv = F.pad(bn.running_var, (0, Hp - H), value=1.0) if bn.running_var is not None else None
+        out = _SetAbstraction.apply(F.pad(feat, (0, Cp - C)), w, F.pad(bn.weight, (0, Hp - H), value=1.0),
+                                    F.pad(bn.bias, (0, Hp - H)), p.contiguous(), new_p.contiguous(),
+                                    knn_idx.contiguous(), rm, rv, bn.eps, momentum, training)
+        if training and rm is not None:
+            bn.running_mean.copy_(rm[:H])
+            bn.running_var.copy_(rv[:H])
+        return out[:, :H]
     return _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
                                  knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training)
 

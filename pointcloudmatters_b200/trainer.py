@@ -213,7 +213,11 @@ class BCTrainer:
         from . import functional as PF
 
         PF.DROPOUT_RNG.new_step()
-        if self.use_cuda_graph and self.flat is not None and self._eager_steps >= 2:
+        # graph capture needs a step without device->host reads: the policy says whether this batch
+        # carries the host-known cloud-size hints that make FPS sync-free (act.ACTPCD.sync_free)
+        sync_free = getattr(self.policy, "sync_free", None)
+        graph_ok = sync_free is None or "pcds" not in batch or sync_free(batch["pcds"])
+        if self.use_cuda_graph and graph_ok and self.flat is not None and self._eager_steps >= 2:
             losses = self._graphed_forward_backward(batch)
         else:
             losses = self._forward_backward(batch)

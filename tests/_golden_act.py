@@ -14,9 +14,10 @@ def load(path):
     g = np.load(path)
     cfg = {k: v for k, v in zip(g["meta/cfg_keys"].tolist(), g["meta/cfg_vals"].tolist())}
     for k in list(cfg):
-        if k not in ("dropout", "kl_weight", "position_loss_weight"):
+        if k not in ("dropout", "kl_weight", "position_loss_weight", "bg_ratio"):
             cfg[k] = int(cfg[k])
     cfg["collision"] = bool(cfg.get("collision", 0))
+    cfg["pre_sample"], cfg["use_mask"] = bool(cfg.get("pre_sample", 0)), bool(cfg.get("use_mask", 0))
     state = {k[len("state/"):]: torch.from_numpy(g[k].astype(np.float32) if g[k].dtype == np.float16 else g[k])
              for k in g.files if k.startswith("state/")}
     batch = {
@@ -25,6 +26,8 @@ def load(path):
         "is_pad": torch.from_numpy(g["in/is_pad"]), "goal_cond": torch.from_numpy(g["in/goal_cond"]),
         "_eps": torch.from_numpy(g["in/eps"]),
     }
+    if "in/pcds/mask" in g.files:
+        batch["pcds"]["mask"] = torch.from_numpy(g["in/pcds/mask"])
     out = {k[len("out/"):]: g[k] for k in g.files if k.startswith("out/")}
     grads = {k[len("grad/"):]: g[k] for k in g.files if k.startswith("grad/")}
     post = {k[len("post/"):]: g[k] for k in g.files if k.startswith("post/")}

@@ -123,3 +123,26 @@ def test_training_steps_track_the_oracle():
             num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
     assert (num / den) ** 0.5 <= 5e-3
     assert torch.equal(policy.is_pad_head.weight.detach().cpu(), sd_o["is_pad_head.weight"])
+
+
+def test_masked_sampling_hints_are_sync_free_and_identical():
+    """use_mask (SURVEY 8 a4'): with the host-known fg/bg cloud-size hints the masked FPS runs without
+    a device->host read and picks exactly the indices of the hint-free (one read per FPS call) path."""
+    from pointcloudmatters_b200.act import build_policy
+
+    path = [p for p in GOLDEN_ACT if "mask" in p][0]
+    cfg, state, batch, *_ = load(path)
+    model = build_policy(cfg).cuda().train()
+    pc = {k: v.cuda() for k, v in batch["pcds"].items()}
+    b = pc["offset"].shape[0]
+    n_o = torch.arange(1, b + 1, dtype=torch.int32, device="cuda") * cfg["pcd_npoints"]
+    ref = model._sample_indices(pc["coord"], pc["offset"].int(), n_o, pc["mask"], {})
+    sizes = torch.diff(pc["offset"].cpu(), prepend=torch.zeros(1, dtype=pc["offset"].dtype))
+    fg = [int(c.sum()) for c in torch.split(batch["pcds"]["mask"], sizes.tolist())]
+    hints = {"fg_n_max": max(fg), "bg_n_max": int(max(s - f for s, f in zip(sizes.tolist(), fg)))}
+    assert model.sync_free(dict(pc, **hints)) and not model.sync_free(pc)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        got = model._sample_indices(pc["coord"], pc["offset"].int(), n_o, pc["mask"], hints)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)
+    assert ref.numel() == b * cfg["pcd_npoints"]
