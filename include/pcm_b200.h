@@ -308,6 +308,38 @@ int pcm_clip_adamw_step_bf16(long long n, float *param, float *grad, float *exp_
                              float *exp_avg_sq, const float *hyper, double *sumsq, float *norm_out,
                              void *param_bf16, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diffusion-Policy denoiser: the non-GEMM kernels of
+ * ConditionalUnet1D (src/models/components/diffusion_policy/diffusion/conditional_unet1d.py:17-297,
+ * conv1d_components.py:8-45).  Activations are channel-last (B, T, C); nn.Conv1d / nn.ConvTranspose1d
+ * (cuDNN in the reference) become pcm_gemm_bf16 over rows = B*T against the weight in its own torch
+ * layout viewed (Cout, Cin*k) / (Cin, Cout*k), with these two kernels in front of / behind the GEMM:
+ *   unfold: col[(b,r), c*k+tap] = x[b, r*stride+tap-pad, c] (0 outside [0,L)); col is bf16 with row
+ *           pitch ldc >= C*k (extra columns zeroed); x is fp32 or bf16 with row pitch ldx.
+ *   fold:   y[b,p,c] = bias[c] + sum over (r,tap) with r*stride+tap-pad == p of col[(b,r), c*k+tap];
+ *           col fp32; y (fp32) and/or y_bf16 are written; bias may be NULL.
+ * Conv1d(k,stride,pad): forward = unfold(R = Tout) -> GEMM; dX = GEMM -> fold(L = Tin).
+ * ConvTranspose1d(k,stride,pad): forward = GEMM -> fold(R = Tin, L = Tout); backward = unfold.
+ * ------------------------------------------------------------------------------------------ */
+int pcm_conv1d_unfold(int B, int L, int C, int k, int stride, int pad, int R, const void *x, int x_bf16,
+                      long long ldx, void *col, long long ldc, pcm_stream_t stream);
+int pcm_conv1d_fold(int B, int L, int C, int k, int stride, int pad, int R, const float *col, long long ldc,
+                    const float *bias, float *y, void *y_bf16, pcm_stream_t stream);
+/* y = film_scale * Mish(GroupNorm_G(x)) + film_bias (+ res): nn.GroupNorm + nn.Mish of Conv1dBlock
+ * (conv1d_components.py:30-41) fused with the FiLM modulation (conditional_unet1d.py:72-77) and the
+ * residual add (:80).  x, res, y (B,T,C) fp32 channel-last; film (B, 2C) = [scale | bias] or NULL;
+ * mean / rstd (B*G) are saved for the backward.  Backward: dx (fp32), dgamma / dbeta ACCUMULATED
+ * with atomics (C), dfilm (B, 2C) written when film != NULL; d(res) = dy is the caller's. */
+int pcm_groupnorm_mish_fwd(int B, int T, int C, int G, const float *x, const float *gamma, const float *beta,
+                           float eps, const float *film, const float *res, float *y, void *y_bf16,
+                           float *mean, float *rstd, pcm_stream_t stream);
+int pcm_groupnorm_mish_bwd(int B, int T, int C, int G, const float *x, const float *gamma, const float *beta,
+                           const float *mean, const float *rstd, const float *film, const float *dy,
+                           float *dx, float *dgamma, float *dbeta, float *dfilm, pcm_stream_t stream);
+/* nn.Mish on a flat fp32 vector (cond_encoder / diffusion_step_encoder, conditional_unet1d.py:44-48,103-108) */
+int pcm_mish_fwd(long long n, const float *x, float *y, void *y_bf16, pcm_stream_t stream);
+int pcm_mish_bwd(long long n, const float *x, const float *dy, float *dx, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
