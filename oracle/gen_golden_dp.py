@@ -40,13 +40,13 @@ CASES = {
     "maniskill_small": dict(qpos_dim=9, action_dim=7, backbone_classes=32, n_obs_steps=2, pcd_nsample=8, pcd_npoints=24,
                             pcd_hidden_dim=32, projector_layers=1, projector_channels=[32, 40, 40], horizon=16,
                             diffusion_step_embed_dim=32, down_dims=[32, 64], kernel_size=5, n_groups=8,
-                            cond_predict_scale=True, goal_dim=0, batch=3, n=70),
+                            cond_predict_scale=True, goal_dim=0, batch=8, n=70),
     # three resolution levels (16 -> 8 -> 4, as the reference's [512, 1024, 2048]), language-goal embedding,
     # 2-layer projector
     "maniskill_goal": dict(qpos_dim=7, action_dim=7, backbone_classes=16, n_obs_steps=2, pcd_nsample=8, pcd_npoints=16,
                            pcd_hidden_dim=16, projector_layers=2, projector_channels=[16, 16, 32], horizon=16,
                            diffusion_step_embed_dim=16, down_dims=[16, 32, 64], kernel_size=5, n_groups=8,
-                           cond_predict_scale=True, goal_dim=12, batch=2, n=50),
+                           cond_predict_scale=True, goal_dim=12, batch=8, n=50),
 }
 
 

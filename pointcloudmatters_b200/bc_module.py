@@ -56,3 +56,38 @@ class ACTBCModule(nn.Module):
         self.logged = {"train/loss": losses["loss"], "train/action_loss": losses["action_loss"],
                        "train/kl_loss": losses["kl_loss"]}
         return losses["loss"]
+
+
+class DiffusionPolicyBCModule(ACTBCModule):
+    """Mirror of `ManiSkill2DiffusionPolicyBCModule` (src/models/maniskill2_dp_bc_module.py:20-99):
+    `model_step` = `policy.compute_loss(batch)` in training mode, `training_step` returns `loss_dict["loss"]`;
+    optimizer / scheduler defaults = configs/model/maniskill2_diffusion_policy_model.yaml:10-25
+    (AdamW lr 1e-4, betas (0.9, 0.95), weight decay 1e-4; OneCycleLR pct_start 0.15)."""
+
+    def __init__(self, policy, optimizer: dict | None = None, lr_scheduler: dict | None = None,
+                 gradient_clip_val: float = 0.5, total_steps: int = 100000, use_cuda_graph: bool = False, **kwargs):
+        super().__init__(policy, dict(type="AdamW", lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.95)) | (optimizer or {}),
+                         lr_scheduler or {"scheduler": dict(pct_start=0.15, div_factor=100.0, final_div_factor=1000.0)},
+                         gradient_clip_val, total_steps, use_cuda_graph)
+
+    def setup(self, normalizer) -> None:
+        """maniskill2_dp_bc_module.py:57-60: copy the dataset's fitted normaliser into the policy."""
+        self.policy.set_normalizer(normalizer)
+
+    def configure_optimizers(self) -> BCTrainer:
+        opt = self.hparams["optimizer"]
+        sch = {k: v for k, v in self.hparams["lr_scheduler"].get("scheduler", {}).items()
+               if k in ("pct_start", "div_factor", "final_div_factor")}
+        self._trainer = BCTrainer(self.policy, lr=opt["lr"], weight_decay=opt.get("weight_decay", 0.01),
+                                  betas=tuple(opt.get("betas", (0.9, 0.999))), clip_norm=self.hparams["gradient_clip_val"],
+                                  total_steps=self.hparams["total_steps"], scheduler=sch,
+                                  use_cuda_graph=self.hparams["use_cuda_graph"],
+                                  input_keys=("obs", "action", "goal", "_noise", "_timesteps"), loss_keys=("loss",))
+        return self._trainer
+
+    def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
+        if self._trainer is None:
+            self.configure_optimizers()
+        losses = self._trainer.training_step(batch)
+        self.logged = {"train/loss": losses["loss"]}
+        return losses["loss"]

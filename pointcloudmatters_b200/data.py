@@ -41,6 +41,33 @@ def synthetic_act_batch(batch_size, n_points, *, num_queries=100, action_dim=7, 
     return batch
 
 
+def synthetic_dp_batch(batch_size, n_points, *, n_obs_steps=2, horizon=16, action_dim=7, qpos_dim=9, goal_dim=0,
+                       seed=1000, ragged=False, device="cpu", pin=False):
+    """Diffusion-Policy batch (maniskill2_single_task_pcd_dp.py:135-224): B * n_obs_steps clouds,
+    `{obs: {qpos (B, horizon, Q), pcds: {...}}, action (B, horizon, A)[, goal: {task_emb (B, G)}]}`."""
+    g = torch.Generator().manual_seed(seed)
+    clouds = batch_size * n_obs_steps
+    sizes = (torch.randint(int(0.75 * n_points), n_points + 1, (clouds,), generator=g) if ragged
+             else torch.full((clouds,), n_points, dtype=torch.int64))
+    total = int(sizes.sum())
+    coord = torch.rand(total, 3, generator=g) - 0.5
+    color = torch.randint(0, 256, (total, 3), generator=g).float() / 127.5 - 1.0
+    grid = torch.floor(coord / 0.005).long()
+    grid = grid - grid.min(0).values
+    batch = {"obs": {"qpos": torch.randn(batch_size, horizon, qpos_dim, generator=g),
+                     "pcds": {"coord": coord, "grid_coord": grid, "feat": torch.cat([color, coord], dim=1),
+                              "offset": torch.cumsum(sizes, 0)}},
+             "action": torch.randn(batch_size, horizon, action_dim, generator=g)}
+    if goal_dim > 0:
+        batch["goal"] = {"task_emb": torch.randn(batch_size, goal_dim, generator=g)}
+    if pin:
+        batch = map_tensors(batch, lambda t: t.pin_memory())
+    if device != "cpu":
+        batch = to_device(batch, device)
+    batch["obs"]["pcds"]["n_max"] = int(sizes.max())
+    return batch
+
+
 def map_tensors(batch, fn):
     return {k: (map_tensors(v, fn) if isinstance(v, dict) else (fn(v) if torch.is_tensor(v) else v))
             for k, v in batch.items()}

@@ -103,8 +103,12 @@ class BCTrainer:
 
     def __init__(self, policy: nn.Module, lr=5e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, input_keys=None, loss_keys=None):
         self.policy = policy
+        if input_keys is not None:
+            self.INPUT_KEYS = tuple(input_keys)
+        if loss_keys is not None:
+            self.LOSS_KEYS = tuple(loss_keys)
         self.lr, self.weight_decay, self.betas, self.eps, self.clip_norm = lr, weight_decay, betas, eps, clip_norm
         sch = dict(pct_start=0.1, div_factor=100.0, final_div_factor=1000.0)
         sch.update(scheduler or {})
@@ -151,20 +155,24 @@ class BCTrainer:
         self.step_num += 1
 
     # -- forward + backward -----------------------------------------------------------------------
-    INPUT_KEYS = ("pcds", "qpos", "actions", "is_pad", "goal_cond", "env_state", "_eps")
+    INPUT_KEYS = ("pcds", "qpos", "actions", "is_pad", "goal_cond", "env_state", "_eps")  # ACT batch contract
+    LOSS_KEYS = ("loss", "action_loss", "kl_loss")
 
-    @classmethod
-    def _inputs_only(cls, batch):
+    @staticmethod
+    def _copy_dicts(v):
+        return {k: BCTrainer._copy_dicts(x) for k, x in v.items()} if isinstance(v, dict) else v
+
+    def _inputs_only(self, batch):
         """The policy's forward writes its intermediates into the dict it is given (reference
-        behaviour, act.py:137-309); work on a shallow copy restricted to the batch-contract keys."""
-        return {k: (dict(batch[k]) if isinstance(batch[k], dict) else batch[k]) for k in cls.INPUT_KEYS if k in batch}
+        behaviour, act.py:137-309); work on a copy of the (nested) dicts restricted to the batch-contract keys."""
+        return {k: self._copy_dicts(batch[k]) for k in self.INPUT_KEYS if k in batch}
 
     def _forward_backward(self, batch):
         if self.flat is not None:
             self.flat.zero_grad()
         out = self.policy(self._inputs_only(batch))
         out["loss"].backward()
-        return {k: out[k].detach() for k in ("loss", "action_loss", "kl_loss")}
+        return {k: out[k].detach() for k in self.LOSS_KEYS}
 
     @staticmethod
     def _signature(batch):
@@ -195,8 +203,9 @@ class BCTrainer:
         sig = self._signature(batch)
         entry = self._graphs.get(sig)
         if entry is None:
-            static = {k: ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict)
-                          else (v.clone() if torch.is_tensor(v) else v)) for k, v in batch.items()}
+            clone = lambda v: ({kk: clone(vv) for kk, vv in v.items()} if isinstance(v, dict)
+                               else (v.clone() if torch.is_tensor(v) else v))
+            static = clone(batch)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -216,7 +225,8 @@ class BCTrainer:
         # graph capture needs a step without device->host reads: the policy says whether this batch
         # carries the host-known cloud-size hints that make FPS sync-free (act.ACTPCD.sync_free)
         sync_free = getattr(self.policy, "sync_free", None)
-        graph_ok = sync_free is None or "pcds" not in batch or sync_free(batch["pcds"])
+        pcds = batch.get("pcds", None) if "pcds" in batch else batch.get("obs", {}).get("pcds", None)
+        graph_ok = sync_free is None or pcds is None or sync_free(pcds)
         if self.use_cuda_graph and graph_ok and self.flat is not None and self._eager_steps >= 2:
             losses = self._graphed_forward_backward(batch)
         else:
