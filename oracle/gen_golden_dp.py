@@ -45,7 +45,7 @@ CASES = {
     # 2-layer projector
     "maniskill_goal": dict(qpos_dim=7, action_dim=7, backbone_classes=16, n_obs_steps=2, pcd_nsample=8, pcd_npoints=16,
                            pcd_hidden_dim=16, projector_layers=2, projector_channels=[16, 16, 32], horizon=16,
-                           diffusion_step_embed_dim=16, down_dims=[16, 32, 64], kernel_size=5, n_groups=8,
+                           diffusion_step_embed_dim=32, down_dims=[32, 64, 128], kernel_size=5, n_groups=8,
                            cond_predict_scale=True, goal_dim=12, batch=8, n=50),
 }
 

@@ -107,6 +107,23 @@ def _grad_bf16(g, rows, C):
     return K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
 
 
+_NO_ROW_SPLIT = bool(int(__import__("os").environ.get("PCM_NO_ROW_SPLIT", "0")))  # A/B switch for tools/
+
+
+def _gemm_rows(a, b, *, b_mn=False, bias=None):
+    """(M, K) x B -> (M, N) fp32 for activation GEMMs with few rows and a long reduction (the Diffusion-Policy
+    denoiser: rows = B*T is 64 ... 2048 while K = Cin*k reaches 10 240): with one CTA per 128-wide output tile only a handful of SMs would stream the
+    weights.  When the tile count is under half the SMs the launcher's K-split (split_k = 0: slices fill one
+    wave, fp32 atomics into a bias-initialised output) is used instead."""
+    M, Kd = a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    if (-(-M // 128)) * (-(-N // 128)) <= 74 and Kd >= 1024 and not _NO_ROW_SPLIT:
+        out = (bias.expand(M, N).contiguous() if bias is not None
+               else torch.zeros((M, N), dtype=torch.float32, device=a.device))
+        return K.gemm_bf16(a, b, b_mn=b_mn, out=out, accumulate=True, split_k=0)
+    return K.gemm_bf16(a, b, b_mn=b_mn, bias=bias)
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T (+b) (ReLU) on the tcgen05 GEMM; backward dX = dY W and dW = dY^T X read dY, W, X in
     place through the MN-major operand forms of the same kernel (no transposes)."""
@@ -115,7 +132,10 @@ class _LinearTC(torch.autograd.Function):
     def forward(ctx, x2, weight, bias, relu, out_bf16, xb_hint=None):
         xb = xb_hint if xb_hint is not None else (x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16))
         wb = _wb(weight)
-        y = K.gemm_bf16(xb, wb, bias=bias, relu=relu, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        if relu or out_bf16:
+            y = K.gemm_bf16(xb, wb, bias=bias, relu=relu, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        else:
+            y = _gemm_rows(xb, wb, bias=bias)
         ctx.relu, ctx.has_bias, ctx.x_dtype = relu, bias is not None, x2.dtype
         ctx.params = (weight, bias)
         ctx.save_for_backward(xb, wb, y if relu else None)
@@ -135,7 +155,7 @@ class _LinearTC(torch.autograd.Function):
         Kin = xb.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = K.gemm_bf16(dyb, wb, b_mn=True)  # (M, N) x W(N, Kin) -> (M, Kin)
+            dx = _gemm_rows(dyb, wb, b_mn=True)  # (M, N) x W(N, Kin) -> (M, Kin)
             if ctx.x_dtype == torch.bfloat16:
                 dx = dx.to(torch.bfloat16)
         weight, bias = ctx.params
@@ -700,9 +720,21 @@ def roofline_for(kstats, peaks, steps):
     have = "bf16_tflops_sustained" in peaks
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = st["flops"] / (st["total_ms"] * 1e-3) / 1e12
+    traffic, traffic_note = None, None
+    try:  # DRAM bytes per launch of the dominant shape from the committed `ncu --set full` capture
+        import json
+        from pathlib import Path
+
+        t = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "r1_gemm_traffic.json").read_text())
+        traffic = t["dram_bytes_per_launch"]
+        traffic_note = (f"dram__bytes_read+write per launch of the dominant shape M={t['shape']['M']} N={t['shape']['N']} "
+                        f"K={t['shape']['K']} (algorithmic {t['algorithmic_bytes_per_launch']} B; output partly L2-resident), "
+                        "profiles/r1_gemm_traffic.json")
+    except Exception:
+        pass
     return {"kernel": "gemm_tcgen05_kernel (all projection / attention / weight-gradient GEMMs of the step)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured"
                             if have else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback"),
             "launches_per_step": st["launches"] / steps, "ms_per_step": st["total_ms"] / steps,

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from . import kernels as K
 from ._lib import check, current_stream, lib, ptr
-from .functional import _grad_slot, _need_cuda, _wb
+from .functional import _gemm_rows, _grad_slot, _need_cuda, _wb
 
 
 def _r8(n):
@@ -102,7 +102,7 @@ class _Conv1dCL(torch.autograd.Function):
             col = _unfold(xb if xb is not None else x, k, stride, pad, R)
         wm = _weight_matrix(weight, Cout, Kc, ldc, Np)
         bp = bias if (bias is None or Np == Cout) else F.pad(bias, (0, Np - Cout))
-        y = K.gemm_bf16(col, wm, bias=bp)
+        y = _gemm_rows(col, wm, bias=bp)
         ctx.geom = (B, L, Cin, Cout, k, stride, pad, R, ldc, Np, pointwise)
         ctx.params = (weight, bias)
         ctx.save_for_backward(col, wm)
@@ -121,7 +121,7 @@ class _Conv1dCL(torch.autograd.Function):
         dyb = K.add_cast_bf16(dy2.contiguous())
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dcol = K.gemm_bf16(dyb, wm, b_mn=True)  # (M, Np) x W(Np, ldc) -> (M, ldc)
+            dcol = _gemm_rows(dyb, wm, b_mn=True)  # (M, Np) x W(Np, ldc) -> (M, ldc)
             dx = dcol.view(B, L, Cin) if pointwise else _fold(dcol, B, L, Cin, k, stride, pad, R)
         if ctx.needs_input_grad[1]:
             dw = _accumulate_dw(weight, Cout, Cin * k, dyb, col, Np != Cout, ldc != Cin * k)
@@ -142,7 +142,7 @@ class _ConvTranspose1dCL(torch.autograd.Function):
             raise NotImplementedError("ConvTranspose1d channels must be multiples of 8 (U-Net widths are)")
         xb = (xb if xb is not None else _bf16_of(x)).reshape(B * L, Cin)
         wm = _wb(weight).reshape(Cin, Cout * k)
-        ycol = K.gemm_bf16(xb, wm, b_mn=True)  # (M, Cin) x W(Cin, Cout*k)
+        ycol = _gemm_rows(xb, wm, b_mn=True)  # (M, Cin) x W(Cin, Cout*k)
         y = _fold(ycol, B, Lout, Cout, k, stride, pad, L, bias)
         ctx.geom = (B, L, Cin, Cout, k, stride, pad, Lout)
         ctx.params = (weight, bias)
@@ -158,7 +158,7 @@ class _ConvTranspose1dCL(torch.autograd.Function):
         dycol = _unfold(dy, k, stride, pad, L)  # (B*L, Cout*k): dycol[(b,l), co*k+tap] = dy[b, l*s+tap-p, co]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = K.gemm_bf16(dycol, wm).view(B, L, Cin)  # (M, Cout*k) x W(Cin, Cout*k)^T
+            dx = _gemm_rows(dycol, wm).view(B, L, Cin)  # (M, Cout*k) x W(Cin, Cout*k)^T
         if ctx.needs_input_grad[1]:
             dw = _accumulate_dw(weight, Cin, Cout * k, xb, dycol, False, False)
         if bias is not None and ctx.needs_input_grad[2]:

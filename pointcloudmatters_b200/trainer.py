@@ -147,7 +147,11 @@ class BCTrainer:
         from . import functional as PF
 
         f = self.flat
-        self._hyper_host.copy_(torch.tensor(self.hyper_values(self.step_num), dtype=torch.float32))
+        # a FRESH pinned staging vector per step: the caching host allocator does not hand the block out again
+        # before the asynchronous copy that used it has completed, so a host running several (graph-replayed)
+        # steps ahead of the device can never overwrite values a queued copy has yet to read
+        vals = torch.tensor(self.hyper_values(self.step_num), dtype=torch.float32)
+        self._hyper_host = vals.pin_memory() if f.param.is_cuda else vals
         self._hyper.copy_(self._hyper_host, non_blocking=True)
         PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq, self._hyper,
                            self._sumsq, self._norm, f.param_bf16[: f.n_active])
