@@ -738,7 +738,10 @@ def roofline_for(kstats, peaks, steps):
             "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured"
                             if have else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md), of fallback"),
             "launches_per_step": st["launches"] / steps, "ms_per_step": st["total_ms"] / steps,
+            "ms_per_step_raw_events": st.get("total_ms_raw_events", st["total_ms"]) / steps,
+            "event_pair_overhead_us": st.get("event_pair_overhead_us", 0.0),
             "algorithmic_gflop_per_step": st["flops"] / steps / 1e9,
             "algorithmic_gbytes_per_step": st["bytes"] / steps / 1e9,
-            "note": "timed with CUDA events around every launch on an eager (non-graph) replica of the step; "
+            "note": "timed with CUDA events around every launch on an eager (non-graph) replica of the step, minus the "
+                    "calibrated cost of an empty event pair (event_pair_overhead_us; raw sum in ms_per_step_raw_events); "
                     "traffic (dram bytes per launch from ncu --set full) is in profiles/ for the dominant shape"}

@@ -15,9 +15,26 @@ class _Timer:
     def __init__(self):
         self.enabled = False
         self.records = {}
+        self.pair_overhead_ms = 0.0
 
     def start(self):
         self.enabled, self.records = True, {}
+        self.pair_overhead_ms = self._calibrate()
+
+    @staticmethod
+    def _calibrate(n=200):
+        """Elapsed time an event pair reports with NOTHING between the two records (median of n, queued behind
+        a device-side spin so the host is ahead of the GPU exactly as in the measured steps).  Each timed launch
+        carries this fixed cost of the second event's timestamp; `summary()` reports raw and corrected times."""
+        torch.cuda._sleep(int(0.01 * 1.9e9))
+        pairs = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); b.record()
+            pairs.append((a, b))
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in pairs)
+        return t[len(t) // 2]
 
     def stop(self):
         self.enabled = False
@@ -45,7 +62,10 @@ class _Timer:
             for r, t in zip(recs, ms):
                 d = shapes.setdefault(r[4], [0, 0.0, 0.0])
                 d[0] += 1; d[1] += t; d[2] += r[2]
-            out[name] = {"launches": len(recs), "total_ms": sum(ms), "avg_ms": sum(ms) / len(ms),
+            raw = sum(ms)
+            ms = [max(t - self.pair_overhead_ms, 0.0) for t in ms]
+            out[name] = {"launches": len(recs), "total_ms": sum(ms), "avg_ms": sum(ms) / len(ms), "total_ms_raw_events": raw,
+                         "event_pair_overhead_us": self.pair_overhead_ms * 1e3,
                          "flops": float(sum(r[2] for r in recs)), "bytes": float(sum(r[3] for r in recs)),
                          "by_shape": {str(k): {"launches": v[0], "total_ms": v[1], "tflops": v[2] / max(v[1], 1e-9) / 1e9}
                                       for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}}
