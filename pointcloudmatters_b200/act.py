@@ -271,12 +271,37 @@ class ACTPCD(nn.Module):
             ["fg_n_max"] + (["bg_n_max"] if self.bg_ratio > 0.0 else []))
         return all(pcds.get(k, None) is not None for k in need)
 
+    def _encode_on_side_stream(self, data_dict):
+        """CVAE posterior (`forward_encoder`) on its own stream.  It depends only on qpos / actions / is_pad and
+        is a chain of ~50 small kernels (102 tokens x B rows: a third of the SMs at best), independent of the
+        PointNet -> FPS/kNN -> set-abstraction chain that produces the observation tokens: the two run side by
+        side until the transformer needs `latent_input`.  Autograd replays each node on the stream of its
+        forward, so the backward passes of the two chains overlap as well; under CUDA-graph capture both become
+        parallel branches of the step graph."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_enc_stream", None) is None:
+            self._enc_stream = torch.cuda.Stream()
+        side = self._enc_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            data_dict = self.forward_encoder(data_dict)
+        return data_dict, side
+
     def forward(self, data_dict):
         self._presampled = None
-        if self.sync_free(data_dict["pcds"]):
+        fork = self.sync_free(data_dict["pcds"]) and data_dict["qpos"].is_cuda
+        if fork:
             self._presample(data_dict)
-        data_dict = self.forward_encoder(data_dict)
+            data_dict, enc_stream = self._encode_on_side_stream(data_dict)
+        else:
+            data_dict = self.forward_encoder(data_dict)
         data_dict = self.forward_obs_embed(data_dict)
+        if fork:  # join: the transformer consumes latent_input, the loss mu / logvar
+            main = torch.cuda.current_stream()
+            main.wait_stream(enc_stream)
+            for k in ("latent_input", "mu", "logvar"):
+                if torch.is_tensor(data_dict.get(k, None)):
+                    data_dict[k].record_stream(main)
         data_dict = self.forward_decoder(data_dict)
         if not data_dict["is_training"]:
             return data_dict

@@ -146,3 +146,31 @@ def test_masked_sampling_hints_are_sync_free_and_identical():
     torch.cuda.synchronize()
     assert torch.equal(ref, got)
     assert ref.numel() == b * cfg["pcd_npoints"]
+
+
+def test_cuda_graph_step_matches_eager():
+    """The graph-captured ACT step (FPS/kNN and the CVAE encoder forked onto side streams, rejoined before the
+    transformer) reproduces the eager step's losses; dropout off so the two runs are comparable.  Bound 5e-3:
+    the step is not bit-reproducible run to run (fp32 atomics), see tests/test_dp_gpu.py."""
+    from pointcloudmatters_b200.act import build_policy
+    from pointcloudmatters_b200.bc_module import ACTBCModule
+    from pointcloudmatters_b200.data import synthetic_act_batch, to_device
+
+    cfg = dict(hidden_dim=128, nhead=2, dim_feedforward=32, enc_layers=2, dec_layers=2, dropout=0.0, num_queries=12,
+               action_dim=7, qpos_dim=9, goal_cond_dim=3, latent_dim=32, kl_weight=10.0, pcd_npoints=64, pcd_nsample=16)
+    losses = {}
+    for graph in (False, True):
+        torch.manual_seed(3)
+        module = ACTBCModule(build_policy(cfg).cuda().train(), total_steps=50, use_cuda_graph=graph)
+        out = []
+        for step in range(6):
+            batch = synthetic_act_batch(4, 256, num_queries=12, seed=700 + step)
+            gb = to_device(batch, "cuda")
+            gb["pcds"]["n_max"] = batch["pcds"]["n_max"]
+            gb["_eps"] = torch.randn(4, 32, generator=torch.Generator().manual_seed(step)).cuda()
+            out.append(float(module.training_step(gb, step)))
+        losses[graph] = out
+        if graph:
+            assert module._trainer._graphs, "graph path was not taken"
+    for a, b in zip(losses[True], losses[False]):
+        assert abs(a - b) <= 5e-3 * abs(b) + 1e-5, losses
