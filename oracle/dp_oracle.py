@@ -62,7 +62,44 @@ class DDPMSchedule:
         else:
             raise NotImplementedError(beta_schedule)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
-        self.config = _Cfg(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type)
+        self.config = _Cfg(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type,
+                           clip_sample=clip_sample, clip_sample_range=1.0, variance_type=variance_type)
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
+
+    # diffusers 0.29.0 scheduling_ddpm.py: set_timesteps ("leading" spacing, the default) / step /
+    # _get_variance ("fixed_small"), restated from the published sampler (Ho et al. 2020, eq. 6-7, 11)
+    def set_timesteps(self, num_inference_steps):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        self.timesteps = torch.arange(num_inference_steps - 1, -1, -1) * ratio
+
+    def step(self, model_output, t, sample, generator=None, noise=None, **_):
+        """-> object with `.prev_sample` (the attribute the reference's sampling loop reads,
+        diffusion_unet_image_policy.py:138-140)."""
+        t = int(t)
+        n = self.num_inference_steps or self.config.num_train_timesteps
+        prev_t = t - self.config.num_train_timesteps // n
+        acp = self.alphas_cumprod.to(sample.device)
+        a_t = acp[t]
+        a_prev = acp[prev_t] if prev_t >= 0 else torch.tensor(1.0, device=sample.device)
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        cur_a = a_t / a_prev
+        cur_b = 1 - cur_a
+        if self.config.prediction_type == "epsilon":
+            x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        else:
+            x0 = model_output
+        if self.config.clip_sample:
+            x0 = x0.clamp(-self.config.clip_sample_range, self.config.clip_sample_range)
+        prev = (a_prev ** 0.5 * cur_b) / b_t * x0 + cur_a ** 0.5 * b_prev / b_t * sample
+        if t > 0:
+            var = torch.clamp(b_prev / b_t * cur_b, min=1e-20)
+            if noise is None:
+                noise = torch.randn(model_output.shape, generator=generator, device=model_output.device,
+                                    dtype=model_output.dtype)
+            prev = prev + var ** 0.5 * noise
+        return _Cfg(prev_sample=prev)
 
     def add_noise(self, x, noise, timesteps):
         acp = self.alphas_cumprod.to(device=x.device, dtype=x.dtype)
@@ -257,6 +294,7 @@ class OracleDiffusionPolicy(nn.Module):
         self.noise_scheduler = noise_scheduler
         self.normalizer = OracleLinearNormalizer()
         self.horizon, self.n_action_steps, self.n_obs_steps = horizon, n_action_steps, n_obs_steps
+        self.num_inference_steps = num_inference_steps or noise_scheduler.config.num_train_timesteps
         self._dummy_variable = nn.Parameter(torch.empty(0))  # ModuleAttrMixin of the policy / mask generator
         self.mask_generator = nn.Module()
         self.mask_generator._dummy_variable = nn.Parameter(torch.empty(0))
@@ -286,6 +324,34 @@ class OracleDiffusionPolicy(nn.Module):
 
     forward = compute_loss
 
+    # diffusion_unet_image_policy.py:106-231 (conditional_sample + predict_action), observations as global
+    # conditioning: no in-painting (the condition mask is all False).  `noises` = [x_T, eps_1, eps_2, ...]
+    # replaces the sampler's draws (trajectory init, then one per step with t > 0).
+    @torch.no_grad()
+    def predict_action(self, obs_dict, noises=None):
+        obs = dict(obs_dict["obs"])
+        pcds = obs.pop("pcds", None)
+        nobs = {k: self.normalizer.normalize_field(k, v) for k, v in obs.items()}
+        bs = next(iter(nobs.values())).shape[0]
+        this = {k: v[:, : self.n_obs_steps].reshape(-1, *v.shape[2:]) for k, v in nobs.items()}
+        if pcds is not None:
+            this["pcds"] = pcds
+        gcond = self.obs_encoder(this).reshape(bs, -1)
+        if "goal" in obs_dict and "task_emb" in obs_dict["goal"]:
+            gcond = torch.cat([gcond, obs_dict["goal"]["task_emb"]], dim=-1)
+        shape = (bs, self.horizon, self.action_dim)
+        it = iter(noises) if noises is not None else None
+        traj = next(it) if it is not None else torch.randn(shape)
+        sch = self.noise_scheduler
+        sch.set_timesteps(self.num_inference_steps)
+        for t in sch.timesteps:
+            out = self.model(traj, t, global_cond=gcond)
+            traj = sch.step(out, t, traj, noise=(next(it) if (it is not None and int(t) > 0) else None)).prev_sample
+        p = self.normalizer.params_dict["action"]
+        action_pred = ((traj.reshape(-1, self.action_dim) - p["offset"]) / p["scale"]).reshape(shape)
+        start = self.n_obs_steps - 1
+        return {"action": action_pred[:, start:start + self.n_action_steps], "action_pred": action_pred}
+
 
 def build_oracle_dp(cfg: dict):
     """cfg keys mirror scratch_pointnet_pcd.yaml + maniskill2_diffusion_policy_model.yaml."""
@@ -301,6 +367,7 @@ def build_oracle_dp(cfg: dict):
                               projector_channels=cfg["projector_channels"])
     return OracleDiffusionPolicy(shape_meta, DDPMSchedule(num_train_timesteps=cfg.get("num_train_timesteps", 100)), enc,
                                  horizon=cfg["horizon"], n_action_steps=cfg.get("n_action_steps", 8),
-                                 n_obs_steps=cfg["n_obs_steps"], diffusion_step_embed_dim=cfg["diffusion_step_embed_dim"],
+                                 n_obs_steps=cfg["n_obs_steps"], num_inference_steps=cfg.get("num_inference_steps", None),
+                                 diffusion_step_embed_dim=cfg["diffusion_step_embed_dim"],
                                  down_dims=cfg["down_dims"], kernel_size=cfg["kernel_size"], n_groups=cfg["n_groups"],
                                  cond_predict_scale=cfg.get("cond_predict_scale", True))

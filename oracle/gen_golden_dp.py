@@ -176,6 +176,29 @@ def main():
         rec = {}
         real_randn, real_randint = torch.randn, torch.randint
 
+        # ---- inference: the reference's predict_action (eval mode, 10 sampling steps) on the same observations,
+        # BEFORE the training step touches the BatchNorm running statistics.  Every torch.randn draw of the
+        # sampling loop (trajectory init, then one per step with t > 0) is recorded in order.
+        draws = []
+
+        def randn_rec(*a, **k):
+            draws.append(real_randn(*a, **k))
+            return draws[-1]
+
+        policy.eval()
+        policy.num_inference_steps = 10
+        obs_in = {"obs": {"qpos": batch["obs"]["qpos"].clone(), "pcds": {k: v.clone() for k, v in batch["obs"]["pcds"].items()}}}
+        if "goal" in batch:
+            obs_in["goal"] = {"task_emb": batch["goal"]["task_emb"].clone()}
+        torch.manual_seed(777)
+        torch.randn = randn_rec
+        try:
+            with torch.no_grad():
+                pred = policy.predict_action(obs_in)
+        finally:
+            torch.randn = real_randn
+        policy.train()
+
         def randn(*a, **k):
             rec["noise"] = real_randn(*a, **k)
             return rec["noise"]
@@ -195,7 +218,9 @@ def main():
         finally:
             torch.randn, torch.randint = real_randn, real_randint
         out["loss"].backward()
-        flat = {"meta/cfg_keys": np.array([k for k in cfg]), "meta/cfg_vals": np.array([repr(cfg[k]) for k in cfg]),
+        flat = {"pred/action": pred["action"].numpy(), "pred/action_pred": pred["action_pred"].numpy(),
+                "pred/noises": np.stack([d.numpy() for d in draws]),
+                "meta/cfg_keys": np.array([k for k in cfg]), "meta/cfg_vals": np.array([repr(cfg[k]) for k in cfg]),
                 "out/loss": out["loss"].detach().numpy(), "in/noise": rec["noise"].numpy(),
                 "in/timesteps": rec["timesteps"].numpy()}
         from tests._golden_act import grad_summary

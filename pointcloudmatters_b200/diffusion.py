@@ -282,8 +282,12 @@ class DDPMScheduler:
             raise NotImplementedError(beta_schedule)
         self.betas = betas
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        if variance_type != "fixed_small":
+            raise NotImplementedError(variance_type)
         self.config = _SchedulerConfig(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type,
-                                       clip_sample=clip_sample, variance_type=variance_type)
+                                       clip_sample=clip_sample, clip_sample_range=1.0, variance_type=variance_type)
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
         self._dev = {}
 
     def _coef(self, device):
@@ -292,6 +296,29 @@ class DDPMScheduler:
             acp = self.alphas_cumprod.to(device)
             c = self._dev[device] = (acp ** 0.5, (1 - acp) ** 0.5)
         return c
+
+    def set_timesteps(self, num_inference_steps):
+        """"leading" spacing (the diffusers default): t_i = i * (T // n), descending."""
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        self.timesteps = torch.arange(self.num_inference_steps - 1, -1, -1) * ratio
+
+    def step_coefficients(self, t: int):
+        """The five scalars of one ancestral sampling step (Ho et al. 2020 eq. 6-7, 11; diffusers `step` with
+        `variance_type="fixed_small"`), so that
+            x0   = (x_t - c0 * eps_hat) * c1            [clamped to +-clip_sample_range when clip_sample]
+            x_t' = c2 * x0 + c3 * x_t + c4 * noise      [c4 = 0 at t = 0]
+        Computed in fp32 from `alphas_cumprod` exactly as the scheduler does."""
+        n = getattr(self, "num_inference_steps", None) or self.config.num_train_timesteps
+        prev_t = t - self.config.num_train_timesteps // n
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else torch.tensor(1.0)
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        cur_a = a_t / a_prev
+        cur_b = 1 - cur_a
+        var = torch.clamp(b_prev / b_t * cur_b, min=1e-20)
+        return torch.stack([b_t ** 0.5, 1.0 / a_t ** 0.5, (a_prev ** 0.5 * cur_b) / b_t, cur_a ** 0.5 * b_prev / b_t,
+                            var ** 0.5 if t > 0 else torch.tensor(0.0)]).float()
 
     def add_noise(self, x, noise, timesteps):
         a, s = self._coef(x.device)
@@ -418,6 +445,7 @@ class DiffusionUnetImagePolicy(nn.Module):
         self.n_action_steps, self.n_obs_steps, self.obs_as_global_cond = n_action_steps, n_obs_steps, obs_as_global_cond
         self.num_inference_steps = num_inference_steps or noise_scheduler.config.num_train_timesteps
         self.kwargs = kwargs
+        self._sample_graphs = {}  # (trajectory shape, cond shape, device) -> (CUDAGraph, static tensors)
 
     def set_normalizer(self, normalizer):
         self.normalizer.load_state_dict(normalizer.state_dict())
@@ -461,10 +489,95 @@ class DiffusionUnetImagePolicy(nn.Module):
         """True when `pcds["n_max"]` (host-known largest cloud) lets FPS run without a device->host read."""
         return pcds.get("n_max", None) is not None
 
+    # ========= inference (diffusion_unet_image_policy.py:106-231) =========
+    def _denoise_step(self, traj, t, coef, noise, global_cond):
+        """One reverse-diffusion step: denoiser forward + the scheduler update, all on device tensors (timestep,
+        the 5 step coefficients and the noise are INPUTS), so the whole step can be captured once and replayed."""
+        out = self.model(traj, t, local_cond=None, global_cond=global_cond)
+        if self.noise_scheduler.config.prediction_type == "epsilon":
+            x0 = (traj - coef[0] * out) * coef[1]
+        else:
+            x0 = out
+        if self.noise_scheduler.config.clip_sample:
+            r = self.noise_scheduler.config.clip_sample_range
+            x0 = x0.clamp(-r, r)
+        return coef[2] * x0 + coef[3] * traj + coef[4] * noise
+
+    @torch.no_grad()
+    def conditional_sample(self, shape, global_cond, noises=None, use_cuda_graph=True):
+        """The reference's sampling loop (:106-146) with observations as global conditioning (its in-painting mask
+        is identically False, so the two masked assignments are no-ops).  `noises` (iterable: x_T, then one
+        tensor per step with t > 0) replaces the sampler's draws -- test hook.
+        B200 path: ONE denoising step (~190 kernels) is captured into a CUDA graph the first time a shape is seen
+        and replayed `num_inference_steps` times; per step only the timestep, 5 coefficients and the noise are
+        copied into the graph's static inputs."""
+        sch = self.noise_scheduler
+        sch.set_timesteps(self.num_inference_steps)
+        dev = global_cond.device
+        it = iter(noises) if noises is not None else None
+        traj = (next(it).to(dev) if it is not None else torch.randn(shape, device=dev)).contiguous()
+        ts = sch.timesteps.to(dev)
+        coefs = torch.stack([sch.step_coefficients(int(t)) for t in sch.timesteps]).to(dev)
+        key = (tuple(shape), tuple(global_cond.shape), str(dev))
+        entry = self._sample_graphs.get(key) if use_cuda_graph else None
+        if use_cuda_graph and entry is None:
+            st = dict(traj=traj.clone(), t=ts[0].clone(), coef=coefs[0].clone(), noise=torch.zeros(shape, device=dev),
+                      cond=global_cond.clone())
+            side = torch.cuda.Stream()  # warm-up off the capture: lazy initialisations, allocator growth
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._denoise_step(st["traj"], st["t"], st["coef"], st["noise"], st["cond"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._denoise_step(st["traj"], st["t"], st["coef"], st["noise"], st["cond"])
+            entry = self._sample_graphs[key] = (graph, st)
+        for i, t in enumerate(sch.timesteps.tolist()):
+            noise = None
+            if t > 0:
+                noise = next(it).to(dev) if it is not None else torch.randn(shape, device=dev)
+            if entry is not None:
+                graph, st = entry
+                if i == 0:
+                    st["cond"].copy_(global_cond)
+                st["traj"].copy_(traj)
+                st["t"].copy_(ts[i])
+                st["coef"].copy_(coefs[i])
+                if noise is not None:
+                    st["noise"].copy_(noise)
+                graph.replay()
+                traj = st["out"]
+            else:
+                traj = self._denoise_step(traj, ts[i], coefs[i], noise if noise is not None else torch.zeros_like(traj),
+                                          global_cond)
+        return traj.clone()
+
+    @torch.no_grad()
+    def predict_action(self, obs_dict, noises=None, use_cuda_graph=True):
+        """obs_dict = {"obs": {qpos (B, To.., Q), pcds: {...}}[, "goal": {task_emb}]} -> {"action", "action_pred"}
+        (:148-231).  The input dict is not mutated (the reference pops `pcds`)."""
+        assert "past_action" not in obs_dict
+        src = obs_dict["obs"] if "obs" in obs_dict else obs_dict
+        pcds = src.get("pcds", None)
+        nobs = self.normalizer.normalize({k: v for k, v in src.items() if k != "pcds"})
+        B = next(iter(nobs.values())).shape[0]
+        this_nobs = {k: v[:, : self.n_obs_steps].reshape(-1, *v.shape[2:]) for k, v in nobs.items()}
+        if pcds is not None:
+            this_nobs["pcds"] = pcds
+        global_cond = self.obs_encoder(this_nobs).reshape(B, -1)
+        goal = obs_dict.get("goal", None)
+        if goal is not None:
+            if "task_emb" not in goal:
+                raise NotImplementedError("image goals belong to the image policy, not the point-cloud path")
+            global_cond = torch.cat([global_cond, goal["task_emb"]], dim=-1)
+        nsample = self.conditional_sample((B, self.horizon, self.action_dim), global_cond.contiguous(), noises, use_cuda_graph)
+        action_pred = self.normalizer.normalize_field("action", nsample[..., : self.action_dim], forward=False)
+        start = self.n_obs_steps - 1
+        return {"action": action_pred[:, start:start + self.n_action_steps], "action_pred": action_pred}
+
     def forward(self, batch):
-        if not self.training:
-            raise NotImplementedError("predict_action (100-step DDPM sampling loop) is SURVEY.md section 8f item 3")
-        return self.compute_loss(batch)
+        """maniskill2_dp_bc_module.py:59-63: training -> compute_loss, evaluation -> predict_action."""
+        return self.compute_loss(batch) if self.training else self.predict_action(batch)
 
 
 def build_dp_policy(cfg: dict):
@@ -481,7 +594,8 @@ def build_dp_policy(cfg: dict):
                         projector_layers=cfg["projector_layers"], projector_channels=cfg["projector_channels"])
     return DiffusionUnetImagePolicy(shape_meta, DDPMScheduler(num_train_timesteps=cfg.get("num_train_timesteps", 100)), enc,
                                     horizon=cfg["horizon"], n_action_steps=cfg.get("n_action_steps", 8),
-                                    n_obs_steps=cfg["n_obs_steps"], diffusion_step_embed_dim=cfg["diffusion_step_embed_dim"],
+                                    n_obs_steps=cfg["n_obs_steps"], num_inference_steps=cfg.get("num_inference_steps", None),
+                                    diffusion_step_embed_dim=cfg["diffusion_step_embed_dim"],
                                     down_dims=cfg["down_dims"], kernel_size=cfg["kernel_size"], n_groups=cfg["n_groups"],
                                     cond_predict_scale=cfg.get("cond_predict_scale", True))
 

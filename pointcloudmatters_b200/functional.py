@@ -34,6 +34,7 @@ class _Bf16Shadow:
 
     def __init__(self):
         self.entries = {}  # id -> (weakref to FlatState, base_ptr, nbytes)
+        self.inference_cache = {}  # base ptr -> (weakref(Parameter), version, bf16 copy); no_grad only
 
     def register(self, flat_state):
         import weakref
@@ -51,6 +52,26 @@ class _Bf16Shadow:
                     fs = ref()
                     if fs is not None and fs.param_bf16.device == w.device:
                         return fs.param_bf16[off // 4: off // 4 + w.numel()].view(w.shape)
+        if not torch.is_grad_enabled() and w.dtype == torch.float32 and w.is_contiguous():
+            # inference (no_grad) outside a trainer: convert each PARAMETER once, not once per call -- a sampling
+            # loop calls the denoiser 100 times on the same 255 M parameters.  An entry is valid only while the very
+            # Parameter object it was made from is alive, sits at the same address and has the same version counter
+            # (torch bumps it on every in-place update, load_state_dict included), so neither a freed-and-reused
+            # address nor changed weights can ever return a stale copy.  Views of a parameter (reshaped conv
+            # weights) resolve to their base.
+            base = w._base if w._base is not None else w
+            if isinstance(base, torch.nn.Parameter) and base.is_contiguous():
+                hit = self.inference_cache.get(base.data_ptr())
+                if hit is None or hit[0]() is not base or hit[1] != base._version:
+                    import weakref
+
+                    hit = self.inference_cache[base.data_ptr()] = (weakref.ref(base), base._version,
+                                                                   base.detach().to(torch.bfloat16))
+                    if len(self.inference_cache) > 4096:  # drop entries of dead parameters
+                        for k in [k for k, v in self.inference_cache.items() if v[0]() is None]:
+                            del self.inference_cache[k]
+                off = (w.data_ptr() - base.data_ptr()) // 4
+                return hit[2].reshape(-1)[off: off + w.numel()].view(w.shape)
         return w.to(torch.bfloat16)
 
 

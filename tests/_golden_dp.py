@@ -22,3 +22,11 @@ def load(path):
     grads = {k[len("grad/"):]: g[k] for k in g.files if k.startswith("grad/")}
     post = {k[len("post/"):]: g[k] for k in g.files if k.startswith("post/")}
     return cfg, state, batch, float(g["out/loss"]), grads, post, g["meta/nograd"].tolist()
+
+
+def load_prediction(path):
+    """Inference fixture: the reference `predict_action` (eval mode, 10 DDPM steps) on the same observations /
+    initial state, with every noise draw of the sampling loop recorded in order."""
+    g = np.load(path)
+    return ([torch.from_numpy(x) for x in g["pred/noises"]], torch.from_numpy(g["pred/action"]),
+            torch.from_numpy(g["pred/action_pred"]))

@@ -174,3 +174,24 @@ def test_cuda_graph_step_matches_eager():
             assert module._trainer._graphs, "graph path was not taken"
     for a, b in zip(losses[True], losses[False]):
         assert abs(a - b) <= 5e-3 * abs(b) + 1e-5, losses
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if "maniskill_small" in p])
+def test_eval_mode_policy_matches_oracle(path):
+    """Inference branch (act.py:177-182: no `actions` -> latent = 0, BatchNorm on running statistics) against
+    the oracle port on the same state (ManiSkill head; the RLBench rot6d -> quaternion branch is not in the oracle)."""
+    from oracle.act_oracle import build_oracle_policy
+    from pointcloudmatters_b200.act import build_policy
+
+    cfg, state, batch, _out, _g, _p, _n, rlbench = load(path)
+    model = build_policy(cfg, rlbench).cuda().eval()
+    oracle = build_oracle_policy(cfg, rlbench).eval()
+    model.load_state_dict(state)
+    oracle.load_state_dict(state)
+    obs = {k: v for k, v in batch.items() if k in ("pcds", "qpos", "goal_cond")}
+    with torch.no_grad():
+        want = oracle({k: (dict(v) if isinstance(v, dict) else v) for k, v in obs.items()})
+        got = model(_to_cuda(obs))
+    assert got["mu"] is None and not got["is_training"]
+    assert got["a_hat"].shape == want["a_hat"].shape
+    assert _rel_l2(got["a_hat"].cpu().numpy(), want["a_hat"].numpy()) <= OUT_TOL

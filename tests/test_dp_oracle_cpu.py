@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from tests._golden_act import grad_summary
-from tests._golden_dp import GOLDEN_DP, load
+from tests._golden_dp import GOLDEN_DP, load, load_prediction
 
 
 def test_fixtures_present():
@@ -34,6 +34,23 @@ def test_oracle_matches_reference_fixture(path):
     sd = model.state_dict()
     for k, v in post.items():
         np.testing.assert_allclose(sd[k].numpy(), v, rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("path", GOLDEN_DP)
+def test_oracle_predict_action_matches_reference_fixture(path):
+    """Sampling loop (normalise -> encode -> 10 x [denoiser, DDPM step] -> unnormalise -> slice) against the
+    reference's own `predict_action` run with the same recorded noise draws."""
+    from oracle.dp_oracle import build_oracle_dp
+
+    cfg, state, batch, *_ = load(path)
+    noises, action, action_pred = load_prediction(path)
+    model = build_oracle_dp(dict(cfg, num_inference_steps=10)).eval()
+    model.load_state_dict(state)
+    obs = {k: v for k, v in batch.items() if k in ("obs", "goal")}
+    out = model.predict_action(obs, noises=noises)
+    assert torch.allclose(out["action_pred"], action_pred, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["action"], action, rtol=1e-4, atol=1e-5)
+    assert out["action"].shape == (action_pred.shape[0], 8, cfg["action_dim"])
 
 
 def test_ddpm_schedule_known_values():
