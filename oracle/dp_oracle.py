@@ -238,17 +238,23 @@ class OraclePCDObsEncoder(nn.Module):
                  use_mask=False, bg_ratio=0.0, pcd_hidden_dim=128, projector_layers=2,
                  projector_channels=(128, 128, 128), pre_sample=False, in_channel=6, **_):
         super().__init__()
-        assert share_pcd_model and not use_mask and not pre_sample  # the variants exercised by the DP configs
+        assert share_pcd_model
+        self.use_mask, self.bg_ratio, self.pre_sample = use_mask, bg_ratio, pre_sample
         self.key_model_map = nn.ModuleDict({"pcd": pcd_model})
         self.shape_meta, self.n_obs_step = shape_meta, n_obs_step
         self.pcd_keys = sorted(k for k, a in shape_meta["obs"].items() if a.get("type", "low_dim") == "pcd")
         self.low_dim_keys = sorted(k for k, a in shape_meta["obs"].items() if a.get("type", "low_dim") == "low_dim")
         self.pcd_nsample, self.pcd_npoints = pcd_nsample, pcd_npoints
-        self.linear = nn.Linear(3 + pcd_model.num_channels, pcd_hidden_dim, bias=False)
-        self.bn = nn.BatchNorm1d(pcd_hidden_dim)
+        if not pre_sample:
+            self.linear = nn.Linear(3 + pcd_model.num_channels, pcd_hidden_dim, bias=False)
+            self.bn = nn.BatchNorm1d(pcd_hidden_dim)
+        else:  # pcd_obs_encoder.py:91-93
+            self.linear = nn.Linear(3 + in_channel, in_channel, bias=False)
+            self.bn = nn.BatchNorm1d(in_channel)
         proj = []
         for i in range(projector_layers):
-            proj += [nn.Conv1d(pcd_hidden_dim, projector_channels[i], 1), nn.BatchNorm1d(projector_channels[i]), nn.ReLU()]
+            cin = pcd_model.num_channels if (i == 0 and pre_sample) else pcd_hidden_dim  # :101-110
+            proj += [nn.Conv1d(cin, projector_channels[i], 1), nn.BatchNorm1d(projector_channels[i]), nn.ReLU()]
         proj += [nn.MaxPool1d(pcd_npoints), nn.Conv1d(projector_channels[i], projector_channels[i + 1], 1),
                  nn.BatchNorm1d(projector_channels[i + 1])]
         self.projector = nn.Sequential(*proj)
@@ -258,16 +264,37 @@ class OraclePCDObsEncoder(nn.Module):
     def output_dim(self):
         return self.projector_channels[-1] + sum(int(self.shape_meta["obs"][k]["shape"][0]) for k in self.low_dim_keys)
 
-    def encode_pcd(self, pcd):
-        feats = self.key_model_map["pcd"](pcd)
-        p, o = pcd["coord"], pcd["offset"]
+    def pcd_sampling(self, p, x, o, mask):
+        """pcd_obs_encoder.py:123-198; the masked branch is the one of ACT (act_oracle.OracleACTPCD.pcd_sampling)."""
         b = o.shape[0]
         n_o = torch.arange(1, b + 1, dtype=torch.int32) * self.pcd_npoints
-        idx = oracle_fps(p, o, n_o)
+        if not self.use_mask or mask is None:
+            idx = oracle_fps(p, o, n_o)
+        else:
+            n_bg = int(self.pcd_npoints * self.bg_ratio)
+            ar = torch.arange(1, b + 1, dtype=torch.int32)
+            ends = o.long()
+            fg_o = torch.cumsum(mask.long(), 0)[ends - 1].int()
+            idx = oracle_fps(p[mask].contiguous(), fg_o, ar * (self.pcd_npoints - n_bg) if self.bg_ratio > 0.0 else n_o)
+            if self.bg_ratio > 0.0:
+                bg_o = torch.cumsum((~mask).long(), 0)[ends - 1].int()
+                idx = torch.cat([idx, oracle_fps(p[~mask].contiguous(), bg_o, ar * n_bg)], 0)
         n_p = p[idx.long(), :]
         kidx = oracle_knn(self.pcd_nsample, p, o, n_p, n_o)
-        g = grouping_with_xyz(kidx, feats, p, n_p)
+        g = grouping_with_xyz(kidx, x, p, n_p)
         y = F.relu(self.bn(self.linear(g).transpose(1, 2).contiguous())).max(dim=-1).values  # (m, c)
+        return n_p, y, n_o, idx
+
+    def encode_pcd(self, pcd):
+        mask = pcd.get("mask") if self.use_mask else None
+        b = pcd["offset"].shape[0]
+        if self.pre_sample:  # pcd_obs_encoder.py:201-218
+            coord, feats, off, idx = self.pcd_sampling(pcd["coord"], pcd["feat"], pcd["offset"], mask)
+            y = self.key_model_map["pcd"](dict(pcd, coord=coord, feat=feats, offset=off,
+                                               grid_coord=pcd["grid_coord"][idx.long()]))
+        else:
+            feats = self.key_model_map["pcd"](pcd)
+            _, y, _, _ = self.pcd_sampling(pcd["coord"], feats, pcd["offset"], mask)
         x = y.view(b, self.pcd_npoints, -1).permute(0, 2, 1)
         return self.projector(x).squeeze(-1)
 

@@ -250,5 +250,68 @@ def main():
               f"nograd={nograd}")
 
 
+# Encoder-only fixtures for the set-abstraction variants of PCDObsEncoder (pcd_obs_encoder.py:91-93,133-177,
+# 201-218): reference `PCDObsEncoder.forward` in train mode, loss = <output, fixed random tensor>.
+ENC_CASES = {
+    "mask": dict(qpos_dim=9, backbone_classes=32, pcd_nsample=8, pcd_npoints=24, pcd_hidden_dim=32, projector_layers=1,
+                 projector_channels=[32, 40, 40], use_mask=True, bg_ratio=0.25, pre_sample=False, clouds=8, n=70),
+    "presample": dict(qpos_dim=9, backbone_classes=32, pcd_nsample=8, pcd_npoints=24, pcd_hidden_dim=32, projector_layers=1,
+                      projector_channels=[32, 40, 40], use_mask=False, bg_ratio=0.0, pre_sample=True, clouds=8, n=70),
+}
+
+
+def main_encoder():
+    from .act_oracle import OraclePointNet
+    from tests._golden_act import grad_summary
+
+    pol, enc = install_dp_shim()
+    for name, cfg in ENC_CASES.items():
+        torch.manual_seed(99)
+        sm = {"obs": {"pcds": {"shape": [6], "type": "pcd"}, "qpos": {"shape": [cfg["qpos_dim"]], "type": "low_dim"}}}
+        e = enc.PCDObsEncoder(shape_meta=sm, pcd_model=OraclePointNet(6, cfg["backbone_classes"]), share_pcd_model=True,
+                              n_obs_step=2, pcd_nsample=cfg["pcd_nsample"], pcd_npoints=cfg["pcd_npoints"],
+                              use_mask=cfg["use_mask"], bg_ratio=cfg["bg_ratio"], pcd_hidden_dim=cfg["pcd_hidden_dim"],
+                              projector_layers=cfg["projector_layers"], projector_channels=cfg["projector_channels"],
+                              pre_sample=cfg["pre_sample"], in_channel=6).train()
+        with torch.no_grad():
+            for k, p_ in e.named_parameters():
+                if p_.dim() == 1 and p_.numel():
+                    p_.add_(0.1 * torch.randn_like(p_))
+        state = {k: v.detach().clone() for k, v in e.state_dict().items()}
+        g = torch.Generator().manual_seed(17)
+        sizes = torch.randint(int(0.75 * cfg["n"]), cfg["n"] + 1, (cfg["clouds"],), generator=g)
+        total = int(sizes.sum())
+        coord = torch.rand(total, 3, generator=g) - 0.5
+        grid = torch.floor(coord / 0.005).long()
+        grid = grid - grid.min(0).values
+        color = torch.randint(0, 256, (total, 3), generator=g).float() / 127.5 - 1
+        pcds = {"coord": coord, "grid_coord": grid, "feat": torch.cat([color, coord], 1), "offset": torch.cumsum(sizes, 0),
+                "mask": torch.rand(total, generator=g) < 0.55}
+        qpos = torch.randn(cfg["clouds"], cfg["qpos_dim"], generator=g)
+        out = e({"pcds": {k: v.clone() for k, v in pcds.items()}, "qpos": qpos})
+        probe = torch.randn(out.shape, generator=g)
+        (out * probe).sum().backward()
+        flat = {"meta/cfg_keys": np.array(list(cfg)), "meta/cfg_vals": np.array([repr(cfg[k]) for k in cfg]),
+                "out/features": out.detach().numpy(), "in/probe": probe.numpy(), "in/qpos": qpos.numpy()}
+        for k, v in pcds.items():
+            flat["in/pcds/" + k] = v.numpy()
+        for k, v in state.items():
+            flat["state/" + k] = v.numpy()
+        for k, p_ in e.named_parameters():
+            if p_.grad is not None:
+                flat["grad/" + k] = grad_summary(p_.grad)
+        for k, v in e.state_dict().items():
+            if "running_" in k:
+                flat["post/" + k] = v.numpy()
+        path = OUT / f"dpenc_{name}.npz"
+        np.savez_compressed(path, **flat)
+        print(path, tuple(out.shape))
+
+
 if __name__ == "__main__":
-    main()
+    import sys as _sys
+
+    if "encoder" in _sys.argv[1:]:
+        main_encoder()
+    else:
+        main()

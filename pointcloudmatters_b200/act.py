@@ -43,6 +43,36 @@ class KLDivergence(nn.Module):
         return klds.sum(1).mean(0, True)[0]
 
 
+def sample_indices(p, o32, npoints, mask, bg_ratio, hints):
+    """FPS picks of the set-abstraction front end, shared by `ACTPCD.pcd_sampling` (act.py:393-442) and
+    `PCDObsEncoder.pcd_sampling` (pcd_obs_encoder.py:123-177).  Plain (mask is None): one FPS over the batch.
+    Masked: FPS separately on the foreground (and, bg_ratio > 0, background) points of the boolean-compacted
+    clouds, with the reference's quirks kept as they are: the indices FPS returns refer to the COMPACTED arrays
+    and are applied to the full cloud unchanged, and all background picks follow all foreground picks
+    (`torch.cat([fg_idx, bg_idx])`, not re-interleaved per cloud).
+
+    The compaction is a stable argsort instead of `p[mask]` (static shapes, no host sync; FPS reads only the rows
+    below its offsets) and the per-cloud counts are one cumsum instead of the reference's O(B) `.sum().item()`
+    loops (act.py:423-426,434-437).  `hints`: host-known largest cloud sizes `n_max` / `fg_n_max` / `bg_n_max`
+    (Python ints) make the call free of device->host reads."""
+    b = o32.shape[0]
+    if mask is None:
+        return pointops.farthest_point_sampling(p, o32, torch.arange(1, b + 1, dtype=torch.int32, device=p.device) * npoints,
+                                                n_max=hints.get("n_max"), m_total=b * npoints)
+    n_bg = int(npoints * bg_ratio) if bg_ratio > 0.0 else 0
+    ar = torch.arange(1, b + 1, dtype=torch.int32, device=p.device)
+    ends = o32.long() - 1
+    picks = []
+    for keep, per, hint in ((mask, npoints - n_bg, "fg_n_max"), (~mask, n_bg, "bg_n_max")):
+        if per == 0:
+            continue
+        order = torch.argsort(~keep, stable=True)  # kept rows first, original order preserved
+        sub_o = torch.cumsum(keep.int(), 0, dtype=torch.int32)[ends].contiguous()
+        picks.append(pointops.farthest_point_sampling(p[order].contiguous(), sub_o, ar * per,
+                                                      n_max=hints.get(hint), m_total=b * per))
+    return picks[0] if len(picks) == 1 else torch.cat(picks, 0)
+
+
 class ACTPCD(nn.Module):
     def __init__(self, backbone, transformer, encoder, hidden_dim, num_queries, num_cameras=0, action_dim=8,
                  qpos_dim=9, env_state_dim=0, latent_dim=32, action_loss=None, klloss=None, kl_weight=20.0,
@@ -124,30 +154,7 @@ class ACTPCD(nn.Module):
 
     # ---- set abstraction (act.py:384-465) ----------------------------------------------------
     def _sample_indices(self, p, o32, n_o, mask, hints):
-        """FPS picks (act.py:393-442).  Plain: one FPS over the batch.  use_mask: FPS separately on the
-        foreground (and, bg_ratio > 0, background) points of the boolean-compacted clouds, with the
-        reference's quirks kept as they are: the indices FPS returns refer to the COMPACTED arrays and
-        are applied to the full cloud unchanged, and all background picks follow all foreground picks
-        (`torch.cat([fg_idx, bg_idx])`, not re-interleaved per cloud).
-
-        The compaction is a stable argsort instead of `p[mask]` (static shapes, no host sync; FPS reads
-        only the rows below its offsets) and the per-cloud counts are one cumsum instead of the
-        reference's O(B) `.sum().item()` loops (act.py:423-426,434-437)."""
-        b = o32.shape[0]
-        if not self.use_mask or mask is None:
-            return pointops.farthest_point_sampling(p, o32, n_o, n_max=hints.get("n_max"), m_total=b * self.pcd_npoints)
-        n_bg = int(self.pcd_npoints * self.bg_ratio) if self.bg_ratio > 0.0 else 0
-        ar = torch.arange(1, b + 1, dtype=torch.int32, device=p.device)
-        ends = o32.long() - 1
-        picks = []
-        for keep, per, hint in ((mask, self.pcd_npoints - n_bg, "fg_n_max"), (~mask, n_bg, "bg_n_max")):
-            if per == 0:
-                continue
-            order = torch.argsort(~keep, stable=True)  # kept rows first, original order preserved
-            sub_o = torch.cumsum(keep.int(), 0, dtype=torch.int32)[ends].contiguous()
-            picks.append(pointops.farthest_point_sampling(p[order].contiguous(), sub_o, ar * per,
-                                                          n_max=hints.get(hint), m_total=b * per))
-        return picks[0] if len(picks) == 1 else torch.cat(picks, 0)
+        return sample_indices(p, o32, self.pcd_npoints, mask if self.use_mask else None, self.bg_ratio, hints)
 
     def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None, hints=None):
         p, x, o = pxo

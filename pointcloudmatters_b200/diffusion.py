@@ -337,9 +337,6 @@ class PCDObsEncoder(nn.Module):
         super().__init__()
         if not share_pcd_model or not isinstance(pcd_model, nn.Module):
             raise NotImplementedError("per-key point-cloud models (share_pcd_model=False) are not used by any config")
-        if use_mask or pre_sample:
-            raise NotImplementedError("use_mask / pre_sample are built for ACT (act.ACTPCD); the Diffusion-Policy "
-                                      "configs run with both off (scratch_pointnet_pcd.yaml)")
         self._dummy_variable = nn.Parameter(torch.empty(0))  # module_attr_mixin.py:7-9 (state_dict key)
         self.key_model_map = nn.ModuleDict({"pcd": pcd_model})
         obs = shape_meta["obs"]
@@ -352,13 +349,18 @@ class PCDObsEncoder(nn.Module):
         self.shape_meta, self.share_pcd_model, self.n_obs_step = shape_meta, share_pcd_model, n_obs_step
         self.pcd_nsample, self.pcd_npoints, self.use_mask, self.bg_ratio, self.pre_sample = (
             pcd_nsample, pcd_npoints, use_mask, bg_ratio, pre_sample)
-        self.linear = nn.Linear(3 + pcd_model.num_channels, pcd_hidden_dim, bias=False)
-        self.bn = nn.BatchNorm1d(pcd_hidden_dim)
+        if not pre_sample:
+            self.linear = nn.Linear(3 + pcd_model.num_channels, pcd_hidden_dim, bias=False)
+            self.bn = nn.BatchNorm1d(pcd_hidden_dim)
+        else:  # pcd_obs_encoder.py:91-93: the head runs on the raw channels, in front of the backbone
+            self.linear = nn.Linear(3 + in_channel, in_channel, bias=False)
+            self.bn = nn.BatchNorm1d(in_channel)
         self.pool = nn.MaxPool1d(pcd_nsample)
         self.relu = nn.ReLU(inplace=True)
         proj = []
         for i in range(projector_layers):
-            proj += [nn.Conv1d(pcd_hidden_dim, projector_channels[i], kernel_size=1), nn.BatchNorm1d(projector_channels[i]),
+            cin = pcd_model.num_channels if (i == 0 and pre_sample) else pcd_hidden_dim  # :101-110
+            proj += [nn.Conv1d(cin, projector_channels[i], kernel_size=1), nn.BatchNorm1d(projector_channels[i]),
                      nn.ReLU(inplace=True)]
         proj += [nn.MaxPool1d(pcd_npoints), nn.Conv1d(projector_channels[i], projector_channels[i + 1], kernel_size=1),
                  nn.BatchNorm1d(projector_channels[i + 1])]
@@ -368,16 +370,29 @@ class PCDObsEncoder(nn.Module):
     def output_shape(self):
         return (self.projector_channels[-1] + sum(int(self.key_shape_map[k][0]) for k in self.low_dim_keys),)
 
-    def encode_pcd(self, pcd_model, pcd):
-        feats = pcd_model(pcd)
-        p, o = pcd["coord"], pcd["offset"]
+    def pcd_sampling(self, pxo, mask, hints):
+        """pcd_obs_encoder.py:123-198 -> (new coords, pooled features (b*M, c), new offsets, picked indices)."""
+        from .act import sample_indices
+
+        p, x, o = pxo
         b = o.shape[0]
         n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
         o32 = o.int() if o.dtype != torch.int32 else o
-        idx = pointops.farthest_point_sampling(p, o32, n_o, n_max=pcd.get("n_max", None), m_total=b * self.pcd_npoints)
+        idx = sample_indices(p, o32, self.pcd_npoints, mask if self.use_mask else None, self.bg_ratio, hints)
         n_p = p[idx.long(), :].contiguous()
         knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
-        x = PF.set_abstraction(p, feats, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)  # (b*M, hidden)
+        return n_p, PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn), n_o, idx
+
+    def encode_pcd(self, pcd_model, pcd):
+        b = pcd["offset"].shape[0]
+        mask = pcd.get("mask", None) if self.use_mask else None
+        hints = {k: pcd.get(k, None) for k in ("n_max", "fg_n_max", "bg_n_max")}
+        if self.pre_sample:  # pcd_obs_encoder.py:201-218 (works on a copy: the caller's dict is not rewritten)
+            coord, feats, offset, idx = self.pcd_sampling((pcd["coord"], pcd["feat"], pcd["offset"]), mask, hints)
+            x = pcd_model(dict(pcd, coord=coord, feat=feats, offset=offset, grid_coord=pcd["grid_coord"][idx.long()]))
+        else:
+            feats = pcd_model(pcd)
+            _, x, _, _ = self.pcd_sampling((pcd["coord"], feats, pcd["offset"]), mask, hints)
         # projector (pcd_obs_encoder.py:100-121): 1x1 Conv1d + BN + ReLU per point, max over the M points,
         # 1x1 Conv1d + BN -- on token-major rows (a 1x1 convolution is a Linear)
         for i in range(self.projector_layers):
@@ -486,8 +501,11 @@ class DiffusionUnetImagePolicy(nn.Module):
         return dict(loss=loss)
 
     def sync_free(self, pcds) -> bool:
-        """True when `pcds["n_max"]` (host-known largest cloud) lets FPS run without a device->host read."""
-        return pcds.get("n_max", None) is not None
+        """True when the host-known cloud-size hints let FPS run without a device->host read."""
+        enc = self.obs_encoder
+        need = ["n_max"] if not (enc.use_mask and pcds.get("mask", None) is not None) else (
+            ["fg_n_max"] + (["bg_n_max"] if enc.bg_ratio > 0.0 else []))
+        return all(pcds.get(k, None) is not None for k in need)
 
     # ========= inference (diffusion_unet_image_policy.py:106-231) =========
     def _denoise_step(self, traj, t, coef, noise, global_cond):

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from tests._golden_act import grad_summary
-from tests._golden_dp import GOLDEN_DP, load
+from tests._golden_dp import GOLDEN_DP, GOLDEN_DPENC, encoder_kwargs, load, load_encoder
 
 pytestmark = pytest.mark.gpu
 
@@ -170,3 +170,42 @@ def test_predict_action_matches_reference_fixture(path, graph):
         assert model._sample_graphs
         again = model.predict_action(obs, noises=noises, use_cuda_graph=True)  # replay of the cached graph
         assert float((again["action_pred"] - out["action_pred"]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("path", GOLDEN_DPENC)
+def test_encoder_variants_match_reference_fixture(path):
+    """`use_mask` (+ bg_ratio, with and without the sync-free size hints) and `pre_sample` variants of
+    PCDObsEncoder against the reference encoder's own output; FPS picks inside are bit-exact, features
+    (after a 8-row training-mode BatchNorm) rel-L2 <= 3e-2, gradient summaries <= ENC_GRAD_TOL."""
+    from pointcloudmatters_b200.diffusion import PCDObsEncoder
+    from pointcloudmatters_b200.pointnet import PointNet
+
+    cfg, state, obs, feats, probe, grads, post = load_encoder(path)
+    sm, kw = encoder_kwargs(cfg)
+    enc = PCDObsEncoder(sm, PointNet(6, cfg["backbone_classes"]), **kw).cuda().train()
+    enc.load_state_dict(state)
+    out = enc(_cuda(obs))
+    rel = float((out.cpu() - feats).norm() / feats.norm())
+    assert rel <= 3e-2, rel
+    (out * probe.cuda()).sum().backward()
+    gmax = max(v[0] for v in grads.values())
+    bad = {}
+    for k, p in enc.named_parameters():
+        if p.grad is None:
+            continue
+        want, got = grads[k], grad_summary(p.grad)
+        # small tensors (BatchNorm affine: 1-2 % of the largest gradient norm) sit on top of a 192-point, 8-cloud
+        # batch-statistics stack: their error is measured on the scale of 3 % of the largest tensor's gradient
+        scale = max(want[0], 3e-2 * gmax)
+        err = max(abs(got[0] - want[0]) / scale, np.abs(got[2:] - want[2:]).max() / scale)
+        if err > ENC_GRAD_TOL:
+            bad[k] = err
+    assert not bad, bad
+    if cfg["use_mask"]:  # hints make the masked FPS sync-free and must not change the picks
+        pc = _cuda(obs)["pcds"]
+        sizes = torch.diff(obs["pcds"]["offset"], prepend=torch.zeros(1, dtype=torch.int64)).tolist()
+        fg = [int(c.sum()) for c in torch.split(obs["pcds"]["mask"], sizes)]
+        hints = {"fg_n_max": max(fg), "bg_n_max": max(s - f for s, f in zip(sizes, fg))}
+        a = enc.pcd_sampling((pc["coord"], pc["feat"].new_zeros(pc["feat"].shape[0], 32), pc["offset"]), pc["mask"], {})[3]
+        b = enc.pcd_sampling((pc["coord"], pc["feat"].new_zeros(pc["feat"].shape[0], 32), pc["offset"]), pc["mask"], hints)[3]
+        assert torch.equal(a, b)

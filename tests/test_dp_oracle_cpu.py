@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from tests._golden_act import grad_summary
-from tests._golden_dp import GOLDEN_DP, load, load_prediction
+from tests._golden_dp import GOLDEN_DP, GOLDEN_DPENC, encoder_kwargs, load, load_encoder, load_prediction
 
 
 def test_fixtures_present():
@@ -51,6 +51,27 @@ def test_oracle_predict_action_matches_reference_fixture(path):
     assert torch.allclose(out["action_pred"], action_pred, rtol=1e-4, atol=1e-5)
     assert torch.allclose(out["action"], action, rtol=1e-4, atol=1e-5)
     assert out["action"].shape == (action_pred.shape[0], 8, cfg["action_dim"])
+
+
+@pytest.mark.parametrize("path", GOLDEN_DPENC)
+def test_oracle_encoder_variants_match_reference_fixture(path):
+    """`use_mask` (+ bg_ratio) and `pre_sample` variants of PCDObsEncoder (pcd_obs_encoder.py:91-93,133-177,201-218)."""
+    from oracle.act_oracle import OraclePointNet
+    from oracle.dp_oracle import OraclePCDObsEncoder
+
+    cfg, state, obs, feats, probe, grads, post = load_encoder(path)
+    sm, kw = encoder_kwargs(cfg)
+    enc = OraclePCDObsEncoder(sm, OraclePointNet(6, cfg["backbone_classes"]), **kw).train()
+    assert sorted(enc.state_dict().keys()) == sorted(state.keys())
+    enc.load_state_dict(state)
+    out = enc(obs)
+    assert torch.allclose(out, feats, rtol=1e-4, atol=1e-5)
+    (out * probe).sum().backward()
+    for k, p in enc.named_parameters():
+        if p.grad is not None:
+            np.testing.assert_allclose(grad_summary(p.grad), grads[k], rtol=2e-3, atol=2e-6 + 1e-4 * abs(grads[k][0]), err_msg=k)
+    for k, v in post.items():
+        np.testing.assert_allclose(enc.state_dict()[k].numpy(), v, rtol=1e-5, atol=1e-6, err_msg=k)
 
 
 def test_ddpm_schedule_known_values():

@@ -79,3 +79,26 @@ def test_gemm_rejects_unaligned():
     b = torch.randn(32, 7, device="cuda").bfloat16()
     with pytest.raises(PcmError):
         gemm_bf16(a, b)
+
+
+@pytest.mark.parametrize("M,N,K,b_mn,bias", [(32, 128, 1280, False, True), (64, 2048, 10240, False, True),
+                                            (64, 10240, 2048, True, False), (16, 408, 4096, True, False),
+                                            (200, 520, 1032, False, False)])
+def test_few_row_long_k_gemm_uses_k_split_and_matches(M, N, K, b_mn, bias):
+    """functional._gemm_rows: activation GEMMs with < 74 output tiles and K >= 1024 (Diffusion-Policy denoiser)
+    go through the launcher's K-split with fp32 atomics into a bias-initialised output; rows / columns that are
+    not tile multiples must not be touched outside [M, N)."""
+    import torch
+
+    from pointcloudmatters_b200.functional import _gemm_rows
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(K, N, device="cuda", generator=g) if b_mn else torch.randn(N, K, device="cuda", generator=g)).bfloat16()
+    bv = torch.randn(N, device="cuda", generator=g) if bias else None
+    got = _gemm_rows(a, w, b_mn=b_mn, bias=bv)
+    want = a.float() @ (w.float() if b_mn else w.float().t())
+    if bv is not None:
+        want = want + bv
+    assert got.shape == (M, N) and got.dtype == torch.float32
+    assert float((got - want).norm() / want.norm()) < 2e-3

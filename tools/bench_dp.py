@@ -15,6 +15,40 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
+def infer(args):
+    """Closed-loop inference latency: encoder + 100 denoising steps (`num_inference_steps: 100`,
+    maniskill2_diffusion_policy_model.yaml:46), CUDA-graphed step vs eager launches."""
+    import torch
+
+    from pointcloudmatters_b200.data import synthetic_dp_batch, to_device
+    from pointcloudmatters_b200.diffusion import DP_MODEL_CFG, build_dp_policy
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1234)
+    cfg = dict(DP_MODEL_CFG, pcd_npoints=args.points // 2, num_inference_steps=100)
+    policy = build_dp_policy(cfg).to(dev).eval()
+    policy.normalizer.set_identity({"qpos": cfg["qpos_dim"], "action": cfg["action_dim"]}).to(dev)
+    h = synthetic_dp_batch(args.batch, args.points, seed=1)
+    obs = to_device({"obs": h["obs"]}, dev)
+    obs["obs"]["pcds"]["n_max"] = h["obs"]["pcds"]["n_max"]
+    out = {}
+    for graph in (True, False):
+        for _ in range(2):
+            policy.predict_action(obs, use_cuda_graph=graph)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 3
+        for _ in range(n):
+            a = policy.predict_action(obs, use_cuda_graph=graph)
+        e1.record()
+        torch.cuda.synchronize()
+        out["graph" if graph else "eager"] = e0.elapsed_time(e1) / n
+    print(json.dumps({"workload": f"DP predict_action, {args.batch} env(s), N={args.points}, 100 DDPM steps, 255.8 M-param U-Net",
+                      "ms_per_call_cuda_graph": out["graph"], "ms_per_call_eager": out["eager"],
+                      "ms_per_denoising_step_cuda_graph": out["graph"] / 100, "action_shape": list(a["action"].shape)}))
+
+
 def main():
     import torch
 
@@ -29,7 +63,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--infer", action="store_true", help="time predict_action (100-step DDPM sampling) instead of training")
     args = ap.parse_args()
+    if args.infer:
+        return infer(args)
     dev = torch.device("cuda", 0)
     torch.manual_seed(1234)
     cfg = dict(DP_MODEL_CFG, pcd_npoints=args.points // 2)
