@@ -286,6 +286,9 @@ int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const floa
                               pcm_stream_t stream);
 int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
                pcm_stream_t stream);
+/* Profiling aid (tools/bench_ln.py): launch-shape knobs of the LayerNorm backward / colsum kernels
+ * (maximum CTAs of the backward, target CTA count and minimum rows per CTA of colsum); <= 0 keeps a value. */
+int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows);
 /* out = bf16(a + b): `with_pos_embed` (transformer.py:235-236) fused with the operand cast of the
  * Q/K projections.  b may be NULL; b_row_div > 1 broadcasts b's rows over the batch. */
 int pcm_add_cast_bf16(long long rows, int C, const float *a, const float *b, int b_row_div, void *out,

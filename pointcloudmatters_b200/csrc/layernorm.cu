@@ -271,6 +271,23 @@ inline int ln_grid(long rows) {
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// Launch-shape knobs of the two kernels that end in one global atomic per column per CTA (LayerNorm backward:
+// dgamma / dbeta, 2C atomics per CTA; colsum: C per CTA).  With one row per warp a 6 400-row backward ran 800 CTAs
+// = 819 200 atomics onto 1 024 addresses and was atomic-bound (21 us against a 9 us HBM floor); fewer, longer-lived
+// CTAs trade a little memory-level parallelism for a 3-8x shorter atomic tail.  Measured with tools/bench_ln.py
+// (CUDA-graph replay, one B200, profiles/r1_ln_colsum_sweep.jsonl): backward, 6 400 rows: 20.6 us at 800 CTAs ->
+// 12.0 us at 296 (2 per SM); 32 960 rows: 57.5 us at 1 184 -> 52.2 us at 222; colsum, 6 400 rows: 5.5 us at 16
+// rows per CTA -> 3.9 us at >= 32, 32 960 rows best with ~592 CTAs (11.8 us).
+int g_ln_bwd_cap = 0;  // 0 = by size: 2 CTAs per SM, 1.5 per SM for the large token sets
+int g_colsum_ctas = 148 * 4;
+int g_colsum_min_rows = 32;
+
+inline int ln_grid_bwd(long rows) {
+    long blocks = (rows + 7) / 8;
+    const long cap = g_ln_bwd_cap > 0 ? g_ln_bwd_cap : (rows > 16384 ? 222L : 296L);
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
 }  // namespace
 
 #define LN_DISPATCH(V, KERNEL, ...)                                   \
@@ -319,7 +336,7 @@ PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, co
     if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
     if (C % 128) return PCM_EUNSUPPORTED;
     cudaStream_t st = pcm_cu_stream(stream);
-    const int grid = ln_grid(rows);
+    const int grid = ln_grid_bwd(rows);
     LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
                 dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16))
     return pcm_launch_status();
@@ -333,13 +350,22 @@ PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const
                                      nullptr, stream);
 }
 
+// Debug aid for tools/bench_ln.py: override the launch-shape knobs above (values <= 0 keep the current one).
+PCM_API int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows) {
+    if (ln_bwd_max_ctas > 0) g_ln_bwd_cap = ln_bwd_max_ctas;
+    if (colsum_ctas > 0) g_colsum_ctas = colsum_ctas;
+    if (colsum_min_rows > 0) g_colsum_min_rows = colsum_min_rows;
+    return PCM_OK;
+}
+
 // out[c] += sum over rows of src[r, c] (bias gradients); src_bf16 selects the element type.
 PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int src_bf16, float* out,
                        pcm_stream_t stream) {
     if (rows <= 0 || C <= 0) return PCM_OK;
     if (!src || !out) return PCM_EINVAL;
-    int rows_per_cta = (int)((rows + 148L * 4 - 1) / (148L * 4));
-    if (rows_per_cta < 16) rows_per_cta = 16;
+    const long ctas = g_colsum_ctas > 0 ? g_colsum_ctas : 148L * 4;
+    int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+    if (rows_per_cta < g_colsum_min_rows) rows_per_cta = g_colsum_min_rows;
     const int grid = (int)((rows + rows_per_cta - 1) / rows_per_cta);
     cudaStream_t st = pcm_cu_stream(stream);
     const int vec = src_bf16 ? 8 : 4;
