@@ -286,6 +286,15 @@ int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const floa
                               pcm_stream_t stream);
 int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
                pcm_stream_t stream);
+/* FFN hidden layer (transformer.py:243-247,336-340: `linear2(dropout(relu(linear1(x))))`): dropout of the
+ * ReLU'd hidden activation h (rows, Hd) bf16 -- the output of pcm_gemm_bf16 with bias+ReLU epilogue -- and its
+ * backward dh = bf16(d(dropped) * keep * scale * [h > 0]) (p_drop = 0: ReLU gate only).  Hd % 8 == 0.  Masks
+ * come from the counter-based RNG of the LayerNorm kernels (seed_base in device memory, seed_offset per call). */
+int pcm_ffn_dropout_fwd(long long rows, int Hd, const void *h, float p_drop, const unsigned long long *seed_base,
+                        unsigned long long seed_offset, void *out, pcm_stream_t stream);
+int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float *dhd, const void *h, float p_drop,
+                             const unsigned long long *seed_base, unsigned long long seed_offset, void *dh,
+                             pcm_stream_t stream);
 /* Profiling aid (tools/bench_ln.py): launch-shape knobs of the LayerNorm backward / colsum kernels
  * (maximum CTAs of the backward, target CTA count and minimum rows per CTA of colsum); <= 0 keeps a value. */
 int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows);

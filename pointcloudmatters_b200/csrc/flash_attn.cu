@@ -450,42 +450,60 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// delta[z, l] = sum_d dO[z, l, d] * O[l * B + b, h * 64 + d]      (one warp per row); also zero-fills
-// the fp32 dQ accumulator the backward kernel reduces into
+// delta[z, l] = sum_d dO[z, l, d] * O[l * B + b, h * 64 + d]; also zero-fills the fp32 dQ accumulator the
+// backward kernel reduces into.  Four rows per warp: 8 lanes own one 64-element row (16-byte loads, a
+// 3-step shuffle reduction), so a warp instruction moves 512 B instead of 128 B.
 __global__ void __launch_bounds__(256) flash_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                                           int ldo, int B, int nh, int L, long rows, float* __restrict__ delta,
                                                           float* __restrict__ dq_acc) {
     pcm_pdl_launch_dependents();
     pcm_pdl_wait();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long r = wid; r < rows; r += nwarps) {
-        const int z = (int)(r / L), l = (int)(r - (long)z * L);
-        const int b = z / nh, h = z - b * nh;
-        const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(dO + (size_t)r * 64)[lane];
-        const __nv_bfloat162 c = reinterpret_cast<const __nv_bfloat162*>(O + ((size_t)l * B + b) * ldo + h * 64)[lane];
-        const float2 af = __bfloat1622float2(a), cf = __bfloat1622float2(c);
-        float s = af.x * cf.x + af.y * cf.y;
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(PCM_FULL_MASK, s, o);
-        if (lane == 0) delta[r] = s;
-        reinterpret_cast<float2*>(dq_acc + (size_t)r * 64)[lane] = make_float2(0.f, 0.f);  // clears the dQ accumulator row
+    for (long r0 = wid * 4; r0 < rows; r0 += nwarps * 4) {
+        const long r = r0 + sub;
+        float s = 0.f;
+        if (r < rows) {
+            const int z = (int)(r / L), l = (int)(r - (long)z * L);
+            const int b = z / nh, h = z - b * nh;
+            const uint4 a = reinterpret_cast<const uint4*>(dO + (size_t)r * 64)[l8];
+            const uint4 c = reinterpret_cast<const uint4*>(O + ((size_t)l * B + b) * ldo + h * 64)[l8];
+            const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* cp = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 af = __bfloat1622float2(ap[k]), cf = __bfloat1622float2(cp[k]);
+                s += af.x * cf.x + af.y * cf.y;
+            }
+            float4* q = reinterpret_cast<float4*>(dq_acc + (size_t)r * 64) + l8 * 2;  // clears the dQ accumulator row
+            q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        s += __shfl_xor_sync(PCM_FULL_MASK, s, 4);
+        s += __shfl_xor_sync(PCM_FULL_MASK, s, 2);
+        s += __shfl_xor_sync(PCM_FULL_MASK, s, 1);
+        if (l8 == 0 && r < rows) delta[r] = s;
     }
 }
 
-// dQ token-major bf16 <- fp32 (Z, L, 64) accumulator          (one warp per row, 8 bytes per lane)
+// dQ token-major bf16 <- fp32 (Z, L, 64) accumulator          (four rows per warp, 32 B in / 16 B out per lane)
 __global__ void __launch_bounds__(256) flash_dq_store_kernel(const float* __restrict__ acc, int B, int nh, int L, long rows,
                                                              __nv_bfloat16* __restrict__ dQ, int ldq) {
     pcm_pdl_launch_dependents();
     pcm_pdl_wait();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
     const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long r = wid; r < rows; r += nwarps) {
+    for (long r = wid * 4 + sub; r < rows; r += nwarps * 4) {
         const int z = (int)(r / L), l = (int)(r - (long)z * L);
         const int b = z / nh, h = z - b * nh;
-        const float2 a = reinterpret_cast<const float2*>(acc + (size_t)r * 64)[lane];
-        reinterpret_cast<uint32_t*>(dQ + ((size_t)l * B + b) * ldq + h * 64)[lane] = pack_bf16(a.x, a.y);
+        const float4* a = reinterpret_cast<const float4*>(acc + (size_t)r * 64) + l8 * 2;
+        const float4 a0 = a[0], a1 = a[1];
+        uint4 pk;
+        pk.x = pack_bf16(a0.x, a0.y); pk.y = pack_bf16(a0.z, a0.w);
+        pk.z = pack_bf16(a1.x, a1.y); pk.w = pack_bf16(a1.z, a1.w);
+        reinterpret_cast<uint4*>(dQ + ((size_t)l * B + b) * ldq + h * 64)[l8] = pk;
     }
 }
 
@@ -998,7 +1016,11 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     }
     cudaStream_t st = pcm_cu_stream(stream);
     const long rows = (long)Z * L;
-    const int g = (int)((rows + 7) / 8 < 148L * 16 ? (rows + 7) / 8 : 148L * 16);
+    if ((ldo % 8) || (ldq % 8) || (reinterpret_cast<uintptr_t>(O) & 15) || (reinterpret_cast<uintptr_t>(dQ) & 15) ||
+        (reinterpret_cast<uintptr_t>(dO) & 15))
+        return PCM_EUNSUPPORTED;  // 16-byte row accesses of the pre / post kernels
+    const long row_ctas = (rows + 31) / 32;  // 8 warps x 4 rows per CTA
+    const int g = (int)(row_ctas < 148L * 8 ? (row_ctas > 0 ? row_ctas : 1) : 148L * 8);
     cudaError_t le = pcm_launch(flash_delta_kernel, dim3(g), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(dO),
                                 reinterpret_cast<const __nv_bfloat16*>(O), ldo, B, nh, L, rows, delta, dQacc);
     if (le != cudaSuccess) return (int)le;

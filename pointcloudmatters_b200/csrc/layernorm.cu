@@ -265,6 +265,89 @@ __global__ void __launch_bounds__(256) add_cast_bf16_kernel(const float* __restr
     }
 }
 
+// ---- FFN hidden layer (dim_feedforward = 32 in the reference configs): dropout of the ReLU'd hidden activation
+// and its backward.  The hidden tensor is (rows, Hd) bf16 straight out of the first GEMM's bias+ReLU epilogue;
+// one thread handles 8 consecutive elements (16-byte accesses), masks come from the counter-based RNG shared with
+// the LayerNorm kernels (stateless: the backward regenerates them).  Replaces six ATen kernels per FFN
+// (fused_dropout, bf16 cast, masked_scale, compare, multiply, bf16 cast) with two.
+__device__ __forceinline__ void ffn_keep8(uint32_t rseed, uint32_t chunk, uint32_t thr16, bool keep[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t hbits = pcm_pair_bits(rseed, chunk * 4 + k);
+        keep[2 * k] = (hbits & 0xFFFFu) >= thr16;
+        keep[2 * k + 1] = (hbits >> 16) >= thr16;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ffn_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ h, long rows, int Hd, float p_drop,
+                       const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset,
+                       __nv_bfloat16* __restrict__ out) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float ks = pcm_keep_scale(thr16);
+    const int cpr = Hd / 8;  // 16-byte chunks per row
+    const long total = rows * cpr;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cpr;
+        const uint32_t c = (uint32_t)(i - r * cpr);
+        const uint4 raw = reinterpret_cast<const uint4*>(h)[i];
+        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        bool keep[8];
+        ffn_keep8(pcm_row_seed(seed, (unsigned long long)r * Hd), c, thr16, keep);
+        uint4 o;
+        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(v[k]);
+            __nv_bfloat162 w = __floats2bfloat162_rn(keep[2 * k] ? f.x * ks : 0.f, keep[2 * k + 1] ? f.y * ks : 0.f);
+            op[k] = *reinterpret_cast<uint32_t*>(&w);
+        }
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+
+// dh = bf16( d(dropped hidden) * keep * scale * [h > 0] ); p_drop = 0 -> ReLU gate only.
+__global__ void __launch_bounds__(256)
+ffn_relu_dropout_bwd_kernel(const float* __restrict__ dhd, const __nv_bfloat16* __restrict__ h, long rows, int Hd,
+                            float p_drop, const unsigned long long* __restrict__ seed_base,
+                            unsigned long long seed_offset, __nv_bfloat16* __restrict__ dh) {
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
+    const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
+    const uint32_t thr16 = pcm_drop_thr16(p_drop);
+    const float ks = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
+    const int cpr = Hd / 8;
+    const long total = rows * cpr;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cpr;
+        const uint32_t c = (uint32_t)(i - r * cpr);
+        const uint4 raw = reinterpret_cast<const uint4*>(h)[i];
+        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float4 g0 = reinterpret_cast<const float4*>(dhd)[2 * i], g1 = reinterpret_cast<const float4*>(dhd)[2 * i + 1];
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        bool keep[8];
+        if (p_drop > 0.f) {
+            ffn_keep8(pcm_row_seed(seed, (unsigned long long)r * Hd), c, thr16, keep);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) keep[k] = true;
+        }
+        uint4 o;
+        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(v[k]);
+            __nv_bfloat162 w = __floats2bfloat162_rn((keep[2 * k] && f.x > 0.f) ? g[2 * k] * ks : 0.f,
+                                                     (keep[2 * k + 1] && f.y > 0.f) ? g[2 * k + 1] * ks : 0.f);
+            op[k] = *reinterpret_cast<uint32_t*>(&w);
+        }
+        reinterpret_cast<uint4*>(dh)[i] = o;
+    }
+}
+
 inline int ln_grid(long rows) {
     long blocks = (rows + 7) / 8;
     const long cap = 148L * 8;
@@ -348,6 +431,35 @@ PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const
                                    float* dx, float* dgamma, float* dbeta, pcm_stream_t stream) {
     return pcm_add_dropout_ln_bwd_ex(rows, C, dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, dres, dx, dgamma, dbeta,
                                      nullptr, stream);
+}
+
+PCM_API int pcm_ffn_dropout_fwd(long long rows, int Hd, const void* h, float p_drop, const unsigned long long* seed_base,
+                                unsigned long long seed_offset, void* out, pcm_stream_t stream) {
+    if (rows <= 0 || Hd <= 0) return PCM_OK;
+    if (!h || !out || p_drop <= 0.f || p_drop >= 1.f) return PCM_EINVAL;
+    if (Hd % 8) return PCM_EUNSUPPORTED;
+    const long total = (long)rows * (Hd / 8);
+    const int grid = (int)((total + 255) / 256 < 148L * 8 ? (total + 255) / 256 : 148L * 8);
+    cudaError_t e = pcm_launch(ffn_dropout_fwd_kernel, dim3(grid), dim3(256), 0, pcm_cu_stream(stream),
+                               reinterpret_cast<const __nv_bfloat16*>(h), (long)rows, Hd, p_drop, seed_base, seed_offset,
+                               reinterpret_cast<__nv_bfloat16*>(out));
+    if (e != cudaSuccess) return (int)e;
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float* dhd, const void* h, float p_drop,
+                                     const unsigned long long* seed_base, unsigned long long seed_offset, void* dh,
+                                     pcm_stream_t stream) {
+    if (rows <= 0 || Hd <= 0) return PCM_OK;
+    if (!dhd || !h || !dh || p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
+    if (Hd % 8) return PCM_EUNSUPPORTED;
+    const long total = (long)rows * (Hd / 8);
+    const int grid = (int)((total + 255) / 256 < 148L * 8 ? (total + 255) / 256 : 148L * 8);
+    cudaError_t e = pcm_launch(ffn_relu_dropout_bwd_kernel, dim3(grid), dim3(256), 0, pcm_cu_stream(stream), dhd,
+                               reinterpret_cast<const __nv_bfloat16*>(h), (long)rows, Hd, p_drop, seed_base, seed_offset,
+                               reinterpret_cast<__nv_bfloat16*>(dh));
+    if (e != cudaSuccess) return (int)e;
+    return pcm_launch_status();
 }
 
 // Debug aid for tools/bench_ln.py: override the launch-shape knobs above (values <= 0 keep the current one).

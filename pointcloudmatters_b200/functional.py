@@ -608,6 +608,79 @@ def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=N
     return F.layer_norm(residual, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
 
 
+class _FFN(torch.autograd.Function):
+    """linear2(dropout(relu(linear1(x)))) (transformer.py:243-247,336-340) as ONE autograd node: the hidden
+    activation (rows, dim_feedforward) lives in bf16 straight out of the first GEMM's bias+ReLU epilogue, dropout
+    and the ReLU/dropout backward are one small kernel each (csrc/layernorm.cu), weight / bias gradients go
+    straight into the parameters' gradient buffers.  Replaces two `_LinearTC` nodes plus six ATen kernels."""
+
+    @staticmethod
+    def forward(ctx, x2, w1, b1, w2, b2, p_drop, xb_hint):
+        from ._lib import check, current_stream, lib, ptr
+
+        xb = xb_hint if xb_hint is not None else (x2 if x2.dtype == torch.bfloat16 else K.add_cast_bf16(x2))
+        w1b, w2b = _wb(w1), _wb(w2)
+        h = K.gemm_bf16(xb, w1b, bias=b1, relu=True, out_dtype=torch.bfloat16)  # (rows, Hd) bf16
+        seed_base, seed = None, 0
+        hd = h
+        if p_drop > 0:
+            seed_base, seed = DROPOUT_RNG.base_for(x2.device), DROPOUT_RNG.next_offset()
+            hd = torch.empty_like(h)
+            check(lib.pcm_ffn_dropout_fwd(h.shape[0], h.shape[1], ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(hd),
+                                          current_stream()), "pcm_ffn_dropout_fwd")
+        y = K.gemm_bf16(hd, w2b, bias=b2)
+        ctx.save_for_backward(xb, h, hd, w1b, w2b, seed_base)
+        ctx.cfg = (float(p_drop), int(seed))
+        ctx.params = (w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from ._lib import check, current_stream, lib, ptr
+
+        xb, h, hd, w1b, w2b, seed_base = ctx.saved_tensors
+        p_drop, seed = ctx.cfg
+        w1, b1, w2, b2 = ctx.params
+        rows, Hd = h.shape
+        dyb = _grad_bf16(dy, rows, dy.shape[1])
+        grads = []
+        for w, a, b in ((w2, dyb, hd), ):
+            slot = _grad_slot(w)
+            dw = slot if slot is not None else torch.zeros(w.shape, dtype=torch.float32, device=dyb.device)
+            _dw(a, b, dw)
+            grads.append(None if slot is not None else dw)
+        slot = _grad_slot(b2)
+        db2 = K.colsum(dyb, slot)
+        dhd = K.gemm_bf16(dyb, w2b, b_mn=True)  # (rows, E) x W2(E, Hd) -> (rows, Hd) fp32
+        dhb = torch.empty_like(h)
+        check(lib.pcm_ffn_relu_dropout_bwd(rows, Hd, ptr(dhd), ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(dhb),
+                                           current_stream()), "pcm_ffn_relu_dropout_bwd")
+        slot1 = _grad_slot(w1)
+        dw1 = slot1 if slot1 is not None else torch.zeros(w1.shape, dtype=torch.float32, device=dyb.device)
+        _dw(dhb, xb, dw1)
+        slotb1 = _grad_slot(b1)
+        db1 = K.colsum(dhb, slotb1)
+        dx = K.gemm_bf16(dhb, w1b, b_mn=True) if ctx.needs_input_grad[0] else None
+        return (dx, None if slot1 is not None else dw1, None if slotb1 is not None else db1, grads[0],
+                None if slot is not None else db2, None, None)
+
+
+def feed_forward(x, linear1, linear2, p_drop, training):
+    """FFN sub-block on token-major activations x (..., E); `linear1` / `linear2` are the nn.Linear parameter
+    containers.  Falls back to two `linear` calls when the shapes are not TMA-legal (never on the reference configs)."""
+    _need_cuda(x)
+    E, Hd = linear1.weight.shape[1], linear1.weight.shape[0]
+    p = float(p_drop) if training else 0.0
+    if E % 8 or Hd % 8 or E < 16 or Hd < 16 or linear1.bias is None or linear2.bias is None:
+        h = linear(x, linear1.weight, linear1.bias, relu=True)
+        return linear(dropout(h, p_drop, training), linear2.weight, linear2.bias)
+    x2 = x.reshape(-1, E)
+    if x2.stride(-1) != 1 or (x2.stride(0) % 8) or (x2.data_ptr() % 16):
+        x2 = x2.contiguous()
+    y = _FFN.apply(x2, linear1.weight, linear1.bias, linear2.weight, linear2.bias, p, _act_bf16(x, x2.shape[0], E))
+    return y.view(*x.shape[:-1], linear2.weight.shape[0])
+
+
 def dropout(x, p, training):
     return F.dropout(x, p, True) if (training and p > 0) else x
 

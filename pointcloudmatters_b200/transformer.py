@@ -37,8 +37,7 @@ class TransformerEncoderLayer(nn.Module):
         self.p = dropout
 
     def _ffn(self, x):
-        h = PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
-        return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+        return PF.feed_forward(x, self.linear1, self.linear2, self.p, self.training)
 
     def forward(self, src, src_mask: Optional[Tensor] = None, src_key_padding_mask: Optional[Tensor] = None,
                 pos: Optional[Tensor] = None, pos_head: Optional[Tensor] = None):
@@ -100,8 +99,7 @@ class TransformerDecoderLayer(nn.Module):
         self.p = dropout
 
     def _ffn(self, x):
-        h = PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
-        return PF.linear(PF.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+        return PF.feed_forward(x, self.linear1, self.linear2, self.p, self.training)
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):

@@ -76,3 +76,48 @@ def test_colsum(dtype):
     out = torch.ones(512, device="cuda")
     colsum(view, out)
     torch.testing.assert_close(out, 1 + view.float().sum(0), rtol=1e-4, atol=2e-2)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_fused_ffn_matches_torch(p):
+    """functional.feed_forward (GEMM+bias+ReLU -> dropout kernel -> GEMM; fused ReLU/dropout backward) against
+    plain torch.  With dropout the realised mask is read back through an identity block planted in linear2, so the
+    torch reference applies exactly the same mask (and the keep rate / scale are checked)."""
+    import torch
+    import torch.nn.functional as F
+
+    from pointcloudmatters_b200 import functional as PF
+
+    torch.manual_seed(11)
+    rows, E, Hd = 1000, 64, 32
+    l1, l2 = torch.nn.Linear(E, Hd).cuda(), torch.nn.Linear(Hd, E).cuda()
+    with torch.no_grad():
+        l2.weight[:Hd] = torch.eye(Hd, device="cuda")
+        l2.bias[:Hd] = 0
+    x = torch.randn(rows, E, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = PF.feed_forward(xa, l1, l2, p, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = (y.detach(), xa.grad.clone(), l1.weight.grad.clone(), l1.bias.grad.clone(), l2.weight.grad.clone(), l2.bias.grad.clone())
+    for m in (l1, l2):
+        m.zero_grad(set_to_none=True)
+    h = F.relu(F.linear(xb, l1.weight, l1.bias))
+    if p > 0:
+        hd_seen = y.detach()[:, :Hd]                      # = dropped hidden (identity block, zero bias)
+        keep = (hd_seen != 0) | (h.detach() <= 0)
+        live = h.detach() > 1e-3
+        rate = float((hd_seen[live] != 0).float().mean())
+        assert abs(rate - (1 - p)) < 0.02, rate
+        scale = float((hd_seen[live & keep] / h.detach()[live & keep]).median())
+        assert abs(scale - 1 / (1 - p)) < 0.02, scale
+        h = h * keep * scale
+    yr = F.linear(h, l2.weight, l2.bias)
+    yr.backward(dy)
+    want = (yr.detach(), xb.grad, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad)
+    # y / dW2 / db2 see only operand rounding (<= 2e-2).  dx / dW1 / db1 pass through the ReLU gate, which the
+    # product evaluates on ITS hidden activation (bf16 operands): ~0.1 % of the units sit close enough to zero to
+    # flip against the fp32 reference, each contributing a whole gradient element (measured 3.5-5e-2 relative).
+    for a, b, name in zip(got, want, ("y", "dx", "dW1", "db1", "dW2", "db2")):
+        rel = float((a - b).norm() / b.norm())
+        assert rel < (8e-2 if name in ("dx", "dW1", "db1") else 2e-2), (name, rel)
