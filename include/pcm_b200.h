@@ -273,13 +273,15 @@ int pcm_add_dropout_ln_bwd(long long rows, int C, const float *dy, const float *
 /* Extended forms: the forward can additionally emit ypos_bf16 = bf16(y + pos[r / pos_row_div]) --
  * the `with_pos_embed` operand of the NEXT attention block (transformer.py:235-236), so no separate
  * add + cast pass reads y again; the backward can emit dx_bf16 = bf16(dx), the operand of the
- * sub-block's backward GEMMs. */
+ * sub-block's backward GEMMs.  Backward: dy_b (may be NULL) is a second gradient of y, summed with dy on
+ * load -- y feeds both the next sub-block and the next residual connection, and handing the two contributions
+ * over separately saves autograd's add kernel. */
 int pcm_add_dropout_ln_fwd_ex(long long rows, int C, const float *x, const float *res,
                               const float *gamma, const float *beta, float eps, float p_drop,
                               const unsigned long long *seed_base, unsigned long long seed_offset,
                               float *y, void *y_bf16, float *h, float *mean, float *rstd,
                               const float *pos, int pos_row_div, void *ypos_bf16, pcm_stream_t stream);
-int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const float *h, const float *mean,
+int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const float *dy_b, const float *h, const float *mean,
                               const float *rstd, const float *gamma, float p_drop,
                               const unsigned long long *seed_base, unsigned long long seed_offset,
                               float *dres, float *dx, float *dgamma, float *dbeta, void *dx_bf16,

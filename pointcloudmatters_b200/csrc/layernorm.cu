@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
 
 template <int V>
 __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
-    const float* __restrict__ dy, const float* __restrict__ h, const float* __restrict__ mean_in,
+    const float* __restrict__ dy, const float* __restrict__ dy_b, const float* __restrict__ h, const float* __restrict__ mean_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, long rows, float p_drop,
     const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset, float* __restrict__ dres,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16) {
@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
-            const float4 d = *reinterpret_cast<const float4*>(dy + e);
+            float4 d = *reinterpret_cast<const float4*>(dy + e);
+            if (dy_b) {  // second gradient contribution (the residual branch of the consumer): summed on load
+                const float4 d2 = *reinterpret_cast<const float4*>(dy_b + e);
+                d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+            }
             const float4 hv = *reinterpret_cast<const float4*>(h + e);
             xh[v] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
             gy[v] = make_float4(d.x * g4[v].x, d.y * g4[v].y, d.z * g4[v].z, d.w * g4[v].w);
@@ -411,7 +415,7 @@ PCM_API int pcm_add_dropout_ln_fwd(long long rows, int C, const float* x, const 
 
 // dres = dLN/dh; dx = dropout-backward(dres) (pass dx == dres or NULL when not needed);
 // dgamma / dbeta are ACCUMULATED (caller zero-fills); dx_bf16 (optional) = bf16(dx).
-PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, const float* h, const float* mean,
+PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, const float* dy_b, const float* h, const float* mean,
                                       const float* rstd, const float* gamma, float p_drop,
                                       const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
                                       float* dx, float* dgamma, float* dbeta, void* dx_bf16, pcm_stream_t stream) {
@@ -420,7 +424,7 @@ PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, co
     if (C % 128) return PCM_EUNSUPPORTED;
     cudaStream_t st = pcm_cu_stream(stream);
     const int grid = ln_grid_bwd(rows);
-    LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
+    LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, dy_b, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
                 dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16))
     return pcm_launch_status();
 }
@@ -429,8 +433,8 @@ PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const
                                    const float* rstd, const float* gamma, float p_drop,
                                    const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
                                    float* dx, float* dgamma, float* dbeta, pcm_stream_t stream) {
-    return pcm_add_dropout_ln_bwd_ex(rows, C, dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, dres, dx, dgamma, dbeta,
-                                     nullptr, stream);
+    return pcm_add_dropout_ln_bwd_ex(rows, C, dy, nullptr, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, dres, dx, dgamma,
+                                     dbeta, nullptr, stream);
 }
 
 PCM_API int pcm_ffn_dropout_fwd(long long rows, int Hd, const void* h, float p_drop, const unsigned long long* seed_base,

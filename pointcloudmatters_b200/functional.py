@@ -554,13 +554,21 @@ class _AddDropoutLN(torch.autograd.Function):
         ctx.save_for_backward(h, mean, rstd, gamma)
         ctx.cfg = (p_drop, seed_base, seed, x is not None, shape)
         ctx.params = (gamma, beta)
-        outs = (y.view(shape), yb, ypb)
-        ctx.mark_non_differentiable(*[t for t in outs[1:] if t is not None])
-        ctx.set_materialize_grads(False)  # no zero-filled "gradients" for the bf16 by-products
+        yv = y.view(shape)
+        # second handle on the same storage (not an autograd view of the first): consumers that use y as the
+        # RESIDUAL operand of the next LayerNorm take this one, so the two gradient contributions of y arrive
+        # here separately and are summed inside the backward kernel instead of by an autograd add kernel
+        y_res = torch.empty(0, dtype=y.dtype, device=y.device).set_(y.untyped_storage(), y.storage_offset(), shape,
+                                                                    yv.stride())
+        outs = (yv, yb, ypb, y_res)
+        ctx.mark_non_differentiable(*[t for t in outs[1:3] if t is not None])
+        ctx.set_materialize_grads(False)  # no zero-filled "gradients" for the bf16 by-products / unused handles
         return outs
 
     @staticmethod
-    def backward(ctx, dy, _dyb=None, _dypb=None):
+    def backward(ctx, dy, _dyb=None, _dypb=None, dy_res=None):
+        if dy is None:
+            dy, dy_res = dy_res, None
         if dy is None:
             return (None,) * 8
         h, mean, rstd, gamma = ctx.saved_tensors
@@ -568,9 +576,14 @@ class _AddDropoutLN(torch.autograd.Function):
         dy2 = dy.reshape(h.shape)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        dyr = None
+        if dy_res is not None:
+            dyr = dy_res.reshape(h.shape)
+            if not dyr.is_contiguous():
+                dyr = dyr.contiguous()
         g_slot, b_slot = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
         dres, dx, dgamma, dbeta, dxb = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
-                                                            dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x)
+                                                            dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x, dy_b=dyr)
         _GRAD_BF16.clear()
         dx_out = None
         if has_x:
@@ -593,8 +606,12 @@ def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=N
         if cast_pos is not None and not (cast_pos.dim() == 3 and cast_pos.shape[0] == residual.shape[0] and residual.dim() == 3
                                          and cast_pos.shape[2] == C and cast_pos.dtype == torch.float32):
             cast_pos = None
-        y, yb, ypb = _AddDropoutLN.apply(xr, residual.contiguous(), norm.weight, norm.bias, norm.eps, p_eff, bool(cast),
-                                         None if cast_pos is None else cast_pos.detach())
+        res_in = getattr(residual, "_pcm_res", None)  # the producing LayerNorm's residual-branch handle
+        if res_in is None or res_in.shape != residual.shape:
+            res_in = residual
+        y, yb, ypb, y_res = _AddDropoutLN.apply(xr, res_in.contiguous(), norm.weight, norm.bias, norm.eps, p_eff, bool(cast),
+                                                None if cast_pos is None else cast_pos.detach())
+        y._pcm_res = y_res
         if yb is not None:
             y._pcm_bf16 = yb
         if ypb is not None:

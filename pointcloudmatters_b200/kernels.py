@@ -191,7 +191,7 @@ def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset,
 
 
 def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None,
-                       want_dx_bf16=False):
+                       want_dx_bf16=False, dy_b=None):
     """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics).
     Returns (dres, dx, dgamma, dbeta, dx_bf16)."""
     rows, C = h.shape
@@ -202,7 +202,7 @@ def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset,
     if dbeta is None:
         dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
     dxb = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device) if (want_dx_bf16 and need_dx) else None
-    check(lib.pcm_add_dropout_ln_bwd_ex(rows, C, ptr(dy), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
+    check(lib.pcm_add_dropout_ln_bwd_ex(rows, C, ptr(dy), ptr(dy_b), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
                                         ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
                                         ptr(dxb), current_stream()), "pcm_add_dropout_ln_bwd_ex")
     return dres, dx, dgamma, dbeta, dxb

@@ -121,3 +121,35 @@ def test_fused_ffn_matches_torch(p):
     for a, b, name in zip(got, want, ("y", "dx", "dW1", "db1", "dW2", "db2")):
         rel = float((a - b).norm() / b.norm())
         assert rel < (8e-2 if name in ("dx", "dW1", "db1") else 2e-2), (name, rel)
+
+
+def test_two_layernorms_chain_splits_the_residual_gradient():
+    """y1 = LN1(res + x) feeds BOTH a sub-block (here: a fixed linear map) and the residual of LN2.  The product
+    hands LN1's backward the two gradient contributions separately (summed inside the kernel, no autograd add);
+    result must equal plain torch, and the residual handle must alias y1's storage."""
+    from pointcloudmatters_b200 import functional as PF
+
+    torch.manual_seed(5)
+    L, B, C = 37, 3, 256
+    n1, n2 = torch.nn.LayerNorm(C).cuda(), torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        for n in (n1, n2):
+            n.weight.add_(0.2 * torch.randn(C, device="cuda")); n.bias.add_(0.2 * torch.randn(C, device="cuda"))
+    W = torch.randn(C, C, device="cuda") / C ** 0.5
+    x, res = torch.randn(L, B, C, device="cuda"), torch.randn(L, B, C, device="cuda")
+    dy = torch.randn(L, B, C, device="cuda")
+
+    def run(ln):
+        xs, rs = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        for n in (n1, n2):
+            n.zero_grad(set_to_none=True)
+        y1 = ln(xs, rs, n1)
+        y2 = ln(y1 @ W, y1, n2)      # y1: sub-block input AND residual
+        (y2 * dy).sum().backward()
+        return y2.detach(), xs.grad, rs.grad, n1.weight.grad.clone(), n1.bias.grad.clone(), n2.weight.grad.clone(), y1
+
+    ref = run(lambda a, r, n: F.layer_norm(r + a, (C,), n.weight, n.bias, n.eps))
+    got = run(lambda a, r, n: PF.add_dropout_layernorm(a, r, n, 0.0, True))
+    assert got[6]._pcm_res.data_ptr() == got[6].data_ptr()
+    for a, b, name in zip(got[:6], ref[:6], ("y2", "dx", "dres", "dg1", "db1", "dg2")):
+        assert float((a - b).norm() / b.norm()) < 1e-4, name
