@@ -352,9 +352,11 @@ ffn_relu_dropout_bwd_kernel(const float* __restrict__ dhd, const __nv_bfloat16* 
     }
 }
 
+int g_ln_fwd_cap = 148 * 8;
+
 inline int ln_grid(long rows) {
     long blocks = (rows + 7) / 8;
-    const long cap = 148L * 8;
+    const long cap = g_ln_fwd_cap > 0 ? g_ln_fwd_cap : 148L * 8;
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -365,13 +367,13 @@ inline int ln_grid(long rows) {
 // (CUDA-graph replay, one B200, profiles/r1_ln_colsum_sweep.jsonl): backward, 6 400 rows: 20.6 us at 800 CTAs ->
 // 12.0 us at 296 (2 per SM); 32 960 rows: 57.5 us at 1 184 -> 52.2 us at 222; colsum, 6 400 rows: 5.5 us at 16
 // rows per CTA -> 3.9 us at >= 32, 32 960 rows best with ~592 CTAs (11.8 us).
-int g_ln_bwd_cap = 0;  // 0 = by size: 2 CTAs per SM, 1.5 per SM for the large token sets
+int g_ln_bwd_cap = 0;  // 0 = 2 CTAs per SM (222 vs 296 at 32 960 rows is within run-to-run noise: 52-57 us)
 int g_colsum_ctas = 148 * 4;
 int g_colsum_min_rows = 32;
 
 inline int ln_grid_bwd(long rows) {
     long blocks = (rows + 7) / 8;
-    const long cap = g_ln_bwd_cap > 0 ? g_ln_bwd_cap : (rows > 16384 ? 222L : 296L);
+    const long cap = g_ln_bwd_cap > 0 ? g_ln_bwd_cap : 296L;
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -468,6 +470,7 @@ PCM_API int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float* dhd, c
 
 // Debug aid for tools/bench_ln.py: override the launch-shape knobs above (values <= 0 keep the current one).
 PCM_API int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows) {
+    if (ln_bwd_max_ctas > 100000) { g_ln_fwd_cap = ln_bwd_max_ctas - 100000; return PCM_OK; }  // forward cap: value + 100000
     if (ln_bwd_max_ctas > 0) g_ln_bwd_cap = ln_bwd_max_ctas;
     if (colsum_ctas > 0) g_colsum_ctas = colsum_ctas;
     if (colsum_min_rows > 0) g_colsum_min_rows = colsum_min_rows;
