@@ -354,6 +354,24 @@ int pcm_groupnorm_mish_bwd(int B, int T, int C, int G, const float *x, const flo
 int pcm_mish_fwd(long long n, const float *x, float *y, void *y_bf16, pcm_stream_t stream);
 int pcm_mish_bwd(long long n, const float *x, const float *dy, float *dx, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm1d + ReLU over token-major rows (R, C) fp32 (the
+ * SubMConv3d(k=1) -> BatchNorm1d -> ReLU chain of src/models/components/pcd_encoder/pointnet.py:29-55,
+ * and the projector of pcd_obs_encoder.py:100-121).  C % 4 == 0, C <= 1024.
+ *   pcm_bn_stats:      stats (2, C) fp64 (caller zero-fills) += [sum_r y, sum_r y^2]
+ *   pcm_sa_bn_finalize (above) turns stats into coef (4, C) = [a, b, mean, invstd] and updates the running buffers
+ *   pcm_bn_apply_relu: out = max(a*y + b, 0) (relu = 0: no clamp) as fp32 and / or bf16
+ *   pcm_bn_relu_bwd:   gstats (2, C) fp64 (caller zero-fills) = [sum dz, sum dz*xhat], dz = dout * [a*y+b > 0];
+ *                      dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or a*dz (eval), as fp32
+ *                      and / or bf16; dgamma / dbeta (may be NULL) are ACCUMULATED into.
+ * ------------------------------------------------------------------------------------------ */
+int pcm_bn_stats(long long R, int C, const float *y, double *stats, pcm_stream_t stream);
+int pcm_bn_apply_relu(long long R, int C, const float *y, const float *coef, int relu, float *out, void *out_bf16,
+                      pcm_stream_t stream);
+int pcm_bn_relu_bwd(long long R, int C, const float *dout, const float *y, const float *coef, int relu,
+                    int training, double *gstats, float *dy, void *dy_bf16, float *dgamma, float *dbeta,
+                    pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,8 +163,9 @@ class ACTPCD(nn.Module):
         if pre is not None:
             side, n_o, o32, idx, n_p, knn_idx = pre
             torch.cuda.current_stream().wait_stream(side)  # join
-            for t in (n_o, idx, n_p, knn_idx):
-                t.record_stream(torch.cuda.current_stream())
+            for t in (n_o, idx, n_p, knn_idx, getattr(self, "_presampled_pos", None)):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
             self._presampled = None
         else:
             hints = dict(hints or {})
@@ -206,7 +207,10 @@ class ACTPCD(nn.Module):
         else:
             features = self.backbone(pcd_dict)
             coord, features, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]), mask, hints=hints)
-        pcd_pos = self.coord_embedding_sine(coord)
+        pcd_pos = getattr(self, "_presampled_pos", None)  # computed on the FPS / kNN side stream when forked
+        self._presampled_pos = None
+        if pcd_pos is None:
+            pcd_pos = self.coord_embedding_sine(coord)
         b = pcd_dict["offset"].shape[0]
         features = features.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)  # (b, c, 1, n)
         pcd_pos = pcd_pos.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)
@@ -270,6 +274,8 @@ class ACTPCD(nn.Module):
             idx = self._sample_indices(p, o32, n_o, pcd.get("mask", None) if self.use_mask else None, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
+            # the sine embedding of the sampled coordinates (a dozen small elementwise kernels) depends on n_p only
+            self._presampled_pos = self.coord_embedding_sine(n_p)
         self._presampled = (side, n_o, o32, idx, n_p, knn_idx)
 
     def sync_free(self, pcds) -> bool:
@@ -295,7 +301,7 @@ class ACTPCD(nn.Module):
         return data_dict, side
 
     def forward(self, data_dict):
-        self._presampled = None
+        self._presampled = self._presampled_pos = None
         fork = self.sync_free(data_dict["pcds"]) and data_dict["qpos"].is_cuda
         if fork:
             self._presample(data_dict)

@@ -702,11 +702,76 @@ def dropout(x, p, training):
     return F.dropout(x, p, True) if (training and p > 0) else x
 
 
-def batchnorm_relu(x, bn):
+class _BatchNormReLU(torch.autograd.Function):
+    """ReLU(BatchNorm1d(y)) over rows (csrc/batchnorm.cu): statistics pass + apply pass forward, reduce pass +
+    apply pass backward; emits the bf16 operand of the next GEMM (forward) and bf16(dy) for the producing
+    linear's backward GEMMs, accumulates dgamma / dbeta into the parameters' gradient buffers."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
+        from ._lib import check, current_stream, lib, ptr
+
+        R, C = y.shape
+        st = current_stream()
+        stats = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+        if training:
+            check(lib.pcm_bn_stats(R, C, ptr(y), ptr(stats), st), "pcm_bn_stats")
+        coef = torch.empty((4, C), dtype=torch.float32, device=y.device)
+        check(lib.pcm_sa_bn_finalize(C, ptr(stats), float(R), ptr(gamma), ptr(beta), float(eps), float(momentum), int(training),
+                                     ptr(running_mean), ptr(running_var), ptr(coef), st), "pcm_sa_bn_finalize")
+        out = torch.empty_like(y)
+        outb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+        check(lib.pcm_bn_apply_relu(R, C, ptr(y), ptr(coef), int(relu), ptr(out), ptr(outb), st), "pcm_bn_apply_relu")
+        ctx.save_for_backward(y, coef)
+        ctx.cfg = (bool(training), bool(relu))
+        ctx.params = (gamma, beta)
+        ctx.mark_non_differentiable(outb)
+        ctx.set_materialize_grads(False)
+        return out, outb
+
+    @staticmethod
+    def backward(ctx, dout, _doutb=None):
+        from ._lib import check, current_stream, lib, ptr
+
+        if dout is None:
+            return (None,) * 9
+        y, coef = ctx.saved_tensors
+        training, relu = ctx.cfg
+        gamma, beta = ctx.params
+        R, C = y.shape
+        dout = dout.contiguous()
+        g_slot, b_slot = _grad_slot(gamma), _grad_slot(beta)
+        dg = g_slot if g_slot is not None else torch.zeros(C, dtype=torch.float32, device=y.device)
+        db = b_slot if b_slot is not None else torch.zeros(C, dtype=torch.float32, device=y.device)
+        gstats = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+        need_dy = ctx.needs_input_grad[0]
+        dy = torch.empty_like(y) if need_dy else None
+        dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+        check(lib.pcm_bn_relu_bwd(R, C, ptr(dout), ptr(y), ptr(coef), int(relu), int(training), ptr(gstats), ptr(dy), ptr(dyb),
+                                  ptr(dg), ptr(db), current_stream()), "pcm_bn_relu_bwd")
+        if dy is not None:
+            _GRAD_BF16[dy.data_ptr()] = (dyb, dy)  # consumed (popped) by the producing linear's backward
+        return (dy, None if g_slot is not None else dg, None if b_slot is not None else db, None, None, None, None, None, None)
+
+
+_NO_FUSED_BN = bool(int(__import__("os").environ.get("PCM_NO_FUSED_BN", "0")))  # A/B switch (ATen composition)
+
+
+def batchnorm_relu(x, bn, relu=True):
     """ReLU(BatchNorm1d(x)) over rows of x (R, C); training mode uses batch statistics and updates
-    the running buffers exactly like nn.BatchNorm1d (momentum, unbiased running_var)."""
-    return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
-                               bn.momentum if bn.momentum is not None else 0.0, bn.eps))
+    the running buffers exactly like nn.BatchNorm1d (momentum, unbiased running_var).  The returned activation
+    carries its bf16 copy (`_pcm_bf16`), the operand of the next layer's GEMM."""
+    C = x.shape[-1]
+    training = bn.training or bn.running_mean is None
+    if (not _NO_FUSED_BN and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and C % 4 == 0 and C <= 1024 and bn.affine
+            and (bn.momentum is not None or not training)):
+        out, outb = _BatchNormReLU.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                                         bn.momentum if bn.momentum is not None else 0.0, training, relu)
+        out._pcm_bf16 = outb
+        return out
+    y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
+                     bn.momentum if bn.momentum is not None else 0.0, bn.eps)
+    return F.relu(y) if relu else y
 
 
 class _SetAbstraction(torch.autograd.Function):
@@ -714,7 +779,7 @@ class _SetAbstraction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, weight, gamma, beta, p, new_p, knn_idx, running_mean, running_var, eps, momentum,
-                training):
+                training, feat_b=None):
         from ._lib import check, current_stream, lib, ptr
 
         n, C = feat.shape
@@ -723,7 +788,7 @@ class _SetAbstraction(torch.autograd.Function):
         dev = feat.device
         st = current_stream()
         weight = weight.contiguous()
-        featb = feat if feat.dtype == torch.bfloat16 else feat.to(torch.bfloat16)
+        featb = feat_b if feat_b is not None else (feat if feat.dtype == torch.bfloat16 else feat.to(torch.bfloat16))
         wfb = weight[:, 3:].to(torch.bfloat16).contiguous()
         Pf = K.gemm_bf16(featb, wfb)  # (n, H) fp32: the only tensor-core work of the layer
         ymax = torch.empty((m, H), dtype=torch.float32, device=dev)
@@ -777,7 +842,7 @@ class _SetAbstraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dfeat = K.gemm_bf16(dPfb, wfb, b_mn=True)  # (n, H) x Wf(H, C)
         K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=0)
-        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn):
@@ -805,7 +870,8 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
             bn.running_var.copy_(rv[:H])
         return out[:, :H]
     return _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
-                                 knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training)
+                                 knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training,
+                                 _act_bf16(feat, feat.shape[0], C))
 
 
 def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):

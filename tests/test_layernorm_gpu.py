@@ -153,3 +153,34 @@ def test_two_layernorms_chain_splits_the_residual_gradient():
     assert got[6]._pcm_res.data_ptr() == got[6].data_ptr()
     for a, b, name in zip(got[:6], ref[:6], ("y2", "dx", "dres", "dg1", "db1", "dg2")):
         assert float((a - b).norm() / b.norm()) < 1e-4, name
+
+
+@pytest.mark.parametrize("R,C,training,relu", [(5000, 64, True, True), (777, 512, True, True), (300, 40, True, False),
+                                               (1000, 128, False, True), (65536, 64, True, True)])
+def test_fused_batchnorm_relu_matches_torch(R, C, training, relu):
+    """csrc/batchnorm.cu (statistics + apply forward, reduce + apply backward) against F.batch_norm + F.relu:
+    outputs, running statistics, dgamma / dbeta / dx; fp32 kernels with fp64 column sums -> 2e-5 relative."""
+    from pointcloudmatters_b200 import functional as PF
+
+    torch.manual_seed(R + C)
+    bn_a, bn_b = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda(), torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda()
+    with torch.no_grad():
+        w, b = 1 + 0.3 * torch.randn(C, device="cuda"), 0.3 * torch.randn(C, device="cuda")
+        rm, rv = 0.2 * torch.randn(C, device="cuda"), 0.5 + torch.rand(C, device="cuda")
+        for bn in (bn_a, bn_b):
+            bn.weight.copy_(w); bn.bias.copy_(b); bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
+            bn.train(training)
+    x = torch.randn(R, C, device="cuda") * 1.7 + 0.4
+    dy = torch.randn(R, C, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = F.batch_norm(xa, bn_a.running_mean, bn_a.running_var, bn_a.weight, bn_a.bias, training, 0.01, 1e-3)
+    ya = F.relu(ya) if relu else ya
+    ya.backward(dy)
+    yb = PF.batchnorm_relu(xb, bn_b, relu=relu)
+    yb.backward(dy)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(yb, ya) < 2e-5
+    assert rel(yb._pcm_bf16.float(), ya) < 1e-2
+    assert rel(xb.grad, xa.grad) < 1e-4
+    assert rel(bn_b.weight.grad, bn_a.weight.grad) < 1e-4 and rel(bn_b.bias.grad, bn_a.bias.grad) < 1e-4
+    assert rel(bn_b.running_mean, bn_a.running_mean) < 1e-5 and rel(bn_b.running_var, bn_a.running_var) < 1e-5
