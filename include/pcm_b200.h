@@ -297,9 +297,9 @@ int pcm_ffn_dropout_fwd(long long rows, int Hd, const void *h, float p_drop, con
 int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float *dhd, const void *h, float p_drop,
                              const unsigned long long *seed_base, unsigned long long seed_offset, void *dh,
                              pcm_stream_t stream);
-/* Profiling aid (tools/bench_ln.py): launch-shape knobs of the LayerNorm backward / colsum kernels
- * (maximum CTAs of the backward, target CTA count and minimum rows per CTA of colsum); <= 0 keeps a value. */
-int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows);
+/* Profiling aid (tools/bench_ln.py): launch-shape knobs of the LayerNorm / colsum kernels (maximum CTAs of the
+ * forward and of the backward, target CTA count and minimum rows per CTA of colsum); <= 0 keeps a value. */
+int pcm_ln_debug_tune(int ln_fwd_max_ctas, int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows);
 /* out = bf16(a + b): `with_pos_embed` (transformer.py:235-236) fused with the operand cast of the
  * Q/K projections.  b may be NULL; b_row_div > 1 broadcasts b's rows over the batch. */
 int pcm_add_cast_bf16(long long rows, int C, const float *a, const float *b, int b_row_div, void *out,

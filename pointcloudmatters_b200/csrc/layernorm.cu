@@ -469,8 +469,8 @@ PCM_API int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float* dhd, c
 }
 
 // Debug aid for tools/bench_ln.py: override the launch-shape knobs above (values <= 0 keep the current one).
-PCM_API int pcm_ln_debug_tune(int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows) {
-    if (ln_bwd_max_ctas > 100000) { g_ln_fwd_cap = ln_bwd_max_ctas - 100000; return PCM_OK; }  // forward cap: value + 100000
+PCM_API int pcm_ln_debug_tune(int ln_fwd_max_ctas, int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows) {
+    if (ln_fwd_max_ctas > 0) g_ln_fwd_cap = ln_fwd_max_ctas;
     if (ln_bwd_max_ctas > 0) g_ln_bwd_cap = ln_bwd_max_ctas;
     if (colsum_ctas > 0) g_colsum_ctas = colsum_ctas;
     if (colsum_min_rows > 0) g_colsum_min_rows = colsum_min_rows;

@@ -9,6 +9,7 @@ CUDA only -- there is no CPU fallback; a CPU tensor raises.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -128,7 +129,7 @@ def _grad_bf16(g, rows, C):
     return K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
 
 
-_NO_ROW_SPLIT = bool(int(__import__("os").environ.get("PCM_NO_ROW_SPLIT", "0")))  # A/B switch for tools/
+_NO_ROW_SPLIT = bool(int(os.environ.get("PCM_NO_ROW_SPLIT", "0")))  # A/B switch for tools/
 
 
 def _gemm_rows(a, b, *, b_mn=False, bias=None):
@@ -754,7 +755,7 @@ class _BatchNormReLU(torch.autograd.Function):
         return (dy, None if g_slot is not None else dg, None if b_slot is not None else db, None, None, None, None, None, None)
 
 
-_NO_FUSED_BN = bool(int(__import__("os").environ.get("PCM_NO_FUSED_BN", "0")))  # A/B switch (ATen composition)
+_NO_FUSED_BN = bool(int(os.environ.get("PCM_NO_FUSED_BN", "0")))  # A/B switch (ATen composition)
 
 
 def batchnorm_relu(x, bn, relu=True):

@@ -50,19 +50,19 @@ def main():
         beta = torch.randn(C, device="cuda")
         pos = torch.randn(rows // 64, C, device="cuda") if rows % 64 == 0 else None
         for cap in (148, 296, 592, 1184):
-            lib.pcm_ln_debug_tune(100000 + cap, 0, 0)
+            lib.pcm_ln_debug_tune(cap, 0, 0, 0)
             us = timeit(lambda i: K.add_dropout_ln_fwd(xs[i % 4], sets[i % 4][1], gamma, beta, 1e-5, 0.1, sb, 7, want_bf16=True,
                                                        pos=pos, pos_row_div=64 if pos is not None else 1))
             print(json.dumps({"kernel": "ln_fwd", "rows": rows, "max_ctas": cap, "us": round(us, 2)}))
-        lib.pcm_ln_debug_tune(100000 + 1184, 0, 0)
+        lib.pcm_ln_debug_tune(1184, 0, 0, 0)
         for cap in (222, 296):
-            lib.pcm_ln_debug_tune(cap, 0, 0)
+            lib.pcm_ln_debug_tune(0, cap, 0, 0)
             us = timeit(lambda i: K.add_dropout_ln_bwd(sets[i % 4][0], sets[i % 4][1], sets[i % 4][2], sets[i % 4][3], gamma,
                                                        0.1, sb, 7, True, dg, db, True))
             print(json.dumps({"kernel": "ln_bwd", "rows": rows, "max_ctas": cap, "us": round(us, 2)}))
         for ctas in (592,):
             for min_rows in (32,):
-                lib.pcm_ln_debug_tune(0, ctas, min_rows)
+                lib.pcm_ln_debug_tune(0, 0, ctas, min_rows)
                 us = timeit(lambda i: K.colsum(sets[i % 4][4], out))
                 print(json.dumps({"kernel": "colsum_bf16", "rows": rows, "ctas": ctas, "min_rows": min_rows, "us": round(us, 2)}))
 
