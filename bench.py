@@ -323,6 +323,13 @@ def b200_arm(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints
+    # "NCCL version ..." there at communicator creation, and its INFO log when NCCL_DEBUG asks for it) are sent to
+    # stderr for the duration of the run; print() is pointed at the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if args.impl == "reference":
         return reference_arm(args)
     return b200_arm(args)
