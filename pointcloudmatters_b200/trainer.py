@@ -243,27 +243,39 @@ class BCTrainer:
         return losses
 
 
+def _shard_clouds(v: dict, lo: int, hi: int) -> dict:
+    """Clouds [lo, hi) of a packed point-cloud dict (cumulative `offset`), offsets rebased to the shard."""
+    off = v["offset"]
+    start = int(off[lo - 1]) if lo > 0 else 0
+    end = int(off[hi - 1])
+    pc = {kk: vv[start:end] for kk, vv in v.items() if torch.is_tensor(vv) and kk != "offset"}
+    pc["offset"] = off[lo:hi] - start
+    sizes = torch.diff(off[lo:hi], prepend=off.new_tensor([start]))
+    for kk, vv in v.items():
+        if not torch.is_tensor(vv):
+            pc[kk] = int(sizes.max()) if kk == "n_max" else vv  # keep the sync-free hint exact for the shard
+    return pc
+
+
 def shard_batch(batch: dict, rank: int, world: int) -> dict:
     """DistributedSampler-style split of one collated global batch by SAMPLE (contiguous blocks):
-    clouds are independent units, so no data-path collective is needed."""
-    b = batch["qpos"].shape[0]
+    clouds are independent units, so no data-path collective is needed.
+    Handles the ACT contract (`pcds` at the top level, one cloud per sample) and the Diffusion-Policy contract
+    (`obs.pcds` with n_obs_steps clouds per sample, `action`, optional `goal`)."""
+    key = "qpos" if "qpos" in batch else "action"
+    b = batch[key].shape[0]
     assert b % world == 0, "global batch must divide evenly across ranks"
     per = b // world
     lo, hi = rank * per, (rank + 1) * per
-    out = {}
-    for k, v in batch.items():
-        if k == "pcds":
-            off = v["offset"]
-            start = int(off[lo - 1]) if lo > 0 else 0
-            end = int(off[hi - 1])
-            pc = {kk: vv[start:end] for kk, vv in v.items() if torch.is_tensor(vv) and kk != "offset"}
-            pc["offset"] = off[lo:hi] - start
-            for kk, vv in v.items():
-                if not torch.is_tensor(vv):
-                    pc[kk] = vv
-            out[k] = pc
-        elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == b:
-            out[k] = v[lo:hi]
-        else:
-            out[k] = v
-    return out
+
+    def split(v, clouds_per_sample=1):
+        if isinstance(v, dict):
+            if "offset" in v and "coord" in v:
+                c = v["offset"].shape[0] // b
+                return _shard_clouds(v, lo * c, hi * c)
+            return {kk: split(vv) for kk, vv in v.items()}
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == b:
+            return v[lo:hi]
+        return v
+
+    return {k: split(v) for k, v in batch.items()}

@@ -105,3 +105,23 @@ def test_gradient_allreduce_world2_gloo():
     (model(x).pow(2).sum() / 8).backward()
     ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 8)) for p in model.parameters()])
     torch.testing.assert_close(g0 * 2, ref, rtol=1e-5, atol=1e-6)  # each rank held half the samples of a /8 loss
+
+
+def test_shard_batch_diffusion_policy_contract():
+    """Data-parallel split of a Diffusion-Policy batch: n_obs_steps clouds per sample stay with their sample,
+    offsets are rebased, per-shard `n_max` is exact, shards tile the global batch."""
+    from pointcloudmatters_b200.data import synthetic_dp_batch
+    from pointcloudmatters_b200.trainer import shard_batch
+
+    g = synthetic_dp_batch(6, 50, n_obs_steps=2, goal_dim=4, seed=9, ragged=True)
+    shards = [shard_batch(g, r, 3) for r in range(3)]
+    assert all(s["action"].shape[0] == 2 and s["obs"]["qpos"].shape[0] == 2 and s["goal"]["task_emb"].shape[0] == 2 for s in shards)
+    assert all(s["obs"]["pcds"]["offset"].shape[0] == 4 for s in shards)
+    assert torch.equal(torch.cat([s["obs"]["pcds"]["coord"] for s in shards]), g["obs"]["pcds"]["coord"])
+    assert torch.equal(torch.cat([s["action"] for s in shards]), g["action"])
+    sizes = torch.diff(g["obs"]["pcds"]["offset"], prepend=torch.zeros(1, dtype=torch.int64))
+    for r, s in enumerate(shards):
+        want = sizes[4 * r: 4 * r + 4]
+        assert torch.equal(torch.diff(s["obs"]["pcds"]["offset"], prepend=torch.zeros(1, dtype=torch.int64)), want)
+        assert s["obs"]["pcds"]["n_max"] == int(want.max())
+        assert int(s["obs"]["pcds"]["offset"][-1]) == s["obs"]["pcds"]["coord"].shape[0]
