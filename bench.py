@@ -206,6 +206,7 @@ def b200_arm(args):
         """Time exactly `steps` steps; returns (seconds, last loss).  Device-timed with CUDA events."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []  # one event per step boundary (a record costs ~1 us of host time, no synchronisation)
         e0.record()
         loss_host = None
         for i in range(steps):
@@ -217,9 +218,15 @@ def b200_arm(args):
             loss = module.training_step(b, i)
             if from_host:
                 loss_host = float(loss)  # device->host read of the step result, every step
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         barrier()
         sec = e0.elapsed_time(e1) / 1e3
+        per = sorted(a.elapsed_time(b_) for a, b_ in zip([e0] + marks[:-1], marks))
+        run.step_ms = {"median": per[len(per) // 2], "p10": per[len(per) // 10], "p90": per[(9 * len(per)) // 10],
+                       "min": per[0], "max": per[-1]} if per else None
         t = torch.tensor([sec], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -236,6 +243,7 @@ def b200_arm(args):
     lib_l0 = _lib.launch_count()
     t_wall0 = time.perf_counter()
     sec, last_loss = run(resident, args.steps, False)
+    step_ms = run.step_ms
     t_wall1 = time.perf_counter()
     launches_outside_graph = _lib.launch_count() - lib_l0
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
@@ -289,7 +297,8 @@ def b200_arm(args):
     roofline = PF.roofline_for(kstats, peaks, 3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * sec / args.steps, "step_ms_rank0": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (activations + 385 MB parameter/optimizer state) exceeds the 126 MB L2; "

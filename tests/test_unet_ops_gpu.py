@@ -123,3 +123,32 @@ def test_mish_matches_torch():
     y2.sum().backward()
     assert torch.allclose(y, y2, rtol=1e-5, atol=1e-6)
     assert torch.allclose(x.grad, x2.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_empty_and_degenerate_shapes_through_the_abi():
+    """Edge cases at the C-ABI level: empty batches are no-ops (status 0), single time step / single group work,
+    invalid geometry is rejected with a negative status instead of launching."""
+    from pointcloudmatters_b200 import functional_unet as UF
+    from pointcloudmatters_b200._lib import current_stream, lib, ptr
+
+    st = current_stream()
+    x = torch.zeros(4, device="cuda")
+    assert lib.pcm_conv1d_unfold(0, 16, 8, 5, 1, 2, 16, ptr(x), 0, 8, ptr(x), 40, st) == 0
+    assert lib.pcm_conv1d_fold(0, 16, 8, 5, 1, 2, 16, ptr(x), 40, None, ptr(x), None, st) == 0
+    assert lib.pcm_groupnorm_mish_fwd(0, 16, 8, 2, ptr(x), ptr(x), ptr(x), 1e-5, None, None, ptr(x), None, ptr(x), ptr(x), st) == 0
+    assert lib.pcm_mish_fwd(0, ptr(x), ptr(x), None, st) == 0
+    assert lib.pcm_bn_stats(0, 8, ptr(x), ptr(x), st) == 0
+    assert lib.pcm_conv1d_unfold(1, 16, 8, 5, 1, 2, 16, ptr(x), 0, 8, ptr(x), 8, st) < 0      # ldc < C*k
+    assert lib.pcm_groupnorm_mish_fwd(1, 16, 10, 4, ptr(x), ptr(x), ptr(x), 1e-5, None, None, ptr(x), None, ptr(x), ptr(x), st) < 0
+    assert lib.pcm_bn_stats(4, 6, ptr(x), ptr(x), st) < 0                                     # C % 4
+    # T = 1 (a single time step), one group, odd length with stride 2
+    gn = torch.nn.GroupNorm(1, 8).cuda()
+    xs = torch.randn(3, 1, 8, device="cuda")
+    want = F.mish(F.group_norm(xs.permute(0, 2, 1), 1, gn.weight, gn.bias, gn.eps)).permute(0, 2, 1)
+    assert torch.allclose(UF.groupnorm_mish(xs, gn), want, rtol=1e-5, atol=1e-6)
+    conv = torch.nn.Conv1d(8, 16, 3, 2, 1).cuda()
+    xo = torch.randn(2, 7, 8, device="cuda")
+    got = UF.conv1d_cl(xo, conv.weight, conv.bias, 2, 1)
+    ref = conv(xo.permute(0, 2, 1)).permute(0, 2, 1)
+    assert got.shape == ref.shape == (2, 4, 16)
+    assert float((got - ref).norm() / ref.norm()) < 1e-2
