@@ -1,5 +1,7 @@
 """Tiny ncu target: a few launches of one kernel family at a BASELINE cfg-2 shape.
-usage: python tools/ncu_target.py gemm|gemm_bf16out|fps|knn|sa|flash"""
+usage: python tools/ncu_target.py gemm|gemm_bf16out|fps|knn|sa|flash|hbm
+(`hbm`: the HBM-bound row kernels at the main-encoder size -- add+dropout+LayerNorm fwd / bwd on 32 960 x 512,
+BatchNorm+ReLU fwd / bwd on 65 536 x 512, colsum)"""
 import sys
 from pathlib import Path
 
@@ -23,6 +25,25 @@ elif which == "flash":
     for _ in range(2):
         O, lse = K.flash_attn_fwd(q, k, v, B, nh, L, S, None, 0.125, 0.1, sb, 77)
         K.flash_attn_bwd(q, k, v, O, do, lse, B, nh, L, S, None, 0.125, 0.1, sb, 77, buf[:, :E], buf[:, E:2 * E], buf[:, 2 * E:])
+elif which == "hbm":
+    from pointcloudmatters_b200 import kernels as K
+    from pointcloudmatters_b200 import functional as PF
+
+    rows, C = 32960, 512
+    sb = torch.tensor([1234567], dtype=torch.int64, device="cuda")
+    x, res = torch.randn(rows, C, device="cuda"), torch.randn(rows, C, device="cuda")
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    pos = torch.randn(rows // 64, C, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    for _ in range(2):
+        y, yb, h, mean, rstd, ypb = K.add_dropout_ln_fwd(x, res, g, b, 1e-5, 0.1, sb, 7, want_bf16=True, pos=pos, pos_row_div=64)
+        K.add_dropout_ln_bwd(y, h, mean, rstd, g, 0.1, sb, 7, True, dg, db, True, dy_b=res)
+        K.colsum(yb, dg)
+    bn = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda().train()
+    z = torch.randn(65536, C, device="cuda", requires_grad=True)
+    for _ in range(2):
+        o = PF.batchnorm_relu(z, bn)
+        o.backward(torch.ones_like(o))
 elif which.startswith("gemm"):
     from pointcloudmatters_b200.kernels import gemm_bf16
 
