@@ -443,8 +443,35 @@ class OracleACTPCD(nn.Module):
         return self.forward_loss(d) if d["is_training"] else d
 
 
+def rotation_6d_to_matrix(d6):
+    """src/utils/rotation_conversions.py:556-577 (Zhou et al. 2019): Gram-Schmidt on the two 3-vectors."""
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = F.normalize(a1, dim=-1)
+    b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    return torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+
+
+def matrix_to_quaternion(m):
+    """src/utils/rotation_conversions.py:102-161 restated element by element: the four |q_i| from the diagonal,
+    the candidate built around the largest one (best conditioned), then standardised to a non-negative real part."""
+    flat = m.reshape(-1, 3, 3)
+    out = torch.empty(flat.shape[0], 4, dtype=m.dtype)
+    for n, r in enumerate(flat):
+        (m00, m01, m02), (m10, m11, m12), (m20, m21, m22) = [[float(v) for v in row] for row in r]
+        q = [max(0.0, 1 + m00 + m11 + m22) ** 0.5, max(0.0, 1 + m00 - m11 - m22) ** 0.5,
+             max(0.0, 1 - m00 + m11 - m22) ** 0.5, max(0.0, 1 - m00 - m11 + m22) ** 0.5]
+        rows = [[q[0] ** 2, m21 - m12, m02 - m20, m10 - m01], [m21 - m12, q[1] ** 2, m10 + m01, m02 + m20],
+                [m02 - m20, m10 + m01, q[2] ** 2, m12 + m21], [m10 - m01, m20 + m02, m21 + m12, q[3] ** 2]]
+        i = max(range(4), key=lambda j: (q[j], -j))  # argmax, first index on ties (torch.argmax)
+        cand = [v / (2.0 * max(q[i], 0.1)) for v in rows[i]]
+        if cand[0] < 0:
+            cand = [-v for v in cand]
+        out[n] = torch.tensor(cand, dtype=m.dtype)
+    return out.reshape(m.shape[:-2] + (4,))
+
+
 class OracleACTRLBenchPCD(OracleACTPCD):
-    """act.py:707-825 (training path: rot6d kept raw, sigmoid gripper / collision)."""
+    """act.py:707-825 (training: rot6d kept raw, sigmoid gripper / collision; inference: rot6d -> quaternion)."""
 
     def __init__(self, *args, rot_type="6d", collision=False, position_loss_weight=1.0, **kwargs):
         super().__init__(*args, **kwargs)
@@ -460,7 +487,9 @@ class OracleACTRLBenchPCD(OracleACTPCD):
         else:
             gripper = torch.sigmoid(a[..., -1:])
             rot = a[..., 3:-1]
-        assert d["is_training"], "oracle covers the training path (eval converts rot6d -> quaternion)"
+        if not d["is_training"]:  # act.py:785-795: rot6d -> matrix -> quaternion (w first, w >= 0)
+            assert self.rot_type == "6d"
+            rot = matrix_to_quaternion(rotation_6d_to_matrix(rot))
         d["a_hat"], d["is_pad_hat"] = torch.cat([position, rot, gripper], -1), self.is_pad_head(hs)
         return d
 

@@ -194,6 +194,13 @@ def main():
         model.train()
         batch = synth_batch(cfg, b, n, seed=77)
         state = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+        # inference branch (act.py:177-182,785-795): no actions -> latent 0, BatchNorm on the (initial) running
+        # statistics, RLBench head converts rot6d -> quaternion.  Run BEFORE the training forward touches the buffers.
+        model.eval()
+        with torch.no_grad():
+            ev = model({k: v for k, v in clone_batch(batch).items() if k in ("pcds", "qpos", "goal_cond")})
+        eval_a_hat = ev["a_hat"].detach().numpy()
+        model.train()
         torch.manual_seed(99)  # -> reparametrize eps
         out = model(clone_batch(batch))
         out["loss"].backward()
@@ -220,6 +227,7 @@ def main():
         for k in ("qpos", "actions", "is_pad", "goal_cond"):
             flat["in/" + k] = batch[k].numpy()
         flat["in/eps"] = eps.numpy()
+        flat["eval/a_hat"] = eval_a_hat
         for k in ("a_hat", "is_pad_hat", "mu", "logvar", "loss", "action_loss", "kl_loss"):
             flat["out/" + k] = out[k].detach().numpy()
         flat["meta/nograd"] = np.array(nograd)

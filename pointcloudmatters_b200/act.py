@@ -378,7 +378,8 @@ def _matrix_to_quaternion(matrix):
     ], dim=-2)
     cand = cand / (2.0 * q_abs[..., None].clamp(min=0.1))
     best = F.one_hot(q_abs.argmax(dim=-1), num_classes=4) > 0.5
-    return cand[best, :].reshape(matrix.shape[:-2] + (4,))
+    out = cand[best, :].reshape(matrix.shape[:-2] + (4,))
+    return torch.where(out[..., 0:1] < 0, -out, out)  # standardize_quaternion (rotation_conversions.py:368-380): w >= 0
 
 
 def build_policy(cfg: dict, rlbench: bool = False):

@@ -41,3 +41,21 @@ def test_oracle_policy_matches_reference_modules(path):
     sd = model.state_dict()
     for k, v in post.items():
         np.testing.assert_allclose(sd[k].numpy(), v, rtol=RTOL, atol=ATOL, err_msg=k)
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith("_small.npz")])
+def test_oracle_eval_mode_matches_reference_fixture(path):
+    """Inference branch (no actions: latent 0, BatchNorm on running statistics; RLBench: rot6d -> quaternion) against
+    the reference module's own eval-mode output stored in the fixture (`eval/a_hat`)."""
+    import numpy as np
+
+    from oracle.act_oracle import build_oracle_policy
+
+    cfg, state, batch, _out, _g, _p, _n, rlbench = load(path)
+    want = np.load(path)["eval/a_hat"]
+    model = build_oracle_policy(cfg, rlbench).eval()
+    model.load_state_dict(state)
+    with torch.no_grad():
+        got = model({k: v for k, v in batch.items() if k in ("pcds", "qpos", "goal_cond")})["a_hat"].numpy()
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
