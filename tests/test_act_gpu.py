@@ -195,3 +195,26 @@ def test_eval_mode_policy_matches_oracle(path):
     assert got["mu"] is None and not got["is_training"]
     assert got["a_hat"].shape == want["a_hat"].shape
     assert _rel_l2(got["a_hat"].cpu().numpy(), want["a_hat"].numpy()) <= OUT_TOL
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith("_small.npz")])
+def test_eval_mode_policy_matches_reference_fixture(path):
+    """Inference branch against the REFERENCE module's own eval-mode output (`eval/a_hat` in the fixture); for the
+    RLBench head the rotation is a quaternion (rot6d -> matrix -> quaternion, w >= 0), compared up to the q ~ -q
+    double cover so that a rotation with w ~ 0 cannot flip the verdict."""
+    from pointcloudmatters_b200.act import build_policy
+
+    cfg, state, batch, _out, _g, _p, _n, rlbench = load(path)
+    want = np.load(path)["eval/a_hat"]
+    model = build_policy(cfg, rlbench).cuda().eval()
+    model.load_state_dict(state)
+    with torch.no_grad():
+        got = model(_to_cuda({k: v for k, v in batch.items() if k in ("pcds", "qpos", "goal_cond")}))["a_hat"].cpu().numpy()
+    assert got.shape == want.shape
+    if rlbench:
+        q0, q1 = got[..., 3:7], want[..., 3:7]
+        flip = np.sign((q0 * q1).sum(-1, keepdims=True))
+        flip[flip == 0] = 1.0
+        got = np.concatenate([got[..., :3], q0 * flip, got[..., 7:]], -1)
+        assert np.allclose(np.linalg.norm(q0, axis=-1), 1.0, atol=1e-3)
+    assert _rel_l2(got, want) <= OUT_TOL
