@@ -150,7 +150,7 @@ def test_masked_sampling_hints_are_sync_free_and_identical():
 
 def test_cuda_graph_step_matches_eager():
     """The graph-captured ACT step (FPS/kNN and the CVAE encoder forked onto side streams, rejoined before the
-    transformer) reproduces the eager step's losses; dropout off so the two runs are comparable.  Bound 5e-3:
+    transformer) reproduces the eager step's losses; dropout off so the two runs are comparable.  Bound 1e-2:
     the step is not bit-reproducible run to run (fp32 atomics), see tests/test_dp_gpu.py."""
     from pointcloudmatters_b200.act import build_policy
     from pointcloudmatters_b200.bc_module import ACTBCModule
@@ -173,7 +173,7 @@ def test_cuda_graph_step_matches_eager():
         if graph:
             assert module._trainer._graphs, "graph path was not taken"
     for a, b in zip(losses[True], losses[False]):
-        assert abs(a - b) <= 5e-3 * abs(b) + 1e-5, losses
+        assert abs(a - b) <= 1e-2 * abs(b) + 1e-5, losses
 
 
 @pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if "maniskill_small" in p])
