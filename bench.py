@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (default: BASELINE cfg-2)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=4, help="clouds in the CPU baseline's untimed warm-up step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (debug / profiling)")
     ap.add_argument("--skip-dead-decoder-layers", action="store_true",
@@ -55,10 +55,10 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm restated (oracle port), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(sample_batch, steps, warmup):
-    """Times `steps` training steps of the oracle port on a `sample_batch`-cloud sample of cfg-2 and
-    scales to the full 64-sample step (per-sample cost is batch-independent: clouds are independent
-    units).  Returns (steps_per_sec_at_full_batch, cores, ms_per_sample_step)."""
+def cpu_reference_run(batch_size, steps, warmup, warmup_batch=None):
+    """Times `steps` FULL training steps (forward + backward + clip + AdamW) of the oracle port on `batch_size`-cloud
+    cfg-2 batches -- nothing is scaled.  `warmup` untimed steps run first on `warmup_batch` clouds (default: the same
+    size; a smaller warm-up batch only pays thread-pool / allocator start-up).  Returns (steps_per_sec, cores, ms_per_step)."""
     import torch
 
     from oracle.act_oracle import build_oracle_policy
@@ -70,10 +70,10 @@ def cpu_reference_run(sample_batch, steps, warmup):
     torch.manual_seed(0)
     model = build_oracle_policy(CFG2).train()
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.05)
-    batches = [synthetic_act_batch(sample_batch, N_POINTS, seed=1000 + i) for i in range(2)]
+    batches = [synthetic_act_batch(batch_size, N_POINTS, seed=1000 + i) for i in range(2)]
+    warm = batches if warmup_batch in (None, batch_size) else [synthetic_act_batch(warmup_batch, N_POINTS, seed=999)]
 
-    def step(i):
-        b = batches[i % len(batches)]
+    def step(b):
         b = {k: (dict(v) if isinstance(v, dict) else v) for k, v in b.items()}
         b["pcds"].pop("n_max", None)
         opt.zero_grad(set_to_none=True)
@@ -81,32 +81,39 @@ def cpu_reference_run(sample_batch, steps, warmup):
         out["loss"].backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
         opt.step()
-        return float(out["loss"])
+        return float(out["loss"].detach())
 
     for i in range(warmup):
-        step(i)
+        step(warm[i % len(warm)])
     t0 = time.perf_counter()
     for i in range(steps):
-        step(i)
+        step(batches[i % len(batches)])
     dt = (time.perf_counter() - t0) / steps
-    full_step_s = dt * (BATCH_PER_GPU / sample_batch)
-    return 1.0 / full_step_s, cores, dt * 1e3
+    return 1.0 / dt, cores, dt * 1e3
+
+
+REF_MAX_STEPS, REF_MAX_WARMUP = 3, 1  # a full cfg-2 step of the CPU port takes ~10 s on 16 cores
 
 
 def reference_arm(args):
+    """`--impl reference`: the reference algorithm on the host cores, FULL cfg-2 batch (64 clouds), unscaled.
+    --steps / --warmup are honoured up to REF_MAX_STEPS / REF_MAX_WARMUP (stated in the line) so the run ends in ~1 min."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    v, cores, ms = cpu_reference_run(args.cpu_sample_batch, steps, warmup)
-    sample = (f"{steps} timed + {warmup} warm-up steps of the oracle port (oracle/act_oracle.py + C pointops oracle, "
-              f"fp32, torch CPU) on {args.cpu_sample_batch}/{BATCH_PER_GPU} clouds of cfg-2, scaled x{BATCH_PER_GPU // args.cpu_sample_batch}")
+    steps = max(1, min(args.steps, REF_MAX_STEPS))
+    warmup = max(1, min(args.warmup, REF_MAX_WARMUP))
+    v, cores, ms = cpu_reference_run(args.batch, steps, warmup)
+    sample = (f"{steps} timed + {warmup} warm-up FULL steps (fwd+bwd+clip+AdamW) of the oracle port (oracle/act_oracle.py + C "
+              f"pointops oracle, fp32, torch CPU, {cores} threads) on {args.batch}-cloud cfg-2 batches, unscaled; "
+              f"--steps/--warmup capped at {REF_MAX_STEPS}/{REF_MAX_WARMUP}")
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores; the reference's own "
-                       "pointops has no CPU implementation, so its kernels are the C restatement pinned to them"},
+            "config": {"workload": WORKLOAD, "global_batch": args.batch, "steps_cap": REF_MAX_STEPS, "warmup_cap": REF_MAX_WARMUP,
+                       "note": "reference algorithm on host CPU cores; the reference's own pointops has no CPU "
+                               "implementation, so its kernels are the C restatement pinned to them; one process on rank 0 "
+                               "(the reference has no multi-process CPU mode), so the value does not grow with --gpus"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -319,11 +326,11 @@ def b200_arm(args):
         "kernel_ms_per_step": {k: v.get("total_ms_isolated", v["total_ms"]) / 3 for k, v in kstats.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, ms = cpu_reference_run(args.cpu_sample_batch, 2, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"2 timed + 1 warm-up steps of the oracle port on {args.cpu_sample_batch}/"
-                                          f"{BATCH_PER_GPU} clouds of cfg-2 (fp32, torch CPU + C pointops oracle), "
-                                          f"scaled x{BATCH_PER_GPU // args.cpu_sample_batch}"}
+        v, cores, ms = cpu_reference_run(args.batch, 1, 1, warmup_batch=args.cpu_sample_batch)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                                "sample": f"1 timed FULL step (fwd+bwd+clip+AdamW, {args.batch} clouds of cfg-2, unscaled) of the "
+                                          f"oracle port (fp32, torch CPU + C pointops oracle, {cores} threads) after 1 warm-up "
+                                          f"step on {args.cpu_sample_batch} clouds"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

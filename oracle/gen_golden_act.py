@@ -119,6 +119,16 @@ CASES = {
                                    dropout=0.0, num_queries=8, action_dim=7, qpos_dim=9, goal_cond_dim=3,
                                    latent_dim=32, kl_weight=10.0, pcd_npoints=32, pcd_nsample=8, use_mask=1,
                                    bg_ratio=0.25), 3, 96),
+    # head_dim 64 and a width that is a multiple of 128: the shapes at which the product takes its FUSED tcgen05
+    # attention (csrc/flash_attn.cu), LayerNorm (csrc/layernorm.cu) and FFN paths -- the smaller cases above fall
+    # to the composed library path.  The CVAE encoder runs under the `is_pad` key-padding mask in both.
+    "maniskill_h128": (False, dict(hidden_dim=128, nhead=2, dim_feedforward=32, enc_layers=2, dec_layers=3,
+                                   dropout=0.0, num_queries=12, action_dim=7, qpos_dim=9, goal_cond_dim=3,
+                                   latent_dim=32, kl_weight=10.0, pcd_npoints=160, pcd_nsample=16), 3, 288),
+    "rlbench_h128": (True, dict(hidden_dim=128, nhead=2, dim_feedforward=32, enc_layers=1, dec_layers=2,
+                                dropout=0.0, num_queries=9, action_dim=11, qpos_dim=4, goal_cond_dim=16,
+                                latent_dim=32, kl_weight=10.0, pcd_npoints=136, pcd_nsample=16, collision=True,
+                                position_loss_weight=3.0), 2, 200),
 }
 
 

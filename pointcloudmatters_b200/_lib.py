@@ -81,6 +81,7 @@ class _CountingLib:
     def __init__(self, handle):
         object.__setattr__(self, "_h", handle)
         object.__setattr__(self, "launches", 0)
+        object.__setattr__(self, "calls", {})  # entry point -> number of calls (tests assert which path ran)
         object.__setattr__(self, "_no_count", {"pcm_abi_version", "pcm_build_info", "pcm_tune_fps_threads", "pcm_launch_count"})
 
     def __getattr__(self, name):
@@ -88,8 +89,12 @@ class _CountingLib:
         if name in self._no_count:
             return fn
 
+        calls = self.calls
+        calls.setdefault(name, 0)
+
         def call(*args):
             object.__setattr__(self, "launches", self.launches + 1)
+            calls[name] += 1
             return fn(*args)
 
         object.__setattr__(self, name, call)

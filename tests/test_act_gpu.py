@@ -33,9 +33,14 @@ def _to_cuda(batch):
 def test_policy_matches_reference_fixture(path):
     from pointcloudmatters_b200.act import build_policy
 
+    from pointcloudmatters_b200._lib import lib
+
     cfg, state, batch, out, grads, post, nograd, rlbench = load(path)
     model = build_policy(cfg, rlbench).cuda().train()
     model.load_state_dict(state)
+    fused_entry_points = ("pcm_flash_attn_fwd", "pcm_flash_attn_bwd", "pcm_add_dropout_ln_fwd_ex", "pcm_add_dropout_ln_bwd_ex",
+                          "pcm_ffn_relu_dropout_bwd")
+    before = {k: lib.calls.get(k, 0) for k in fused_entry_points}
     d = model(_to_cuda(batch))
     for k in ("a_hat", "mu", "logvar"):
         assert _rel_l2(d[k].detach().cpu().numpy(), out[k]) <= OUT_TOL, k
@@ -45,6 +50,15 @@ def test_policy_matches_reference_fixture(path):
     for k in ("loss", "action_loss", "kl_loss"):
         assert abs(float(d[k]) - float(out[k])) <= LOSS_TOL * abs(float(out[k])) + 1e-5, k
     d["loss"].backward()
+    if cfg["hidden_dim"] % 128 == 0 and cfg["hidden_dim"] // cfg["nhead"] == 64:
+        # head_dim 64, width % 128 == 0: this fixture must have gone through the FUSED tcgen05 attention, LayerNorm
+        # and FFN kernels (the ones the training step runs), not the composed library path of the small cases
+        n_mha = 2 * cfg["enc_layers"] + 2 * cfg["dec_layers"]  # CVAE encoder + encoder + decoder self / cross
+        n_ln = 4 * cfg["enc_layers"] + 3 * cfg["dec_layers"] + cfg["dec_layers"]
+        ran = {k: lib.calls.get(k, 0) - before[k] for k in fused_entry_points}
+        assert ran["pcm_flash_attn_fwd"] >= n_mha and ran["pcm_add_dropout_ln_fwd_ex"] >= n_ln, ran
+        assert ran["pcm_flash_attn_bwd"] >= 2 * cfg["enc_layers"] + 2 and ran["pcm_add_dropout_ln_bwd_ex"] > 0, ran
+        assert ran["pcm_ffn_relu_dropout_bwd"] >= 2 * cfg["enc_layers"] + 1, ran
     got_nograd = sorted(k for k, p in model.named_parameters() if p.grad is None)
     assert got_nograd == sorted(nograd)
     worst = {}
@@ -197,7 +211,7 @@ def test_eval_mode_policy_matches_oracle(path):
     assert _rel_l2(got["a_hat"].cpu().numpy(), want["a_hat"].numpy()) <= OUT_TOL
 
 
-@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith("_small.npz")])
+@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith(("_small.npz", "_h128.npz"))])
 def test_eval_mode_policy_matches_reference_fixture(path):
     """Inference branch against the REFERENCE module's own eval-mode output (`eval/a_hat` in the fixture); for the
     RLBench head the rotation is a quaternion (rot6d -> matrix -> quaternion, w >= 0), compared up to the q ~ -q

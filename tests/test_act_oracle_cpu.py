@@ -43,7 +43,7 @@ def test_oracle_policy_matches_reference_modules(path):
         np.testing.assert_allclose(sd[k].numpy(), v, rtol=RTOL, atol=ATOL, err_msg=k)
 
 
-@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith("_small.npz")])
+@pytest.mark.parametrize("path", [p for p in GOLDEN_ACT if p.endswith(("_small.npz", "_h128.npz"))])
 def test_oracle_eval_mode_matches_reference_fixture(path):
     """Inference branch (no actions: latent 0, BatchNorm on running statistics; RLBench: rot6d -> quaternion) against
     the reference module's own eval-mode output stored in the fixture (`eval/a_hat`)."""

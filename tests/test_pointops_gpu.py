@@ -293,6 +293,130 @@ def test_ball_queries_bit_exact_vs_reference_kernels(P, kind):
     assert torch.equal(ri, gi) and torch.equal(torch.sqrt(rd2), gd)
 
 
+@needs_ref
+def test_gather_scatter_ops_vs_reference_kernels(P):
+    """grouping / interpolation / subtraction / aggregation / scatter-attention (forward AND backward) against the
+    UNMODIFIED reference launchers (libs/pointops/src/{grouping,interpolation,subtraction,aggregation,attention}/
+    *_cuda_kernel.cu in oracle/_ref): pure gathers bit-exact, atomically accumulated results to fp32 reassociation
+    noise -- and the C oracle against the same reference outputs, which pins the oracle for these ops on this box."""
+    rng = np.random.default_rng(16)
+    n, m, ns, c = 700, 260, 12, 40
+    inp = rng.standard_normal((n, c)).astype(np.float32)
+    idx = rng.integers(0, n, (m, ns)).astype(np.int32)
+    go = rng.standard_normal((m, ns, c)).astype(np.float32)
+    t_inp, t_idx, t_go = _dev(inp, idx, go)
+    # grouping2 == grouping_forward / backward launchers
+    x = t_inp.clone().requires_grad_(True)
+    out = P.grouping2(x, t_idx)
+    want = _ref.grouping_forward(t_inp, t_idx)
+    assert torch.equal(out.detach(), want)
+    assert np.array_equal(O.grouping_forward(inp, idx), want.cpu().numpy())
+    out.backward(t_go)
+    wgi = _ref.grouping_backward(t_go, t_idx, n)
+    torch.testing.assert_close(x.grad, wgi, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(O.grouping_backward(go, idx, n), wgi.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+    # interpolation launchers (weights as functions/interpolation.py:33-36 builds them)
+    k = 3
+    idx3 = rng.integers(0, m, (n, k)).astype(np.int32)
+    w3 = rng.random((n, k)).astype(np.float32)
+    w3 /= w3.sum(1, keepdims=True)
+    coarse = rng.standard_normal((m, c)).astype(np.float32)
+    g3 = rng.standard_normal((n, c)).astype(np.float32)
+    t_i3, t_w3, t_coarse, t_g3 = _dev(idx3, w3, coarse, g3)
+    want = _ref.interpolation_forward(t_coarse, t_i3, t_w3)
+    np.testing.assert_allclose(O.interpolation_forward(coarse, idx3, w3), want.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    wgi = _ref.interpolation_backward(t_g3, t_i3, t_w3, m)
+    np.testing.assert_allclose(O.interpolation_backward(g3, idx3, w3, m), wgi.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    from pointcloudmatters_b200._lib import check, current_stream, lib, ptr
+
+    got = torch.zeros((n, c), device="cuda")
+    check(lib.pcm_interpolation_forward(n, c, k, ptr(t_coarse), ptr(t_i3), ptr(t_w3), ptr(got), current_stream()), "interp fwd")
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    gotg = torch.zeros((m, c), device="cuda")
+    check(lib.pcm_interpolation_backward(n, c, k, ptr(t_g3), ptr(t_i3), ptr(t_w3), ptr(gotg), current_stream()), "interp bwd")
+    torch.testing.assert_close(gotg, wgi, rtol=1e-4, atol=1e-5)
+
+    # subtraction
+    i1 = rng.standard_normal((n, c)).astype(np.float32)
+    idx2 = rng.integers(0, n, (n, ns)).astype(np.int32)
+    go2 = rng.standard_normal((n, ns, c)).astype(np.float32)
+    a, bb, ti, tg2 = _dev(i1, inp, idx2, go2)
+    a.requires_grad_(True); bb.requires_grad_(True)
+    s_ = P.subtraction(a, bb, ti)
+    want = _ref.subtraction_forward(a.detach(), bb.detach(), ti)
+    assert torch.equal(s_.detach(), want)
+    assert np.array_equal(O.subtraction_forward(i1, inp, idx2), want.cpu().numpy())
+    s_.backward(tg2)
+    w1, w2 = _ref.subtraction_backward(ti, tg2)
+    torch.testing.assert_close(a.grad, w1, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(bb.grad, w2, rtol=1e-5, atol=1e-5)
+    o1, o2 = O.subtraction_backward(idx2, go2)
+    np.testing.assert_allclose(o1, w1.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(o2, w2.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+    # aggregation (w_c divides c)
+    c2, w_c = 32, 8
+    inp2 = rng.standard_normal((n, c2)).astype(np.float32)
+    pos = rng.standard_normal((n, ns, c2)).astype(np.float32)
+    wt = rng.standard_normal((n, ns, w_c)).astype(np.float32)
+    go3 = rng.standard_normal((n, c2)).astype(np.float32)
+    ti2, tp, tw, tg3 = _dev(inp2, pos, wt, go3)
+    want = _ref.aggregation_forward(ti2, tp, tw, ti)
+    wgi, wgp, wgw = _ref.aggregation_backward(ti2, tp, tw, ti, tg3)
+    for t in (ti2, tp, tw):
+        t.requires_grad_(True)
+    ag = P.aggregation(ti2, tp, tw, ti)
+    assert torch.equal(ag.detach(), want)  # same FMA chain
+    assert np.array_equal(O.aggregation_forward(inp2, pos, wt, idx2), want.cpu().numpy())
+    ag.backward(tg3)
+    torch.testing.assert_close(ti2.grad, wgi, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(tp.grad, wgp, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tw.grad, wgw, rtol=1e-4, atol=1e-5)
+    ogi, ogp, ogw = O.aggregation_backward(inp2, pos, wt, idx2, go3)
+    np.testing.assert_allclose(ogi, wgi.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ogp, wgp.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ogw, wgw.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+    # scatter attention
+    nn_, g, ca, ma = 90, 4, 24, 800
+    q = rng.standard_normal((nn_, g, ca)).astype(np.float32)
+    kk = rng.standard_normal((nn_, g, ca)).astype(np.float32)
+    w = rng.standard_normal((ca,)).astype(np.float32)
+    it = rng.integers(0, nn_, ma).astype(np.int32)
+    ir = rng.integers(0, nn_, ma).astype(np.int32)
+    gor = rng.standard_normal((ma, g)).astype(np.float32)
+    tq, tk, tw_, tit, tir, tgor = _dev(q, kk, w, it, ir, gor)
+    want = _ref.attention_relation_step_forward(tq, tk, tw_, tit, tir)
+    wgq, wgk, _wgw = _ref.attention_relation_step_backward(tq, tk, tw_, tit, tir, tgor)
+    tq.requires_grad_(True); tk.requires_grad_(True)
+    rel = P.attention_relation_step(tq, tk, tw_, tit, tir)
+    torch.testing.assert_close(rel.detach(), want, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(O.attention_relation_step_forward(q, kk, w, it, ir), want.cpu().numpy(), rtol=1e-4, atol=1e-4)
+    rel.backward(tgor)
+    torch.testing.assert_close(tq.grad, wgq, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(tk.grad, wgk, rtol=1e-3, atol=1e-4)
+    oq, ok, _ow = O.attention_relation_step_backward(q, kk, w, it, ir, gor)
+    np.testing.assert_allclose(oq, wgq.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(ok, wgk.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    aw = rng.standard_normal((ma, g)).astype(np.float32)
+    v = rng.standard_normal((nn_, g, ca)).astype(np.float32)
+    gof = rng.standard_normal((nn_, g, ca)).astype(np.float32)
+    taw, tv, tgof = _dev(aw, v, gof)
+    want = _ref.attention_fusion_step_forward(taw, tv, tit, tir)
+    wgw2, wgv = _ref.attention_fusion_step_backward(taw, tv, tit, tir, tgof)
+    taw.requires_grad_(True); tv.requires_grad_(True)
+    fu = P.attention_fusion_step(taw, tv, tit, tir)
+    torch.testing.assert_close(fu.detach(), want, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(O.attention_fusion_step_forward(aw, v, it, ir), want.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    fu.backward(tgof)
+    torch.testing.assert_close(taw.grad, wgw2, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(tv.grad, wgv, rtol=1e-3, atol=1e-4)
+    ogw2, ogv = O.attention_fusion_step_backward(aw, v, it, ir, gof)
+    np.testing.assert_allclose(ogw2, wgw2.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(ogv, wgv.cpu().numpy(), rtol=1e-3, atol=1e-4)
+
+
 # ---------------------------------------------------------------------------------------------
 # Full BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------
