@@ -461,6 +461,7 @@ class DiffusionUnetImagePolicy(nn.Module):
         self.num_inference_steps = num_inference_steps or noise_scheduler.config.num_train_timesteps
         self.kwargs = kwargs
         self._sample_graphs = {}  # (trajectory shape, cond shape, device) -> (CUDAGraph, static tensors)
+        self._sample_graphs_fp = None  # weight fingerprint the cached graphs were captured under
 
     def set_normalizer(self, normalizer):
         self.normalizer.load_state_dict(normalizer.state_dict())
@@ -537,6 +538,18 @@ class DiffusionUnetImagePolicy(nn.Module):
         ts = sch.timesteps.to(dev)
         coefs = torch.stack([sch.step_coefficients(int(t)) for t in sch.timesteps]).to(dev)
         key = (tuple(shape), tuple(global_cond.shape), str(dev))
+        if use_cuda_graph:
+            # A captured step bakes in ADDRESSES: the fp32 biases / GroupNorm parameters and the bf16 operand copies
+            # `functional._wb` made of the weights at capture time.  Any change of the weights behind those addresses
+            # (load_state_dict, an in-place torch.optim step: both bump Parameter._version; .to() / re-assignment:
+            # new data_ptr) would leave the graph computing with the weights of its first call, so the cache is
+            # keyed on a fingerprint of every denoiser parameter and dropped when it changes.  Under a BCTrainer the
+            # operands are views of the flat buffers the fused AdamW kernel updates in place (same address, current
+            # values, no version bump) -- the graph stays valid there by construction.
+            fp = tuple((p_.data_ptr(), p_._version) for p_ in self.model.parameters())
+            if fp != self._sample_graphs_fp:
+                self._sample_graphs.clear()
+                self._sample_graphs_fp = fp
         entry = self._sample_graphs.get(key) if use_cuda_graph else None
         if use_cuda_graph and entry is None:
             st = dict(traj=traj.clone(), t=ts[0].clone(), coef=coefs[0].clone(), noise=torch.zeros(shape, device=dev),

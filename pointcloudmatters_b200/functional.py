@@ -35,14 +35,29 @@ class _Bf16Shadow:
 
     def __init__(self):
         self.entries = {}  # id -> (weakref to FlatState, base_ptr, nbytes)
+        self.grad_ranges = {}  # id -> (grad base_ptr, nbytes) of the same FlatStates' flat gradient buffers
         self.inference_cache = {}  # base ptr -> (weakref(Parameter), version, bf16 copy); no_grad only
 
     def register(self, flat_state):
         import weakref
 
         key = id(flat_state)
-        ref = weakref.ref(flat_state, lambda _r, k=key: self.entries.pop(k, None))
+
+        def _drop(_r, k=key):
+            self.entries.pop(k, None)
+            self.grad_ranges.pop(k, None)
+
+        ref = weakref.ref(flat_state, _drop)
         self.entries[key] = (ref, flat_state.param.data_ptr(), flat_state.param.numel() * 4)
+        self.grad_ranges[key] = (flat_state.grad.data_ptr(), flat_state.grad.numel() * 4)
+
+    def owns_grad(self, g):
+        """True when `g` lives inside the flat gradient buffer of a live trainer (FlatState)."""
+        ptr_ = g.data_ptr()
+        for base, nbytes in self.grad_ranges.values():
+            if 0 <= ptr_ - base < nbytes:
+                return True
+        return False
 
     def view(self, w):
         if self.entries and w.dtype == torch.float32 and w.is_contiguous():
@@ -85,11 +100,15 @@ def _wb(w):
 
 
 def _grad_slot(p):
-    """The fp32 gradient buffer a parameter already owns (the trainer's flat-gradient view, or a
-    .grad left by an earlier backward): weight-gradient kernels accumulate straight into it and the
-    backward returns None for that input, so autograd launches no zero-fill / add kernels."""
+    """The trainer's flat-gradient view of a parameter: weight-gradient kernels accumulate straight into it and the
+    backward returns None for that input, so autograd launches no zero-fill / add kernels.
+    ONLY gradients that live inside a registered `trainer.FlatState` buffer are taken (address-range test, like the
+    bf16 shadow): for any other `.grad` (torch DDP / Lightning with `accumulate_grad_batches`,
+    `zero_grad(set_to_none=False)`, `gradient_as_bucket_view`) the gradient is RETURNED to autograd, so
+    AccumulateGrad and the hooks registered on it (the DDP reducer's) run as usual."""
     g = p.grad if (p is not None and p.is_leaf) else None
-    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape and g.device == p.device:
+    if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape and g.device == p.device
+            and BF16_SHADOW.owns_grad(g)):
         return g
     return None
 

@@ -15,6 +15,7 @@ the dead decoder layers receive exact zeros and are therefore only weight-decaye
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from typing import Iterable
 
 import torch
@@ -103,7 +104,8 @@ class BCTrainer:
 
     def __init__(self, policy: nn.Module, lr=5e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None,
-                 use_cuda_graph: bool = False, input_keys=None, loss_keys=None):
+                 use_cuda_graph: bool = False, input_keys=None, loss_keys=None, accumulate_grad_batches: int = 1,
+                 max_cached_graphs: int = 4, debug_hints: bool = False):
         self.policy = policy
         if input_keys is not None:
             self.INPUT_KEYS = tuple(input_keys)
@@ -119,8 +121,19 @@ class BCTrainer:
         self.step_num = 0
         self.last_grad_norm = None
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}  # shape signature -> (graph, static batch, static outputs)
+        # shape signature -> (graph, static batch, static outputs); LRU-bounded: every entry owns a private activation
+        # pool, and ragged real data produces a new signature (sum N of the packed cloud) for almost every batch
+        self._graphs = OrderedDict()
+        self.max_cached_graphs = max(1, int(max_cached_graphs))
+        self._graph_lookups = self._graph_misses = 0
+        self.graph_disabled_reason = None
         self._eager_steps = 0
+        # reference presets use accumulate_grad_batches 2 (exp_maniskill2_act_policy/base.yaml:26-28): gradients of
+        # k micro-batches are summed in the flat buffer, ONE all-reduce + optimizer step closes the group
+        self.accumulate_grad_batches = max(1, int(accumulate_grad_batches))
+        self._micro = 0
+        self.debug_hints = bool(debug_hints)
+        self._hook_handle = None
 
     # -- gradient exchange: ONE collective over the flat buffer -----------------------------------
     def reduce_gradients(self):
@@ -131,7 +144,23 @@ class BCTrainer:
     def _build_flat(self):
         inactive = [p for p in self.policy.parameters() if p.requires_grad and p.grad is None]
         self.flat = FlatState(self.policy.parameters(), inactive)
+        self._finish_flat()
+
+    def _finish_flat(self):
+        import weakref
+
         dev = self.flat.param.device
+        # `policy.load_state_dict` copies into the fp32 masters behind the optimizer's back: refresh the bf16 operand
+        # copy the GEMMs read (a stale shadow would silently keep computing with the old weights)
+        if self._hook_handle is None and hasattr(self.policy, "register_load_state_dict_post_hook"):
+            me = weakref.ref(self)
+
+            def _resync(_module, _incompatible):
+                t = me()
+                if t is not None and t.flat is not None:
+                    t.flat.sync_shadow()
+
+            self._hook_handle = self.policy.register_load_state_dict_post_hook(_resync)
         self._hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(9)
         self._hyper = torch.zeros(9, dtype=torch.float32, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -141,7 +170,7 @@ class BCTrainer:
         lr, beta1 = self.schedule.at(min(step_num, self.schedule.total_steps - 1))
         t = step_num + 1
         return [lr, beta1, self.betas[1], self.eps, self.weight_decay, 1.0 - beta1 ** t, 1.0 - self.betas[1] ** t,
-                self.clip_norm if self.clip_norm else 0.0, 1.0 / self.world]
+                self.clip_norm if self.clip_norm else 0.0, 1.0 / (self.world * self.accumulate_grad_batches)]
 
     def optimizer_step(self):
         from . import functional as PF
@@ -171,12 +200,30 @@ class BCTrainer:
         behaviour, act.py:137-309); work on a copy of the (nested) dicts restricted to the batch-contract keys."""
         return {k: self._copy_dicts(batch[k]) for k in self.INPUT_KEYS if k in batch}
 
-    def _forward_backward(self, batch):
-        if self.flat is not None:
+    def _forward_backward(self, batch, zero=True):
+        if self.flat is not None and zero:
             self.flat.zero_grad()
         out = self.policy(self._inputs_only(batch))
         out["loss"].backward()
         return {k: out[k].detach() for k in self.LOSS_KEYS}
+
+    HINT_KEYS = ("n_max", "fg_n_max", "bg_n_max")
+    HINT_BUCKET = 128
+
+    @classmethod
+    def _bucket_hints(cls, batch):
+        """Cloud-size hints are UPPER bounds for the kernels (FPS sizes its per-thread strips from them and reads
+        only rows below the offsets): rounding them up to a multiple of HINT_BUCKET keeps batches whose largest
+        cloud differs by a few points on ONE captured graph."""
+        out = {}
+        for k, v in batch.items():
+            if isinstance(v, dict):
+                out[k] = cls._bucket_hints(v)
+            elif k in cls.HINT_KEYS and isinstance(v, int):
+                out[k] = -(-v // cls.HINT_BUCKET) * cls.HINT_BUCKET
+            else:
+                out[k] = v
+        return out
 
     @staticmethod
     def _signature(batch):
@@ -199,30 +246,54 @@ class BCTrainer:
             elif torch.is_tensor(v):
                 static[k].copy_(v, non_blocking=True)
 
-    def _graphed_forward_backward(self, batch):
+    def _graphed_forward_backward(self, batch, zero=True):
         """Replay (capturing on first use per batch-shape signature) the forward+backward graph.
-        ~2000 kernel launches per step become one cudaGraphLaunch; inputs are copied into static
-        buffers, dropout seeds come from device memory so every replay draws fresh masks."""
-        batch = self._inputs_only(batch)
-        sig = self._signature(batch)
+        ~900 kernel launches per step become one cudaGraphLaunch; inputs are copied into static
+        buffers, dropout seeds come from device memory so every replay draws fresh masks.
+        The cache holds at most `max_cached_graphs` entries (least recently used evicted -- its private memory pool
+        is released with it); when captures keep missing (ragged clouds: a new sum-N almost every batch) the
+        trainer stops capturing and runs eagerly (`graph_disabled_reason` says so) instead of re-capturing each step."""
+        batch = self._bucket_hints(self._inputs_only(batch))
+        sig = (self._signature(batch), bool(zero))
+        self._graph_lookups += 1
         entry = self._graphs.get(sig)
         if entry is None:
+            self._graph_misses += 1
+            if self._graph_lookups >= 16 and self._graph_misses > 0.5 * self._graph_lookups:
+                self.graph_disabled_reason = (f"{self._graph_misses} captures in {self._graph_lookups} steps: batch shapes "
+                                              "do not repeat (ragged clouds); running eagerly")
+                self._graphs.clear()
+                return self._forward_backward(batch, zero)
+            while len(self._graphs) >= self.max_cached_graphs:
+                self._graphs.popitem(last=False)
             clone = lambda v: ({kk: clone(vv) for kk, vv in v.items()} if isinstance(v, dict)
                                else (v.clone() if torch.is_tensor(v) else v))
             static = clone(batch)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = self._forward_backward(static)
+                outs = self._forward_backward(static, zero)
             entry = (graph, static, outs)
             self._graphs[sig] = entry
+        else:
+            self._graphs.move_to_end(sig)
         graph, static, outs = entry
         self._copy_into(static, batch)
         graph.replay()
         return outs
 
+    def _check_hints(self, pcds):
+        """debug_hints=True: one device->host read per step that verifies the host-provided cloud-size hints really are
+        upper bounds (fps.cu clamps the cloud to the hint, so an undersized `n_max` would silently drop points)."""
+        off = pcds["offset"]
+        sizes = torch.diff(off, prepend=off.new_zeros(1))
+        if pcds.get("n_max", None) is not None and int(sizes.max()) > int(pcds["n_max"]):
+            raise ValueError(f"pcds['n_max']={pcds['n_max']} is smaller than the largest cloud ({int(sizes.max())})")
+
     def training_step(self, batch):
-        """One full step on this rank's shard; returns the (detached) loss dict."""
+        """One full step on this rank's shard; returns the (detached) loss dict.  With `accumulate_grad_batches`
+        = k the first k-1 calls of a group only add their gradients into the flat buffer; the k-th also runs the
+        all-reduce, clip and AdamW (the kernel divides the summed gradient by world * k)."""
         from . import functional as PF
 
         PF.DROPOUT_RNG.new_step()
@@ -230,17 +301,75 @@ class BCTrainer:
         # carries the host-known cloud-size hints that make FPS sync-free (act.ACTPCD.sync_free)
         sync_free = getattr(self.policy, "sync_free", None)
         pcds = batch.get("pcds", None) if "pcds" in batch else batch.get("obs", {}).get("pcds", None)
+        if self.debug_hints and pcds is not None:
+            self._check_hints(pcds)
         graph_ok = sync_free is None or pcds is None or sync_free(pcds)
-        if self.use_cuda_graph and graph_ok and self.flat is not None and self._eager_steps >= 2:
-            losses = self._graphed_forward_backward(batch)
+        zero = self._micro == 0
+        if (self.use_cuda_graph and graph_ok and self.flat is not None and self._eager_steps >= 2
+                and self.graph_disabled_reason is None):
+            losses = self._graphed_forward_backward(batch, zero)
         else:
-            losses = self._forward_backward(batch)
+            if self.flat is None and not zero:
+                raise RuntimeError("internal: flat state must exist before an accumulation group continues")
+            losses = self._forward_backward(batch, zero)
             self._eager_steps += 1
             if self.flat is None:  # first step: discover never-used parameters, then go flat
                 self._build_flat()
-        self.reduce_gradients()
-        self.optimizer_step()
+        self._micro += 1
+        if self._micro >= self.accumulate_grad_batches:
+            self._micro = 0
+            self.reduce_gradients()
+            self.optimizer_step()
         return losses
+
+    # -- checkpoint surface (Lightning saves optimizer + scheduler state next to the weights) ---------------
+    def state_dict(self):
+        """Optimizer / schedule state: Adam moments per parameter NAME (layout-independent), the step counter and the
+        dropout seed base.  Weights travel in `policy.state_dict()` as usual."""
+        from . import functional as PF
+
+        if self.flat is None:
+            return {"step_num": self.step_num, "exp_avg": {}, "exp_avg_sq": {}, "dropout_seed": None}
+        names = {id(p): n for n, p in self.policy.named_parameters()}
+        f = self.flat
+        avg, sq = {}, {}
+        off = 0
+        for p in f.active:
+            n = p.numel()
+            avg[names[id(p)]] = f.exp_avg[off:off + n].view_as(p).detach().clone()
+            sq[names[id(p)]] = f.exp_avg_sq[off:off + n].view_as(p).detach().clone()
+            off += (n + 7) // 8 * 8
+        seed = PF.DROPOUT_RNG.base.get(str(f.param.device))
+        return {"step_num": self.step_num, "exp_avg": avg, "exp_avg_sq": sq,
+                "dropout_seed": None if seed is None else seed.detach().cpu().clone(),
+                "inactive": [names[id(p)] for p in f.inactive]}
+
+    def load_state_dict(self, state):
+        """Restore what `state_dict` saved (call after `policy.load_state_dict`).  Builds the flat buffers if the trainer
+        has not stepped yet; the bf16 operand copy is refreshed from the fp32 masters."""
+        from . import functional as PF
+
+        if self.flat is None:
+            named = dict(self.policy.named_parameters())
+            inactive = [named[n] for n in state.get("inactive", []) if n in named]
+            self.flat = FlatState(self.policy.parameters(), inactive)
+            self._finish_flat()
+            self._eager_steps = max(self._eager_steps, 2)
+        names = {id(p): n for n, p in self.policy.named_parameters()}
+        f = self.flat
+        off = 0
+        for p in f.active:
+            n = p.numel()
+            k = names[id(p)]
+            if k in state["exp_avg"]:
+                f.exp_avg[off:off + n].copy_(state["exp_avg"][k].reshape(-1))
+                f.exp_avg_sq[off:off + n].copy_(state["exp_avg_sq"][k].reshape(-1))
+            off += (n + 7) // 8 * 8
+        self.step_num = int(state["step_num"])
+        if state.get("dropout_seed", None) is not None and f.param.is_cuda:
+            PF.DROPOUT_RNG.base_for(f.param.device).copy_(state["dropout_seed"])
+        f.sync_shadow()
+        self._graphs.clear()
 
 
 def _shard_clouds(v: dict, lo: int, hi: int) -> dict:

@@ -172,6 +172,38 @@ def test_predict_action_matches_reference_fixture(path, graph):
         assert float((again["action_pred"] - out["action_pred"]).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("path", GOLDEN_DP[:1])
+def test_predict_action_graph_follows_weight_changes(path):
+    """a cached sampling graph bakes in the addresses of the bf16 weight copies made at capture time.
+    After the weights change (load_state_dict / an in-place optimizer step outside BCTrainer) the graphed sampler must
+    use the NEW weights: it is compared with the eager sampler on the same noise after each change."""
+    from pointcloudmatters_b200.diffusion import build_dp_policy
+    from tests._golden_dp import load_prediction
+
+    cfg, state, batch, *_ = load(path)
+    noises, _action, _pred = load_prediction(path)
+    model = build_dp_policy(dict(cfg, num_inference_steps=10)).cuda().eval()
+    model.load_state_dict(state)
+    obs = _cuda({k: v for k, v in batch.items() if k in ("obs", "goal")})
+    first = model.predict_action(obs, noises=noises, use_cuda_graph=True)["action_pred"].clone()
+    assert model._sample_graphs
+    g = torch.Generator().manual_seed(5)
+    changed = {k: (v + 0.05 * torch.randn(v.shape, generator=g) * v.abs().mean() if v.dtype.is_floating_point and k.startswith("model.")
+                   else v) for k, v in state.items()}
+    model.load_state_dict(changed)  # in-place copy_: same addresses, bumped versions
+    want = model.predict_action(obs, noises=noises, use_cuda_graph=False)["action_pred"]
+    got = model.predict_action(obs, noises=noises, use_cuda_graph=True)["action_pred"]
+    assert float((want - first).abs().max()) > 2e-2  # the change is visible in the output, 10x above the bound below
+    # graph vs eager run the same kernels; the bound covers the fp32-atomic K-split noise fed back through 10 steps
+    assert float((got - want).abs().max()) <= 2e-3, "graphed sampler replayed stale weights"
+    with torch.no_grad():  # an in-place optimizer-style update
+        for p_ in model.model.parameters():
+            p_.mul_(0.97)
+    want2 = model.predict_action(obs, noises=noises, use_cuda_graph=False)["action_pred"]
+    got2 = model.predict_action(obs, noises=noises, use_cuda_graph=True)["action_pred"]
+    assert float((got2 - want2).abs().max()) <= 2e-3 and float((want2 - want).abs().max()) > 2e-2
+
+
 @pytest.mark.parametrize("path", GOLDEN_DPENC)
 def test_encoder_variants_match_reference_fixture(path):
     """`use_mask` (+ bg_ratio, with and without the sync-free size hints) and `pre_sample` variants of
