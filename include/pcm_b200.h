@@ -244,6 +244,20 @@ int pcm_sa_bwd_scatter(int m, int k, int H, const float *dout, const float *out,
                        const unsigned char *jsel, const int *idx, const float *xyz,
                        const float *new_xyz, const float *coef, float *dPf, double *gstats,
                        pcm_stream_t stream);
+/* Token-layout variants (the set-abstraction head feeding the transformer): query q = b * per_cloud + mi is row
+ * (head_rows + mi) * batch + b of the seq-first (S, B, H) token tensor that transformer.py:75-92 builds with
+ * flatten / permute / cat passes.  pcm_sa_output_tokens also emits the bf16 operand copies bf16(out) and
+ * bf16(out + pos) of the first encoder layer's projections (either may be NULL); pcm_sa_bwd_scatter_tokens reads
+ * dout (+ optional second gradient dout2, summed on load) and out in that layout. */
+int pcm_sa_output_tokens(int m, int H, int per_cloud, int batch, int head_rows, const float *ymax,
+                         const float *ymin, const unsigned char *jmax, const unsigned char *jmin,
+                         const float *coef, const float *pos, float *out, void *out_bf16,
+                         void *out_pos_bf16, unsigned char *jsel, pcm_stream_t stream);
+int pcm_sa_bwd_scatter_tokens(int m, int k, int H, int per_cloud, int batch, int head_rows,
+                              const float *dout, const float *dout2, const float *out,
+                              const unsigned char *jsel, const int *idx, const float *xyz,
+                              const float *new_xyz, const float *coef, float *dPf, double *gstats,
+                              pcm_stream_t stream);
 int pcm_sa_edge_stats(int m, int k, const int *idx, const float *xyz, const float *new_xyz,
                       float *cnt, float *sq, double *sdtot, pcm_stream_t stream);
 int pcm_sa_bwd_coef(int H, const double *gstats, const double *fstats, const double *sdtot,
@@ -371,6 +385,44 @@ int pcm_bn_apply_relu(long long R, int C, const float *y, const float *coef, int
 int pcm_bn_relu_bwd(long long R, int C, const float *dout, const float *y, const float *coef, int relu,
                     int training, double *gstats, float *dy, void *dy_bf16, float *dgamma, float *dbeta,
                     pcm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Observation tokens and action heads of ACT.
+ *   pcm_coord_embed_sine_tokens: ACTPCD.coord_embedding_sine (src/models/components/act/act.py:467-506,
+ *     normalize=False; dim_t (npf) = temperature ** (2 * (j // 2) / npf) supplied by the caller) written straight
+ *     into the positional tensor pos (S, B, E), S = head_rows + per_cloud: rows < head_rows = add_pos
+ *     (additional_pos_embed, transformer.py:82-88) broadcast over the batch, row (head_rows + mi, b) = embedding of
+ *     coord[b * per_cloud + mi]: per axis [sin(x / dim_t[0::2]) | cos(x / dim_t[1::2])] (act.py:494-502; npf even);
+ *     channels [3 * npf, E) are zero (act.py:505).
+ *   pcm_fill_head_rows: rows 0 .. head_rows-1 of the token tensor = [latent (B, E) ; proprio (head_rows-1, B, E)]
+ *     (transformer.py:89-92) + optional bf16(tokens) / bf16(tokens + pos) for those rows.
+ *   pcm_act_heads_loss_fwd / _bwd: a_hat = action_head(hs) (outputs d >= sig_start through a sigmoid: RLBench
+ *     gripper / collision, act.py:770-795), is_pad_hat = is_pad_head(hs), action_loss = mean(w_d * (a_hat - a)^2 *
+ *     ~is_pad) with w_d = w_pos for d < n_pos else 1 (act.py:272-291,800-825), kl = KLDivergence(mu, logvar)
+ *     (loss/misc.py:11-26), losses = [action_loss + kl_weight * kl, action_loss, kl].  hs row (b, q) lives at
+ *     hs + b * ld_b + q * ld_q (the decoder output is (Q, B, E) in memory).  actions == NULL: heads only.
+ *     acc (1 double) / ticket (1 uint32) are a zero-initialised workspace the kernel leaves zeroed.
+ *     Backward: upstream scalars g_loss / g_action / g_kl and optional g_a_hat (B, Q, A) / g_pad (B, Q); writes d_hs,
+ *     dmu, dlogvar and ACCUMULATES dWa, dba (and dWp, dbp when g_pad is given).
+ * ------------------------------------------------------------------------------------------ */
+int pcm_coord_embed_sine_tokens(int per_cloud, int batch, int head_rows, int E, int npf, const float *coord,
+                                const float *dim_t, const float *add_pos, float *pos, pcm_stream_t stream);
+int pcm_fill_head_rows(int batch, int head_rows, int E, const float *latent, const float *proprio,
+                       const float *pos, float *tokens, void *tokens_bf16, void *tokens_pos_bf16,
+                       pcm_stream_t stream);
+int pcm_act_heads_loss_fwd(int B, int Q, int E, int A, int L, int sig_start, int n_pos, float w_pos,
+                           float kl_weight, const float *hs, long long ld_b, long long ld_q, const float *Wa,
+                           const float *ba, const float *Wp, const float *bp, const float *actions,
+                           const unsigned char *is_pad, const float *mu, const float *logvar, float *a_hat,
+                           float *is_pad_hat, float *losses, double *acc, unsigned int *ticket,
+                           pcm_stream_t stream);
+int pcm_act_heads_loss_bwd(int B, int Q, int E, int A, int L, int sig_start, int n_pos, float w_pos,
+                           float kl_weight, const float *hs, long long ld_b, long long ld_q, const float *Wa,
+                           const float *Wp, const float *actions, const unsigned char *is_pad, const float *mu,
+                           const float *logvar, const float *a_hat, const float *g_loss, const float *g_action,
+                           const float *g_kl, const float *g_a_hat, const float *g_pad, float *d_hs,
+                           long long dld_b, long long dld_q, float *dWa, float *dba, float *dWp, float *dbp,
+                           float *dmu, float *dlogvar, pcm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -156,7 +156,38 @@ class ACTPCD(nn.Module):
     def _sample_indices(self, p, o32, n_o, mask, hints):
         return sample_indices(p, o32, self.pcd_npoints, mask if self.use_mask else None, self.bg_ratio, hints)
 
-    def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None, hints=None):
+    def _n_head_rows(self):
+        """Non-point rows in front of the encoder sequence: latent, proprio (+ goal) (transformer.py:89-92)."""
+        return 2 + int(self.goal_cond_dim > 0)
+
+    def _token_fast_path(self, feat):
+        """True when the set-abstraction head can write the transformer's (S, B, E) token tensor directly (and the sine
+        embedding its positional tensor): our own Transformer, fused-kernel widths, CUDA, head in front of the encoder."""
+        return (not self.pre_sample and feat.is_cuda and getattr(self.transformer, "accepts_token_buffers", False)
+                and self.hidden_dim % 4 == 0 and self.linear.weight.shape[0] == self.hidden_dim
+                and feat.shape[1] % 8 == 0 and self.hidden_dim % 8 == 0)
+
+    def coord_embedding_sine_tokens(self, coord, b, temperature=10000):
+        """`coord_embedding_sine` of the sampled coordinates, written by ONE kernel straight into the transformer's
+        positional tensor (S, B, E) = [additional_pos_embed rows (broadcast over the batch) ; sine rows] -- replaces the
+        dozen elementwise kernels below plus the flatten / permute / repeat / cat passes of transformer.py:75-88."""
+        from ._lib import check, current_stream, lib, ptr
+
+        E, head = self.hidden_dim, self._n_head_rows()
+        npf = E // 3
+        dt = getattr(self, "_dim_t", None)
+        if dt is None or dt.device != coord.device or dt.numel() != npf:
+            j = torch.arange(npf, dtype=torch.float32, device=coord.device)
+            dt = self._dim_t = (temperature ** (2 * (j // 2) / npf)).contiguous()
+        per = coord.shape[0] // b
+        pos = torch.empty((head + per, b, E), dtype=torch.float32, device=coord.device)
+        add = self.additional_pos_embed.weight.detach()
+        check(lib.pcm_coord_embed_sine_tokens(per, b, head, E, npf, ptr(coord.contiguous()), ptr(dt), ptr(add), ptr(pos),
+                                              current_stream()), "pcm_coord_embed_sine_tokens")
+        pos._pcm_add_pos = self.additional_pos_embed.weight
+        return pos
+
+    def pcd_sampling(self, pxo, mask=None, return_index=False, n_max=None, hints=None, tokens=False):
         p, x, o = pxo
         b = o.shape[0]
         pre = getattr(self, "_presampled", None)
@@ -175,7 +206,14 @@ class ACTPCD(nn.Module):
             idx = self._sample_indices(p, o32, n_o, mask, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
-        x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
+        if tokens:
+            pos = getattr(self, "_presampled_pos", None)
+            if pos is None or pos.dim() != 3:
+                pos = self._presampled_pos = self.coord_embedding_sine_tokens(n_p, b)
+            x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn,
+                                   tokens=(b, self._n_head_rows(), pos))
+        else:
+            x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
         if return_index:
             return [n_p, x, n_o, idx]
         return [n_p, x, n_o]
@@ -206,10 +244,21 @@ class ACTPCD(nn.Module):
             features = self.backbone(pcd_dict)
         else:
             features = self.backbone(pcd_dict)
+            if self._token_fast_path(features):
+                # the head writes the (S, B, E) token tensor itself; hand the transformer (b, c, 1, n) VIEWS of the point
+                # rows (the reference's shapes) that carry the full buffers (`_pcm_tokens`)
+                coord, tok, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]), mask, hints=hints, tokens=True)
+                pos_tok = self._presampled_pos
+                self._presampled_pos = None
+                head = self._n_head_rows()
+                fv = tok[head:].permute(1, 2, 0).unsqueeze(2)
+                pv = pos_tok[head:].permute(1, 2, 0).unsqueeze(2)
+                fv._pcm_tokens, pv._pcm_tokens = tok, pos_tok
+                return fv, pv
             coord, features, _ = self.pcd_sampling((pcd_dict["coord"], features, pcd_dict["offset"]), mask, hints=hints)
         pcd_pos = getattr(self, "_presampled_pos", None)  # computed on the FPS / kNN side stream when forked
         self._presampled_pos = None
-        if pcd_pos is None:
+        if pcd_pos is None or pcd_pos.dim() != 2:
             pcd_pos = self.coord_embedding_sine(coord)
         b = pcd_dict["offset"].shape[0]
         features = features.view(b, self.pcd_npoints, -1).permute(0, 2, 1).unsqueeze(2)  # (b, c, 1, n)
@@ -240,7 +289,9 @@ class ACTPCD(nn.Module):
 
     # ---- heads + loss (act.py:255-291) -------------------------------------------------------
     def forward_decoder(self, data_dict):
-        hs = self._decode(data_dict)
+        hs = data_dict.pop("_hs", None)  # already decoded by a `_fused_heads` attempt that fell back
+        if hs is None:
+            hs = self._decode(data_dict)
         data_dict["a_hat"] = PF.linear(hs, self.action_head.weight, self.action_head.bias)
         data_dict["is_pad_hat"] = PF.linear(hs, self.is_pad_head.weight, self.is_pad_head.bias)
         return data_dict
@@ -252,6 +303,33 @@ class ACTPCD(nn.Module):
         data_dict["action_loss"], data_dict["kl_loss"] = action_loss, total_kld
         data_dict["loss"] = action_loss + total_kld * self.kl_weight
         return data_dict
+
+    def _head_cfg(self):
+        """(sigmoid start index, position dims, position loss weight) of the action head; ManiSkill: plain MSE."""
+        return self.action_dim, 0, 1.0
+
+    def _fused_heads(self, data_dict):
+        """Heads (+ loss when training) as ONE kernel each way (csrc/tokens.cu); returns False when the configuration
+        needs the composed path (custom loss modules, widths the kernel does not cover)."""
+        if not (type(self.action_loss) is nn.MSELoss and self.action_loss.reduction == "none"
+                and type(self.klloss).__name__ == "KLDivergence"):
+            return False
+        hs = self._decode(data_dict)
+        data_dict["_hs"] = hs
+        if not hs.is_cuda:
+            return False
+        training = data_dict["is_training"]
+        sig, n_pos, w_pos = self._head_cfg()
+        out = PF.act_heads_loss(hs, self.action_head, self.is_pad_head, data_dict["actions"] if training else None,
+                                data_dict["is_pad"] if training else None, data_dict["mu"] if training else None,
+                                data_dict["logvar"] if training else None, self.kl_weight, sig, n_pos, w_pos)
+        if out is None:
+            return False
+        data_dict["a_hat"], data_dict["is_pad_hat"] = out[0], out[1]
+        if training:
+            data_dict["loss"], data_dict["action_loss"], data_dict["kl_loss"] = out[2], out[3], out[4]
+        data_dict.pop("_hs", None)
+        return True
 
     def _presample(self, data_dict):
         """FPS + kNN depend only on the input coordinates and are latency-bound (a chain of M-1
@@ -274,8 +352,12 @@ class ACTPCD(nn.Module):
             idx = self._sample_indices(p, o32, n_o, pcd.get("mask", None) if self.use_mask else None, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
-            # the sine embedding of the sampled coordinates (a dozen small elementwise kernels) depends on n_p only
-            self._presampled_pos = self.coord_embedding_sine(n_p)
+            # the sine embedding of the sampled coordinates depends on n_p only
+            if (not self.pre_sample and getattr(self.transformer, "accepts_token_buffers", False)
+                    and self.linear.weight.shape[0] == self.hidden_dim and self.hidden_dim % 8 == 0):
+                self._presampled_pos = self.coord_embedding_sine_tokens(n_p, b)
+            else:
+                self._presampled_pos = self.coord_embedding_sine(n_p)
         self._presampled = (side, n_o, o32, idx, n_p, knn_idx)
 
     def sync_free(self, pcds) -> bool:
@@ -315,10 +397,15 @@ class ACTPCD(nn.Module):
             for k in ("latent_input", "mu", "logvar"):
                 if torch.is_tensor(data_dict.get(k, None)):
                     data_dict[k].record_stream(main)
+        if self._fused_heads(data_dict):
+            return self._finish_inference(data_dict) if not data_dict["is_training"] else data_dict
         data_dict = self.forward_decoder(data_dict)
         if not data_dict["is_training"]:
             return data_dict
         return self.forward_loss(data_dict)
+
+    def _finish_inference(self, data_dict):
+        return data_dict
 
 
 class ACTRLBenchPCD(ACTPCD):
@@ -328,8 +415,23 @@ class ACTRLBenchPCD(ACTPCD):
         super().__init__(*args, **kwargs)
         self.rot_type, self.collision, self.position_loss_weight = rot_type, collision, position_loss_weight
 
+    def _head_cfg(self):
+        return self.action_dim - (2 if self.collision else 1), 3, float(self.position_loss_weight)
+
+    def _finish_inference(self, data_dict):
+        """act.py:785-795 after the fused heads (sigmoids already applied): rot6d -> quaternion."""
+        if self.rot_type != "6d":
+            raise NotImplementedError
+        a = data_dict["a_hat"]
+        sig = self._head_cfg()[0]
+        rot = _matrix_to_quaternion(_rotation_6d_to_matrix(a[..., 3:sig]))
+        data_dict["a_hat"] = torch.cat([a[..., :3], rot, a[..., sig:]], dim=-1)
+        return data_dict
+
     def forward_decoder(self, data_dict):
-        hs = self._decode(data_dict)
+        hs = data_dict.pop("_hs", None)
+        if hs is None:
+            hs = self._decode(data_dict)
         a_hat = PF.linear(hs, self.action_head.weight, self.action_head.bias)
         position = a_hat[..., :3]
         if self.collision:

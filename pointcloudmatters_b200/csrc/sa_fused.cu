@@ -140,12 +140,58 @@ __global__ void __launch_bounds__(256) sa_output_kernel(const float* __restrict_
     }
 }
 
+// ---- token-layout variant of sa_output_kernel -------------------------------------------------
+// Query q = b * per + mi of cloud b is written to row (head + mi) * batch + b of the transformer's seq-first
+// (S, B, H) token tensor (transformer.py:75-92 builds it with flatten / permute / cat passes), together with the
+// bf16 operand copies of the first encoder layer's projections: bf16(out) and bf16(out + pos).
+__global__ void __launch_bounds__(256) sa_output_tokens_kernel(
+    const float* __restrict__ ymax, const float* __restrict__ ymin, const unsigned char* __restrict__ jmax,
+    const unsigned char* __restrict__ jmin, const float* __restrict__ coef, long total, int H, int per, int batch, int head,
+    const float* __restrict__ pos, float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
+    __nv_bfloat16* __restrict__ out_pb, unsigned char* __restrict__ jsel) {
+    for (long e = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < total; e += (long)gridDim.x * blockDim.x * 4) {
+        const long q = e / H;
+        const int c = (int)(e - q * H);
+        const long row = (long)(head + (int)(q % per)) * batch + q / per;
+        const long d = row * H + c;
+        const float4 a = ld4(coef + c), b = ld4(coef + H + c);
+        const float4 hi = ld4(ymax + e), lo = ld4(ymin + e);
+        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = *reinterpret_cast<const uchar4*>(jmin + e);
+        float4 o;
+        uchar4 js;
+        o.x = fmaxf(fmaf(a.x, a.x >= 0.f ? hi.x : lo.x, b.x), 0.f); js.x = a.x >= 0.f ? jh.x : jl.x;
+        o.y = fmaxf(fmaf(a.y, a.y >= 0.f ? hi.y : lo.y, b.y), 0.f); js.y = a.y >= 0.f ? jh.y : jl.y;
+        o.z = fmaxf(fmaf(a.z, a.z >= 0.f ? hi.z : lo.z, b.z), 0.f); js.z = a.z >= 0.f ? jh.z : jl.z;
+        o.w = fmaxf(fmaf(a.w, a.w >= 0.f ? hi.w : lo.w, b.w), 0.f); js.w = a.w >= 0.f ? jh.w : jl.w;
+        *reinterpret_cast<float4*>(out + d) = o;
+        *reinterpret_cast<uchar4*>(jsel + e) = js;
+        if (out_b) {
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(o.x, o.y), h2 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&l2);
+            pk.y = *reinterpret_cast<uint32_t*>(&h2);
+            *reinterpret_cast<uint2*>(out_b + d) = pk;
+        }
+        if (out_pb) {
+            const float4 p4 = ld4(pos + d);
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(o.x + p4.x, o.y + p4.y), h2 = __floats2bfloat162_rn(o.z + p4.z, o.w + p4.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&l2);
+            pk.y = *reinterpret_cast<uint32_t*>(&h2);
+            *reinterpret_cast<uint2*>(out_pb + d) = pk;
+        }
+    }
+}
+
 // ---- backward pass 1: per-channel reductions + sparse scatter ----------------------------------
 // gstats rows: 0 dbeta = sum dz, 1 dgamma = sum dz*xhat_sel, 2..4 sum a*dz*dxyz_sel (sparse dWx)
 __global__ void __launch_bounds__(256) sa_bwd_scatter_kernel(
     const float* __restrict__ dout, const float* __restrict__ out, const unsigned char* __restrict__ jsel,
     const int* __restrict__ idx, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-    const float* __restrict__ coef, int m, int k, int H, float* __restrict__ dPf, double* __restrict__ gstats) {
+    const float* __restrict__ coef, int m, int k, int H, float* __restrict__ dPf, double* __restrict__ gstats,
+    int per, int batch, int head, const float* __restrict__ dout2) {
+    // per > 0: dout / out (and the optional second gradient dout2, summed on load) are in the token layout of
+    // sa_output_tokens_kernel; per == 0: query-major rows.
     const int c0 = threadIdx.x * 4;
     const bool act = c0 < H;
     float a[4], b[4], mean[4], invstd[4];
@@ -160,7 +206,13 @@ __global__ void __launch_bounds__(256) sa_bwd_scatter_kernel(
     for (int q = blockIdx.x; q < m; q += gridDim.x) {
         if (!act) continue;
         const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
-        const float4 d4 = ld4(dout + (size_t)q * H + c0), o4 = ld4(out + (size_t)q * H + c0);
+        const size_t row = per > 0 ? (size_t)(head + q % per) * batch + q / per : (size_t)q;
+        float4 d4 = ld4(dout + row * H + c0);
+        const float4 o4 = ld4(out + row * H + c0);
+        if (dout2) {
+            const float4 e4 = ld4(dout2 + row * H + c0);
+            d4.x += e4.x; d4.y += e4.y; d4.z += e4.z; d4.w += e4.w;
+        }
         const uchar4 j4 = *reinterpret_cast<const uchar4*>(jsel + (size_t)q * H + c0);
         const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
         const int jv[4] = {j4.x, j4.y, j4.z, j4.w};
@@ -334,7 +386,32 @@ PCM_API int pcm_sa_bwd_scatter(int m, int k, int H, const float* dout, const flo
     if (!dout || !out || !jsel || !idx || !xyz || !new_xyz || !coef || !dPf || !gstats) return PCM_EINVAL;
     if (H % 4 || H > 4096) return PCM_EUNSUPPORTED;
     sa_bwd_scatter_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(dout, out, jsel, idx, xyz, new_xyz, coef, m, k, H,
-                                                                                  dPf, gstats);
+                                                                                  dPf, gstats, 0, 0, 0, nullptr);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_output_tokens(int m, int H, int per_cloud, int batch, int head_rows, const float* ymax, const float* ymin,
+                                 const unsigned char* jmax, const unsigned char* jmin, const float* coef, const float* pos,
+                                 float* out, void* out_bf16, void* out_pos_bf16, unsigned char* jsel, pcm_stream_t stream) {
+    const long total = (long)m * H;
+    if (total <= 0) return PCM_OK;
+    if (!ymax || !ymin || !jmax || !jmin || !coef || !out || !jsel || (out_pos_bf16 && !pos)) return PCM_EINVAL;
+    if (H % 4 || per_cloud <= 0 || batch <= 0 || head_rows < 0 || (long)per_cloud * batch != m) return PCM_EUNSUPPORTED;
+    sa_output_tokens_kernel<<<sa_grid((total / 4 + 255) / 256), 256, 0, pcm_cu_stream(stream)>>>(
+        ymax, ymin, jmax, jmin, coef, total, H, per_cloud, batch, head_rows, pos, out, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+        reinterpret_cast<__nv_bfloat16*>(out_pos_bf16), jsel);
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_bwd_scatter_tokens(int m, int k, int H, int per_cloud, int batch, int head_rows, const float* dout,
+                                      const float* dout2, const float* out, const unsigned char* jsel, const int* idx,
+                                      const float* xyz, const float* new_xyz, const float* coef, float* dPf, double* gstats,
+                                      pcm_stream_t stream) {
+    if (m <= 0) return PCM_OK;
+    if (!dout || !out || !jsel || !idx || !xyz || !new_xyz || !coef || !dPf || !gstats) return PCM_EINVAL;
+    if (H % 4 || H > 4096 || per_cloud <= 0 || batch <= 0 || head_rows < 0 || (long)per_cloud * batch != m) return PCM_EUNSUPPORTED;
+    sa_bwd_scatter_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(dout, out, jsel, idx, xyz, new_xyz, coef, m, k, H,
+                                                                                  dPf, gstats, per_cloud, batch, head_rows, dout2);
     return pcm_launch_status();
 }
 

@@ -121,6 +121,9 @@ def _grad_slot(p):
 #    a reference to the fp32 gradient (its memory cannot be recycled under a live key) and the table
 #    is emptied by the next LayerNorm backward, so a key can never outlive its tensor.
 _GRAD_BF16 = {}
+# second gradient tensor travelling with the one autograd carries (two-handle outputs, see _FillHeadRows): keyed by the
+# carried gradient's address, value (second gradient, carried gradient); popped by the consumer
+_GRAD_EXTRA = {}
 
 
 def _act_bf16(x, rows, C):
@@ -799,7 +802,10 @@ class _SetAbstraction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, weight, gamma, beta, p, new_p, knn_idx, running_mean, running_var, eps, momentum,
-                training, feat_b=None):
+                training, feat_b=None, tok=None):
+        """`tok` = (batch, head_rows, pos or None, out_bf16, out_pos_bf16 or None): write the result straight into the
+        transformer's seq-first token tensor (S, B, H) -- query b * M + mi -> row (head_rows + mi) * B + b; the head rows
+        are left for `fill_head_rows` -- and emit bf16(out) / bf16(out + pos), the operands of the first encoder layer."""
         from ._lib import check, current_stream, lib, ptr
 
         n, C = feat.shape
@@ -822,10 +828,23 @@ class _SetAbstraction(torch.autograd.Function):
         check(lib.pcm_sa_bn_finalize(H, ptr(stats), float(m * k), ptr(gamma), ptr(beta), float(eps), float(momentum),
                                      int(training), ptr(running_mean), ptr(running_var), ptr(coef), st),
               "pcm_sa_bn_finalize")
-        out = torch.empty((m, H), dtype=torch.float32, device=dev)
-        check(lib.pcm_sa_output(m, H, ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(coef), ptr(out), ptr(jmax), st),
-              "pcm_sa_output")  # jsel overwrites jmax in place
-        ctx.save_for_backward(featb, wfb, Pf, p, new_p, knn_idx, weight, out, jmax, coef, stats)
+        ctx.tok = None
+        if tok is None:
+            out = torch.empty((m, H), dtype=torch.float32, device=dev)
+            check(lib.pcm_sa_output(m, H, ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(coef), ptr(out), ptr(jmax), st),
+                  "pcm_sa_output")  # jsel overwrites jmax in place
+            saved_out = out
+        else:
+            B, head, pos, out_b, out_pb = tok
+            per = m // B
+            out = torch.empty((head + per, B, H), dtype=torch.float32, device=dev)
+            check(lib.pcm_sa_output_tokens(m, H, per, B, head, ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(coef), ptr(pos),
+                                           ptr(out), ptr(out_b), ptr(out_pb), ptr(jmax), st), "pcm_sa_output_tokens")
+            ctx.tok = (B, head, per)
+            # a second handle on the storage for backward: `fill_head_rows` writes the head rows of `out` in place later
+            # (which bumps the version counter of `out` itself)
+            saved_out = torch.empty(0, dtype=out.dtype, device=dev).set_(out.untyped_storage(), 0, out.shape, out.stride())
+        ctx.save_for_backward(featb, wfb, Pf, p, new_p, knn_idx, weight, saved_out, jmax, coef, stats)
         ctx.training = training
         return out
 
@@ -842,8 +861,16 @@ class _SetAbstraction(torch.autograd.Function):
         dout = dout.contiguous().float()
         dPf = torch.zeros((n, H), dtype=torch.float32, device=dev)
         gstats = torch.zeros((5, H), dtype=torch.float64, device=dev)
-        check(lib.pcm_sa_bwd_scatter(m, k, H, ptr(dout), ptr(out), ptr(jsel), ptr(knn_idx), ptr(p), ptr(new_p), ptr(coef),
-                                     ptr(dPf), ptr(gstats), st), "pcm_sa_bwd_scatter")
+        if ctx.tok is None:
+            check(lib.pcm_sa_bwd_scatter(m, k, H, ptr(dout), ptr(out), ptr(jsel), ptr(knn_idx), ptr(p), ptr(new_p), ptr(coef),
+                                         ptr(dPf), ptr(gstats), st), "pcm_sa_bwd_scatter")
+        else:
+            B, head, per = ctx.tok
+            e = _GRAD_EXTRA.pop(dout.data_ptr(), None)  # second gradient of the token tensor (residual branch)
+            dout2 = e[0] if (e is not None and e[1].data_ptr() == dout.data_ptr() and e[0].shape == dout.shape) else None
+            check(lib.pcm_sa_bwd_scatter_tokens(m, k, H, per, B, head, ptr(dout), ptr(dout2), ptr(out), ptr(jsel), ptr(knn_idx),
+                                                ptr(p), ptr(new_p), ptr(coef), ptr(dPf), ptr(gstats), st),
+                  "pcm_sa_bwd_scatter_tokens")
         cnt = torch.zeros(n, dtype=torch.float32, device=dev)
         sq = torch.zeros((n, 3), dtype=torch.float32, device=dev)
         sdtot = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -862,12 +889,14 @@ class _SetAbstraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dfeat = K.gemm_bf16(dPfb, wfb, b_mn=True)  # (n, H) x Wf(H, C)
         K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=0)
-        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
-def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn):
+def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn, tokens=None):
     """Grouped Linear(3+C -> H, no bias) + BatchNorm1d + ReLU + max over the k neighbours
-    (act.py:446-460) as ONE fused operator.  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H)."""
+    (act.py:446-460) as ONE fused operator.  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H).
+    `tokens` = (batch, head_rows, pos (S, B, H) or None): return the transformer's seq-first token tensor (S, B, H)
+    instead, with the point rows filled (see `fill_head_rows` for the rest) and the bf16 operand copies attached."""
     _need_cuda(feat)
     training = bn.training or (bn.running_mean is None)
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -889,9 +918,169 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
             bn.running_mean.copy_(rm[:H])
             bn.running_var.copy_(rv[:H])
         return out[:, :H]
-    return _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
-                                 knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training,
-                                 _act_bf16(feat, feat.shape[0], C))
+    tok = None
+    if tokens is not None:
+        B, head, pos = tokens
+        m = knn_idx.shape[0]
+        if H % 4 or m % B:
+            raise PcmError("token-layout set abstraction needs H % 4 == 0 and the same number of queries per cloud")
+        S = head + m // B
+        if pos is not None and (tuple(pos.shape) != (S, B, H) or not pos.is_contiguous() or pos.dtype != torch.float32):
+            raise PcmError("pos must be a contiguous fp32 (S, B, H) tensor")
+        out_b = torch.empty((S, B, H), dtype=torch.bfloat16, device=feat.device)
+        out_pb = torch.empty_like(out_b) if pos is not None else None
+        tok = (B, head, pos, out_b, out_pb)
+    out = _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
+                                knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training,
+                                _act_bf16(feat, feat.shape[0], C), tok)
+    if tok is not None:
+        out._pcm_bf16 = tok[3]
+        if tok[4] is not None:
+            out._pcm_bf16_pos = (pos, tok[4])
+    return out
+
+
+class _FillHeadRows(torch.autograd.Function):
+    """Rows 0 .. head-1 of the seq-first token tensor (S, B, E) = [latent ; proprio / goal] (transformer.py:89-92), written
+    IN PLACE by one small kernel (the point rows come from the token-layout set abstraction), together with the bf16
+    operand copies of those rows.  Returns two handles on the same storage (see _AddDropoutLN): the second one is what
+    the first LayerNorm takes as its residual operand, so the two gradient contributions of the tokens arrive
+    separately and are summed inside the set-abstraction backward kernel instead of by an autograd add pass."""
+
+    @staticmethod
+    def forward(ctx, tokens, latent, proprio, pos, tok_b, tok_pb):
+        from ._lib import check, current_stream, lib, ptr
+
+        S, B, E = tokens.shape
+        head = 1 + (proprio.shape[0] if proprio is not None else 0)
+        latent2 = latent.reshape(B, E).contiguous()
+        prop2 = proprio.reshape(head - 1, B, E).contiguous() if proprio is not None else None
+        check(lib.pcm_fill_head_rows(B, head, E, ptr(latent2), ptr(prop2), ptr(pos), ptr(tokens), ptr(tok_b),
+                                     ptr(tok_pb if pos is not None else None), current_stream()), "pcm_fill_head_rows")
+        ctx.mark_dirty(tokens)
+        ctx.head = head
+        ctx.shapes = (latent.shape, None if proprio is None else proprio.shape)
+        res = torch.empty(0, dtype=tokens.dtype, device=tokens.device).set_(tokens.untyped_storage(), tokens.storage_offset(),
+                                                                            tokens.shape, tokens.stride())
+        ctx.set_materialize_grads(False)
+        return tokens, res
+
+    @staticmethod
+    def backward(ctx, d_tok, d_res):
+        if d_tok is None:
+            d_tok, d_res = d_res, None
+        if d_tok is None:
+            return (None,) * 6
+        head = ctx.head
+        lat_shape, prop_shape = ctx.shapes
+        d_tok = d_tok.contiguous()
+        dh = d_tok[:head]
+        if d_res is not None:
+            d_res = d_res.contiguous()
+            dh = dh + d_res[:head]
+            _GRAD_EXTRA[d_tok.data_ptr()] = (d_res, d_tok)  # popped by the set-abstraction backward
+        d_lat = dh[0].reshape(lat_shape) if ctx.needs_input_grad[1] else None
+        d_prop = dh[1:].reshape(prop_shape) if (prop_shape is not None and ctx.needs_input_grad[2]) else None
+        return d_tok, d_lat, d_prop, None, None, None
+
+
+def fill_head_rows(tokens, latent, proprio, pos=None):
+    """Complete the token tensor produced by `set_abstraction(..., tokens=...)`; returns it with the bf16 operand copies
+    (`_pcm_bf16`, `_pcm_bf16_pos`) and the residual-branch handle (`_pcm_res`) attached."""
+    tok_b = getattr(tokens, "_pcm_bf16", None)
+    pe = getattr(tokens, "_pcm_bf16_pos", None)
+    tok_pb = pe[1] if (pe is not None and pe[0] is pos) else None
+    out, res = _FillHeadRows.apply(tokens, latent, proprio, pos if tok_pb is not None else None, tok_b, tok_pb)
+    out._pcm_res = res
+    if tok_b is not None:
+        out._pcm_bf16 = tok_b
+    if tok_pb is not None:
+        out._pcm_bf16_pos = (pos, tok_pb)
+    return out
+
+
+class _ActHeadsLoss(torch.autograd.Function):
+    """action_head + is_pad_head + masked MSE + KL (act.py:255-291, RLBench :770-825) as one kernel each way
+    (csrc/tokens.cu).  Outputs (a_hat, is_pad_hat, losses[3]); `actions is None`: heads only."""
+
+    @staticmethod
+    def forward(ctx, hs, Wa, ba, Wp, bp, actions, is_pad, mu, logvar, cfg):
+        from ._lib import check, current_stream, lib, ptr
+
+        sig_start, n_pos, w_pos, kl_weight = cfg
+        B, Q, E = hs.shape
+        A = Wa.shape[0]
+        dev = hs.device
+        assert hs.stride(2) == 1
+        a_hat = torch.empty((B, Q, A), dtype=torch.float32, device=dev)
+        pad_hat = torch.empty((B, Q, 1), dtype=torch.float32, device=dev)
+        losses = torch.zeros(3, dtype=torch.float32, device=dev) if actions is not None else None
+        ws = _workspace("heads_loss_ws", (4,), torch.float64, dev, zero=True)  # acc (1 double) + ticket; self-cleaning
+        pad_u8 = is_pad.contiguous().view(torch.uint8) if is_pad is not None else None
+        act_c = actions.contiguous().float() if actions is not None else None
+        mu_c = mu.contiguous() if mu is not None else None
+        lv_c = logvar.contiguous() if logvar is not None else None
+        L = mu.shape[1] if mu is not None else 0
+        check(lib.pcm_act_heads_loss_fwd(B, Q, E, A, L, int(sig_start), int(n_pos), float(w_pos), float(kl_weight), ptr(hs),
+                                         hs.stride(0), hs.stride(1), ptr(Wa), ptr(ba), ptr(Wp), ptr(bp), ptr(act_c), ptr(pad_u8),
+                                         ptr(mu_c), ptr(lv_c), ptr(a_hat), ptr(pad_hat), ptr(losses), ptr(ws), ptr(ws[1:]),
+                                         current_stream()), "pcm_act_heads_loss_fwd")
+        ctx.save_for_backward(hs, Wa, Wp, act_c, pad_u8, mu_c, lv_c, a_hat)
+        ctx.cfg = cfg
+        ctx.params = (Wa, ba, Wp, bp)
+        ctx.set_materialize_grads(False)
+        if losses is None:
+            return a_hat, pad_hat, None, None, None
+        return a_hat, pad_hat, losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_a_hat, g_pad, g_loss, g_action, g_kl):
+        from ._lib import check, current_stream, lib, ptr
+
+        hs, Wa, Wp, act_c, pad_u8, mu_c, lv_c, a_hat = ctx.saved_tensors
+        sig_start, n_pos, w_pos, kl_weight = ctx.cfg
+        B, Q, E = hs.shape
+        A = Wa.shape[0]
+        dev = hs.device
+        pWa, pba, pWp, pbp = ctx.params
+        g_loss, g_action, g_kl = (None if g is None else g.reshape(1).float() for g in (g_loss, g_action, g_kl))
+        slots = [_grad_slot(pWa), _grad_slot(pba)]
+        dWa = slots[0] if slots[0] is not None else torch.zeros_like(Wa)
+        dba = slots[1] if slots[1] is not None else torch.zeros(A, dtype=torch.float32, device=dev)
+        dWp = dbp = None
+        pslots = [None, None]
+        if g_pad is not None:
+            pslots = [_grad_slot(pWp), _grad_slot(pbp)]
+            dWp = pslots[0] if pslots[0] is not None else torch.zeros_like(Wp)
+            dbp = pslots[1] if pslots[1] is not None else torch.zeros(1, dtype=torch.float32, device=dev)
+            g_pad = g_pad.contiguous().float()
+        if g_a_hat is not None:
+            g_a_hat = g_a_hat.contiguous().float()
+        d_hs = torch.empty((Q, B, E), dtype=torch.float32, device=dev)  # the decoder's (Q, B, E) memory order
+        dmu = torch.empty_like(mu_c) if mu_c is not None else None
+        dlv = torch.empty_like(lv_c) if lv_c is not None else None
+        L = mu_c.shape[1] if mu_c is not None else 0
+        check(lib.pcm_act_heads_loss_bwd(B, Q, E, A, L, int(sig_start), int(n_pos), float(w_pos), float(kl_weight), ptr(hs),
+                                         hs.stride(0), hs.stride(1), ptr(Wa), ptr(Wp), ptr(act_c), ptr(pad_u8), ptr(mu_c),
+                                         ptr(lv_c), ptr(a_hat), ptr(g_loss), ptr(g_action), ptr(g_kl), ptr(g_a_hat), ptr(g_pad), ptr(d_hs),
+                                         E, B * E, ptr(dWa), ptr(dba), ptr(dWp), ptr(dbp), ptr(dmu), ptr(dlv),
+                                         current_stream()), "pcm_act_heads_loss_bwd")
+        return (d_hs.transpose(0, 1), None if slots[0] is not None else dWa, None if slots[1] is not None else dba,
+                None if (g_pad is None or pslots[0] is not None) else dWp, None if (g_pad is None or pslots[1] is not None) else dbp,
+                None, None, dmu, dlv, None)
+
+
+def act_heads_loss(hs, action_head, is_pad_head, actions, is_pad, mu, logvar, kl_weight, sig_start=None, n_pos=0, w_pos=1.0):
+    """(a_hat, is_pad_hat, loss, action_loss, kl_loss) of the ACT heads on decoder features hs (B, Q, E) (any (b, q)
+    strides, contiguous channels); `actions is None` -> (a_hat, is_pad_hat, None, None, None).  Outputs
+    d >= sig_start pass through a sigmoid, the first n_pos dims of the squared error are weighted by w_pos (RLBench)."""
+    _need_cuda(hs)
+    A, E = action_head.weight.shape
+    if E % 128 or E > 1024 or A + 1 > 16 or hs.dtype != torch.float32 or hs.stride(2) != 1 or hs.stride(0) % 4 or hs.stride(1) % 4:
+        return None  # caller composes the heads from linear() (test fixtures with odd widths only)
+    cfg = (A if sig_start is None else sig_start, n_pos, w_pos, kl_weight)
+    return _ActHeadsLoss.apply(hs, action_head.weight, action_head.bias, is_pad_head.weight, is_pad_head.bias, actions, is_pad,
+                               mu, logvar, cfg)
 
 
 def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):

@@ -172,6 +172,9 @@ class Transformer(nn.Module):
         self._reset_parameters()
         self.d_model = d_model
         self.nhead = nhead
+        # `src` / `pos_embed` may be (b, c, 1, n) views that carry the complete seq-first (S, B, E) buffers they were cut
+        # from (attribute `_pcm_tokens`, see act.ACTPCD.forward_pcd_embed): the concatenations below are then skipped
+        self.accepts_token_buffers = True
 
     def _reset_parameters(self):
         for p in self.parameters():
@@ -181,6 +184,22 @@ class Transformer(nn.Module):
     def forward(self, src, mask, query_embed, pos_embed, latent_input=None, proprio_input=None,
                 additional_pos_embed=None):
         bs = src.shape[0]
+        tok, ptk = getattr(src, "_pcm_tokens", None), getattr(pos_embed, "_pcm_tokens", None)
+        if (tok is not None and ptk is not None and latent_input is not None and proprio_input is not None
+                and additional_pos_embed is not None and getattr(ptk, "_pcm_add_pos", None) is additional_pos_embed
+                and tok.shape == ptk.shape):
+            E = tok.shape[2]
+            prop = proprio_input.reshape(-1, bs, E)
+            if 1 + prop.shape[0] + src.shape[-1] == tok.shape[0]:
+                # token buffers written by the set-abstraction head / the sine-embedding kernel: only the latent / proprio
+                # rows are missing (one small kernel), the learned positional rows get their gradient through `pos_head`
+                src_tok = PF.fill_head_rows(tok, latent_input.reshape(bs, E), prop, ptk)
+                pos_head = additional_pos_embed.unsqueeze(1) if additional_pos_embed.requires_grad else None
+                query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
+                tgt = torch.zeros_like(query_embed)
+                memory = self.encoder(src_tok, src_key_padding_mask=mask, pos=ptk, pos_head=pos_head)
+                hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head)
+                return hs.transpose(1, 2)
         src = src.flatten(2).permute(2, 0, 1)
         pos_embed = pos_embed.flatten(2).permute(2, 0, 1)
         if pos_embed.shape[1] == 1:
