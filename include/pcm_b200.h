@@ -175,6 +175,18 @@ int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void *A, int lda, int
                      long long b_rows_total, long long b_batch_rows, void *C, int ldc, int c_bf16,
                      int c_mode, long long c_batch_rows, int hs_B, int hs_nh, int hs_L, float alpha,
                      const float *bias, int relu, int accumulate, int split_k, pcm_stream_t stream);
+/* _ex2: (1) a second A operand A2 (same shape, majorness and batching as A; row pitch lda2) from which the output
+ * columns n >= a2_from_col are computed (a2_from_col must be a multiple of the output tile width: any multiple of
+ * 256) -- nn.MultiheadAttention's fused in-projection reads bf16(x + pos) for Q, K and bf16(x) for V in ONE launch
+ * (transformer.py:238-240 q = k = with_pos_embed(src, pos), value = src); A2 = NULL: off.  (2) head-split output
+ * (c_mode 1) in parts: column n goes to part n / hs_part_cols, whose (B, nh, L, 64) tensor starts hs_part_stride
+ * elements after the previous part's (the Q | K | V buffers); hs_part_cols = 0: a single part. */
+int pcm_gemm_bf16_ex2(int M, int N, int K, int batch, const void *A, int lda, int a_mn,
+                      long long a_rows_total, long long a_batch_rows, const void *B, int ldb, int b_mn,
+                      long long b_rows_total, long long b_batch_rows, void *C, int ldc, int c_bf16,
+                      int c_mode, long long c_batch_rows, int hs_B, int hs_nh, int hs_L, float alpha,
+                      const float *bias, int relu, int accumulate, int split_k, const void *A2, int lda2,
+                      int a2_from_col, int hs_part_cols, long long hs_part_stride, pcm_stream_t stream);
 
 /* Debug aid for tile-shape sweeps (tools/bench_gemm.py): force the N extent of the output tile
  * of subsequent GEMM launches (64 / 128 / 256; 0 = heuristic). */
@@ -300,6 +312,13 @@ int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float *dy, const floa
                               const unsigned long long *seed_base, unsigned long long seed_offset,
                               float *dres, float *dx, float *dgamma, float *dbeta, void *dx_bf16,
                               pcm_stream_t stream);
+/* _ex2: additionally ACCUMULATES the column sums of dx into dx_colsum (C floats; NULL = off): the bias gradient of the
+ * linear layer that produced x (out_proj / linear2), formed while dx is in registers. */
+int pcm_add_dropout_ln_bwd_ex2(long long rows, int C, const float *dy, const float *dy_b, const float *h,
+                               const float *mean, const float *rstd, const float *gamma, float p_drop,
+                               const unsigned long long *seed_base, unsigned long long seed_offset,
+                               float *dres, float *dx, float *dgamma, float *dbeta, void *dx_bf16,
+                               float *dx_colsum, pcm_stream_t stream);
 int pcm_colsum(long long rows, int C, const void *src, long long ld, int src_bf16, float *out,
                pcm_stream_t stream);
 /* FFN hidden layer (transformer.py:243-247,336-340: `linear2(dropout(relu(linear1(x))))`): dropout of the
@@ -311,6 +330,11 @@ int pcm_ffn_dropout_fwd(long long rows, int Hd, const void *h, float p_drop, con
 int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float *dhd, const void *h, float p_drop,
                              const unsigned long long *seed_base, unsigned long long seed_offset, void *dh,
                              pcm_stream_t stream);
+/* _ex: additionally ACCUMULATES the column sums of dh into dh_colsum (Hd floats; NULL = off; Hd <= 256, Hd / 8 a
+ * power of two): the gradient of linear1's bias. */
+int pcm_ffn_relu_dropout_bwd_ex(long long rows, int Hd, const float *dhd, const void *h, float p_drop,
+                                const unsigned long long *seed_base, unsigned long long seed_offset, void *dh,
+                                float *dh_colsum, pcm_stream_t stream);
 /* Profiling aid (tools/bench_ln.py): launch-shape knobs of the LayerNorm / colsum kernels (maximum CTAs of the
  * forward and of the backward, target CTA count and minimum rows per CTA of colsum); <= 0 keeps a value. */
 int pcm_ln_debug_tune(int ln_fwd_max_ctas, int ln_bwd_max_ctas, int colsum_ctas, int colsum_min_rows);
@@ -423,6 +447,13 @@ int pcm_act_heads_loss_bwd(int B, int Q, int E, int A, int L, int sig_start, int
                            const float *g_kl, const float *g_a_hat, const float *g_pad, float *d_hs,
                            long long dld_b, long long dld_q, float *dWa, float *dba, float *dWp, float *dbp,
                            float *dmu, float *dlogvar, pcm_stream_t stream);
+
+/* Slice lists: n equally sized slices at unrelated addresses (ptrs: DEVICE array of n addresses, 16-byte aligned) --
+ * the same sub-block of every decoder layer's in_proj_weight / in_proj_bias inside the flat parameter and gradient
+ * buffers.  gather: dst[s] = *ptrs[s] (stack the slices into one GEMM operand; the reference recomputes the memory
+ * K / V projections layer by layer, transformer.py:317-346); add: *ptrs[s] += src[s] (hand the stacked gradient back). */
+int pcm_gather_slices(int n, long long bytes_per_slice, const long long *ptrs, void *dst, pcm_stream_t stream);
+int pcm_add_slices(int n, long long floats_per_slice, const long long *ptrs, const float *src, pcm_stream_t stream);
 
 #ifdef __cplusplus
 }

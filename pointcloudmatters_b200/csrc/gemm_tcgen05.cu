@@ -58,6 +58,14 @@ struct GemmParams {
     int c_bf16;
     int atomic;  // red.global.add.f32 (split-K / gradient accumulation); C must be fp32
     float alpha;  // C = alpha * acc (+ bias)
+    // second A operand: output columns n >= a2_from_col (a multiple of BLOCK_N) are computed from tensor map A2 instead
+    // of A -- the fused Q|K|V in-projection of nn.MultiheadAttention reads bf16(x + pos) for Q, K and bf16(x) for V in
+    // ONE launch.  INT_MAX = off.
+    int a2_from_col;
+    // head-split output in parts (c_mode 1): column n belongs to part n / hs_part_cols, whose (B, nh, L, 64) tensor
+    // starts hs_part_stride elements after the previous part's (Q | K | V buffers).  0 = a single part.
+    int hs_part_cols;
+    long long hs_part_stride;
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
@@ -66,9 +74,21 @@ struct GemmParams {
 // columns) let the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
 enum { EPI_F32 = 0, EPI_BF16 = 1, EPI_ATOMIC = 2 };
 
+// head-split destination offset of output column `col` relative to the row's offset: (part, head, d)
+__device__ __forceinline__ size_t hs_col_off(const GemmParams& p, int col) {
+    size_t off = 0;
+    if (p.hs_part_cols > 0) {
+        const int part = col / p.hs_part_cols;
+        col -= part * p.hs_part_cols;
+        off = (size_t)part * (size_t)p.hs_part_stride;
+    }
+    return off + (size_t)(col >> 6) * p.hs_L * 64 + (col & 63);
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                       const __grid_constant__ CUtensorMap tmap_b,
+                                                                      const __grid_constant__ CUtensorMap tmap_a2,
                                                                       const GemmParams p) {
     constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -97,6 +117,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
+        if (p.a2_from_col < p.N) prefetch_tmap(&tmap_a2);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS); }
         fence_barrier_init();
@@ -121,6 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int a_off = (int)(zb * p.a_batch_rows), b_off = (int)(zb * p.b_batch_rows);
             const int kb0 = ks * p.k_blocks_per_split;
             const int kb1 = min(kblocks_total, kb0 + p.k_blocks_per_split);
+            const CUtensorMap* amap = n_blk * BLOCK_N >= p.a2_from_col ? &tmap_a2 : &tmap_a;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -131,11 +153,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     const int k0 = kb * BLOCK_K;
                     if (!A_MN) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[s], k0, a_off + m_blk * BLOCK_M);
+                        tma_load_2d(sa, amap, &full_bar[s], k0, a_off + m_blk * BLOCK_M);
                     } else {
 #pragma unroll
                         for (int c = 0; c < BLOCK_M / 64; ++c)
-                            tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m_blk * BLOCK_M + c * 64, a_off + k0);
+                            tma_load_2d(sa + c * (BLOCK_K * 128), amap, &full_bar[s], m_blk * BLOCK_M + c * 64, a_off + k0);
                     }
                     if (!B_MN) {
                         tma_load_2d(sb, &tmap_b, &full_bar[s], k0, b_off + n_blk * BLOCK_N);
@@ -267,8 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         const size_t rd = __shfl_sync(PCM_FULL_MASK, row_dst, rl);
                         const float x = *reinterpret_cast<const float*>(stage + rl * 128 + (((lane >> 2) ^ (rl & 7)) << 4) + ((lane & 3) << 2));
                         if (row_base + rl < p.M && scol0 + lane < col_lim) {
-                            const size_t dst = p.c_mode == 1 ? rd + (size_t)((scol0 + lane) >> 6) * p.hs_L * 64 + ((scol0 + lane) & 63)
-                                                             : rd + scol0 + lane;
+                            const size_t dst = p.c_mode == 1 ? rd + hs_col_off(p, scol0 + lane) : rd + scol0 + lane;
                             atomicAdd(reinterpret_cast<float*>(p.C) + dst, x);
                         }
                     }
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         const uint4 pk = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((chunk ^ (rl & 7)) << 4));
                         const int ecol = scol0 + chunk * (16 / ESZ);  // first element column of this 16-byte piece
                         if (row_base + rl < p.M && ecol < col_lim) {
-                            const size_t dst = p.c_mode == 1 ? rd + (size_t)(ecol >> 6) * p.hs_L * 64 + (ecol & 63) : rd + ecol;
+                            const size_t dst = p.c_mode == 1 ? rd + hs_col_off(p, ecol) : rd + ecol;
                             uint8_t* g = reinterpret_cast<uint8_t*>(p.C) + dst * ESZ;
                             if (ecol + 16 / ESZ <= col_lim && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
                                 *reinterpret_cast<uint4*>(g) = pk;
@@ -389,7 +410,8 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
+int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const GemmParams& p, int split_k, int batch,
+               cudaStream_t st) {
     constexpr size_t SMEM = StagesFor<BLOCK_N>::value * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * 4096;
     static bool attr = false;
     if (!attr) {
@@ -407,16 +429,17 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
     }
     const long tiles = (long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * split_k * batch;
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    cudaError_t le = pcm_launch(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>, dim3(grid), dim3(NUM_THREADS), SMEM, st, ta, tb, p);
+    cudaError_t le = pcm_launch(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>, dim3(grid), dim3(NUM_THREADS), SMEM, st, ta, tb, ta2, p);
     if (le != cudaSuccess) return (int)le;
     return pcm_launch_status();
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int split_k, int batch, cudaStream_t st) {
-    if (p.atomic) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_ATOMIC>(ta, tb, p, split_k, batch, st);
-    if (p.c_bf16) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_BF16>(ta, tb, p, split_k, batch, st);
-    return launch_epi<BLOCK_N, A_MN, B_MN, EPI_F32>(ta, tb, p, split_k, batch, st);
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const GemmParams& p, int split_k, int batch,
+           cudaStream_t st) {
+    if (p.atomic) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_ATOMIC>(ta, tb, ta2, p, split_k, batch, st);
+    if (p.c_bf16) return launch_epi<BLOCK_N, A_MN, B_MN, EPI_BF16>(ta, tb, ta2, p, split_k, batch, st);
+    return launch_epi<BLOCK_N, A_MN, B_MN, EPI_F32>(ta, tb, ta2, p, split_k, batch, st);
 }
 
 int g_force_bn = 0;
@@ -438,8 +461,23 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
                              long long b_batch_rows, void* C, int ldc, int c_bf16, int c_mode, long long c_batch_rows,
                              int hs_B, int hs_nh, int hs_L, float alpha, const float* bias, int relu, int accumulate,
                              int split_k, pcm_stream_t stream) {
+    return pcm_gemm_bf16_ex2(M, N, K, batch, A, lda, a_mn, a_rows_total, a_batch_rows, B, ldb, b_mn, b_rows_total, b_batch_rows, C,
+                             ldc, c_bf16, c_mode, c_batch_rows, hs_B, hs_nh, hs_L, alpha, bias, relu, accumulate, split_k,
+                             nullptr, 0, 0, 0, 0, stream);
+}
+
+// _ex2: + second A operand for output columns >= a2_from_col (same shape / majorness / batching as A, row pitch lda2)
+// and head-split output in parts of hs_part_cols columns, hs_part_stride elements apart (see GemmParams).
+PCM_API int pcm_gemm_bf16_ex2(int M, int N, int K, int batch, const void* A, int lda, int a_mn, long long a_rows_total,
+                              long long a_batch_rows, const void* B, int ldb, int b_mn, long long b_rows_total,
+                              long long b_batch_rows, void* C, int ldc, int c_bf16, int c_mode, long long c_batch_rows,
+                              int hs_B, int hs_nh, int hs_L, float alpha, const float* bias, int relu, int accumulate,
+                              int split_k, const void* A2, int lda2, int a2_from_col, int hs_part_cols,
+                              long long hs_part_stride, pcm_stream_t stream) {
     if (M <= 0 || N <= 0 || batch <= 0) return PCM_OK;
     if (!A || !B || !C || K <= 0) return PCM_EINVAL;
+    if (A2 && ((lda2 % 8) || (reinterpret_cast<uintptr_t>(A2) & 15) || a2_from_col <= 0)) return PCM_EUNSUPPORTED;
+    if (hs_part_cols < 0 || (hs_part_cols > 0 && (c_mode != 1 || (hs_part_cols % 64)))) return PCM_EINVAL;
     if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return PCM_EUNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
     if ((split_k > 1 || accumulate) && c_bf16) return PCM_EINVAL;
@@ -466,6 +504,7 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
         split_k = want < cap ? want : cap;
     }
     if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) BN = g_force_bn;  // tools/bench_gemm_sweep.py
+    while (A2 && BN > 64 && (a2_from_col % BN)) BN >>= 1;  // the operand switch happens on output-tile boundaries
     if (split_k > kblocks) split_k = kblocks;
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
@@ -478,31 +517,42 @@ PCM_API int pcm_gemm_bf16_ex(int M, int N, int K, int batch, const void* A, int 
     p.hs_B = hs_B; p.hs_nh = hs_nh; p.hs_L = hs_L;
     p.bias = bias; p.relu = relu; p.c_bf16 = c_bf16; p.alpha = alpha;
     p.atomic = (accumulate || split_k > 1) ? 1 : 0;
-    CUtensorMap ta, tb;
+    p.a2_from_col = 0x7fffffff;
+    p.hs_part_cols = hs_part_cols;
+    p.hs_part_stride = hs_part_stride;
+    CUtensorMap ta, tb, ta2;
     int r;
     if (!a_mn) r = get_tensor_map(A, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_M, &ta);
     else r = get_tensor_map(A, (uint64_t)M, (uint64_t)a_rows_total, (uint64_t)lda, 64, BLOCK_K, &ta);
     if (r) return r;
+    ta2 = ta;
+    if (A2) {
+        if (a2_from_col % BN) return PCM_EUNSUPPORTED;  // the switch happens on output-tile boundaries
+        if (!a_mn) r = get_tensor_map(A2, (uint64_t)K, (uint64_t)a_rows_total, (uint64_t)lda2, 64, BLOCK_M, &ta2);
+        else r = get_tensor_map(A2, (uint64_t)M, (uint64_t)a_rows_total, (uint64_t)lda2, 64, BLOCK_K, &ta2);
+        if (r) return r;
+        p.a2_from_col = a2_from_col;
+    }
     if (!b_mn) r = get_tensor_map(B, (uint64_t)K, (uint64_t)b_rows_total, (uint64_t)ldb, 64, BN, &tb);
     else r = get_tensor_map(B, (uint64_t)N, (uint64_t)b_rows_total, (uint64_t)ldb, 64, BLOCK_K, &tb);
     if (r) return r;
     cudaStream_t st = pcm_cu_stream(stream);
     if (BN == 64) {
-        if (!a_mn && !b_mn) return launch<64, false, false>(ta, tb, p, split_k, batch, st);
-        if (!a_mn && b_mn) return launch<64, false, true>(ta, tb, p, split_k, batch, st);
-        if (a_mn && !b_mn) return launch<64, true, false>(ta, tb, p, split_k, batch, st);
-        return launch<64, true, true>(ta, tb, p, split_k, batch, st);
+        if (!a_mn && !b_mn) return launch<64, false, false>(ta, tb, ta2, p, split_k, batch, st);
+        if (!a_mn && b_mn) return launch<64, false, true>(ta, tb, ta2, p, split_k, batch, st);
+        if (a_mn && !b_mn) return launch<64, true, false>(ta, tb, ta2, p, split_k, batch, st);
+        return launch<64, true, true>(ta, tb, ta2, p, split_k, batch, st);
     }
     if (BN == 256) {
-        if (!a_mn && !b_mn) return launch<256, false, false>(ta, tb, p, split_k, batch, st);
-        if (!a_mn && b_mn) return launch<256, false, true>(ta, tb, p, split_k, batch, st);
-        if (a_mn && !b_mn) return launch<256, true, false>(ta, tb, p, split_k, batch, st);
-        return launch<256, true, true>(ta, tb, p, split_k, batch, st);
+        if (!a_mn && !b_mn) return launch<256, false, false>(ta, tb, ta2, p, split_k, batch, st);
+        if (!a_mn && b_mn) return launch<256, false, true>(ta, tb, ta2, p, split_k, batch, st);
+        if (a_mn && !b_mn) return launch<256, true, false>(ta, tb, ta2, p, split_k, batch, st);
+        return launch<256, true, true>(ta, tb, ta2, p, split_k, batch, st);
     }
-    if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, p, split_k, batch, st);
-    if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, p, split_k, batch, st);
-    if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, p, split_k, batch, st);
-    return launch<128, true, true>(ta, tb, p, split_k, batch, st);
+    if (!a_mn && !b_mn) return launch<128, false, false>(ta, tb, ta2, p, split_k, batch, st);
+    if (!a_mn && b_mn) return launch<128, false, true>(ta, tb, ta2, p, split_k, batch, st);
+    if (a_mn && !b_mn) return launch<128, true, false>(ta, tb, ta2, p, split_k, batch, st);
+    return launch<128, true, true>(ta, tb, ta2, p, split_k, batch, st);
 }
 
 // C[m, n] (+)= sum_k A(m, k) B(n, k) (+ bias[n]) (ReLU).  a_mn / b_mn = 0: operand stored row-major

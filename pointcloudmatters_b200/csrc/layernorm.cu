@@ -101,12 +101,15 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     }
 }
 
-template <int V>
-__global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
+template <int V, bool CS>
+__global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) add_dropout_ln_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ dy_b, const float* __restrict__ h, const float* __restrict__ mean_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, long rows, float p_drop,
     const unsigned long long* __restrict__ seed_base, unsigned long long seed_offset, float* __restrict__ dres,
-    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16) {
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
+    float* __restrict__ dx_colsum) {
+    // dx_colsum (optional, C floats, accumulated): column sums of dx = the bias gradient of the linear layer that produced
+    // x (out_proj / linear2) -- formed here, where dx is in registers, instead of by a colsum pass re-reading dx
     constexpr int C = 128 * V;
     __shared__ float sg[C], sb[C];
     pcm_pdl_launch_dependents();
@@ -119,12 +122,15 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     const float ks = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
     for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
     __syncthreads();
-    float4 g4[V], ag[V], abt[V];
+    // register budget: 2 CTAs per SM need <= 128 registers per thread; with the third accumulator set (CS) gamma is
+    // re-read per row (an L1 hit) instead of living in registers
+    float4 g4[CS ? 1 : V], ag[V], abt[V], axs[CS ? V : 1];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        g4[v] = reinterpret_cast<const float4*>(gamma)[v * 32 + lane];
+        if (!CS) g4[v] = reinterpret_cast<const float4*>(gamma)[v * 32 + lane];
         ag[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         abt[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CS) axs[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (long r = wid; r < rows; r += nwarps) {
         const float mean = mean_in[r], rstd = rstd_in[r];
@@ -141,7 +147,8 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
             }
             const float4 hv = *reinterpret_cast<const float4*>(h + e);
             xh[v] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
-            gy[v] = make_float4(d.x * g4[v].x, d.y * g4[v].y, d.z * g4[v].z, d.w * g4[v].w);
+            const float4 gm = CS ? __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane) : g4[CS ? 0 : v];
+            gy[v] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
             s1 += (gy[v].x + gy[v].y) + (gy[v].z + gy[v].w);
             s2 += (gy[v].x * xh[v].x + gy[v].y * xh[v].y) + (gy[v].z * xh[v].z + gy[v].w * xh[v].w);
             ag[v].x += d.x * xh[v].x; ag[v].y += d.y * xh[v].y; ag[v].z += d.z * xh[v].z; ag[v].w += d.w * xh[v].w;
@@ -169,6 +176,7 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
                 }
                 *reinterpret_cast<float4*>(dx + e) = o;
             }
+            if (CS) { axs[v].x += o.x; axs[v].y += o.y; axs[v].z += o.z; axs[v].w += o.w; }
             if (dx_bf16) {  // bf16 copy of dx: the operand of the sub-block's backward GEMMs
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                 uint2 pk;
@@ -189,6 +197,18 @@ __global__ void __launch_bounds__(256) add_dropout_ln_bwd_kernel(
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         atomicAdd(dgamma + i, sg[i]);
         atomicAdd(dbeta + i, sb[i]);
+    }
+    if (CS) {  // third per-column reduction reuses sg after the flush above
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sg[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int c = (v * 32 + lane) * 4;
+            atomicAdd(&sg[c + 0], axs[v].x); atomicAdd(&sg[c + 1], axs[v].y); atomicAdd(&sg[c + 2], axs[v].z); atomicAdd(&sg[c + 3], axs[v].w);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dx_colsum + i, sg[i]);
     }
 }
 
@@ -317,7 +337,11 @@ ffn_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ h, long rows, int Hd, f
 __global__ void __launch_bounds__(256)
 ffn_relu_dropout_bwd_kernel(const float* __restrict__ dhd, const __nv_bfloat16* __restrict__ h, long rows, int Hd,
                             float p_drop, const unsigned long long* __restrict__ seed_base,
-                            unsigned long long seed_offset, __nv_bfloat16* __restrict__ dh) {
+                            unsigned long long seed_offset, __nv_bfloat16* __restrict__ dh, float* __restrict__ dh_colsum) {
+    // dh_colsum (optional, Hd floats, accumulated) = column sums of dh = the gradient of linear1's bias; the launcher passes
+    // it only when every thread keeps the same 8-column chunk over its grid-stride loop ((grid * block) % (Hd / 8) == 0)
+    __shared__ float scs[256];
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     pcm_pdl_launch_dependents();
     pcm_pdl_wait();
     const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
@@ -344,11 +368,23 @@ ffn_relu_dropout_bwd_kernel(const float* __restrict__ dhd, const __nv_bfloat16* 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float2 f = __bfloat1622float2(v[k]);
-            __nv_bfloat162 w = __floats2bfloat162_rn((keep[2 * k] && f.x > 0.f) ? g[2 * k] * ks : 0.f,
-                                                     (keep[2 * k + 1] && f.y > 0.f) ? g[2 * k + 1] * ks : 0.f);
+            const float w0 = (keep[2 * k] && f.x > 0.f) ? g[2 * k] * ks : 0.f;
+            const float w1 = (keep[2 * k + 1] && f.y > 0.f) ? g[2 * k + 1] * ks : 0.f;
+            cs[2 * k] += w0;
+            cs[2 * k + 1] += w1;
+            __nv_bfloat162 w = __floats2bfloat162_rn(w0, w1);
             op[k] = *reinterpret_cast<uint32_t*>(&w);
         }
         reinterpret_cast<uint4*>(dh)[i] = o;
+    }
+    if (dh_colsum) {
+        for (int i = threadIdx.x; i < Hd; i += blockDim.x) scs[i] = 0.f;
+        __syncthreads();
+        const int c = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) % cpr) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&scs[c + k], cs[k]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < Hd; i += blockDim.x) atomicAdd(dh_colsum + i, scs[i]);
     }
 }
 
@@ -388,6 +424,15 @@ inline int ln_grid_bwd(long rows) {
         default: return PCM_EUNSUPPORTED;                             \
     }
 
+#define LN_DISPATCH2(V, KERNEL, FLAG, ...)                            \
+    switch (V) {                                                      \
+        case 1: pcm_launch(KERNEL<1, FLAG>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 2: pcm_launch(KERNEL<2, FLAG>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 4: pcm_launch(KERNEL<4, FLAG>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        case 8: pcm_launch(KERNEL<8, FLAG>, dim3(grid), dim3(256), 0, st, __VA_ARGS__); break;  \
+        default: return PCM_EUNSUPPORTED;                             \
+    }
+
 // y = LayerNorm(res + dropout(x)) (x may be NULL = plain LayerNorm(res)); C in {128, 256, 512, 1024}.
 // Optional outputs: y_bf16 (operand of the next GEMM), h (= res + dropout(x), saved for backward),
 // mean / rstd (rows).
@@ -417,18 +462,33 @@ PCM_API int pcm_add_dropout_ln_fwd(long long rows, int C, const float* x, const 
 
 // dres = dLN/dh; dx = dropout-backward(dres) (pass dx == dres or NULL when not needed);
 // dgamma / dbeta are ACCUMULATED (caller zero-fills); dx_bf16 (optional) = bf16(dx).
+PCM_API int pcm_add_dropout_ln_bwd_ex2(long long rows, int C, const float* dy, const float* dy_b, const float* h, const float* mean,
+                                       const float* rstd, const float* gamma, float p_drop,
+                                       const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
+                                       float* dx, float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum,
+                                       pcm_stream_t stream) {
+    if (rows <= 0) return PCM_OK;
+    if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
+    if (dx_colsum && !dx) return PCM_EINVAL;
+    if (C % 128) return PCM_EUNSUPPORTED;
+    cudaStream_t st = pcm_cu_stream(stream);
+    const int grid = ln_grid_bwd(rows);
+    if (dx_colsum) {
+        LN_DISPATCH2(C / 128, add_dropout_ln_bwd_kernel, true, dy, dy_b, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset,
+                     dres, dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dx_colsum)
+    } else {
+        LN_DISPATCH2(C / 128, add_dropout_ln_bwd_kernel, false, dy, dy_b, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset,
+                     dres, dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dx_colsum)
+    }
+    return pcm_launch_status();
+}
+
 PCM_API int pcm_add_dropout_ln_bwd_ex(long long rows, int C, const float* dy, const float* dy_b, const float* h, const float* mean,
                                       const float* rstd, const float* gamma, float p_drop,
                                       const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
                                       float* dx, float* dgamma, float* dbeta, void* dx_bf16, pcm_stream_t stream) {
-    if (rows <= 0) return PCM_OK;
-    if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
-    if (C % 128) return PCM_EUNSUPPORTED;
-    cudaStream_t st = pcm_cu_stream(stream);
-    const int grid = ln_grid_bwd(rows);
-    LN_DISPATCH(C / 128, add_dropout_ln_bwd_kernel, dy, dy_b, h, mean, rstd, gamma, rows, p_drop, seed_base, seed_offset, dres,
-                dx, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16))
-    return pcm_launch_status();
+    return pcm_add_dropout_ln_bwd_ex2(rows, C, dy, dy_b, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, dres, dx, dgamma,
+                                      dbeta, dx_bf16, nullptr, stream);
 }
 
 PCM_API int pcm_add_dropout_ln_bwd(long long rows, int C, const float* dy, const float* h, const float* mean,
@@ -456,14 +516,23 @@ PCM_API int pcm_ffn_dropout_fwd(long long rows, int Hd, const void* h, float p_d
 PCM_API int pcm_ffn_relu_dropout_bwd(long long rows, int Hd, const float* dhd, const void* h, float p_drop,
                                      const unsigned long long* seed_base, unsigned long long seed_offset, void* dh,
                                      pcm_stream_t stream) {
+    return pcm_ffn_relu_dropout_bwd_ex(rows, Hd, dhd, h, p_drop, seed_base, seed_offset, dh, nullptr, stream);
+}
+
+PCM_API int pcm_ffn_relu_dropout_bwd_ex(long long rows, int Hd, const float* dhd, const void* h, float p_drop,
+                                        const unsigned long long* seed_base, unsigned long long seed_offset, void* dh,
+                                        float* dh_colsum, pcm_stream_t stream) {
     if (rows <= 0 || Hd <= 0) return PCM_OK;
     if (!dhd || !h || !dh || p_drop < 0.f || p_drop >= 1.f) return PCM_EINVAL;
     if (Hd % 8) return PCM_EUNSUPPORTED;
+    if (dh_colsum && (Hd > 256 || 256 % (Hd / 8))) return PCM_EUNSUPPORTED;  // see the kernel: fixed chunk per thread
     const long total = (long)rows * (Hd / 8);
-    const int grid = (int)((total + 255) / 256 < 148L * 8 ? (total + 255) / 256 : 148L * 8);
+    // with the column sums every CTA ends in Hd global atomics onto the same Hd addresses: one CTA per SM keeps that tail short
+    const long cap = dh_colsum ? 148L : 148L * 8;
+    const int grid = (int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
     cudaError_t e = pcm_launch(ffn_relu_dropout_bwd_kernel, dim3(grid), dim3(256), 0, pcm_cu_stream(stream), dhd,
                                reinterpret_cast<const __nv_bfloat16*>(h), (long)rows, Hd, p_drop, seed_base, seed_offset,
-                               reinterpret_cast<__nv_bfloat16*>(dh));
+                               reinterpret_cast<__nv_bfloat16*>(dh), dh_colsum);
     if (e != cudaSuccess) return (int)e;
     return pcm_launch_status();
 }

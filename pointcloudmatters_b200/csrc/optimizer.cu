@@ -71,7 +71,50 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
     }
 }
 
+// Slice lists: n equally sized slices that live at unrelated addresses (the same sub-block of every decoder layer's
+// in_proj_weight inside the flat parameter / gradient buffers).  ptrs[] is a device array of n addresses.
+//   gather: dst[s * elems + i]  = src_s[i]     (stack the slices into one GEMM operand)
+//   add:    dst_s[i]           += src[s * elems + i]   (hand a stacked gradient back to the slices)
+template <typename T>
+__global__ void __launch_bounds__(256) gather_slices_kernel(const long long* __restrict__ ptrs, long elems16, T* __restrict__ dst) {
+    const uint4* src = reinterpret_cast<const uint4*>(ptrs[blockIdx.y]);
+    uint4* d = reinterpret_cast<uint4*>(dst) + (size_t)blockIdx.y * elems16;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < elems16; i += (long)gridDim.x * blockDim.x) d[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) add_slices_kernel(const long long* __restrict__ ptrs, long elems4, const float* __restrict__ src) {
+    float4* d = reinterpret_cast<float4*>(ptrs[blockIdx.y]);
+    const float4* s = reinterpret_cast<const float4*>(src) + (size_t)blockIdx.y * elems4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < elems4; i += (long)gridDim.x * blockDim.x) {
+        float4 a = d[i];
+        const float4 b = s[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        d[i] = a;
+    }
+}
+
 }  // namespace
+
+// bytes_per_slice % 16 == 0, all addresses 16-byte aligned.
+PCM_API int pcm_gather_slices(int n, long long bytes_per_slice, const long long* ptrs, void* dst, pcm_stream_t stream) {
+    if (n <= 0 || bytes_per_slice <= 0) return PCM_OK;
+    if (!ptrs || !dst) return PCM_EINVAL;
+    if ((bytes_per_slice % 16) || (reinterpret_cast<uintptr_t>(dst) & 15)) return PCM_EUNSUPPORTED;
+    const long e16 = bytes_per_slice / 16;
+    const int gx = (int)((e16 + 255) / 256 < 64 ? (e16 + 255) / 256 : 64);
+    gather_slices_kernel<uint4><<<dim3(gx, n), 256, 0, pcm_cu_stream(stream)>>>(ptrs, e16, reinterpret_cast<uint4*>(dst));
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_add_slices(int n, long long floats_per_slice, const long long* ptrs, const float* src, pcm_stream_t stream) {
+    if (n <= 0 || floats_per_slice <= 0) return PCM_OK;
+    if (!ptrs || !src) return PCM_EINVAL;
+    if ((floats_per_slice % 4) || (reinterpret_cast<uintptr_t>(src) & 15)) return PCM_EUNSUPPORTED;
+    const long e4 = floats_per_slice / 4;
+    const int gx = (int)((e4 + 255) / 256 < 64 ? (e4 + 255) / 256 : 64);
+    add_slices_kernel<<<dim3(gx, n), 256, 0, pcm_cu_stream(stream)>>>(ptrs, e4, src);
+    return pcm_launch_status();
+}
 
 // n must be a multiple of 4 and the buffers 16-byte aligned (FlatState pads every tensor to 4).
 // sumsq: one zero-initialised fp64 scratch scalar (re-zeroed by this call for the next step).

@@ -281,20 +281,29 @@ __global__ void __launch_bounds__(256) act_heads_loss_bwd_kernel(HeadsLossBwdPar
             }
         }
     }
+    // combine the row groups of the CTA in shared memory (the weight tile is no longer needed), then ONE global atomic per
+    // weight element per CTA: 24 CTAs x (A + 1) x E atomics instead of one per owner thread
+    __syncthreads();
+    for (int i = threadIdx.x; i < nout * f.E; i += blockDim.x) sW[i] = 0.f;
+    __syncthreads();
     if (owner) {
 #pragma unroll
         for (int d = 0; d < HL_MAX_OUT; ++d) {
             if (d < nout) {
-                float* dst = d < f.A ? p.dWa + (size_t)d * f.E + cq : (p.dWp ? p.dWp + cq : nullptr);
-                if (dst) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dw[d][u] != 0.f) atomicAdd(dst + u, dw[d][u]);
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (dw[d][u] != 0.f) atomicAdd(&sW[d * f.E + cq + u], dw[d][u]);
             }
         }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < nout * f.E; i += blockDim.x) {
+        const float v = sW[i];
+        if (v != 0.f) {
+            if (i < f.A * f.E) atomicAdd(p.dWa + i, v);
+            else if (p.dWp) atomicAdd(p.dWp + (i - f.A * f.E), v);
+        }
+    }
     if (threadIdx.x < nout && sdb[threadIdx.x] != 0.f) {
         if (threadIdx.x < f.A) atomicAdd(p.dba + threadIdx.x, sdb[threadIdx.x]);
         else if (p.dbp) atomicAdd(p.dbp, sdb[threadIdx.x]);
@@ -388,7 +397,7 @@ PCM_API int pcm_act_heads_loss_bwd(int B, int Q, int E, int A, int L, int sig_st
         attr = true;
     }
     const long rows = (long)B * Q;
-    const int grid = (int)(rows / 32 < 64 ? (rows + 31) / 32 : 64);
+    const int grid = (int)(rows / 32 < 24 ? (rows + 31) / 32 : 24);
     act_heads_loss_bwd_kernel<<<grid, 256, smem, pcm_cu_stream(stream)>>>(p);
     return pcm_launch_status();
 }

@@ -142,13 +142,17 @@ def _act_pos_bf16(x, pos, rows, C):
     return None
 
 
-def _grad_bf16(g, rows, C):
-    """bf16 copy of incoming gradient `g` left by the kernel that produced it, else a cast pass."""
+def _grad_bf16(g, rows, C, bias=None):
+    """bf16 copy of incoming gradient `g` left by the kernel that produced it, else a cast pass.
+    With `bias` (the bias Parameter of the linear layer whose output gradient `g` is): returns (bf16 copy, done) where
+    `done` says the producing kernel has already accumulated colsum(g) into that parameter's flat gradient."""
     e = _GRAD_BF16.pop(g.data_ptr(), None)
     if e is not None and e[1].data_ptr() == g.data_ptr() and e[1].numel() == g.numel() == rows * C and g.is_contiguous():
-        return e[0].view(rows, C)
+        out = e[0].view(rows, C)
+        return (out, len(e) > 2 and e[2] is bias and bias is not None) if bias is not None else out
     g2 = g.reshape(rows, C)
-    return K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
+    out = K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
+    return (out, False) if bias is not None else out
 
 
 _NO_ROW_SPLIT = bool(int(os.environ.get("PCM_NO_ROW_SPLIT", "0")))  # A/B switch for tools/
@@ -379,12 +383,12 @@ class _MHASelf(torch.autograd.Function):
         xv_b = (xv_hint if xv_hint is not None else _tok_bf16(x, None, L, B, E)) if pos is not None else xqk_b
         wb, wo_b = _wb(w_in), _wb(w_out)
         Z = B * nh
-        Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
-        Kh = torch.empty((Z * L, 64), dtype=bf, device=dev)
-        Vh = torch.empty((Z * L, 64), dtype=bf, device=dev)
-        for dst, src, j in ((Qh, xqk_b, 0), (Kh, xqk_b, 1), (Vh, xv_b, 2)):
-            K.gemm_ex(L * B, E, E, 1, src, False, 0, wb[j * E:(j + 1) * E], False, 0, dst, c_mode=1, hs=(B, nh, L), ldc=64,
-                      bias=b_in[j * E:(j + 1) * E])
+        # ONE in-projection launch: output columns [0, 2E) = Q | K from bf16(x + pos), [2E, 3E) = V from bf16(x) (second A
+        # operand), written head-split into the three (B, nh, L, 64) parts of one buffer
+        qkv = torch.empty((3, Z * L, 64), dtype=bf, device=dev)
+        Qh, Kh, Vh = qkv[0], qkv[1], qkv[2]
+        K.gemm_ex(L * B, 3 * E, E, 1, xqk_b, False, 0, wb, False, 0, qkv, c_mode=1, hs=(B, nh, L), ldc=64, bias=b_in,
+                  a2=xv_b if xv_b is not xqk_b else None, a2_from_col=2 * E, hs_parts=(E, Z * L * 64))
         O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, L, B, nh, kpm, p_drop, dev)
         out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
         ctx.save_for_backward(xqk_b, xv_b, wb, wo_b, Qh, Kh, Vh, lse, kpm_u8, O_tok, pos_head)
@@ -399,9 +403,10 @@ class _MHASelf(torch.autograd.Function):
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
         (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
-        dout_b = _grad_bf16(dout, L * B, E)
+        dout_b, bias_done = _grad_bf16(dout, L * B, E, ctx.params[3])
         _dw(dout_b, O_tok, dWo)
-        K.colsum(dout_b, dbo)
+        if not bias_done:
+            K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         buf = torch.empty((L * B, 3 * E), dtype=bf, device=dev)  # [dQ | dK | dV], token-major
@@ -468,9 +473,10 @@ class _MHACross(torch.autograd.Function):
         dev, bf = dout.device, torch.bfloat16
         Z = B * nh
         (dW_in, db_in, dWo, dbo), rets = _param_grads(ctx.params, E, dev)
-        dout_b = _grad_bf16(dout, L * B, E)
+        dout_b, bias_done = _grad_bf16(dout, L * B, E, ctx.params[3])
         _dw(dout_b, O_tok, dWo)
-        K.colsum(dout_b, dbo)
+        if not bias_done:
+            K.colsum(dout_b, dbo)
         dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
         K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
         dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
@@ -505,8 +511,209 @@ class _MHACross(torch.autograd.Function):
         return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None, None, None, None)
 
 
+_PTR_CACHE = {}
+
+
+def _ptr_table(ptrs, device):
+    """Device int64 array of addresses (cached per address tuple: under a trainer the flat buffers never move, so the
+    table is built once, before any CUDA-graph capture).  Returns None when it would have to be built during a capture."""
+    key = (tuple(ptrs), str(device))
+    t = _PTR_CACHE.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        if len(_PTR_CACHE) > 256:
+            _PTR_CACHE.clear()
+        t = _PTR_CACHE[key] = torch.tensor(list(ptrs), dtype=torch.int64, device=device)
+    return t
+
+
+class _MemKV(torch.autograd.Function):
+    """K / V projections of the encoder memory for ALL decoder layers in one launch (the reference recomputes
+    `multihead_attn`'s k = W_k (memory + pos), v = W_v memory inside every layer, transformer.py:317-346: 14 GEMMs of
+    32 960 x 512 x 512 at cfg-2).  The layers' weight slices are stacked (K blocks, then V blocks) by one gather kernel;
+    ONE tcgen05 GEMM with N = 2 n E reads bf16(memory + pos) for the K half and bf16(memory) for the V half and writes
+    the 2n head-split (B, h, S, 64) tensors.  Backward: every layer's fused attention backward writes its token-major
+    dK / dV into a column block of one shared (S B, 2 n E) buffer; d(memory) is then ONE K = 2 n E GEMM (instead of n
+    GEMMs plus n-1 full-size adds), the weight gradients two GEMMs into a stacked buffer that one kernel adds into the
+    layers' gradient slots."""
+
+    @staticmethod
+    def forward(ctx, mem, mpos, mpos_head, xk_hint, xv_hint, nh, shared, *params):
+        from ._lib import check, current_stream, lib, ptr
+
+        S, B, E = mem.shape
+        n = len(params) // 2
+        dev, bf = mem.device, torch.bfloat16
+        xk_b = xk_hint if xk_hint is not None else _tok_bf16(mem, mpos, S, B, E)
+        xv_b = (xv_hint if xv_hint is not None else _tok_bf16(mem, None, S, B, E)) if mpos is not None else xk_b
+        wbs = [_wb(params[2 * l]) for l in range(n)]
+        bs = [params[2 * l + 1] for l in range(n)]
+        w_slices = [w[E:2 * E] for w in wbs] + [w[2 * E:] for w in wbs]
+        b_slices = [b[E:2 * E] for b in bs] + [b[2 * E:] for b in bs]
+        Wkv = torch.empty((2 * n * E, E), dtype=bf, device=dev)
+        bkv = torch.empty(2 * n * E, dtype=torch.float32, device=dev)
+        tw = _ptr_table([w.data_ptr() for w in w_slices], dev)
+        tb = _ptr_table([b.data_ptr() for b in b_slices], dev)
+        if tw is not None and tb is not None:
+            check(lib.pcm_gather_slices(2 * n, E * E * 2, ptr(tw), ptr(Wkv), current_stream()), "pcm_gather_slices")
+            check(lib.pcm_gather_slices(2 * n, E * 4, ptr(tb), ptr(bkv), current_stream()), "pcm_gather_slices")
+        else:
+            torch.cat(w_slices, 0, out=Wkv)
+            torch.cat([b.detach() for b in b_slices], 0, out=bkv)
+        Z = B * nh
+        KV = torch.empty((2 * n, Z * S, 64), dtype=bf, device=dev)
+        K.gemm_ex(S * B, 2 * n * E, E, 1, xk_b, False, 0, Wkv, False, 0, KV, c_mode=1, hs=(B, nh, S), ldc=64, bias=bkv,
+                  a2=xv_b if xv_b is not xk_b else None, a2_from_col=n * E, hs_parts=(E, Z * S * 64))
+        ctx.save_for_backward(xk_b, xv_b, Wkv, mpos_head)
+        ctx.dims = (S, B, E, n, mpos is not None, None if mpos is None else tuple(mpos.shape))
+        ctx.params, ctx.shared = params, shared
+        return KV
+
+    @staticmethod
+    def backward(ctx, dKV):
+        from ._lib import check, current_stream, lib, ptr
+
+        xk_b, xv_b, Wkv, mpos_head = ctx.saved_tensors
+        S, B, E, n, has_pos, mpos_shape = ctx.dims
+        params, shared = ctx.params, ctx.shared
+        G = shared.pop("G", None)
+        written = shared.pop("written", set())
+        none = (None,) * (7 + 2 * n)
+        if G is None:
+            return none
+        dev = G.device
+        for l in range(n):  # layers whose backward never ran contribute nothing
+            if l not in written:
+                G[:, l * E:(l + 1) * E].zero_()
+                G[:, (n + l) * E:(n + l + 1) * E].zero_()
+        dmem = K.gemm_bf16(G, Wkv, b_mn=True).view(S, B, E) if ctx.needs_input_grad[0] else None  # ONE K = 2nE GEMM
+        dmpos = dhead = None
+        if has_pos and ctx.needs_input_grad[1]:
+            d_k = K.gemm_bf16(G[:, :n * E], Wkv[:n * E], b_mn=True)
+            dmpos = d_k.view(S, B, E) if mpos_shape[1] == B else d_k.view(S, B, E).sum(1, keepdim=True)
+        if mpos_head is not None and ctx.needs_input_grad[2]:
+            h = mpos_head.shape[0]
+            d_k = K.gemm_bf16(G[: h * B, :n * E], Wkv[:n * E], b_mn=True)  # learned leading rows only: a tiny GEMM
+            dhead = _pos_head_grad(d_k, mpos_head, h, B, E)
+        dW = torch.zeros((2 * n * E, E), dtype=torch.float32, device=dev)
+        _dw(G[:, :n * E], xk_b, dW[:n * E])
+        _dw(G[:, n * E:], xv_b, dW[n * E:])
+        db = torch.zeros(2 * n * E, dtype=torch.float32, device=dev)
+        step = 1792 if (2 * n * E) % 1792 == 0 else E  # column slices the vectorised column-sum kernel accepts (<= 2048)
+        for c0 in range(0, 2 * n * E, step):
+            K.colsum(G[:, c0:c0 + step], db[c0:c0 + step])
+        w_slots = [_grad_slot(params[2 * l]) for l in range(n)]
+        b_slots = [_grad_slot(params[2 * l + 1]) for l in range(n)]
+        grads = [None] * (2 * n)
+        tw = tb = None
+        if all(s_ is not None for s_ in w_slots + b_slots):
+            tw = _ptr_table([s_.data_ptr() + E * E * 4 for s_ in w_slots] + [s_.data_ptr() + 2 * E * E * 4 for s_ in w_slots], dev)
+            tb = _ptr_table([s_.data_ptr() + E * 4 for s_ in b_slots] + [s_.data_ptr() + 2 * E * 4 for s_ in b_slots], dev)
+        if tw is not None and tb is not None:
+            check(lib.pcm_add_slices(2 * n, E * E, ptr(tw), ptr(dW), current_stream()), "pcm_add_slices")
+            check(lib.pcm_add_slices(2 * n, E, ptr(tb), ptr(db), current_stream()), "pcm_add_slices")
+        else:
+            for l in range(n):
+                gw = torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
+                gw[E:2 * E], gw[2 * E:] = dW[l * E:(l + 1) * E], dW[(n + l) * E:(n + l + 1) * E]
+                gb = torch.zeros(3 * E, dtype=torch.float32, device=dev)
+                gb[E:2 * E], gb[2 * E:] = db[l * E:(l + 1) * E], db[(n + l) * E:(n + l + 1) * E]
+                if w_slots[l] is not None:
+                    w_slots[l].add_(gw)
+                else:
+                    grads[2 * l] = gw
+                if b_slots[l] is not None:
+                    b_slots[l].add_(gb)
+                else:
+                    grads[2 * l + 1] = gb
+        return (dmem, dmpos, dhead, None, None, None, None, *grads)
+
+
+def memory_kv(mhas, mem, mem_pos, mem_pos_head=None):
+    """Project the encoder memory to the keys / values of every decoder layer's cross-attention at once.  `mhas`: the
+    layers' nn.MultiheadAttention parameter containers.  Returns an opaque handle for `multi_head_attention(...,
+    memkv=(handle, layer_index))`, or None when the shapes are outside the fused kernels (composed path)."""
+    S, B, E = mem.shape
+    h = mhas[0].num_heads
+    if not (mem.is_cuda and E // h == 64 and E % 128 == 0 and all(m.in_proj_weight is not None for m in mhas)):
+        return None
+    shared = {"consumers": 0}
+    xk_hint = _act_bf16(mem, S * B, E) if mem_pos is None else _act_pos_bf16(mem, mem_pos, S * B, E)
+    params = []
+    for m in mhas:
+        params += [m.in_proj_weight, m.in_proj_bias]
+    KV = _MemKV.apply(mem, mem_pos, mem_pos_head, xk_hint, _act_bf16(mem, S * B, E), h, shared, *params)
+    return KV, shared, len(mhas), S
+
+
+class _MHACrossKV(torch.autograd.Function):
+    """Cross-attention block on keys / values precomputed by `_MemKV` (layer `li` of `n`): Q in-projection, fused
+    attention, out-projection.  Backward writes dK / dV token-major into this layer's column blocks of the shared
+    (S B, 2 n E) buffer; the K / V weight gradients and d(memory) are formed once for all layers in `_MemKV.backward`."""
+
+    @staticmethod
+    def forward(ctx, x, qpos, KV, li, n, S, shared, w_in, b_in, w_out, b_out, nh, kpm, p_drop, xq_hint=None):
+        L, B, E = x.shape
+        dev, bf = x.device, torch.bfloat16
+        xq_b = xq_hint if xq_hint is not None else _tok_bf16(x, qpos, L, B, E)
+        wb, wo_b = _wb(w_in), _wb(w_out)
+        Z = B * nh
+        Qh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        K.gemm_ex(L * B, E, E, 1, xq_b, False, 0, wb[:E], False, 0, Qh, c_mode=1, hs=(B, nh, L), ldc=64, bias=b_in[:E])
+        Kh, Vh = KV[li], KV[n + li]
+        O_tok, lse, kpm_u8, aux = _attn_core_fwd(Qh, Kh, Vh, L, S, B, nh, kpm, p_drop, dev)
+        out = K.gemm_bf16(O_tok, wo_b, bias=b_out)
+        ctx.save_for_backward(xq_b, wb, wo_b, Qh, KV, lse, kpm_u8, O_tok)
+        ctx.aux = aux
+        ctx.dims = (L, S, B, E, nh, p_drop, li, n, None if qpos is None else tuple(qpos.shape))
+        ctx.params, ctx.shared = (w_in, b_in, w_out, b_out), shared
+        shared["consumers"] += 1
+        return out.view(L, B, E)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xq_b, wb, wo_b, Qh, KV, lse, kpm_u8, O_tok = ctx.saved_tensors
+        L, S, B, E, nh, p_drop, li, n, qpos_shape = ctx.dims
+        w_in, b_in, w_out, b_out = ctx.params
+        shared = ctx.shared
+        dev, bf = dout.device, torch.bfloat16
+        Z = B * nh
+        slots = [_grad_slot(w_in), _grad_slot(b_in), _grad_slot(w_out), _grad_slot(b_out)]
+        dW_in = slots[0] if slots[0] is not None else torch.zeros((3 * E, E), dtype=torch.float32, device=dev)
+        db_in = slots[1] if slots[1] is not None else torch.zeros(3 * E, dtype=torch.float32, device=dev)
+        dWo = slots[2] if slots[2] is not None else torch.zeros((E, E), dtype=torch.float32, device=dev)
+        dbo = slots[3] if slots[3] is not None else torch.zeros(E, dtype=torch.float32, device=dev)
+        dout_b, bias_done = _grad_bf16(dout, L * B, E, b_out)
+        _dw(dout_b, O_tok, dWo)
+        if not bias_done:
+            K.colsum(dout_b, dbo)
+        dOh = torch.empty((Z * L, 64), dtype=bf, device=dev)
+        K.gemm_ex(L * B, E, E, 1, dout_b, False, 0, wo_b, True, 0, dOh, c_mode=1, hs=(B, nh, L), ldc=64)
+        first = "G" not in shared
+        if first:
+            shared["G"] = torch.empty((S * B, 2 * n * E), dtype=bf, device=dev)
+            shared["written"] = set()
+        G = shared["G"]
+        dQ_tok = torch.empty((L * B, E), dtype=bf, device=dev)
+        _attn_core_bwd(dOh, Qh, KV[li], KV[n + li], O_tok, lse, kpm_u8, L, S, B, nh, ctx.aux, p_drop, dQ_tok,
+                       G[:, li * E:(li + 1) * E], G[:, (n + li) * E:(n + li + 1) * E])
+        shared["written"].add(li)
+        _dw(dQ_tok, xq_b, dW_in[:E])
+        K.colsum(dQ_tok, db_in[:E])
+        dx = K.gemm_bf16(dQ_tok, wb[:E], b_mn=True)
+        dqpos = None
+        if qpos_shape is not None and ctx.needs_input_grad[1]:
+            dqpos = dx.view(L, B, E) if qpos_shape[1] == B else dx.view(L, B, E).sum(1, keepdim=True)
+        # the gradient autograd carries for KV is only a token: the first layer to run hands over the shared buffer
+        # (reinterpreted in KV's shape), the others return None, so autograd never adds anything up
+        dKV = G.view(KV.shape) if first else None
+        rets = [None if sl is not None else t for sl, t in zip(slots, (dW_in, db_in, dWo, dbo))]
+        return (dx.view(L, B, E), dqpos, dKV, None, None, None, None, *rets, None, None, None, None)
+
+
 def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=None, training=False, pos_head=None,
-                         mem_pos_head=None):
+                         mem_pos_head=None, memkv=None):
     """nn.MultiheadAttention semantics of the reference's call sites (seq-first (L, B, E) tensors;
     only the attended output is returned -- the reference discards the averaged weights it asks
     for, transformer.py:246-248):
@@ -524,13 +731,20 @@ def multi_head_attention(mha, x, pos, mem=None, mem_pos=None, key_padding_mask=N
         # bf16 operand copies left on the activations by the LayerNorm that produced them
         xq_hint = _act_bf16(x, L * B, E) if pos is None else _act_pos_bf16(x, pos, L * B, E)
         if mem is None:
-            return _MHASelf.apply(x, pos, pos_head, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
-                                  mha.out_proj.bias, h, key_padding_mask, p, xq_hint, _act_bf16(x, L * B, E))
-        S = mem.shape[0]
-        xk_hint = _act_bf16(mem, S * B, E) if mem_pos is None else _act_pos_bf16(mem, mem_pos, S * B, E)
-        return _MHACross.apply(x, pos, mem, mem_pos, mem_pos_head, mha.in_proj_weight, mha.in_proj_bias,
-                               mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p, xq_hint, xk_hint,
-                               _act_bf16(mem, S * B, E))
+            out = _MHASelf.apply(x, pos, pos_head, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight,
+                                 mha.out_proj.bias, h, key_padding_mask, p, xq_hint, _act_bf16(x, L * B, E))
+        elif memkv is not None:  # keys / values of this layer were projected together with all other layers' (memory_kv)
+            (KV, shared, n_layers, S), li = memkv
+            out = _MHACrossKV.apply(x, pos, KV, li, n_layers, S, shared, mha.in_proj_weight, mha.in_proj_bias,
+                                    mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p, xq_hint)
+        else:
+            S = mem.shape[0]
+            xk_hint = _act_bf16(mem, S * B, E) if mem_pos is None else _act_pos_bf16(mem, mem_pos, S * B, E)
+            out = _MHACross.apply(x, pos, mem, mem_pos, mem_pos_head, mha.in_proj_weight, mha.in_proj_bias,
+                                  mha.out_proj.weight, mha.out_proj.bias, h, key_padding_mask, p, xq_hint, xk_hint,
+                                  _act_bf16(mem, S * B, E))
+        out._pcm_bias = mha.out_proj.bias  # the LayerNorm that consumes `out` forms this bias gradient (colsum of dx)
+        return out
     if pos_head is not None:  # restore the differentiable concatenation for the composed path
         pos = torch.cat([pos_head.expand(-1, B, -1), pos[pos_head.shape[0]:]], dim=0)
     if mem_pos_head is not None:
@@ -560,7 +774,9 @@ class _AddDropoutLN(torch.autograd.Function):
     GEMMs; the backward leaves bf16(dx) for the sub-block backward that consumes dx."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps, p_drop, want_bf16, pos):
+    def forward(ctx, x, res, gamma, beta, eps, p_drop, want_bf16, pos, x_bias=None):
+        """`x_bias`: the bias Parameter of the linear layer that produced `x` (out_proj.bias / linear2.bias): its gradient
+        is colsum(dx), accumulated by the backward kernel itself when the parameter owns a flat-gradient slot."""
         shape = res.shape
         C = shape[-1]
         res2 = res.reshape(-1, C)
@@ -576,7 +792,7 @@ class _AddDropoutLN(torch.autograd.Function):
                                                          want_bf16=want_bf16, pos=pos2, pos_row_div=div)
         ctx.save_for_backward(h, mean, rstd, gamma)
         ctx.cfg = (p_drop, seed_base, seed, x is not None, shape)
-        ctx.params = (gamma, beta)
+        ctx.params = (gamma, beta, x_bias if x is not None else None)
         yv = y.view(shape)
         # second handle on the same storage (not an autograd view of the first): consumers that use y as the
         # RESIDUAL operand of the next LayerNorm take this one, so the two gradient contributions of y arrive
@@ -593,7 +809,7 @@ class _AddDropoutLN(torch.autograd.Function):
         if dy is None:
             dy, dy_res = dy_res, None
         if dy is None:
-            return (None,) * 8
+            return (None,) * 9
         h, mean, rstd, gamma = ctx.saved_tensors
         p_drop, seed_base, seed, has_x, shape = ctx.cfg
         dy2 = dy.reshape(h.shape)
@@ -605,15 +821,18 @@ class _AddDropoutLN(torch.autograd.Function):
             if not dyr.is_contiguous():
                 dyr = dyr.contiguous()
         g_slot, b_slot = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
+        x_bias = ctx.params[2]
+        xb_slot = _grad_slot(x_bias) if x_bias is not None else None
         dres, dx, dgamma, dbeta, dxb = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
-                                                            dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x, dy_b=dyr)
+                                                            dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x, dy_b=dyr,
+                                                            dx_colsum=xb_slot)
         _GRAD_BF16.clear()
         dx_out = None
         if has_x:
             dx_out = dx.view(shape)
-            _GRAD_BF16[dx_out.data_ptr()] = (dxb, dx_out)
+            _GRAD_BF16[dx_out.data_ptr()] = (dxb, dx_out, x_bias if xb_slot is not None else None)
         return (dx_out, dres.view(shape), None if g_slot is not None else dgamma, None if b_slot is not None else dbeta,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=None):
@@ -633,7 +852,8 @@ def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=N
         if res_in is None or res_in.shape != residual.shape:
             res_in = residual
         y, yb, ypb, y_res = _AddDropoutLN.apply(xr, res_in.contiguous(), norm.weight, norm.bias, norm.eps, p_eff, bool(cast),
-                                                None if cast_pos is None else cast_pos.detach())
+                                                None if cast_pos is None else cast_pos.detach(),
+                                                getattr(x, "_pcm_bias", None) if x is not None else None)
         y._pcm_res = y_res
         if yb is not None:
             y._pcm_bf16 = yb
@@ -682,7 +902,7 @@ class _FFN(torch.autograd.Function):
         p_drop, seed = ctx.cfg
         w1, b1, w2, b2 = ctx.params
         rows, Hd = h.shape
-        dyb = _grad_bf16(dy, rows, dy.shape[1])
+        dyb, b2_done = _grad_bf16(dy, rows, dy.shape[1], b2)
         grads = []
         for w, a, b in ((w2, dyb, hd), ):
             slot = _grad_slot(w)
@@ -690,16 +910,19 @@ class _FFN(torch.autograd.Function):
             _dw(a, b, dw)
             grads.append(None if slot is not None else dw)
         slot = _grad_slot(b2)
-        db2 = K.colsum(dyb, slot)
+        db2 = slot if b2_done else K.colsum(dyb, slot)
         dhd = K.gemm_bf16(dyb, w2b, b_mn=True)  # (rows, E) x W2(E, Hd) -> (rows, Hd) fp32
         dhb = torch.empty_like(h)
-        check(lib.pcm_ffn_relu_dropout_bwd(rows, Hd, ptr(dhd), ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(dhb),
-                                           current_stream()), "pcm_ffn_relu_dropout_bwd")
+        slotb1 = _grad_slot(b1)
+        fuse_b1 = Hd <= 256 and 256 % (Hd // 8) == 0  # the gate kernel can form colsum(dh) = db1 itself
+        db1 = slotb1 if slotb1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dyb.device)
+        check(lib.pcm_ffn_relu_dropout_bwd_ex(rows, Hd, ptr(dhd), ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(dhb),
+                                              ptr(db1 if fuse_b1 else None), current_stream()), "pcm_ffn_relu_dropout_bwd_ex")
         slot1 = _grad_slot(w1)
         dw1 = slot1 if slot1 is not None else torch.zeros(w1.shape, dtype=torch.float32, device=dyb.device)
         _dw(dhb, xb, dw1)
-        slotb1 = _grad_slot(b1)
-        db1 = K.colsum(dhb, slotb1)
+        if not fuse_b1:
+            K.colsum(dhb, db1)
         dx = K.gemm_bf16(dhb, w1b, b_mn=True) if ctx.needs_input_grad[0] else None
         return (dx, None if slot1 is not None else dw1, None if slotb1 is not None else db1, grads[0],
                 None if slot is not None else db2, None, None)
@@ -718,7 +941,9 @@ def feed_forward(x, linear1, linear2, p_drop, training):
     if x2.stride(-1) != 1 or (x2.stride(0) % 8) or (x2.data_ptr() % 16):
         x2 = x2.contiguous()
     y = _FFN.apply(x2, linear1.weight, linear1.bias, linear2.weight, linear2.bias, p, _act_bf16(x, x2.shape[0], E))
-    return y.view(*x.shape[:-1], linear2.weight.shape[0])
+    y = y.view(*x.shape[:-1], linear2.weight.shape[0])
+    y._pcm_bias = linear2.bias  # see multi_head_attention
+    return y
 
 
 def dropout(x, p, training):

@@ -103,19 +103,25 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32
 
 
 def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, *, c_mode=0, c_batch_rows=0,
-            hs=(0, 0, 0), ldc=None, alpha=1.0, bias=None, relu=False, accumulate=False, split_k=1):
-    """Batched tcgen05 GEMM with head-split / head-merge output addressing (pcm_gemm_bf16_ex).
-    a, b: 2-D bf16 tensors spanning all batches (last dim contiguous); out: destination tensor."""
+            hs=(0, 0, 0), ldc=None, alpha=1.0, bias=None, relu=False, accumulate=False, split_k=1, a2=None, a2_from_col=0,
+            hs_parts=(0, 0)):
+    """Batched tcgen05 GEMM with head-split / head-merge output addressing (pcm_gemm_bf16_ex2).
+    a, b: 2-D bf16 tensors spanning all batches (last dim contiguous); out: destination tensor.
+    `a2` / `a2_from_col`: second A operand for the output columns >= a2_from_col; `hs_parts` = (columns per part,
+    elements between the parts' tensors) for a head-split output that spans several (B, nh, L, 64) tensors."""
     require_cuda(a, b, out)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and a2.shape == a.shape and a2.stride(1) == 1
     if ldc is None:
         ldc = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
     t0 = TIMER.begin()
-    check(lib.pcm_gemm_bf16_ex(M, N, Kd, batch, ptr(a), a.stride(0), int(a_mn), a.shape[0], a_batch_rows,
-                               ptr(b), b.stride(0), int(b_mn), b.shape[0], b_batch_rows, ptr(out), ldc,
-                               int(out.dtype == torch.bfloat16), c_mode, c_batch_rows, hs[0], hs[1], hs[2],
-                               float(alpha), ptr(bias), int(relu), int(accumulate), int(split_k), current_stream()),
-          "pcm_gemm_bf16_ex")
+    check(lib.pcm_gemm_bf16_ex2(M, N, Kd, batch, ptr(a), a.stride(0), int(a_mn), a.shape[0], a_batch_rows,
+                                ptr(b), b.stride(0), int(b_mn), b.shape[0], b_batch_rows, ptr(out), ldc,
+                                int(out.dtype == torch.bfloat16), c_mode, c_batch_rows, hs[0], hs[1], hs[2],
+                                float(alpha), ptr(bias), int(relu), int(accumulate), int(split_k), ptr(a2),
+                                a2.stride(0) if a2 is not None else 0, int(a2_from_col), int(hs_parts[0]), int(hs_parts[1]),
+                                current_stream()), "pcm_gemm_bf16_ex2")
     TIMER.end(t0, "gemm_tcgen05", 2.0 * M * N * Kd * batch,
               batch * (2.0 * (M * Kd + N * Kd) + M * N * out.element_size()),
               (M, N, Kd, batch, int(a_mn), int(b_mn), str(out.dtype)[6:], int(split_k)))
@@ -191,8 +197,9 @@ def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset,
 
 
 def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None,
-                       want_dx_bf16=False, dy_b=None):
-    """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics).
+                       want_dx_bf16=False, dy_b=None, dx_colsum=None):
+    """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics); so is `dx_colsum` (C floats):
+    the column sums of dx = the bias gradient of the linear layer that produced x.
     Returns (dres, dx, dgamma, dbeta, dx_bf16)."""
     rows, C = h.shape
     dres = torch.empty_like(h)
@@ -202,9 +209,10 @@ def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset,
     if dbeta is None:
         dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
     dxb = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device) if (want_dx_bf16 and need_dx) else None
-    check(lib.pcm_add_dropout_ln_bwd_ex(rows, C, ptr(dy), ptr(dy_b), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
-                                        ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
-                                        ptr(dxb), current_stream()), "pcm_add_dropout_ln_bwd_ex")
+    check(lib.pcm_add_dropout_ln_bwd_ex2(rows, C, ptr(dy), ptr(dy_b), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
+                                         ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                         ptr(dxb), ptr(dx_colsum if need_dx else None), current_stream()),
+          "pcm_add_dropout_ln_bwd_ex2")
     return dres, dx, dgamma, dbeta, dxb
 
 

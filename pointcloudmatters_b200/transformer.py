@@ -102,7 +102,9 @@ class TransformerDecoderLayer(nn.Module):
         return PF.feed_forward(x, self.linear1, self.linear2, self.p, self.training)
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
-                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):
+                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None, memkv=None):
+        """`memkv` (extension): this layer's slot of the memory keys / values projected for all layers at once by
+        `TransformerDecoder.forward` (functional.memory_kv)."""
         assert tgt_mask is None and memory_mask is None and tgt_key_padding_mask is None
         tr = self.training
         if self.normalize_before:
@@ -117,7 +119,7 @@ class TransformerDecoderLayer(nn.Module):
         a = PF.multi_head_attention(self.self_attn, tgt, query_pos, None, None, None, tr)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr, cast_pos=query_pos)  # -> cross-attention queries
         a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr,
-                                    mem_pos_head=pos_head)
+                                    mem_pos_head=pos_head, memkv=memkv)
         tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr, cast=True)  # -> FFN
         # -> next layer's self-attention
         return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr, cast=True, cast_pos=query_pos)
@@ -136,14 +138,21 @@ class TransformerDecoder(nn.Module):
         self.norm = norm
         self.return_intermediate = return_intermediate
         self.skip_dead_layers = False
+        self.group_memory_kv = True  # A/B switch: False = every layer projects the memory itself (reference structure)
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):
         out, inter = tgt, []
         ln = (lambda x: PF.add_dropout_layernorm(None, x, self.norm, 0.0, False))
+        # the memory is the same for every layer: project it to all layers' keys / values in ONE launch
+        # (post-LN layers only; the reference recomputes the projections inside each layer, transformer.py:317-346)
+        live = self.layers[:1] if (self.skip_dead_layers and self.return_intermediate) else self.layers
+        kv = None
+        if self.group_memory_kv and not self.layers[0].normalize_before and len(live) > 0:
+            kv = PF.memory_kv([l.multihead_attn for l in live], memory, pos, pos_head)
         for li, layer in enumerate(self.layers):
             out = layer(out, memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos,
-                        pos_head=pos_head)
+                        pos_head=pos_head, memkv=None if (kv is None or li >= len(live)) else (kv, li))
             if self.return_intermediate:
                 inter.append(ln(out))
                 if self.skip_dead_layers and li == 0:

@@ -133,3 +133,72 @@ def test_token_fast_path_equals_the_concatenating_path():
     scale = max(float(v.norm()) for v in g2.values())
     for k in g1:
         assert float((g1[k] - g2[k]).norm()) <= 2e-3 * max(float(g2[k].norm()), 1e-3 * scale), k
+
+
+def test_grouped_memory_kv_equals_per_layer_projection():
+    """Decoder cross-attention keys / values projected for all layers in ONE launch (functional.memory_kv) vs. inside each
+    layer (the reference's structure, transformer.py:317-346): same outputs and the same gradients for every parameter,
+    the memory and the learned positional rows."""
+    from pointcloudmatters_b200._lib import lib
+    from pointcloudmatters_b200.data import synthetic_act_batch, to_device
+
+    policy, cfg = _policy(128, enc_layers=1, dec_layers=3)
+    h = synthetic_act_batch(4, 256, num_queries=12, seed=8)
+    results = []
+    for grouped in (True, False):
+        policy.zero_grad(set_to_none=True)
+        policy.transformer.decoder.group_memory_kv = grouped
+        b = to_device(h, "cuda")
+        b["pcds"]["n_max"] = h["pcds"]["n_max"]
+        b["_eps"] = torch.randn(4, 32, generator=torch.Generator().manual_seed(2)).cuda()
+        n0 = lib.calls.get("pcm_gather_slices", 0)
+        out = policy(b)
+        # make every decoder layer live for this comparison: add the later intermediate outputs to the loss
+        hs_all = policy.transformer.decoder  # noqa: F841  (layers 1.. are dead for the ACT loss itself)
+        out["loss"].backward()
+        assert (lib.calls.get("pcm_gather_slices", 0) > n0) == grouped
+        results.append((out["loss"].detach().clone(), out["a_hat"].detach().clone(),
+                        {k: p.grad.clone() for k, p in policy.named_parameters() if p.grad is not None}))
+    (l1, a1, g1), (l2, a2, g2) = results
+    torch.testing.assert_close(l1, l2, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(a1, a2, rtol=1e-3, atol=1e-4)
+    assert g1.keys() == g2.keys()
+    scale = max(float(v.norm()) for v in g2.values())
+    for k in g1:
+        assert float((g1[k] - g2[k]).norm()) <= 2e-3 * max(float(g2[k].norm()), 1e-3 * scale), k
+
+
+def test_grouped_memory_kv_with_all_layers_live():
+    """Same comparison on the bare Transformer with a loss over ALL intermediate decoder outputs, so that every layer's
+    dK / dV block of the shared buffer carries a real gradient."""
+    from pointcloudmatters_b200.transformer import Transformer
+
+    torch.manual_seed(4)
+    tr = Transformer(d_model=128, nhead=2, num_encoder_layers=1, num_decoder_layers=3, dim_feedforward=32, dropout=0.0,
+                     return_intermediate_dec=True).cuda().train()
+    B, M, E, Q = 3, 70, 128, 9
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(B, E, 1, M, generator=g).cuda().requires_grad_(True)
+    pos = torch.randn(B, E, 1, M, generator=g).cuda()
+    qe = torch.randn(Q, E, generator=g).cuda().requires_grad_(True)
+    lat = torch.randn(1, B, E, generator=g).cuda().requires_grad_(True)
+    prop = torch.randn(2, B, E, generator=g).cuda()
+    add = torch.randn(3, E, generator=g).cuda().requires_grad_(True)
+    wts = torch.randn(3, B, Q, E, generator=g).cuda()
+    res = []
+    for grouped in (True, False):
+        for t in (src, qe, lat, add):
+            t.grad = None
+        tr.zero_grad(set_to_none=True)
+        tr.decoder.group_memory_kv = grouped
+        hs = tr(src, None, qe, pos, lat, prop, add)
+        (hs * wts).sum().backward()
+        res.append((hs.detach().clone(), [t.grad.clone() for t in (src, qe, lat, add)],
+                    {k: p.grad.clone() for k, p in tr.named_parameters()}))
+    (h1, i1, p1), (h2, i2, p2) = res
+    torch.testing.assert_close(h1, h2, rtol=1e-3, atol=1e-4)
+    for a, b_ in zip(i1, i2):
+        assert float((a - b_).norm()) <= 3e-3 * float(b_.norm()) + 1e-6
+    scale = max(float(v.norm()) for v in p2.values())
+    for k in p1:
+        assert float((p1[k] - p2[k]).norm()) <= 3e-3 * max(float(p2[k].norm()), 1e-3 * scale), k

@@ -42,7 +42,10 @@ def main(path):
         fam["gemm_tcgen05" if "gemm_tcgen05" in name else "flash_attn" if name.startswith("flash_") else
             "layernorm/colsum/cast" if any(s in name for s in ("add_dropout_ln", "colsum", "add_cast")) else
             "set abstraction + pointops" if any(s in name for s in ("sa_", "knn_", "fps_")) else
-            "optimizer" if any(s in name for s in ("adamw", "sumsq")) else "ATen / library glue"] += ns
+            "optimizer" if any(s in name for s in ("adamw", "sumsq", "_slices_kernel")) else
+            "batchnorm / ffn gate / heads / tokens (own)" if any(s in name for s in ("bn_", "ffn_", "act_heads", "coord_embed", "fill_head",
+                                                                                   "unet", "groupnorm", "mish", "grid_", "spconv"))
+            else "ATen / library glue"] += ns
     for f_, ns in sorted(fam.items(), key=lambda kv: -kv[1]):
         print(f"# family {f_:28s} {ns / steps / 1e3:9.1f} us/step {100 * ns / total:5.1f}%")
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
