@@ -455,6 +455,32 @@ int pcm_act_heads_loss_bwd(int B, int Q, int E, int A, int L, int sig_start, int
 int pcm_gather_slices(int n, long long bytes_per_slice, const long long *ptrs, void *dst, pcm_stream_t stream);
 int pcm_add_slices(int n, long long floats_per_slice, const long long *ptrs, const float *src, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GPU data path: voxel-grid subsampling of a packed batch of raw clouds, replacing the
+ * per-sample CPU transform GridSamplePCD (src/data/components/transformpcd.py:684-793, hash_type "fnv") and the
+ * packing of pcd_collate_fn (src/utils/sparse_tensor_utils.py:65-82).
+ *   grid = floor(coord / grid_size) (float64 arithmetic like numpy >= 2; f32_div = 1: float32 like numpy 1.x),
+ *   grid -= per-cloud minimum, key = FNV64-1A(grid) (:775-793), one survivor per distinct key, output ordered by
+ *   ascending key (:693-704).  Survivor = the member with the smallest prio[i] (uint32; NULL: the point's index inside
+ *   its cloud, i.e. the first member = the reference's test-mode part 0 under a stable argsort; a random priority =
+ *   its train mode), ties by index.
+ * pcm_grid_sample_select: workspace grid (n,3) i32, gmin (b,3) i32 preset to INT_MAX, tkey / tbest (2n) u64 preset to
+ *   all-ones, scratch_key (2n) u64 / scratch_val (2n) u32; outputs at RAW offsets: idx_raw (n) i64, grid_raw (n,3) i64,
+ *   counts (b) i32 = voxels per cloud.
+ * pcm_grid_sample_gather: dense packing once the counts are known: coord_out (m,3), grid_out (m,3) i64, feat_out
+ *   (m, fc [+3]) = [feat / feat_scale - feat_shift (NormalizeColorPCD) , coord (CollectPCD feat_keys)], index_out (m).
+ * ------------------------------------------------------------------------------------------ */
+int pcm_grid_sample_select(int b, long long n, const float *coord, const long long *offset, double gsx, double gsy,
+                           double gsz, int f32_div, const unsigned int *prio, int *grid, int *gmin,
+                           unsigned long long *tkey, unsigned long long *tbest, unsigned long long *scratch_key,
+                           unsigned int *scratch_val, long long *idx_raw, long long *grid_raw, int *counts,
+                           pcm_stream_t stream);
+int pcm_grid_sample_gather(int b, long long m, const long long *raw_offset, const long long *new_offset,
+                           const long long *idx_raw, const long long *grid_raw, const float *coord,
+                           const float *feat, int fc, float feat_scale, float feat_shift, int append_coord,
+                           float *coord_out, long long *grid_out, float *feat_out, long long *index_out,
+                           pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
