@@ -481,6 +481,40 @@ int pcm_grid_sample_gather(int b, long long m, const long long *raw_offset, cons
                            float *coord_out, long long *grid_out, float *feat_out, long long *index_out,
                            pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Sparse convolutions of the SpUNet encoder (reference
+ * src/models/components/pcd_encoder/spunet.py:95-122,159-217,368-372 on the un-vendored `spconv` library): rules
+ * (integer work) + gathers; the contraction itself is pcm_gemm_bf16 on the (rows, k^3 * Cin) column matrix with the
+ * weight (Cout, k, k, k, Cin) read in place.  coords (n, 4) int32 = [batch, x, y, z], 0 <= value < 65536.
+ *   pcm_spconv_build_table: open-addressing table (tkey (cap) u64 preset to all-ones, tval (cap) i32 preset to INT_MAX,
+ *     cap a power of two >= 2n) of the voxels (shift 0) or of their stride-2 parents coord >> 1 (shift 1, value = the
+ *     smallest child row).
+ *   pcm_spconv_subm_rules: nbr (n, k^3): row of the active voxel at coord + (ox, oy, oz) - k/2, offset index
+ *     o = (ox k + oy) k + oz, or -1 (SubMConv3d: output set = input set).
+ *   pcm_spconv_down_rules (SparseConv3d k = 2, stride 2 / SparseInverseConv3d): parent (n), kidx (n) = ((x&1) 2 + (y&1)) 2
+ *     + (z&1), child (n, 8) preset to -1, coarse_coords (n, 4), m_out (1) = number of coarse voxels (numbered by their
+ *     smallest child row); scratch leader (n), excl (n).
+ *   pcm_spconv_gather: col[i, o Cp + c] = x[nbr[i, o], c] as bf16 (0 where nbr = -1 or c >= C), Cp = C rounded up to 8.
+ *   pcm_spconv_gather_bwd: dx[j, c] = sum_o dcol[nbr[j, k^3-1-o], o Cp + c] (mode 0, submanifold) or
+ *     dcol[parent[j], kidx[j] Cp + c] (mode 1, stride-2).
+ *   pcm_spconv_inverse_pick / _place: out[i, co] = Z[parent[i], co 8 + kidx[i]]; dZ[m, co 8 + kk] = dout[child[m, kk], co].
+ * ------------------------------------------------------------------------------------------ */
+int pcm_spconv_build_table(long long n, const int *coords, int shift, unsigned long long *tkey, int *tval,
+                           long long cap, pcm_stream_t stream);
+int pcm_spconv_subm_rules(long long n, int k, const int *coords, const unsigned long long *tkey, const int *tval,
+                          long long cap, int *nbr, pcm_stream_t stream);
+int pcm_spconv_down_rules(long long n, const int *coords, const unsigned long long *tkey, const int *tval,
+                          long long cap, int *leader, int *excl, int *parent, int *kidx, int *child,
+                          int *coarse_coords, int *m_out, pcm_stream_t stream);
+int pcm_spconv_gather(long long rows, int kvol, int C, int Cp, const void *x, long long ldx, int x_bf16,
+                      const int *nbr, void *col, pcm_stream_t stream);
+int pcm_spconv_gather_bwd(long long rows, int kvol, int C, int Cp, int mode, const float *dcol, const int *nbr,
+                          const int *parent, const int *kidx, float *dx, pcm_stream_t stream);
+int pcm_spconv_inverse_pick(long long rows, int Cout, const float *Z, const int *parent, const int *kidx,
+                            float *out, pcm_stream_t stream);
+int pcm_spconv_inverse_place(long long coarse_rows, int Cout, const float *dout, const int *child, void *dZ,
+                             pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -956,7 +956,9 @@ class _BatchNormReLU(torch.autograd.Function):
     linear's backward GEMMs, accumulates dgamma / dbeta into the parameters' gradient buffers."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, relu, extra=None):
+        """`extra`: [(running_mean, running_var, momentum), ...] of further BatchNorm layers that are fed the SAME input in
+        training mode and only need their running statistics updated (PDBatchNorm's non-selected conditions)."""
         from ._lib import check, current_stream, lib, ptr
 
         R, C = y.shape
@@ -965,6 +967,10 @@ class _BatchNormReLU(torch.autograd.Function):
         if training:
             check(lib.pcm_bn_stats(R, C, ptr(y), ptr(stats), st), "pcm_bn_stats")
         coef = torch.empty((4, C), dtype=torch.float32, device=y.device)
+        if training and extra:
+            for rm, rv, mom in extra:
+                check(lib.pcm_sa_bn_finalize(C, ptr(stats), float(R), ptr(gamma), ptr(beta), float(eps), float(mom), 1, ptr(rm), ptr(rv),
+                                             ptr(coef), st), "pcm_sa_bn_finalize")
         check(lib.pcm_sa_bn_finalize(C, ptr(stats), float(R), ptr(gamma), ptr(beta), float(eps), float(momentum), int(training),
                                      ptr(running_mean), ptr(running_var), ptr(coef), st), "pcm_sa_bn_finalize")
         out = torch.empty_like(y)
@@ -982,7 +988,7 @@ class _BatchNormReLU(torch.autograd.Function):
         from ._lib import check, current_stream, lib, ptr
 
         if dout is None:
-            return (None,) * 9
+            return (None,) * 10
         y, coef = ctx.saved_tensors
         training, relu = ctx.cfg
         gamma, beta = ctx.params
@@ -999,7 +1005,7 @@ class _BatchNormReLU(torch.autograd.Function):
                                   ptr(dg), ptr(db), current_stream()), "pcm_bn_relu_bwd")
         if dy is not None:
             _GRAD_BF16[dy.data_ptr()] = (dyb, dy)  # consumed (popped) by the producing linear's backward
-        return (dy, None if g_slot is not None else dg, None if b_slot is not None else db, None, None, None, None, None, None)
+        return (dy, None if g_slot is not None else dg, None if b_slot is not None else db, None, None, None, None, None, None, None)
 
 
 _NO_FUSED_BN = bool(int(os.environ.get("PCM_NO_FUSED_BN", "0")))  # A/B switch (ATen composition)
