@@ -35,6 +35,19 @@ CFG2 = dict(hidden_dim=512, nhead=8, dim_feedforward=32, enc_layers=4, dec_layer
             action_dim=7, qpos_dim=9, goal_cond_dim=3, latent_dim=32, kl_weight=10.0, pcd_npoints=512, pcd_nsample=16)
 BATCH_PER_GPU = 64
 N_POINTS = 1024
+# Other BASELINE.json configs, selectable with --config (the headline stays cfg2; these are extra bench lines):
+#   cfg3: Diffusion Policy (PCDObsEncoder + ConditionalUnet1D, 255.8 M parameters), N=1024, 128 samples over 8 GPUs =
+#         16 per GPU, PointNet backbone (scratch_pointnet_pcd.yaml) or --backbone spunet (the config as written);
+#   cfg4: RLBench ACT, N=4096 (M=2048, S=2051), action_dim 11 (rot6d + gripper + collision), 512-d goal embedding,
+#         32 samples over 8 GPUs = 4 per GPU.
+CONFIGS = {
+    "cfg2": dict(workload=WORKLOAD, batch=64, n_points=1024, kind="act"),
+    "cfg3": dict(workload="cfg3: ManiSkill2 StackCube, {backbone} encoder + Diffusion Policy (U-Net 255.8 M), N=1024 pts, "
+                          "bs=128 global / 8 GPUs = 16/GPU", batch=16, n_points=1024, kind="dp"),
+    "cfg4": dict(workload="cfg4: RLBench multi-view, PointNet-MLP + SA(FPS+kNN16) + ACT (rot6d/gripper/collision heads), N=4096 pts, "
+                          "M=2048, bs=32 global / 8 GPUs = 4/GPU", batch=4, n_points=4096, kind="act_rlbench"),
+}
+CFG4 = dict(CFG2, action_dim=11, qpos_dim=4, goal_cond_dim=512, pcd_npoints=2048, collision=True, position_loss_weight=1.0)
 
 
 def parse():
@@ -43,7 +56,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (default: BASELINE cfg-2)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json config (headline: cfg2)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's per-GPU batch on every rank; strong: that batch x 1 GPU split over the ranks")
+    ap.add_argument("--backbone", default="pointnet", choices=["pointnet", "spunet"], help="cfg3 encoder backbone")
+    ap.add_argument("--sync-batchnorm", action="store_true", help="SyncBatchNorm (configs/trainer/ddp.yaml:9); default local statistics")
+    ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of bucketed overlap")
+    ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"], help="gradient all-reduce wire format")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--cpu-sample-batch", type=int, default=4, help="clouds in the CPU baseline's untimed warm-up step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (debug / profiling)")
@@ -103,6 +123,11 @@ def reference_arm(args):
         return 0
     steps = max(1, min(args.steps, REF_MAX_STEPS))
     warmup = max(1, min(args.warmup, REF_MAX_WARMUP))
+    if args.config != "cfg2":
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU reference arm is implemented for the headline config (cfg2) only, not {args.config}"}),
+              flush=True)
+        return 0
+    args.batch = args.batch or BATCH_PER_GPU
     v, cores, ms = cpu_reference_run(args.batch, steps, warmup)
     sample = (f"{steps} timed + {warmup} warm-up FULL steps (fwd+bwd+clip+AdamW) of the oracle port (oracle/act_oracle.py + C "
               f"pointops oracle, fp32, torch CPU, {cores} threads) on {args.batch}-cloud cfg-2 batches, unscaled; "
@@ -188,19 +213,56 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
+    cfgd = CONFIGS[args.config]
+    kind = cfgd["kind"]
+    per_gpu = args.batch if args.batch is not None else cfgd["batch"]
+    if args.scaling == "strong":
+        assert per_gpu % world == 0, "strong scaling splits the single-GPU batch over the ranks"
+        per_gpu //= world
+    n_points = cfgd["n_points"]
+    workload = cfgd["workload"].format(backbone="SpUNet" if args.backbone == "spunet" else "PointNet-MLP")
     torch.manual_seed(1234)  # identical initial weights on every rank (DDP broadcast equivalent)
-    policy = build_policy(CFG2).to(dev).train()
-    policy.transformer.decoder.skip_dead_layers = bool(args.skip_dead_decoder_layers)
     total_steps = max(1000, args.steps + args.warmup + 8)
-    module = ACTBCModule(policy, total_steps=total_steps, use_cuda_graph=not args.no_cuda_graph)
+    dist_kw = dict(sync_batchnorm=args.sync_batchnorm, overlap_allreduce=not args.no_overlap,
+                   grad_wire_dtype=torch.bfloat16 if args.grad_wire == "bf16" else None)
+    if kind == "dp":
+        from pointcloudmatters_b200.bc_module import DiffusionPolicyBCModule
+        from pointcloudmatters_b200.data import synthetic_dp_batch
+        from pointcloudmatters_b200.diffusion import DP_MODEL_CFG, build_dp_policy
+
+        policy = build_dp_policy(dict(DP_MODEL_CFG, pcd_npoints=n_points // 2)).to(dev).train()
+        if args.backbone == "spunet":
+            from pointcloudmatters_b200.spunet import SpUNet
+
+            policy.obs_encoder.key_model_map["pcd"] = SpUNet(6, num_classes=96).to(dev).train()
+        policy.normalizer.set_identity({"qpos": 9, "action": 7}).to(dev)
+        graph = not args.no_cuda_graph and args.backbone != "spunet"  # SpUNet level sizes need device->host reads
+        module = DiffusionPolicyBCModule(policy, total_steps=total_steps, use_cuda_graph=graph, **dist_kw)
+        make = lambda seed, pin: synthetic_dp_batch(per_gpu, n_points, seed=seed, pin=pin)
+        pcds_of = lambda b: b["obs"]["pcds"]
+    else:
+        mcfg = CFG2 if kind == "act" else CFG4
+        policy = build_policy(mcfg, rlbench=kind == "act_rlbench").to(dev).train()
+        policy.transformer.decoder.skip_dead_layers = bool(args.skip_dead_decoder_layers)
+        module = ACTBCModule(policy, total_steps=total_steps, use_cuda_graph=not args.no_cuda_graph, **dist_kw)
+
+        def make(seed, pin):
+            b = synthetic_act_batch(per_gpu, n_points, action_dim=mcfg["action_dim"], qpos_dim=mcfg["qpos_dim"],
+                                    goal_cond_dim=mcfg["goal_cond_dim"], seed=seed, pin=pin)
+            if kind == "act_rlbench":
+                b["actions"][..., -2:] = torch.rand(per_gpu, mcfg["num_queries"], 2)
+            return b
+
+        pcds_of = lambda b: b["pcds"]
     module.configure_optimizers()
+    args.batch = per_gpu
 
     # per-rank shard of the global batch: distinct synthetic batches, pinned on the host
     n_pool = 4
-    host = [synthetic_act_batch(args.batch, N_POINTS, seed=1000 + rank * 97 + i, pin=True) for i in range(n_pool)]
+    host = [make(1000 + rank * 97 + i, True) for i in range(n_pool)]
     resident = [to_device(b, dev) for b in host]
     for r, h in zip(resident, host):
-        r["pcds"]["n_max"] = h["pcds"]["n_max"]
+        pcds_of(r)["n_max"] = pcds_of(h)["n_max"]
     h2d = batch_nbytes(host[0])
     torch.cuda.synchronize()
 
@@ -219,9 +281,9 @@ def b200_arm(args):
         for i in range(steps):
             b = batches[i % len(batches)]
             if from_host:
-                nm = b["pcds"]["n_max"]
+                nm = pcds_of(b)["n_max"]
                 b = to_device(b, dev, non_blocking=True)
-                b["pcds"]["n_max"] = nm
+                pcds_of(b)["n_max"] = nm
             loss = module.training_step(b, i)
             if from_host:
                 loss_host = float(loss)  # device->host read of the step result, every step
@@ -294,8 +356,9 @@ def b200_arm(args):
 
     # whole-job aggregate: every rank processes one cfg-2 step-unit (64 samples) per iteration, so
     # the job processes `world` units per global iteration (weak scaling)
-    value = world * args.steps * 1.0 / sec
-    e2e_value = world * args.steps * 1.0 / sec_e2e
+    units = world if args.scaling == "weak" else 1
+    value = units * args.steps * 1.0 / sec
+    e2e_value = units * args.steps * 1.0 / sec_e2e
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -304,16 +367,22 @@ def b200_arm(args):
     roofline = PF.roofline_for(kstats, peaks, 3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": 1e3 * sec / args.steps, "step_ms_rank0": step_ms, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * sec / args.steps, "step_ms_rank0": step_ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+        "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "batchnorm": "sync (all-reduced statistics, ddp.yaml:9)" if args.sync_batchnorm else
+                                "local statistics per rank (= reference with trainer.sync_batchnorm=false)",
+                   "allreduce": ("one collective after backward" if args.no_overlap else
+                                 "bucketed (decoder | encoder | rest), overlapped with backward") + f", {args.grad_wire} wire",
                    "l2": "per-step working set (activations + 385 MB parameter/optimizer state) exceeds the 126 MB L2; "
                          "4 distinct input batches cycled; no explicit flush",
-                   "dropout": CFG2["dropout"], "decoder_layers_computed": 1 if args.skip_dead_decoder_layers else CFG2["dec_layers"],
-                   "unit_definition": "one step = fwd+bwd+allreduce+clip+AdamW on one 64-sample cfg-2 batch; value = "
-                                      "step-units completed per second summed over ranks (N ranks finish N units per "
-                                      "global iteration)",
+                   "dropout": CFG2["dropout"] if kind != "dp" else 0.0,
+                   "decoder_layers_computed": None if kind == "dp" else (1 if args.skip_dead_decoder_layers else CFG2["dec_layers"]),
+                   "unit_definition": (f"one step = fwd+bwd+allreduce+clip+AdamW on one {cfgd['batch']}-sample {args.config} batch; "
+                                       "weak: value = step-units completed per second summed over ranks (N ranks finish N units "
+                                       "per global iteration); strong: the unit is split over the ranks, value = global "
+                                       "iterations per second"),
                    "global_iterations_per_sec": args.steps / sec,
                    "samples_per_sec": value * args.batch, "last_loss": last_loss},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -325,7 +394,7 @@ def b200_arm(args):
         "roofline": roofline,
         "kernel_ms_per_step": {k: v.get("total_ms_isolated", v["total_ms"]) / 3 for k, v in kstats.items()},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "cfg2" and args.scaling == "weak":
         v, cores, ms = cpu_reference_run(args.batch, 1, 1, warmup_batch=args.cpu_sample_batch)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                                 "sample": f"1 timed FULL step (fwd+bwd+clip+AdamW, {args.batch} clouds of cfg-2, unscaled) of the "

@@ -515,6 +515,24 @@ int pcm_spconv_inverse_pick(long long rows, int Cout, const float *Z, const int 
 int pcm_spconv_inverse_place(long long coarse_rows, int Cout, const float *dout, const int *child, void *dZ,
                              pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SyncBatchNorm support (reference DDP preset: configs/trainer/ddp.yaml:9 `sync_batchnorm: true`): the statistics buffers
+ * are all-reduced over the ranks BETWEEN the reduce and the finalize / apply kernels, together with the row count, which
+ * the kernels then read from device memory (n_rows_dev / n_total_dev; NULL = the host value, single-rank behaviour).
+ * Weight / bias gradients stay local sums (torch.nn.SyncBatchNorm semantics; the gradient all-reduce averages them).
+ * ------------------------------------------------------------------------------------------ */
+int pcm_sa_bn_finalize_ex(int H, const double *stats, double n_rows, const double *n_rows_dev, const float *gamma,
+                          const float *beta, float eps, float momentum, int training, float *running_mean,
+                          float *running_var, float *coef, pcm_stream_t stream);
+int pcm_sa_bwd_coef_ex(int H, const double *gstats, const double *fstats, const double *sdtot, const float *coef,
+                       double n_rows, const double *n_rows_dev, int training, float *ab, float *dW, int ldw,
+                       float *dgamma, float *dbeta, pcm_stream_t stream);
+int pcm_bn_relu_bwd_reduce(long long R, int C, const float *dout, const float *y, const float *coef, int relu,
+                           double *gstats, pcm_stream_t stream);
+int pcm_bn_relu_bwd_apply(long long R, int C, const float *dout, const float *y, const float *coef, int relu,
+                          int training, const double *gstats, const double *n_total_dev, float *dy, void *dy_bf16,
+                          float *dgamma, float *dbeta, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,6 +331,14 @@ class ACTPCD(nn.Module):
         data_dict.pop("_hs", None)
         return True
 
+    def grad_buckets(self):
+        """Parameter-name prefixes of the gradient buckets in the order their gradients become final during backward, with
+        the boundary tag (functional.grad_boundary) that closes each; the last bucket (None) is everything else and closes
+        when backward returns.  The trainer lays the flat gradient out in this order and all-reduces bucket by bucket."""
+        return [("transformer.decoder", ("transformer.decoder.", "action_head.", "is_pad_head.")),
+                ("transformer.encoder", ("transformer.encoder.",)),
+                (None, ("",))]
+
     def _presample(self, data_dict):
         """FPS + kNN depend only on the input coordinates and are latency-bound (a chain of M-1
         dependent rounds on 64 of the 148 SMs): run them on a side stream while the CVAE encoder

@@ -22,14 +22,16 @@ from .trainer import BCTrainer
 class ACTBCModule(nn.Module):
     def __init__(self, policy, optimizer: dict | None = None, lr_scheduler: dict | None = None,
                  gradient_clip_val: float = 0.5, total_steps: int = 100000, use_cuda_graph: bool = False,
-                 accumulate_grad_batches: int = 1, debug_hints: bool = False, **kwargs):
+                 accumulate_grad_batches: int = 1, debug_hints: bool = False, sync_batchnorm: bool = False,
+                 overlap_allreduce: bool = True, grad_wire_dtype=None, **kwargs):
         super().__init__()
         self.policy = policy
         # defaults = configs/model/maniskill2_act_pcd_model.yaml:11-25, configs/trainer/ddp.yaml:12
         self.hparams = dict(optimizer=dict(type="AdamW", lr=5e-5, weight_decay=0.05) | (optimizer or {}),
                             lr_scheduler=lr_scheduler, gradient_clip_val=gradient_clip_val, total_steps=total_steps,
                             use_cuda_graph=use_cuda_graph, accumulate_grad_batches=accumulate_grad_batches,
-                            debug_hints=debug_hints)
+                            debug_hints=debug_hints, sync_batchnorm=sync_batchnorm, overlap_allreduce=overlap_allreduce,
+                            grad_wire_dtype=grad_wire_dtype)
         self._trainer: BCTrainer | None = None
         self.logged: dict[str, Any] = {}
 
@@ -49,8 +51,11 @@ class ACTBCModule(nn.Module):
                                   clip_norm=self.hparams["gradient_clip_val"], total_steps=self.hparams["total_steps"],
                                   scheduler=sch, use_cuda_graph=self.hparams["use_cuda_graph"],
                                   accumulate_grad_batches=self.hparams["accumulate_grad_batches"],
-                                  debug_hints=self.hparams["debug_hints"])
+                                  debug_hints=self.hparams["debug_hints"], **self._dist_kwargs())
         return self._trainer
+
+    def _dist_kwargs(self):
+        return {k: self.hparams[k] for k in ("sync_batchnorm", "overlap_allreduce", "grad_wire_dtype")}
 
     def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
         """forward + backward + gradient all-reduce + clip + AdamW + LR step; returns the loss."""
@@ -73,7 +78,7 @@ class DiffusionPolicyBCModule(ACTBCModule):
                  accumulate_grad_batches: int = 1, debug_hints: bool = False, **kwargs):
         super().__init__(policy, dict(type="AdamW", lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.95)) | (optimizer or {}),
                          lr_scheduler or {"scheduler": dict(pct_start=0.15, div_factor=100.0, final_div_factor=1000.0)},
-                         gradient_clip_val, total_steps, use_cuda_graph, accumulate_grad_batches, debug_hints)
+                         gradient_clip_val, total_steps, use_cuda_graph, accumulate_grad_batches, debug_hints, **kwargs)
 
     def setup(self, normalizer) -> None:
         """maniskill2_dp_bc_module.py:57-60: copy the dataset's fitted normaliser into the policy."""
@@ -88,7 +93,7 @@ class DiffusionPolicyBCModule(ACTBCModule):
                                   total_steps=self.hparams["total_steps"], scheduler=sch,
                                   use_cuda_graph=self.hparams["use_cuda_graph"],
                                   accumulate_grad_batches=self.hparams["accumulate_grad_batches"],
-                                  debug_hints=self.hparams["debug_hints"],
+                                  debug_hints=self.hparams["debug_hints"], **self._dist_kwargs(),
                                   input_keys=("obs", "action", "goal", "_noise", "_timesteps"), loss_keys=("loss",))
         return self._trainer
 

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ coef,
                          const double* __restrict__ gstats, long R, int C, int relu, int training,
                          float* __restrict__ dy, __nv_bfloat16* __restrict__ dy_bf16, float* __restrict__ dgamma,
-                         float* __restrict__ dbeta) {
+                         float* __restrict__ dbeta, const double* __restrict__ n_total_dev) {
+    // n_total_dev (SyncBatchNorm): gstats holds the sums over ALL ranks' rows and *n_total_dev their total row count
     pcm_pdl_wait();
     if (blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -136,7 +137,7 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict
     }
     const int c4 = C >> 2;
     const long n4 = R * c4;
-    const float inv_n = 1.0f / (float)R;
+    const float inv_n = n_total_dev ? (float)(1.0 / *n_total_dev) : 1.0f / (float)R;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4) * 4;
         const float4 v = ldg4(y + i * 4), a = ldg4(coef + c), b = ldg4(coef + C + c);
@@ -220,7 +221,40 @@ PCM_API int pcm_bn_relu_bwd(long long R, int C, const float* dout, const float* 
     if (r) return r;
     const long n4 = (long)R * (C / 4);
     e = pcm_launch(bn_relu_bwd_apply_kernel, dim3(bn_flat_grid(n4)), dim3(BN_THREADS), 0, st, dout, y, coef,
-                   (const double*)gstats, (long)R, C, relu, training, dy, reinterpret_cast<__nv_bfloat16*>(dy_bf16), dgamma, dbeta);
+                   (const double*)gstats, (long)R, C, relu, training, dy, reinterpret_cast<__nv_bfloat16*>(dy_bf16), dgamma, dbeta,
+                   (const double*)nullptr);
+    if (e != cudaSuccess) return (int)e;
+    return pcm_launch_status();
+}
+
+// The two passes of pcm_bn_relu_bwd as separate entry points, for SyncBatchNorm (configs/trainer/ddp.yaml:9): the caller
+// all-reduces gstats (2, C) between them and passes the global row count in device memory (n_total_dev); dgamma / dbeta are
+// taken from the LOCAL sums by the caller (torch.nn.SyncBatchNorm semantics: weight gradients stay per rank until DDP
+// averages them), so the apply pass is given NULL for them.
+PCM_API int pcm_bn_relu_bwd_reduce(long long R, int C, const float* dout, const float* y, const float* coef, int relu,
+                                   double* gstats, pcm_stream_t stream) {
+    if (R <= 0) return PCM_OK;
+    if (!dout || !y || !coef || !gstats) return PCM_EINVAL;
+    if (!bn_shape_ok(C)) return PCM_EUNSUPPORTED;
+    const int rpc = bn_rows_per_cta(R);
+    const int grid = (int)((R + rpc - 1) / rpc);
+    const size_t smem = (size_t)2 * (BN_THREADS / (C / 4)) * C * sizeof(float);
+    cudaError_t e = pcm_launch(bn_relu_bwd_reduce_kernel, dim3(grid), dim3(BN_THREADS), smem, pcm_cu_stream(stream), dout, y, coef,
+                               (long)R, C, relu, rpc, gstats);
+    if (e != cudaSuccess) return (int)e;
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_bn_relu_bwd_apply(long long R, int C, const float* dout, const float* y, const float* coef, int relu,
+                                  int training, const double* gstats, const double* n_total_dev, float* dy, void* dy_bf16,
+                                  float* dgamma, float* dbeta, pcm_stream_t stream) {
+    if (R <= 0) return PCM_OK;
+    if (!dout || !y || !coef || !gstats || (!dy && !dy_bf16)) return PCM_EINVAL;
+    if (!bn_shape_ok(C)) return PCM_EUNSUPPORTED;
+    const long n4 = (long)R * (C / 4);
+    cudaError_t e = pcm_launch(bn_relu_bwd_apply_kernel, dim3(bn_flat_grid(n4)), dim3(BN_THREADS), 0, pcm_cu_stream(stream), dout, y,
+                               coef, gstats, (long)R, C, relu, training, dy, reinterpret_cast<__nv_bfloat16*>(dy_bf16), dgamma, dbeta,
+                               n_total_dev);
     if (e != cudaSuccess) return (int)e;
     return pcm_launch_status();
 }

@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
 __global__ void sa_bn_finalize_kernel(const double* __restrict__ stats, double n_rows, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, float momentum, int training,
                                       float* __restrict__ running_mean, float* __restrict__ running_var,
-                                      float* __restrict__ coef, int H) {
+                                      float* __restrict__ coef, int H, const double* __restrict__ n_rows_dev) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= H) return;
+    if (n_rows_dev) n_rows = *n_rows_dev;  // SyncBatchNorm: global row count, all-reduced together with the statistics
     double mean, var;
     if (training) {
         mean = stats[c] / n_rows;
@@ -282,9 +283,10 @@ __global__ void __launch_bounds__(256) sa_edge_stats_kernel(const int* __restric
 __global__ void sa_bwd_coef_kernel(const double* __restrict__ gstats, const double* __restrict__ fstats,
                                    const double* __restrict__ sdtot, const float* __restrict__ coef, double n_rows,
                                    int training, int H, float* __restrict__ ab, float* __restrict__ dW, int ldw,
-                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta, const double* __restrict__ n_rows_dev) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= H) return;
+    if (n_rows_dev) n_rows = *n_rows_dev;
     const double a = coef[c], mean = coef[2 * H + c], invstd = coef[3 * H + c];
     const double dbe = gstats[c], dga = gstats[H + c];
     double alpha = 0.0, betap = 0.0;
@@ -361,10 +363,18 @@ PCM_API int pcm_sa_gather_stats(int m, int k, int H, const float* Pf, const floa
 PCM_API int pcm_sa_bn_finalize(int H, const double* stats, double n_rows, const float* gamma, const float* beta,
                                float eps, float momentum, int training, float* running_mean, float* running_var,
                                float* coef, pcm_stream_t stream) {
+    return pcm_sa_bn_finalize_ex(H, stats, n_rows, nullptr, gamma, beta, eps, momentum, training, running_mean, running_var, coef,
+                                 stream);
+}
+
+// n_rows_dev != NULL: the row count is read from device memory (SyncBatchNorm: statistics and count all-reduced over ranks)
+PCM_API int pcm_sa_bn_finalize_ex(int H, const double* stats, double n_rows, const double* n_rows_dev, const float* gamma,
+                                  const float* beta, float eps, float momentum, int training, float* running_mean,
+                                  float* running_var, float* coef, pcm_stream_t stream) {
     if (H <= 0) return PCM_OK;
     if (!stats || !gamma || !beta || !coef || (!training && (!running_mean || !running_var))) return PCM_EINVAL;
     sa_bn_finalize_kernel<<<pcm_divup(H, 128), 128, 0, pcm_cu_stream(stream)>>>(stats, n_rows, gamma, beta, eps, momentum, training,
-                                                                               running_mean, running_var, coef, H);
+                                                                               running_mean, running_var, coef, H, n_rows_dev);
     return pcm_launch_status();
 }
 
@@ -427,10 +437,16 @@ PCM_API int pcm_sa_edge_stats(int m, int k, const int* idx, const float* xyz, co
 PCM_API int pcm_sa_bwd_coef(int H, const double* gstats, const double* fstats, const double* sdtot, const float* coef,
                             double n_rows, int training, float* ab, float* dW, int ldw, float* dgamma, float* dbeta,
                             pcm_stream_t stream) {
+    return pcm_sa_bwd_coef_ex(H, gstats, fstats, sdtot, coef, n_rows, nullptr, training, ab, dW, ldw, dgamma, dbeta, stream);
+}
+
+PCM_API int pcm_sa_bwd_coef_ex(int H, const double* gstats, const double* fstats, const double* sdtot, const float* coef,
+                               double n_rows, const double* n_rows_dev, int training, float* ab, float* dW, int ldw,
+                               float* dgamma, float* dbeta, pcm_stream_t stream) {
     if (H <= 0) return PCM_OK;
     if (!gstats || !fstats || !sdtot || !coef || !ab) return PCM_EINVAL;
     sa_bwd_coef_kernel<<<pcm_divup(H, 128), 128, 0, pcm_cu_stream(stream)>>>(gstats, fstats, sdtot, coef, n_rows, training, H, ab, dW,
-                                                                            ldw, dgamma, dbeta);
+                                                                            ldw, dgamma, dbeta, n_rows_dev);
     return pcm_launch_status();
 }
 

@@ -490,6 +490,7 @@ class DiffusionUnetImagePolicy(nn.Module):
         else:
             timesteps = torch.randint(0, self.noise_scheduler.config.num_train_timesteps, (bs,), device=nactions.device).long()
         noisy = self.noise_scheduler.add_noise(nactions, noise, timesteps)
+        PF.grad_boundary(global_cond, "model")  # d(global_cond) available = the denoiser's (255 M) gradients are final
         pred = self.model(noisy, timesteps, local_cond=None, global_cond=global_cond)
         pred_type = self.noise_scheduler.config.prediction_type
         if pred_type == "epsilon":
@@ -500,6 +501,10 @@ class DiffusionUnetImagePolicy(nn.Module):
             raise ValueError(f"Unsupported prediction type {pred_type}")
         loss = F.mse_loss(pred, target, reduction="none").reshape(bs, -1).mean(dim=1).mean()
         return dict(loss=loss)
+
+    def grad_buckets(self):
+        """See act.ACTPCD.grad_buckets: the denoiser (the ~1 GB gradient) finishes its backward before the encoder starts."""
+        return [("model", ("model.",)), (None, ("",))]
 
     def sync_free(self, pcds) -> bool:
         """True when the host-known cloud-size hints let FPS run without a device->host read."""

@@ -511,6 +511,24 @@ class _MHACross(torch.autograd.Function):
         return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None, None, None, None)
 
 
+# Gradient-bucket boundaries: the policy marks the activations whose gradient becoming available means "every parameter
+# gradient of bucket <tag> is final" (e.g. d(memory): the whole decoder has run its backward); the trainer installs a
+# callback that starts that bucket's all-reduce while the rest of the backward is still running.
+GRAD_BOUNDARY_CB = None
+
+
+def grad_boundary(t, tag):
+    if torch.is_tensor(t) and t.requires_grad:
+        def _hook(_g, tag=tag):
+            cb = GRAD_BOUNDARY_CB
+            if cb is not None:
+                cb(tag)
+            return None
+
+        t.register_hook(_hook)
+    return t
+
+
 _PTR_CACHE = {}
 
 
@@ -950,6 +968,41 @@ def dropout(x, p, training):
     return F.dropout(x, p, True) if (training and p > 0) else x
 
 
+class _SyncBN:
+    """SyncBatchNorm switch (reference DDP preset: configs/trainer/ddp.yaml:9 `sync_batchnorm: true`).  When enabled, every
+    training-mode BatchNorm of the path (PointNet / projector layers: `_BatchNormReLU`; the set-abstraction head:
+    `_SetAbstraction`) all-reduces its (sum, sum of squares, row count) between the statistics kernel and the finalize
+    kernel, and its two gradient sums between the backward's reduce and apply kernels -- one small collective per layer
+    each way, sequentially dependent, exactly like torch.nn.SyncBatchNorm.  Off (default) = per-rank statistics = the
+    reference with `trainer.sync_batchnorm=false`."""
+
+    def __init__(self):
+        self.enabled, self.group = False, None
+
+    def active(self):
+        import torch.distributed as dist
+
+        return self.enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+
+SYNC_BN = _SyncBN()
+
+
+def set_sync_batchnorm(enabled: bool, process_group=None):
+    SYNC_BN.enabled, SYNC_BN.group = bool(enabled), process_group
+
+
+def _allreduce_stats(rows, count):
+    """All-reduce the fp64 statistics rows (k, C) together with the local row count; returns the global count as a (1,)
+    fp64 DEVICE tensor (read by the kernels through their n_rows_dev argument: no host synchronisation)."""
+    import torch.distributed as dist
+
+    buf = torch.cat([rows.reshape(-1), torch.full((1,), float(count), dtype=torch.float64, device=rows.device)])
+    dist.all_reduce(buf, group=SYNC_BN.group)
+    rows.copy_(buf[:-1].view_as(rows))
+    return buf[-1:]
+
+
 class _BatchNormReLU(torch.autograd.Function):
     """ReLU(BatchNorm1d(y)) over rows (csrc/batchnorm.cu): statistics pass + apply pass forward, reduce pass +
     apply pass backward; emits the bf16 operand of the next GEMM (forward) and bf16(dy) for the producing
@@ -964,15 +1017,19 @@ class _BatchNormReLU(torch.autograd.Function):
         R, C = y.shape
         st = current_stream()
         stats = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+        n_dev = None
         if training:
             check(lib.pcm_bn_stats(R, C, ptr(y), ptr(stats), st), "pcm_bn_stats")
+            if SYNC_BN.active():
+                n_dev = _allreduce_stats(stats, R)
         coef = torch.empty((4, C), dtype=torch.float32, device=y.device)
         if training and extra:
             for rm, rv, mom in extra:
-                check(lib.pcm_sa_bn_finalize(C, ptr(stats), float(R), ptr(gamma), ptr(beta), float(eps), float(mom), 1, ptr(rm), ptr(rv),
-                                             ptr(coef), st), "pcm_sa_bn_finalize")
-        check(lib.pcm_sa_bn_finalize(C, ptr(stats), float(R), ptr(gamma), ptr(beta), float(eps), float(momentum), int(training),
-                                     ptr(running_mean), ptr(running_var), ptr(coef), st), "pcm_sa_bn_finalize")
+                check(lib.pcm_sa_bn_finalize_ex(C, ptr(stats), float(R), ptr(n_dev), ptr(gamma), ptr(beta), float(eps), float(mom), 1,
+                                                ptr(rm), ptr(rv), ptr(coef), st), "pcm_sa_bn_finalize_ex")
+        check(lib.pcm_sa_bn_finalize_ex(C, ptr(stats), float(R), ptr(n_dev), ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                        int(training), ptr(running_mean), ptr(running_var), ptr(coef), st), "pcm_sa_bn_finalize_ex")
+        ctx.n_dev = n_dev
         out = torch.empty_like(y)
         outb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
         check(lib.pcm_bn_apply_relu(R, C, ptr(y), ptr(coef), int(relu), ptr(out), ptr(outb), st), "pcm_bn_apply_relu")
@@ -1001,8 +1058,20 @@ class _BatchNormReLU(torch.autograd.Function):
         need_dy = ctx.needs_input_grad[0]
         dy = torch.empty_like(y) if need_dy else None
         dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
-        check(lib.pcm_bn_relu_bwd(R, C, ptr(dout), ptr(y), ptr(coef), int(relu), int(training), ptr(gstats), ptr(dy), ptr(dyb),
-                                  ptr(dg), ptr(db), current_stream()), "pcm_bn_relu_bwd")
+        if ctx.n_dev is not None:  # SyncBatchNorm: global sums for dx, LOCAL sums for the affine gradients
+            import torch.distributed as dist
+
+            check(lib.pcm_bn_relu_bwd_reduce(R, C, ptr(dout), ptr(y), ptr(coef), int(relu), ptr(gstats), current_stream()),
+                  "pcm_bn_relu_bwd_reduce")
+            local = gstats.clone()
+            dist.all_reduce(gstats, group=SYNC_BN.group)
+            check(lib.pcm_bn_relu_bwd_apply(R, C, ptr(dout), ptr(y), ptr(coef), int(relu), int(training), ptr(gstats), ptr(ctx.n_dev),
+                                            ptr(dy), ptr(dyb), None, None, current_stream()), "pcm_bn_relu_bwd_apply")
+            db += local[0].float()
+            dg += local[1].float()
+        else:
+            check(lib.pcm_bn_relu_bwd(R, C, ptr(dout), ptr(y), ptr(coef), int(relu), int(training), ptr(gstats), ptr(dy), ptr(dyb),
+                                      ptr(dg), ptr(db), current_stream()), "pcm_bn_relu_bwd")
         if dy is not None:
             _GRAD_BF16[dy.data_ptr()] = (dyb, dy)  # consumed (popped) by the producing linear's backward
         return (dy, None if g_slot is not None else dg, None if b_slot is not None else db, None, None, None, None, None, None, None)
@@ -1056,9 +1125,13 @@ class _SetAbstraction(torch.autograd.Function):
         check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
                                       ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
         coef = torch.empty((4, H), dtype=torch.float32, device=dev)
-        check(lib.pcm_sa_bn_finalize(H, ptr(stats), float(m * k), ptr(gamma), ptr(beta), float(eps), float(momentum),
-                                     int(training), ptr(running_mean), ptr(running_var), ptr(coef), st),
-              "pcm_sa_bn_finalize")
+        n_dev = None
+        if training and SYNC_BN.active():  # rows 0-1 (sum y, sum y^2) global; rows 2-4 (sum y dxyz) stay local (backward dW)
+            n_dev = _allreduce_stats(stats[:2], m * k)
+        ctx.n_dev = n_dev
+        check(lib.pcm_sa_bn_finalize_ex(H, ptr(stats), float(m * k), ptr(n_dev), ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                        int(training), ptr(running_mean), ptr(running_var), ptr(coef), st),
+              "pcm_sa_bn_finalize_ex")
         ctx.tok = None
         if tok is None:
             out = torch.empty((m, H), dtype=torch.float32, device=dev)
@@ -1111,8 +1184,18 @@ class _SetAbstraction(torch.autograd.Function):
         ab = torch.empty((2, H), dtype=torch.float32, device=dev)
         dgamma = torch.empty(H, dtype=torch.float32, device=dev)
         dbeta = torch.empty(H, dtype=torch.float32, device=dev)
-        check(lib.pcm_sa_bwd_coef(H, ptr(gstats), ptr(stats), ptr(sdtot), ptr(coef), float(m * k), int(ctx.training),
-                                  ptr(ab), ptr(dW), dW.stride(0), ptr(dgamma), ptr(dbeta), st), "pcm_sa_bwd_coef")
+        local = None
+        if ctx.n_dev is not None:  # SyncBatchNorm: alpha / beta' from the global sums, dgamma / dbeta from the local ones
+            import torch.distributed as dist
+
+            local = gstats[:2].clone()
+            dist.all_reduce(gstats[:2], group=SYNC_BN.group)
+        check(lib.pcm_sa_bwd_coef_ex(H, ptr(gstats), ptr(stats), ptr(sdtot), ptr(coef), float(m * k), ptr(ctx.n_dev),
+                                     int(ctx.training), ptr(ab), ptr(dW), dW.stride(0), ptr(dgamma), ptr(dbeta), st),
+              "pcm_sa_bwd_coef_ex")
+        if local is not None:
+            dbeta.copy_(local[0])
+            dgamma.copy_(local[1])
         dPfb = torch.empty((n, H), dtype=torch.bfloat16, device=dev)
         check(lib.pcm_sa_bwd_dense(n, H, ptr(Pf), ptr(p), ptr(cnt), ptr(sq), ptr(weight), weight.stride(0), ptr(ab),
                                    ptr(dPf), ptr(dPfb), st), "pcm_sa_bwd_dense")

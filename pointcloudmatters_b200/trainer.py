@@ -105,7 +105,8 @@ class BCTrainer:
     def __init__(self, policy: nn.Module, lr=5e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  clip_norm=0.5, total_steps=100000, scheduler: dict | None = None, process_group=None,
                  use_cuda_graph: bool = False, input_keys=None, loss_keys=None, accumulate_grad_batches: int = 1,
-                 max_cached_graphs: int = 4, debug_hints: bool = False):
+                 max_cached_graphs: int = 4, debug_hints: bool = False, sync_batchnorm: bool = False,
+                 overlap_allreduce: bool = True, grad_wire_dtype=None):
         self.policy = policy
         if input_keys is not None:
             self.INPUT_KEYS = tuple(input_keys)
@@ -134,16 +135,97 @@ class BCTrainer:
         self._micro = 0
         self.debug_hints = bool(debug_hints)
         self._hook_handle = None
+        # multi-rank options.  sync_batchnorm: exact parity with the reference DDP preset (configs/trainer/ddp.yaml:9) -- one
+        # small collective per BatchNorm layer each way (functional.SYNC_BN); default off = local statistics.
+        # overlap_allreduce: the flat gradient is laid out in the policy's bucket order (grad_buckets()) and each bucket's
+        # all-reduce starts as soon as its gradients are final (functional.grad_boundary), overlapping the remaining
+        # backward; off = ONE all-reduce after backward.  grad_wire_dtype=torch.bfloat16: all-reduce a bf16 copy (half the
+        # NVLink bytes, like DDP's bf16 compression hook; not bit-compatible with the fp32 exchange).
+        self.sync_batchnorm = bool(sync_batchnorm)
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self.grad_wire_dtype = grad_wire_dtype
+        self.bucket_ranges = []  # [(tag, start, end)] element ranges of the flat gradient, in completion order
+        self._works, self._launched, self._reduced = [], 0, False
+        if self.sync_batchnorm:
+            from . import functional as PF
+
+            PF.set_sync_batchnorm(True, process_group)
 
     # -- gradient exchange: ONE collective over the flat buffer -----------------------------------
+    def _all_reduce(self, g, async_op=False):
+        """SUM all-reduce of one slice of the flat gradient (optionally through a bf16 wire copy)."""
+        if self.grad_wire_dtype is None or self.grad_wire_dtype == g.dtype:
+            return dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
+        wire = g.to(self.grad_wire_dtype)
+        dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.pg)
+        g.copy_(wire)
+        return None
+
     def reduce_gradients(self):
-        """SUM all-reduce of the flat gradient; the 1/world average is folded into the optimizer kernel."""
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad[: self.flat.n_active], op=dist.ReduceOp.SUM, group=self.pg)
+        """SUM all-reduce of the flat gradient; the 1/world average is folded into the optimizer kernel.  No-op when the
+        buckets were already exchanged during backward (overlap_allreduce)."""
+        if self.world > 1 and not self._reduced:
+            self._all_reduce(self.flat.grad[: self.flat.n_active])
+        self._reduced = False
+
+    # -- overlapped exchange: buckets start as soon as their gradients are final ---------------------
+    def _launch_buckets(self, upto):
+        """Start the all-reduce of buckets [launched, upto) on NCCL's stream (it waits for the calling stream's work so
+        far; the caller keeps computing)."""
+        while self._launched < upto:
+            _tag, s0, e0 = self.bucket_ranges[self._launched]
+            if e0 > s0:
+                w = self._all_reduce(self.flat.grad[s0:e0], async_op=True)
+                if w is not None:
+                    self._works.append(w)
+            self._launched += 1
+
+    def _on_boundary(self, tag):
+        for i, (t, _s, _e) in enumerate(self.bucket_ranges):
+            if t == tag:
+                self._launch_buckets(i + 1)
+                return
+
+    def broadcast_buffers(self, average=True):
+        """BatchNorm running statistics diverge across ranks when statistics are local (sync_batchnorm=False): average them
+        (or take rank 0's) -- call before saving a checkpoint so that it does not depend on which rank saves."""
+        if self.world <= 1:
+            return
+        for b in self.policy.buffers():
+            if b.dtype.is_floating_point:
+                if average:
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.pg)
+                    b.div_(self.world)
+                else:
+                    dist.broadcast(b, src=0, group=self.pg)
+
+    def _bucketed_parameters(self):
+        """(parameters in bucket order, [(tag, [params])]).  Order = the policy's `grad_buckets()` (completion order of the
+        backward) so that every bucket is ONE contiguous slice of the flat gradient."""
+        named = [(n, p) for n, p in self.policy.named_parameters() if p.requires_grad]
+        spec = self.policy.grad_buckets() if hasattr(self.policy, "grad_buckets") else [(None, ("",))]
+        buckets = [(tag, []) for tag, _ in spec]
+        for n, p in named:
+            for i, (_tag, prefixes) in enumerate(spec):
+                if any(n.startswith(pre) for pre in prefixes):
+                    buckets[i][1].append(p)
+                    break
+            else:
+                buckets[-1][1].append(p)
+        return [p for _t, ps in buckets for p in ps], buckets
 
     def _build_flat(self):
         inactive = [p for p in self.policy.parameters() if p.requires_grad and p.grad is None]
-        self.flat = FlatState(self.policy.parameters(), inactive)
+        ordered, buckets = self._bucketed_parameters()
+        self.flat = FlatState(ordered, inactive)
+        inactive_ids = {id(p) for p in inactive}
+        pad8 = lambda n: (n + 7) // 8 * 8
+        off, self.bucket_ranges = 0, []
+        for tag, ps in buckets:
+            size = sum(pad8(p.numel()) for p in ps if id(p) not in inactive_ids)
+            self.bucket_ranges.append((tag, off, off + size))
+            off += size
+        assert off == self.flat.n_active
         self._finish_flat()
 
     def _finish_flat(self):
@@ -201,10 +283,26 @@ class BCTrainer:
         return {k: self._copy_dicts(batch[k]) for k in self.INPUT_KEYS if k in batch}
 
     def _forward_backward(self, batch, zero=True):
+        from . import functional as PF
+
         if self.flat is not None and zero:
             self.flat.zero_grad()
         out = self.policy(self._inputs_only(batch))
-        out["loss"].backward()
+        exchange = (self.world > 1 and self.overlap_allreduce and self.flat is not None and self.bucket_ranges
+                    and self._micro + 1 >= self.accumulate_grad_batches and self.accumulate_grad_batches == 1)
+        if exchange:
+            self._works, self._launched = [], 0
+            PF.GRAD_BOUNDARY_CB = self._on_boundary
+        try:
+            out["loss"].backward()
+        finally:
+            PF.GRAD_BOUNDARY_CB = None
+        if exchange:
+            self._launch_buckets(len(self.bucket_ranges))
+            for w in self._works:
+                w.wait()
+            self._works = []
+            self._reduced = True
         return {k: out[k].detach() for k in self.LOSS_KEYS}
 
     HINT_KEYS = ("n_max", "fg_n_max", "bg_n_max")
@@ -273,13 +371,14 @@ class BCTrainer:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 outs = self._forward_backward(static, zero)
-            entry = (graph, static, outs)
+            entry = (graph, static, outs, self._reduced)  # was the (bucketed) gradient exchange captured with the step?
             self._graphs[sig] = entry
         else:
             self._graphs.move_to_end(sig)
-        graph, static, outs = entry
+        graph, static, outs, reduced_inside = entry
         self._copy_into(static, batch)
         graph.replay()
+        self._reduced = reduced_inside
         return outs
 
     def _check_hints(self, pcds):

@@ -203,10 +203,12 @@ class Transformer(nn.Module):
                 # token buffers written by the set-abstraction head / the sine-embedding kernel: only the latent / proprio
                 # rows are missing (one small kernel), the learned positional rows get their gradient through `pos_head`
                 src_tok = PF.fill_head_rows(tok, latent_input.reshape(bs, E), prop, ptk)
+                PF.grad_boundary(src_tok, "transformer.encoder")
                 pos_head = additional_pos_embed.unsqueeze(1) if additional_pos_embed.requires_grad else None
                 query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
                 tgt = torch.zeros_like(query_embed)
                 memory = self.encoder(src_tok, src_key_padding_mask=mask, pos=ptk, pos_head=pos_head)
+                PF.grad_boundary(memory, "transformer.decoder")
                 hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head)
                 return hs.transpose(1, 2)
         src = src.flatten(2).permute(2, 0, 1)
@@ -228,8 +230,10 @@ class Transformer(nn.Module):
         else:
             addition_input = torch.cat([latent_input, proprio_input], dim=0)
         src = torch.cat([addition_input, src], dim=0)
+        PF.grad_boundary(src, "transformer.encoder")
         tgt = torch.zeros_like(query_embed)
         memory = self.encoder(src, src_key_padding_mask=mask, pos=pos_embed, pos_head=pos_head)
+        PF.grad_boundary(memory, "transformer.decoder")
         hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed,
                           pos_head=pos_head)
         return hs.transpose(1, 2)

@@ -125,3 +125,65 @@ def test_shard_batch_diffusion_policy_contract():
         assert torch.equal(torch.diff(s["obs"]["pcds"]["offset"], prepend=torch.zeros(1, dtype=torch.int64)), want)
         assert s["obs"]["pcds"]["n_max"] == int(want.max())
         assert int(s["obs"]["pcds"]["offset"][-1]) == s["obs"]["pcds"]["coord"].shape[0]
+
+
+class _ToyPolicy(nn.Module):
+    """Two-stage policy with a gradient-bucket boundary between the stages (like decoder | encoder | rest)."""
+
+    def __init__(self):
+        super().__init__()
+        self.front, self.back = nn.Linear(4, 8), nn.Linear(8, 2)
+        self.unused = nn.Linear(3, 3)
+
+    def grad_buckets(self):
+        return [("back", ("back.",)), (None, ("",))]
+
+    def forward(self, batch):
+        from pointcloudmatters_b200 import functional as PF
+
+        h = torch.relu(self.front(batch["x"]))
+        PF.grad_boundary(h, "back")  # d(h) available = self.back's gradients are final
+        return {"loss": self.back(h).pow(2).sum() / 8}
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    pol = _ToyPolicy()
+    tr = BCTrainer(pol, lr=1e-3, total_steps=100, input_keys=("x",), loss_keys=("loss",), overlap_allreduce=True)
+    x = torch.randn(8, 4, generator=torch.Generator().manual_seed(7))
+    batch = {"x": x[rank * 4:(rank + 1) * 4]}
+    tr._forward_backward(batch)  # eager, no flat state yet: plain autograd
+    tr._build_flat()
+    launched = []
+    orig = tr._launch_buckets
+    tr._launch_buckets = lambda upto: (launched.append(upto), orig(upto))[1]
+    tr._forward_backward(batch)  # zeroes the flat gradient, exchanges bucket by bucket during backward
+    names = [t for t, _s, _e in tr.bucket_ranges]
+    q.put((rank, tr.flat.grad[: tr.flat.n_active].clone(), names, list(tr.bucket_ranges), launched, tr._reduced,
+           pol.back.weight.grad.data_ptr() == tr.flat.grad.data_ptr()))
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_world2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    (_, g0, names, ranges, launched, reduced, back_first), (_, g1, *_rest) = res
+    assert torch.equal(g0, g1) and reduced
+    assert names == ["back", None] and back_first  # the flat layout follows the bucket (completion) order
+    assert ranges[0][2] - ranges[0][1] == 16 + 8 and ranges[1][1] == ranges[0][2]  # back: (2x8 -> 16) + (2 -> 8)
+    assert launched[0] == 1 and launched[-1] == 2  # bucket 0 went out at its boundary, the rest after backward
+    # equals the single-process gradient of the mean loss over the GLOBAL batch (sum over ranks of /8 losses)
+    torch.manual_seed(0)
+    pol = _ToyPolicy()
+    x = torch.randn(8, 4, generator=torch.Generator().manual_seed(7))
+    pol({"x": x})["loss"].backward()
+    pad = lambda t: torch.nn.functional.pad(t.reshape(-1), (0, (-t.numel()) % 8))
+    ref = torch.cat([pad(pol.back.weight.grad), pad(pol.back.bias.grad), pad(pol.front.weight.grad), pad(pol.front.bias.grad)])
+    torch.testing.assert_close(g0, ref, rtol=1e-5, atol=1e-6)
