@@ -349,9 +349,23 @@ def b200_arm(args):
     run(host, 2, True)
     sec_e2e, loss_e2e = run(host, args.steps, True)
 
-    if rank != 0:
+    def teardown():
+        """NCCL kernels captured in the step graphs keep the communicator busy: drop the graphs first, and never let a hung
+        communicator teardown turn a finished benchmark into a timeout (the JSON line is already out)."""
+        sys.stdout.flush()
         if world > 1:
+            import gc
+
+            trainer._graphs.clear()
+            gc.collect()
+            torch.cuda.synchronize()
+            t = threading.Timer(20.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return 0
 
     # whole-job aggregate: every rank processes one cfg-2 step-unit (64 samples) per iteration, so
@@ -401,8 +415,7 @@ def b200_arm(args):
                                           f"oracle port (fp32, torch CPU + C pointops oracle, {cores} threads) after 1 warm-up "
                                           f"step on {args.cpu_sample_batch} clouds"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
     return 0
 
 

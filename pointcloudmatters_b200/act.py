@@ -394,18 +394,24 @@ class ACTPCD(nn.Module):
         self._presampled = self._presampled_pos = None
         fork = self.sync_free(data_dict["pcds"]) and data_dict["qpos"].is_cuda
         if fork:
-            self._presample(data_dict)
-            data_dict, enc_stream = self._encode_on_side_stream(data_dict)
+            with PF.stage("fps+knn+sine (side stream)"):
+                self._presample(data_dict)
+            with PF.stage("cvae encoder (side stream)"):
+                data_dict, enc_stream = self._encode_on_side_stream(data_dict)
         else:
-            data_dict = self.forward_encoder(data_dict)
-        data_dict = self.forward_obs_embed(data_dict)
+            with PF.stage("cvae encoder"):
+                data_dict = self.forward_encoder(data_dict)
+        with PF.stage("pointnet + set abstraction"):
+            data_dict = self.forward_obs_embed(data_dict)
         if fork:  # join: the transformer consumes latent_input, the loss mu / logvar
             main = torch.cuda.current_stream()
             main.wait_stream(enc_stream)
             for k in ("latent_input", "mu", "logvar"):
                 if torch.is_tensor(data_dict.get(k, None)):
                     data_dict[k].record_stream(main)
-        if self._fused_heads(data_dict):
+        with PF.stage("transformer + heads + loss"):
+            fused = self._fused_heads(data_dict)
+        if fused:
             return self._finish_inference(data_dict) if not data_dict["is_training"] else data_dict
         data_dict = self.forward_decoder(data_dict)
         if not data_dict["is_training"]:

@@ -511,6 +511,38 @@ class _MHACross(torch.autograd.Function):
         return (dx.view(L, B, E), dqpos, dmem, dmpos, dhead, *rets, None, None, None, None, None, None)
 
 
+# ------------------------------------------------------------------------------------------------
+# stage markers: NVTX ranges (PCM_NVTX=1, for ncu --nvtx / Nsight) and optional CUDA-event stage timing
+# (tools/stage_times.py).  A no-op otherwise.
+# ------------------------------------------------------------------------------------------------
+_NVTX = bool(int(os.environ.get("PCM_NVTX", "0")))
+STAGE_EVENTS = None  # set to a list by tools/stage_times.py: [(name, start event, end event)]
+
+
+class stage:
+    """`with PF.stage("encoder"):` -- marks one stage of the step on the current stream."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        if STAGE_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STAGE_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            STAGE_EVENTS.append((self.name, self.e0, e1))
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 # Gradient-bucket boundaries: the policy marks the activations whose gradient becoming available means "every parameter
 # gradient of bucket <tag> is final" (e.g. d(memory): the whole decoder has run its backward); the trainer installs a
 # callback that starts that bucket's all-reduce while the rest of the backward is still running.

@@ -287,14 +287,16 @@ class BCTrainer:
 
         if self.flat is not None and zero:
             self.flat.zero_grad()
-        out = self.policy(self._inputs_only(batch))
+        with PF.stage("forward"):
+            out = self.policy(self._inputs_only(batch))
         exchange = (self.world > 1 and self.overlap_allreduce and self.flat is not None and self.bucket_ranges
                     and self._micro + 1 >= self.accumulate_grad_batches and self.accumulate_grad_batches == 1)
         if exchange:
             self._works, self._launched = [], 0
             PF.GRAD_BOUNDARY_CB = self._on_boundary
         try:
-            out["loss"].backward()
+            with PF.stage("backward"):
+                out["loss"].backward()
         finally:
             PF.GRAD_BOUNDARY_CB = None
         if exchange:
@@ -417,8 +419,10 @@ class BCTrainer:
         self._micro += 1
         if self._micro >= self.accumulate_grad_batches:
             self._micro = 0
-            self.reduce_gradients()
-            self.optimizer_step()
+            with PF.stage("all-reduce (exposed part)"):
+                self.reduce_gradients()
+            with PF.stage("clip + AdamW"):
+                self.optimizer_step()
         return losses
 
     # -- checkpoint surface (Lightning saves optimizer + scheduler state next to the weights) ---------------

@@ -207,9 +207,11 @@ class Transformer(nn.Module):
                 pos_head = additional_pos_embed.unsqueeze(1) if additional_pos_embed.requires_grad else None
                 query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
                 tgt = torch.zeros_like(query_embed)
-                memory = self.encoder(src_tok, src_key_padding_mask=mask, pos=ptk, pos_head=pos_head)
+                with PF.stage("encoder x%d" % self.encoder.num_layers):
+                    memory = self.encoder(src_tok, src_key_padding_mask=mask, pos=ptk, pos_head=pos_head)
                 PF.grad_boundary(memory, "transformer.decoder")
-                hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head)
+                with PF.stage("decoder x%d" % self.decoder.num_layers):
+                    hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head)
                 return hs.transpose(1, 2)
         src = src.flatten(2).permute(2, 0, 1)
         pos_embed = pos_embed.flatten(2).permute(2, 0, 1)

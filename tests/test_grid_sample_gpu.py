@@ -92,7 +92,7 @@ def test_train_mode_draws_a_member_of_every_voxel_and_feeds_the_policy():
     cfg = dict(hidden_dim=128, nhead=2, dim_feedforward=32, enc_layers=1, dec_layers=1, dropout=0.0, num_queries=12,
                action_dim=7, qpos_dim=9, goal_cond_dim=3, latent_dim=32, kl_weight=10.0, pcd_npoints=64, pcd_nsample=16)
     torch.manual_seed(0)
-    module = ACTBCModule(build_policy(cfg).cuda().train(), total_steps=10)
+    module = ACTBCModule(build_policy(cfg).cuda().train(), total_steps=100)
     batch = {"pcds": {k: b[k] for k in ("coord", "grid_coord", "feat", "offset", "n_max")}, "qpos": torch.randn(4, 9).cuda(),
              "actions": torch.randn(4, 12, 7).cuda(), "is_pad": torch.zeros(4, 12, dtype=torch.bool).cuda(),
              "goal_cond": torch.randn(4, 3).cuda()}
