@@ -533,6 +533,15 @@ int pcm_bn_relu_bwd_apply(long long R, int C, const float *dout, const float *y,
                           int training, const double *gstats, const double *n_total_dev, float *dy, void *dy_bf16,
                           float *dgamma, float *dbeta, pcm_stream_t stream);
 
+/* Grouped weight-gradient GEMM: n independent problems C_p (M_p x N_p fp32, pitch ldc_p) += A_p^T B_p, A_p = (K_p x M_p)
+ * bf16 (pitch lda_p), B_p = (K_p x N_p) bf16 (pitch ldb_p) -- dW = dY^T X with both operands read in place -- run as ONE
+ * persistent tcgen05 launch per tile-width class (<= 40 problems per launch).  All arrays are HOST arrays of length n.
+ * The reference forms these products one nn.Linear backward at a time (~110 per step); here the operator layer queues
+ * them during backward and flushes the queue at the gradient-bucket boundaries. */
+int pcm_gemm_dw_grouped(int n, const void *const *A, const int *lda, const void *const *B, const int *ldb,
+                        float *const *C, const int *ldc, const int *M, const int *N, const int *K,
+                        pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -353,7 +353,7 @@ class ACTPCD(nn.Module):
             self._side_stream = torch.cuda.Stream()
         side = self._side_stream
         side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), PF.stage("fps+knn+sine (side stream)"):
             n_o = torch.arange(1, b + 1, dtype=torch.int32, device=o.device) * self.pcd_npoints
             o32 = o.int() if o.dtype != torch.int32 else o
             hints = {k: pcd.get(k, None) for k in ("n_max", "fg_n_max", "bg_n_max")}
@@ -386,7 +386,7 @@ class ACTPCD(nn.Module):
             self._enc_stream = torch.cuda.Stream()
         side = self._enc_stream
         side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), PF.stage("cvae encoder (side stream)"):
             data_dict = self.forward_encoder(data_dict)
         return data_dict, side
 
@@ -394,10 +394,8 @@ class ACTPCD(nn.Module):
         self._presampled = self._presampled_pos = None
         fork = self.sync_free(data_dict["pcds"]) and data_dict["qpos"].is_cuda
         if fork:
-            with PF.stage("fps+knn+sine (side stream)"):
-                self._presample(data_dict)
-            with PF.stage("cvae encoder (side stream)"):
-                data_dict, enc_stream = self._encode_on_side_stream(data_dict)
+            self._presample(data_dict)
+            data_dict, enc_stream = self._encode_on_side_stream(data_dict)
         else:
             with PF.stage("cvae encoder"):
                 data_dict = self.forward_encoder(data_dict)

@@ -446,6 +446,12 @@ int g_force_bn = 0;
 
 }  // namespace
 
+// shared with gemm_grouped.cu (hidden visibility: internal to the library)
+int pcm_get_tensor_map_2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                          CUtensorMap* out) {
+    return get_tensor_map(ptr, inner, outer, ld, box_inner, box_outer, out);
+}
+
 // Debug aid for tile-shape sweeps (tools/bench_gemm.py): force the N extent of the output tile of
 // subsequent GEMM launches (64 / 128 / 256; 0 = heuristic).
 PCM_API int pcm_gemm_debug_force_bn(int bn) {

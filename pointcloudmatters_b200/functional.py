@@ -210,7 +210,7 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             slot = _grad_slot(weight)
             dw = slot if slot is not None else torch.zeros((N, Kin), dtype=torch.float32, device=dyb.device)
-            K.gemm_bf16(dyb, xb, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=0)  # 0: tile / split auto
+            _dw(dyb, xb, dw)
             if slot is not None:
                 dw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -340,10 +340,35 @@ def _attn_core_bwd(dOh, Qh, Kh, Vh, O_tok, lse, kpm_u8, L, S, B, nh, aux, p_drop
                      dQ_out, dK_out, dV_out)
 
 
+# Weight-gradient products whose destination is a trainer's flat gradient are not on the backward's critical path (nothing
+# downstream reads them before the gradient exchange): while a queue is installed (trainer, during backward) they are
+# collected and run as ONE grouped tcgen05 launch per flush (kernels.gemm_dw_grouped) instead of ~110 small launches.
+DW_QUEUE = None  # None = launch immediately; list = [(stream id, dtok, xb, out)]
+
+
 def _dw(dtok, xb, out):
     """out (N, K) += dtok^T xb -- weight gradient in the tensors' own layouts (MN-major operands);
     tile width and K split are chosen by the launcher (split_k = 0)."""
+    if (DW_QUEUE is not None and out.dim() == 2 and out.stride(1) == 1 and dtok.stride(1) == 1 and xb.stride(1) == 1
+            and BF16_SHADOW.owns_grad(out)):
+        DW_QUEUE.append((torch.cuda.current_stream().cuda_stream, dtok, xb, out))
+        return
     K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=0)
+
+
+def flush_dw_queue(final=False):
+    """Run the queued weight-gradient products.  Mid-backward (a gradient-bucket boundary) only the products queued on
+    the CURRENT stream are run -- their operands are ordered before this point on that stream; `final=True` (after
+    backward() has returned and joined its streams) runs everything that is left."""
+    q = DW_QUEUE
+    if not q:
+        return
+    cur = torch.cuda.current_stream().cuda_stream
+    now = [e for e in q if final or e[0] == cur]
+    if not now:
+        return
+    q[:] = [e for e in q if not (final or e[0] == cur)]
+    K.gemm_dw_grouped([(a, b, o) for _s, a, b, o in now])
 
 
 def _param_grads(ctx_params, E, dev):
@@ -1455,7 +1480,12 @@ def retime_gemm_shapes(kstats, iters=20):
         return None
     total_ms, dev = 0.0, torch.device("cuda", torch.cuda.current_device())
     for tag, rec in st["by_shape"].items():
-        M, N, Kd, batch, a_mn, b_mn, dt, split_k = eval(tag)  # tags are tuples written by kernels._Timer
+        t = eval(tag)  # tags are tuples written by kernels._Timer
+        if len(t) != 8:  # grouped weight-gradient launches (dozens of problems each): long enough for their own event pair
+            rec["isolated_us"] = max(rec["total_ms"] / rec["launches"] - st.get("event_pair_overhead_us", 0.0) * 1e-3, 0.0) * 1e3
+            total_ms += rec["isolated_us"] * 1e-3 * rec["launches"]
+            continue
+        M, N, Kd, batch, a_mn, b_mn, dt, split_k = t
         sets = []
         for _ in range(2):
             a = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)

@@ -128,6 +128,32 @@ def gemm_ex(M, N, Kd, batch, a, a_mn, a_batch_rows, b, b_mn, b_batch_rows, out, 
     return out
 
 
+def gemm_dw_grouped(problems):
+    """Run a list of weight-gradient products  out (M, N) fp32 += a^T b  -- a (K, M) bf16, b (K, N) bf16, last dim
+    contiguous -- as ONE grouped tcgen05 launch per tile-width class (pcm_gemm_dw_grouped)."""
+    import ctypes
+
+    n = len(problems)
+    if n == 0:
+        return
+    PA, PI = ctypes.c_void_p * n, ctypes.c_int * n
+    A, B, C = PA(), PA(), PA()
+    lda, ldb, ldc, M, N, Kd = PI(), PI(), PI(), PI(), PI(), PI()
+    flops = nbytes = 0.0
+    for i, (a, b, out) in enumerate(problems):
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.float32
+        assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1 and a.shape[0] == b.shape[0]
+        assert out.shape == (a.shape[1], b.shape[1])
+        A[i], B[i], C[i] = a.data_ptr(), b.data_ptr(), out.data_ptr()
+        lda[i], ldb[i], ldc[i] = a.stride(0), b.stride(0), out.stride(0)
+        M[i], N[i], Kd[i] = a.shape[1], b.shape[1], a.shape[0]
+        flops += 2.0 * a.shape[1] * b.shape[1] * a.shape[0]
+        nbytes += 2.0 * a.shape[0] * (a.shape[1] + b.shape[1]) + 4.0 * a.shape[1] * b.shape[1]
+    t0 = TIMER.begin()
+    check(lib.pcm_gemm_dw_grouped(n, A, lda, B, ldb, C, ldc, M, N, Kd, current_stream()), "pcm_gemm_dw_grouped")
+    TIMER.end(t0, "gemm_tcgen05", flops, nbytes, ("grouped_dw", n, int(flops)))
+
+
 def attn_softmax_fwd(S, Y, Zd, Z, L, Lp, Sk, Sp, nh, kpm, scale, p_drop, seed_base, seed_offset):
     check(lib.pcm_attn_softmax_fwd(Z, L, Lp, Sk, Sp, nh, ptr(S), ptr(kpm), float(scale), float(p_drop), ptr(seed_base),
                                    int(seed_offset), ptr(Y), ptr(Zd), current_stream()), "pcm_attn_softmax_fwd")

@@ -145,7 +145,12 @@ class BCTrainer:
         self.overlap_allreduce = bool(overlap_allreduce)
         self.grad_wire_dtype = grad_wire_dtype
         self.bucket_ranges = []  # [(tag, start, end)] element ranges of the flat gradient, in completion order
-        self._works, self._launched, self._reduced = [], 0, False
+        self._works, self._launched, self._reduced, self._exchange_now = [], 0, False, False
+        # weight-gradient GEMMs into the flat gradient are queued during backward and run as grouped launches at the
+        # bucket boundaries (functional.DW_QUEUE); PCM_NO_GROUPED_DW=1 restores one launch per product (A/B switch)
+        import os
+
+        self.group_weight_grads = not bool(int(os.environ.get("PCM_NO_GROUPED_DW", "0")))
         if self.sync_batchnorm:
             from . import functional as PF
 
@@ -181,6 +186,11 @@ class BCTrainer:
             self._launched += 1
 
     def _on_boundary(self, tag):
+        from . import functional as PF
+
+        PF.flush_dw_queue()  # the bucket's queued weight gradients must be in the flat buffer before it is exchanged
+        if not self._exchange_now:
+            return
         for i, (t, _s, _e) in enumerate(self.bucket_ranges):
             if t == tag:
                 self._launch_buckets(i + 1)
@@ -291,14 +301,22 @@ class BCTrainer:
             out = self.policy(self._inputs_only(batch))
         exchange = (self.world > 1 and self.overlap_allreduce and self.flat is not None and self.bucket_ranges
                     and self._micro + 1 >= self.accumulate_grad_batches and self.accumulate_grad_batches == 1)
+        self._exchange_now = exchange
         if exchange:
             self._works, self._launched = [], 0
+        group_dw = self.group_weight_grads and self.flat is not None and self.flat.param.is_cuda
+        if group_dw:
+            PF.DW_QUEUE = []
+        if exchange or group_dw:
             PF.GRAD_BOUNDARY_CB = self._on_boundary
         try:
             with PF.stage("backward"):
                 out["loss"].backward()
+            if group_dw:
+                PF.flush_dw_queue(final=True)
         finally:
             PF.GRAD_BOUNDARY_CB = None
+            PF.DW_QUEUE = None
         if exchange:
             self._launch_buckets(len(self.bucket_ranges))
             for w in self._works:

@@ -102,3 +102,30 @@ def test_few_row_long_k_gemm_uses_k_split_and_matches(M, N, K, b_mn, bias):
         want = want + bv
     assert got.shape == (M, N) and got.dtype == torch.float32
     assert float((got - want).norm() / want.norm()) < 2e-3
+
+
+def test_grouped_weight_gradient_gemm_matches_individual_products():
+    """pcm_gemm_dw_grouped: a mixed list of dW = dY^T X problems (decoder-size, encoder-size, FFN-32 both ways, ragged
+    sizes, column-slice operands, more than 40 problems, two tile-width classes) accumulated into existing buffers."""
+    from pointcloudmatters_b200.kernels import gemm_dw_grouped
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(512, 512, 6400)] * 9 + [(512, 512, 32960)] * 2 + [(32, 512, 6400), (512, 32, 6400), (1024, 512, 6528), (512, 1024, 700),
+                                                                   (136, 200, 1000), (64, 16, 4096), (512, 512, 64), (96, 520, 333 * 8)]
+    shapes = shapes + [(128, 64, 520)] * 30  # > 40 narrow problems: several launches of the 64-wide class
+    probs, wants = [], []
+    wide = torch.randn(6400, 1536, device="cuda", generator=g).bfloat16()  # column slices (pitch != width)
+    for i, (M, N, K) in enumerate(shapes):
+        if (M, N, K) == (512, 512, 6400) and i < 3:
+            a = wide[:, i * 512:(i + 1) * 512]
+        else:
+            a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+        b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+        base = torch.randn(M, N, device="cuda", generator=g)
+        out = base.clone()
+        probs.append((a, b, out))
+        wants.append(base + a.float().t() @ b.float())
+    gemm_dw_grouped(probs)
+    torch.cuda.synchronize()
+    for (a, b, out), want, (M, N, K) in zip(probs, wants, shapes):
+        torch.testing.assert_close(out, want, rtol=1e-3, atol=2e-4 * math.sqrt(K / 64) * 4, msg=str((M, N, K)))

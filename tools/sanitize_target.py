@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Target for compute-sanitizer (memcheck / racecheck / synccheck): one small invocation of every kernel family of
+libpcm_b200.so -- the smoke path (FPS, kNN, fused set abstraction, tcgen05 GEMMs, fused attention fwd/bwd, LayerNorm,
+BatchNorm, token / head kernels, optimizer, Diffusion-Policy U-Net kernels) plus the grid-sample and sparse-convolution
+kernels -- at sizes that finish in minutes under the tools' 10-100x slowdown.
+
+    compute-sanitizer --tool memcheck  --log-file profiles/rN_sanitizer_memcheck.log  python tools/sanitize_target.py
+    compute-sanitizer --tool racecheck --log-file profiles/rN_sanitizer_racecheck.log python tools/sanitize_target.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as G  # noqa: E402
+
+G.smoke()
+from pointcloudmatters_b200.data_gpu import collate_raw_clouds  # noqa: E402
+from pointcloudmatters_b200.spunet import SpUNet  # noqa: E402
+
+rng = np.random.default_rng(0)
+clouds = [(rng.normal(0, 0.03, (1500, 3)).astype(np.float32), rng.integers(0, 256, (1500, 3)).astype(np.float32)) for _ in range(3)]
+out = collate_raw_clouds(clouds, "cuda", grid_size=0.01, mode="train", seed=1)
+torch.manual_seed(0)
+net = SpUNet(6, num_classes=16, base_channels=16, channels=(16, 32, 32, 32), layers=(1, 1, 1, 1)).cuda().train()
+y = net(dict(grid_coord=out["grid_coord"], feat=out["feat"], offset=out["offset"]))
+y.pow(2).sum().backward()
+torch.cuda.synchronize()
+print("sanitize target OK:", tuple(y.shape))
