@@ -542,6 +542,11 @@ int pcm_gemm_dw_grouped(int n, const void *const *A, const int *lda, const void 
                         float *const *C, const int *ldc, const int *M, const int *N, const int *K,
                         pcm_stream_t stream);
 
+/* n bf16 column-sum problems out_p[c] += sum_r src_p[r, c] in one launch (HOST arrays of length n; C_p % 8 == 0,
+ * C_p <= 2048, ld_p % 8 == 0): the in-projection bias gradients, queued with the weight-gradient GEMMs. */
+int pcm_colsum_grouped(int n, const void *const *src, const long long *rows, const int *C, const long long *ld,
+                       float *const *out, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,8 +18,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Register budget: the kernel is HBM-bound and its only latency hiding is warps in flight (each warp has 2 V 16-byte loads
+// outstanding, then two dependent shuffle reductions, then the stores).  gamma / beta are therefore NOT kept in registers
+// (2 V float4 per thread) but re-read per row -- L1 hits -- which brings V = 4 from 126 to <= 64 registers: 4 CTAs (32 warps)
+// per SM instead of 2 (ncu r1: 59 % of the HBM peak at 25 % warps active).
 template <int V>
-__global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
+__global__ void __launch_bounds__(256, V <= 4 ? 4 : 1) add_dropout_ln_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, long rows, float eps, float p_drop, const unsigned long long* __restrict__ seed_base,
     unsigned long long seed_offset, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ h_out,
@@ -34,12 +38,6 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
     const unsigned long long seed = (seed_base ? *seed_base : 0ULL) * 0xD1342543DE82EF95ULL + seed_offset;
     const uint32_t thr16 = pcm_drop_thr16(p_drop);
     const float ks = p_drop > 0.f ? pcm_keep_scale(thr16) : 1.0f;
-    float4 g4[V], b4[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        g4[v] = reinterpret_cast<const float4*>(gamma)[v * 32 + lane];
-        b4[v] = reinterpret_cast<const float4*>(beta)[v * 32 + lane];
-    }
     for (long r = wid; r < rows; r += nwarps) {
         float4 h[V];
         float s = 0.f;
@@ -71,11 +69,13 @@ __global__ void __launch_bounds__(256) add_dropout_ln_fwd_kernel(
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const size_t e = (size_t)r * C + (size_t)(v * 32 + lane) * 4;
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane);
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(beta) + v * 32 + lane);
             float4 o;
-            o.x = (h[v].x - mean) * rstd * g4[v].x + b4[v].x;
-            o.y = (h[v].y - mean) * rstd * g4[v].y + b4[v].y;
-            o.z = (h[v].z - mean) * rstd * g4[v].z + b4[v].z;
-            o.w = (h[v].w - mean) * rstd * g4[v].w + b4[v].w;
+            o.x = (h[v].x - mean) * rstd * gv.x + bv.x;
+            o.y = (h[v].y - mean) * rstd * gv.y + bv.y;
+            o.z = (h[v].z - mean) * rstd * gv.z + bv.z;
+            o.w = (h[v].w - mean) * rstd * gv.w + bv.w;
             *reinterpret_cast<float4*>(y + e) = o;
             if (y_bf16) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
@@ -253,6 +253,48 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ s
         float t = 0.f;
         for (int g = 0; g < groups; ++g) t += part[g * C + c];
         atomicAdd(out + c, t);
+    }
+}
+
+// Grouped form: up to CS_MAX independent bf16 column-sum problems (bias gradients of the in-projections: colsum of the
+// [dQ | dK | dV] buffers) in ONE launch.  They are off the backward's critical path, so the operator layer queues them
+// next to the weight-gradient GEMMs (functional.DW_QUEUE) instead of launching ~30 latency-bound kernels per step.
+constexpr int CS_MAX = 64;
+struct ColsumProblem { const __nv_bfloat16* src; float* out; long rows, ld; int C, rows_per_cta; };
+struct ColsumGroup { int n; int cta_prefix[CS_MAX + 1]; ColsumProblem prob[CS_MAX]; };
+
+__global__ void __launch_bounds__(256) colsum_grouped_kernel(const __grid_constant__ ColsumGroup g) {
+    extern __shared__ float part[];
+    pcm_pdl_launch_dependents();
+    pcm_pdl_wait();
+    int lo = 0, hi = g.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (g.cta_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const ColsumProblem& q = g.prob[lo];
+    const int C = q.C, tpr = C / 8, groups = max(1, 256 / tpr);
+    const int rg = threadIdx.x / tpr, tc = threadIdx.x - rg * tpr;
+    const long r0 = (long)((int)blockIdx.x - g.cta_prefix[lo]) * q.rows_per_cta;
+    const long r1 = r0 + q.rows_per_cta < q.rows ? r0 + q.rows_per_cta : q.rows;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rg < groups) {
+        const int c0 = tc * 8;
+#pragma unroll 4
+        for (long r = r0 + rg; r < r1; r += groups) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(q.src + r * q.ld + c0);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[rg * C + c0 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int gg = 0; gg < groups; ++gg) t += part[gg * C + c];
+        atomicAdd(q.out + c, t);
     }
 }
 
@@ -575,6 +617,42 @@ PCM_API int pcm_colsum(long long rows, int C, const void* src, long long ld, int
                    rows_per_cta, out);
     }
     return pcm_launch_status();
+}
+
+// n bf16 column-sum problems out_p[c] += sum_r src_p[r, c] (HOST arrays of length n; C_p % 8 == 0, C_p <= 2048, ld_p % 8 == 0,
+// 16-byte aligned sources) in one launch per 64 problems.
+PCM_API int pcm_colsum_grouped(int n, const void* const* src, const long long* rows, const int* C, const long long* ld,
+                               float* const* out, pcm_stream_t stream) {
+    if (n <= 0) return PCM_OK;
+    if (!src || !rows || !C || !ld || !out) return PCM_EINVAL;
+    cudaStream_t st = pcm_cu_stream(stream);
+    for (int base = 0; base < n; base += CS_MAX) {
+        const int cnt = n - base < CS_MAX ? n - base : CS_MAX;
+        ColsumGroup g;
+        g.n = cnt;
+        int ctas = 0;
+        size_t smem = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const int p = base + j;
+            if (!src[p] || !out[p] || rows[p] < 0) return PCM_EINVAL;
+            if ((C[p] % 8) || C[p] <= 0 || C[p] / 8 > 256 || (ld[p] % 8) || (reinterpret_cast<uintptr_t>(src[p]) & 15)) return PCM_EUNSUPPORTED;
+            int rpc = (int)((rows[p] + 148L * 2 - 1) / (148L * 2));
+            if (rpc < 64) rpc = 64;
+            g.prob[j] = ColsumProblem{reinterpret_cast<const __nv_bfloat16*>(src[p]), out[p], (long)rows[p], (long)ld[p], C[p], rpc};
+            g.cta_prefix[j] = ctas;
+            ctas += (int)((rows[p] + rpc - 1) / rpc);
+            const int groups = 256 / (C[p] / 8) > 0 ? 256 / (C[p] / 8) : 1;
+            const size_t need = (size_t)groups * C[p] * sizeof(float);
+            smem = need > smem ? need : smem;
+        }
+        for (int j = cnt; j <= CS_MAX; ++j) g.cta_prefix[j] = ctas;
+        if (ctas == 0) continue;
+        cudaError_t e = pcm_launch(colsum_grouped_kernel, dim3(ctas), dim3(256), smem, st, g);
+        if (e != cudaSuccess) return (int)e;
+        const int r = pcm_launch_status();
+        if (r) return r;
+    }
+    return PCM_OK;
 }
 
 // out = bf16(a + b) -- the fused `with_pos_embed` + operand cast in front of the Q/K projections

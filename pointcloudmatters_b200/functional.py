@@ -356,6 +356,17 @@ def _dw(dtok, xb, out):
     K.gemm_bf16(dtok, xb, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=0)
 
 
+def _colsum_bias(src, out):
+    """out (C) += column sums of the bf16 gradient matrix `src` (a bias gradient); queued with the weight gradients when a
+    queue is installed and `out` lives in a trainer's flat gradient."""
+    if (DW_QUEUE is not None and src.dtype == torch.bfloat16 and src.stride(1) == 1 and src.shape[1] % 8 == 0
+            and src.shape[1] <= 2048 and src.stride(0) % 8 == 0 and src.data_ptr() % 16 == 0 and out.is_contiguous()
+            and BF16_SHADOW.owns_grad(out)):
+        DW_QUEUE.append((torch.cuda.current_stream().cuda_stream, src, None, out))
+        return
+    K.colsum(src, out)
+
+
 def flush_dw_queue(final=False):
     """Run the queued weight-gradient products.  Mid-backward (a gradient-bucket boundary) only the products queued on
     the CURRENT stream are run -- their operands are ordered before this point on that stream; `final=True` (after
@@ -368,7 +379,8 @@ def flush_dw_queue(final=False):
     if not now:
         return
     q[:] = [e for e in q if not (final or e[0] == cur)]
-    K.gemm_dw_grouped([(a, b, o) for _s, a, b, o in now])
+    K.gemm_dw_grouped([(a, b, o) for _s, a, b, o in now if b is not None])
+    K.colsum_grouped([(a, o) for _s, a, b, o in now if b is None])
 
 
 def _param_grads(ctx_params, E, dev):
@@ -439,7 +451,7 @@ class _MHASelf(torch.autograd.Function):
                        buf[:, 2 * E:])
         _dw(buf[:, :2 * E], xqk_b, dW_in[:2 * E])
         _dw(buf[:, 2 * E:], xv_b, dW_in[2 * E:])
-        K.colsum(buf, db_in)
+        _colsum_bias(buf, db_in)
         dpos = dhead = None
         need_pos = has_pos and ctx.needs_input_grad[1]
         need_head = pos_head is not None and ctx.needs_input_grad[2]
@@ -775,7 +787,7 @@ class _MHACrossKV(torch.autograd.Function):
                        G[:, li * E:(li + 1) * E], G[:, (n + li) * E:(n + li + 1) * E])
         shared["written"].add(li)
         _dw(dQ_tok, xq_b, dW_in[:E])
-        K.colsum(dQ_tok, db_in[:E])
+        _colsum_bias(dQ_tok, db_in[:E])
         dx = K.gemm_bf16(dQ_tok, wb[:E], b_mn=True)
         dqpos = None
         if qpos_shape is not None and ctx.needs_input_grad[1]:

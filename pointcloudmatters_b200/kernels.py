@@ -253,6 +253,21 @@ def colsum(src, out=None):
     return out
 
 
+def colsum_grouped(problems):
+    """[(src bf16 (rows, C), out fp32 (C))]: out += column sums of src, all problems in one launch (pcm_colsum_grouped)."""
+    import ctypes
+
+    n = len(problems)
+    if n == 0:
+        return
+    PA, PI, PL = ctypes.c_void_p * n, ctypes.c_int * n, ctypes.c_longlong * n
+    S, O, R, C, L = PA(), PA(), PL(), PI(), PL()
+    for i, (src, out) in enumerate(problems):
+        assert src.dtype == torch.bfloat16 and src.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+        S[i], O[i], R[i], C[i], L[i] = src.data_ptr(), out.data_ptr(), src.shape[0], src.shape[1], src.stride(0)
+    check(lib.pcm_colsum_grouped(n, S, R, C, L, O, current_stream()), "pcm_colsum_grouped")
+
+
 def add_cast_bf16(a, b=None, b_row_div=1):
     """bf16(a + b) for token-major (rows, C) fp32 activations; b may be None or row-broadcast."""
     rows, C = a.shape
