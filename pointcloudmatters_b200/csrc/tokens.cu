@@ -266,10 +266,13 @@ __global__ void __launch_bounds__(256) act_heads_loss_bwd_kernel(HeadsLossBwdPar
         }
         // phase 3: dW[d, cq..cq+3] += sum_rows dpre[row, d] * hs[row, cq..cq+3] (registers; rows strided over groups)
         if (owner) {
+            // independent iterations: unrolled so that several rows' loads are in flight (a serial chain of L2 / HBM latencies
+            // was 100+ us of this kernel with one load outstanding per thread)
+#pragma unroll 8
             for (int rr = grp; rr < n; rr += ngrp) {
                 const long r = r0 + rr;
                 const int b = (int)(r / f.Q), q = (int)(r % f.Q);
-                const float4 xv = *reinterpret_cast<const float4*>(f.hs + b * f.ld_b + q * f.ld_q + cq);
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(f.hs + b * f.ld_b + q * f.ld_q + cq));
 #pragma unroll
                 for (int d = 0; d < HL_MAX_OUT; ++d) {
                     if (d < nout) {
@@ -397,7 +400,7 @@ PCM_API int pcm_act_heads_loss_bwd(int B, int Q, int E, int A, int L, int sig_st
         attr = true;
     }
     const long rows = (long)B * Q;
-    const int grid = (int)(rows / 32 < 24 ? (rows + 31) / 32 : 24);
+    const int grid = (int)(rows / 32 < 74 ? (rows + 31) / 32 : 74);
     act_heads_loss_bwd_kernel<<<grid, 256, smem, pcm_cu_stream(stream)>>>(p);
     return pcm_launch_status();
 }

@@ -1550,11 +1550,11 @@ def roofline_for(kstats, peaks, steps):
         import json
         from pathlib import Path
 
-        t = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "r1_gemm_traffic.json").read_text())
+        t = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "r2_gemm_traffic.json").read_text())
         traffic = t["dram_bytes_per_launch"]
         traffic_note = (f"dram__bytes_read+write per launch of the dominant shape M={t['shape']['M']} N={t['shape']['N']} "
                         f"K={t['shape']['K']} (algorithmic {t['algorithmic_bytes_per_launch']} B; output partly L2-resident), "
-                        "profiles/r1_gemm_traffic.json")
+                        "profiles/r2_gemm_traffic.json")
     except Exception:
         pass
     return {"kernel": "gemm_tcgen05_kernel (all projection / attention / weight-gradient GEMMs of the step)",

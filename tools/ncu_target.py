@@ -44,6 +44,30 @@ elif which == "hbm":
     for _ in range(2):
         o = PF.batchnorm_relu(z, bn)
         o.backward(torch.ones_like(o))
+elif which == "gemm_grouped":
+    # the decoder bucket's queue of one training step: 7 layers x (self dWo, dW_qk, dW_v, cross dWo, dW_q, FFN dW1, dW2)
+    from pointcloudmatters_b200.kernels import gemm_dw_grouped
+
+    rows = 6400
+    mk = lambda r, c: torch.randn(r, c, device="cuda").bfloat16()
+    probs = []
+    for _ in range(7):
+        for (m, n) in ((512, 512), (1024, 512), (512, 512), (512, 512), (512, 512), (32, 512), (512, 32)):
+            probs.append((mk(rows, m), mk(rows, n), torch.zeros(m, n, device="cuda")))
+    for _ in range(3):
+        gemm_dw_grouped(probs)
+elif which == "gemm_inproj":
+    # fused Q|K|V in-projection of a main-encoder layer: two A operands, parted head-split bf16 output
+    from pointcloudmatters_b200 import kernels as K
+
+    L, B, E, nh = 515, 64, 512, 8
+    Z = B * nh
+    xqk, xv = torch.randn(L * B, E, device="cuda").bfloat16(), torch.randn(L * B, E, device="cuda").bfloat16()
+    w, bias = torch.randn(3 * E, E, device="cuda").bfloat16(), torch.randn(3 * E, device="cuda")
+    qkv = torch.empty(3, Z * L, 64, device="cuda", dtype=torch.bfloat16)
+    for _ in range(4):
+        K.gemm_ex(L * B, 3 * E, E, 1, xqk, False, 0, w, False, 0, qkv, c_mode=1, hs=(B, nh, L), ldc=64, bias=bias, a2=xv,
+                  a2_from_col=2 * E, hs_parts=(E, Z * L * 64))
 elif which.startswith("gemm"):
     from pointcloudmatters_b200.kernels import gemm_bf16
 

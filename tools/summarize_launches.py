@@ -39,7 +39,7 @@ def main(path):
     fam = defaultdict(float)
     for k, (n, ns) in agg.items():
         name = k.split("(")[0].split("<")[0]
-        fam["gemm_tcgen05" if "gemm_tcgen05" in name else "flash_attn" if name.startswith("flash_") else
+        fam["gemm_tcgen05" if ("gemm_tcgen05" in name or "gemm_dw_grouped" in name) else "flash_attn" if name.startswith("flash_") else
             "layernorm/colsum/cast" if any(s in name for s in ("add_dropout_ln", "colsum", "add_cast")) else
             "set abstraction + pointops" if any(s in name for s in ("sa_", "knn_", "fps_")) else
             "optimizer" if any(s in name for s in ("adamw", "sumsq", "_slices_kernel")) else
