@@ -11,7 +11,7 @@
 // Same machine mapping as gemm_tcgen05.cu (warp 0 TMA producer, warp 1 MMA issuer, 8 epilogue warps, 2 TMEM accumulators,
 // SWIZZLE_128B ring), specialised to MN-major A and B (both operands are read in the layout the activations already
 // have) and the red.global.add.f32 epilogue.  Per-problem tensor maps and shapes travel in the kernel parameter block
-// (__grid_constant__, ~12 KB for 40 problems): nothing is staged through device memory, so a CUDA-graph capture of the
+// (__grid_constant__, ~17 KB for 56 problems): nothing is staged through device memory, so a CUDA-graph capture of the
 // launch is self-contained.
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
@@ -25,7 +25,7 @@ namespace {
 
 using namespace pcm_tc;
 
-constexpr int GP_MAX = 40;  // problems per launch
+constexpr int GP_MAX = 56;  // problems per launch (parameter block: 56 x (2 x 128 B maps + 40 B) = 16.6 KB)
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
@@ -237,7 +237,7 @@ int launch_group(const GroupedMaps& maps, const GroupedParams& g, cudaStream_t s
 // n problems  C_p (M_p x N_p fp32, row pitch ldc_p) += A_p^T B_p  with A_p = (K_p x M_p) bf16 (row pitch lda_p) and
 // B_p = (K_p x N_p) bf16 (row pitch ldb_p): the weight-gradient form dW = dY^T X with both operands read in place.
 // All arrays are HOST arrays of length n.  Problems are bucketed by tile width (N <= 64: 128 x 64 tiles, else 128 x 256)
-// and launched in chunks of at most 40; k is sliced so that no work item exceeds 128 k-blocks and one launch offers at
+// and launched in chunks of at most 56; k is sliced so that no work item exceeds 128 k-blocks and one launch offers at
 // least two waves of work items.
 PCM_API int pcm_gemm_dw_grouped(int n, const void* const* A, const int* lda, const void* const* B, const int* ldb, float* const* C,
                                 const int* ldc, const int* M, const int* N, const int* K, pcm_stream_t stream) {
