@@ -283,9 +283,11 @@ class ACTPCD(nn.Module):
         return data_dict
 
     def _decode(self, data_dict):
-        return self.transformer(data_dict["src"], None, self.query_embed.weight, data_dict["pos"],
-                                data_dict["latent_input"], data_dict["proprio_input"],
-                                self.additional_pos_embed.weight)[0]
+        args = (data_dict["src"], None, self.query_embed.weight, data_dict["pos"], data_dict["latent_input"],
+                data_dict["proprio_input"], self.additional_pos_embed.weight)
+        if getattr(self.transformer, "accepts_token_buffers", False):  # our Transformer: hs[0] without building the stack
+            return self.transformer(*args, first_only=True)
+        return self.transformer(*args)[0]
 
     # ---- heads + loss (act.py:255-291) -------------------------------------------------------
     def forward_decoder(self, data_dict):

@@ -125,6 +125,24 @@ class TransformerDecoderLayer(nn.Module):
         return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr, cast=True, cast_pos=query_pos)
 
 
+class _FirstOfStack(torch.autograd.Function):
+    """`torch.stack(intermediate)[0]` for a consumer that reads only the first decoder layer's output (ACT: act.py:262-270)
+    without materialising the stack: returns intermediate[0]; in backward the other layers receive ONE shared zero tensor
+    (they still run their backward, like the reference's select-of-stack does, but the 7-fold zero-filled stack, its
+    copy and the seven strided-to-contiguous copies in front of the LayerNorm backward kernels are gone)."""
+
+    @staticmethod
+    def forward(ctx, *inter):
+        ctx.n = len(inter)
+        return inter[0].view_as(inter[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        z = torch.zeros_like(g) if ctx.n > 1 else None
+        return (g,) + (z,) * (ctx.n - 1)
+
+
 class TransformerDecoder(nn.Module):
     """transformer.py:161-207.  `skip_dead_layers` (off by default = like-for-like with the
     reference) stops after the first layer when only intermediate [0] is consumed downstream."""
@@ -141,7 +159,8 @@ class TransformerDecoder(nn.Module):
         self.group_memory_kv = True  # A/B switch: False = every layer projects the memory itself (reference structure)
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
-                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None):
+                memory_key_padding_mask=None, pos=None, query_pos=None, pos_head=None, first_only=False):
+        """`first_only` (extension): return intermediate[0] (Q, B, E) instead of the stack -- see _FirstOfStack."""
         out, inter = tgt, []
         ln = (lambda x: PF.add_dropout_layernorm(None, x, self.norm, 0.0, False))
         # the memory is the same for every layer: project it to all layers' keys / values in ONE launch
@@ -156,12 +175,14 @@ class TransformerDecoder(nn.Module):
             if self.return_intermediate:
                 inter.append(ln(out))
                 if self.skip_dead_layers and li == 0:
-                    return torch.stack(inter)
+                    return inter[0] if first_only else torch.stack(inter)
         if self.norm is not None:
             out = ln(out)
             if self.return_intermediate:
                 inter[-1] = out
         if self.return_intermediate:
+            if first_only:
+                return _FirstOfStack.apply(*inter)
             return torch.stack(inter)
         return out.unsqueeze(0)
 
@@ -191,7 +212,9 @@ class Transformer(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     def forward(self, src, mask, query_embed, pos_embed, latent_input=None, proprio_input=None,
-                additional_pos_embed=None):
+                additional_pos_embed=None, first_only=False):
+        """`first_only` (extension, used by act.ACTPCD): return hs[0] as a (B, Q, E) view instead of the (n_layers, B, Q, E)
+        stack the reference returns (transformer.py:106-115) -- every layer is still computed, forward and backward."""
         bs = src.shape[0]
         tok, ptk = getattr(src, "_pcm_tokens", None), getattr(pos_embed, "_pcm_tokens", None)
         if (tok is not None and ptk is not None and latent_input is not None and proprio_input is not None
@@ -211,7 +234,10 @@ class Transformer(nn.Module):
                     memory = self.encoder(src_tok, src_key_padding_mask=mask, pos=ptk, pos_head=pos_head)
                 PF.grad_boundary(memory, "transformer.decoder")
                 with PF.stage("decoder x%d" % self.decoder.num_layers):
-                    hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head)
+                    hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=ptk, query_pos=query_embed, pos_head=pos_head,
+                                      first_only=first_only and self.decoder.return_intermediate)
+                if first_only and self.decoder.return_intermediate:
+                    return hs.transpose(0, 1)
                 return hs.transpose(1, 2)
         src = src.flatten(2).permute(2, 0, 1)
         pos_embed = pos_embed.flatten(2).permute(2, 0, 1)
@@ -238,4 +264,6 @@ class Transformer(nn.Module):
         PF.grad_boundary(memory, "transformer.decoder")
         hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed,
                           pos_head=pos_head)
+        if first_only:
+            return hs.transpose(1, 2)[0]
         return hs.transpose(1, 2)
