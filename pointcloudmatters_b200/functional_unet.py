@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from . import kernels as K
 from ._lib import check, current_stream, lib, ptr
-from .functional import _gemm_rows, _grad_slot, _need_cuda, _wb
+from .functional import _dw, _gemm_rows, _grad_slot, _need_cuda, _wb
 
 
 def _r8(n):
@@ -68,7 +68,7 @@ def _accumulate_dw(weight, rows, cols, a, b, pad_rows, pad_cols):
     slot = _grad_slot(weight)
     if not pad_rows and not pad_cols:
         dw = slot.view(rows, cols) if slot is not None else torch.zeros((rows, cols), dtype=torch.float32, device=a.device)
-        K.gemm_bf16(a, b, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=0)
+        _dw(a, b, dw)  # queued with the step's other weight gradients when the destination is the flat gradient
         return None if slot is not None else dw.view(weight.shape)
     tmp = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float32, device=a.device)
     K.gemm_bf16(a, b, a_mn=True, b_mn=True, out=tmp, accumulate=True, split_k=0)
