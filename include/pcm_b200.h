@@ -359,6 +359,11 @@ int pcm_clip_adamw_step(long long n, float *param, float *grad, float *exp_avg, 
 int pcm_clip_adamw_step_bf16(long long n, float *param, float *grad, float *exp_avg,
                              float *exp_avg_sq, const float *hyper, double *sumsq, float *norm_out,
                              void *param_bf16, pcm_stream_t stream);
+/* _ex: zero_grad = 1 leaves the flat gradient ZEROED (ready for the next step's in-place accumulation) instead of holding
+ * the clipped gradient: the separate zero-fill pass of the next step disappears. */
+int pcm_clip_adamw_step_ex(long long n, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                           const float *hyper, double *sumsq, float *norm_out, void *param_bf16, int zero_grad,
+                           pcm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diffusion-Policy denoiser: the non-GEMM kernels of

@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long n4, const float* __restrict__ hyper,
                                                     const double* __restrict__ sumsq, float* __restrict__ norm_out,
-                                                    __nv_bfloat16* __restrict__ p_bf16) {
+                                                    __nv_bfloat16* __restrict__ p_bf16, int zero_grad) {
+    // zero_grad: leave the gradient buffer ZEROED instead of writing the clipped gradient back (same 4 B/param of stores):
+    // the next step's separate zero-fill pass over the flat gradient (96 MB ACT, 1 GB Diffusion Policy) disappears
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
     const float bc1 = hyper[5], bc2 = hyper[6], clip = hyper[7], gscale = hyper[8];
     const float norm = (float)sqrt(*sumsq) * gscale;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
             __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
             reinterpret_cast<uint2*>(p_bf16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         }
-        reinterpret_cast<float4*>(g)[i] = gg;
+        reinterpret_cast<float4*>(g)[i] = zero_grad ? make_float4(0.f, 0.f, 0.f, 0.f) : gg;
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
     }
@@ -121,6 +123,14 @@ PCM_API int pcm_add_slices(int n, long long floats_per_slice, const long long* p
 PCM_API int pcm_clip_adamw_step_bf16(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                                      const float* hyper, double* sumsq, float* norm_out, void* param_bf16,
                                      pcm_stream_t stream) {
+    return pcm_clip_adamw_step_ex(n, param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16, 0, stream);
+}
+
+// zero_grad = 1: the gradient buffer is left zeroed (ready for the next step's accumulation) instead of holding the
+// clipped gradient (what torch.nn.utils.clip_grad_norm_ leaves behind).
+PCM_API int pcm_clip_adamw_step_ex(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                   const float* hyper, double* sumsq, float* norm_out, void* param_bf16, int zero_grad,
+                                   pcm_stream_t stream) {
     if (n <= 0) return PCM_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !sumsq) return PCM_EINVAL;
     if (n % 4) return PCM_EUNSUPPORTED;
@@ -134,7 +144,7 @@ PCM_API int pcm_clip_adamw_step_bf16(long long n, float* param, float* grad, flo
     int r = pcm_launch_status();
     if (r) return r;
     adamw_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4, hyper, sumsq, norm_out,
-                                       reinterpret_cast<__nv_bfloat16*>(param_bf16));
+                                       reinterpret_cast<__nv_bfloat16*>(param_bf16), zero_grad);
     return pcm_launch_status();
 }
 

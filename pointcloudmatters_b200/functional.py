@@ -1466,11 +1466,11 @@ def act_heads_loss(hs, action_head, is_pad_head, actions, is_pad, mu, logvar, kl
                                mu, logvar, cfg)
 
 
-def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None, zero_grad=False):
     """Fused clip-by-global-norm + AdamW over flat fp32 buffers, in place (csrc/optimizer.cu).
     `hyper` = device tensor [lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2, clip_norm, grad_scale]."""
     _need_cuda(param)
-    K.clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16)
+    K.clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16, zero_grad)
     return norm_out
 
 

@@ -197,13 +197,14 @@ def flash_attn_bwd(Qh, Kh, Vh, O_tok, dOh, lse, B, nh, L, S, kpm, scale, p_drop,
     TIMER.end(t0, "flash_attn_bwd", 10.0 * Z * L * S * 64, 2.0 * Z * (4 * L + 4 * S) * 64 + 8.0 * Z * L * 64, (Z, L, S))
 
 
-def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None):
-    """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step_bf16); hyper is a 9-float device
-    tensor; `param_bf16` (optional) receives the bf16 copy of the updated parameters."""
+def clip_adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, sumsq, norm_out, param_bf16=None, zero_grad=False):
+    """Fused clip + AdamW over flat fp32 buffers (pcm_clip_adamw_step_ex); hyper is a 9-float device
+    tensor; `param_bf16` (optional) receives the bf16 copy of the updated parameters; `zero_grad`: leave the
+    gradient buffer zeroed instead of holding the clipped gradient."""
     require_cuda(param, grad, exp_avg, exp_avg_sq, hyper, sumsq)
-    check(lib.pcm_clip_adamw_step_bf16(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
-                                       ptr(sumsq), ptr(norm_out), ptr(param_bf16), current_stream()),
-          "pcm_clip_adamw_step_bf16")
+    check(lib.pcm_clip_adamw_step_ex(param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(hyper),
+                                     ptr(sumsq), ptr(norm_out), ptr(param_bf16), int(zero_grad), current_stream()),
+          "pcm_clip_adamw_step_ex")
 
 
 def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset, want_bf16=False, pos=None, pos_row_div=1):

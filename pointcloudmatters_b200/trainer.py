@@ -151,6 +151,11 @@ class BCTrainer:
         import os
 
         self.group_weight_grads = not bool(int(os.environ.get("PCM_NO_GROUPED_DW", "0")))
+        # the fused AdamW kernel leaves the gradient buffer zeroed, so the next step starts accumulating without a separate
+        # zero-fill pass (p.grad reads as zeros after training_step; `last_grad_norm` keeps the pre-clip norm).
+        # optimizer_zeroes_grad=False restores torch's behaviour (clipped gradients stay in p.grad).
+        self.optimizer_zeroes_grad = True
+        self._grads_clean = False
         if self.sync_batchnorm:
             from . import functional as PF
 
@@ -275,7 +280,8 @@ class BCTrainer:
         self._hyper_host = vals.pin_memory() if f.param.is_cuda else vals
         self._hyper.copy_(self._hyper_host, non_blocking=True)
         PF.clip_adamw_step(f.param[: f.n_active], f.grad[: f.n_active], f.exp_avg, f.exp_avg_sq, self._hyper,
-                           self._sumsq, self._norm, f.param_bf16[: f.n_active])
+                           self._sumsq, self._norm, f.param_bf16[: f.n_active], zero_grad=self.optimizer_zeroes_grad)
+        self._grads_clean = self.optimizer_zeroes_grad  # the kernel left the flat gradient zeroed (the inactive tail never changes)
         self.last_grad_norm = self._norm
         self.step_num += 1
 
@@ -297,6 +303,7 @@ class BCTrainer:
 
         if self.flat is not None and zero:
             self.flat.zero_grad()
+        self._grads_clean = False
         with PF.stage("forward"):
             out = self.policy(self._inputs_only(batch))
         exchange = (self.world > 1 and self.overlap_allreduce and self.flat is not None and self.bucket_ranges
@@ -423,7 +430,7 @@ class BCTrainer:
         if self.debug_hints and pcds is not None:
             self._check_hints(pcds)
         graph_ok = sync_free is None or pcds is None or sync_free(pcds)
-        zero = self._micro == 0
+        zero = self._micro == 0 and not self._grads_clean
         if (self.use_cuda_graph and graph_ok and self.flat is not None and self._eager_steps >= 2
                 and self.graph_disabled_reason is None):
             losses = self._graphed_forward_backward(batch, zero)
@@ -434,6 +441,7 @@ class BCTrainer:
             self._eager_steps += 1
             if self.flat is None:  # first step: discover never-used parameters, then go flat
                 self._build_flat()
+        self._grads_clean = False  # (a graph replay does not run _forward_backward's bookkeeping)
         self._micro += 1
         if self._micro >= self.accumulate_grad_batches:
             self._micro = 0
