@@ -552,6 +552,18 @@ int pcm_gemm_dw_grouped(int n, const void *const *A, const int *lda, const void 
 int pcm_colsum_grouped(int n, const void *const *src, const long long *rows, const int *C, const long long *ld,
                        float *const *out, pcm_stream_t stream);
 
+/* Fused feed-forward sub-block for dim_feedforward = 32 (transformer.py:243-247,336-340; maniskill2_act_pcd_model.yaml
+ * dim_feedforward: 32), one kernel each way; E % 64 == 0, 64 <= E <= 512, Hd must be 32.
+ *   pcm_ffn32_fwd: hd (rows, 32) bf16 = dropout(relu(x W1^T + b1)) (saved for the backward; clipped / dropped units are
+ *     exactly 0), y (rows, E) fp32 = hd W2^T + b2.  x (rows, E) bf16 (pitch ldx), W1 (32, E) bf16, W2 (E, 32) bf16.
+ *   pcm_ffn32_bwd: dh (rows, 32) bf16 = (dy W2) * keep_scale(p_drop) * [hd > 0], dx (rows, E) fp32 = dh W1; the weight /
+ *     bias gradients are ordinary dW = dY^T X products (pcm_gemm_dw_grouped / pcm_colsum_grouped). */
+int pcm_ffn32_fwd(long long rows, int E, int Hd, const void *x, long long ldx, const void *w1, const float *b1,
+                  const void *w2, const float *b2, float p_drop, const unsigned long long *seed_base,
+                  unsigned long long seed_offset, void *hd, float *y, pcm_stream_t stream);
+int pcm_ffn32_bwd(long long rows, int E, int Hd, const void *dy, long long lddy, const void *hd, const void *w1,
+                  const void *w2, float p_drop, void *dh, float *dx, pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

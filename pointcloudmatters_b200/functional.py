@@ -955,11 +955,14 @@ def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=N
     return F.layer_norm(residual, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
 
 
+_NO_FUSED_FFN = bool(int(os.environ.get("PCM_NO_FUSED_FFN", "0")))  # A/B switch: GEMM -> dropout -> GEMM
+
+
 class _FFN(torch.autograd.Function):
-    """linear2(dropout(relu(linear1(x)))) (transformer.py:243-247,336-340) as ONE autograd node: the hidden
-    activation (rows, dim_feedforward) lives in bf16 straight out of the first GEMM's bias+ReLU epilogue, dropout
-    and the ReLU/dropout backward are one small kernel each (csrc/layernorm.cu), weight / bias gradients go
-    straight into the parameters' gradient buffers.  Replaces two `_LinearTC` nodes plus six ATen kernels."""
+    """linear2(dropout(relu(linear1(x)))) (transformer.py:243-247,336-340) as ONE autograd node.  dim_feedforward = 32 (the
+    reference configuration): ONE kernel each way (csrc/ffn_fused.cu: the hidden tile never leaves registers; y / dx are
+    written once).  Other widths: tcgen05 GEMM with bias+ReLU epilogue -> dropout kernel -> GEMM.  Weight / bias gradients
+    go to the parameters' gradient buffers through the grouped queue."""
 
     @staticmethod
     def forward(ctx, x2, w1, b1, w2, b2, p_drop, xb_hint):
@@ -967,17 +970,29 @@ class _FFN(torch.autograd.Function):
 
         xb = xb_hint if xb_hint is not None else (x2 if x2.dtype == torch.bfloat16 else K.add_cast_bf16(x2))
         w1b, w2b = _wb(w1), _wb(w2)
-        h = K.gemm_bf16(xb, w1b, bias=b1, relu=True, out_dtype=torch.bfloat16)  # (rows, Hd) bf16
+        rows, E = xb.shape
+        Hd = w1.shape[0]
         seed_base, seed = None, 0
-        hd = h
         if p_drop > 0:
             seed_base, seed = DROPOUT_RNG.base_for(x2.device), DROPOUT_RNG.next_offset()
-            hd = torch.empty_like(h)
-            check(lib.pcm_ffn_dropout_fwd(h.shape[0], h.shape[1], ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(hd),
-                                          current_stream()), "pcm_ffn_dropout_fwd")
-        y = K.gemm_bf16(hd, w2b, bias=b2)
+        fused = (not _NO_FUSED_FFN and Hd == 32 and E % 64 == 0 and 64 <= E <= 512 and xb.stride(1) == 1 and xb.stride(0) % 8 == 0
+                 and w1b.is_contiguous() and w2b.is_contiguous() and w2.shape[0] == E)
+        if fused:
+            hd = torch.empty((rows, Hd), dtype=torch.bfloat16, device=xb.device)
+            y = torch.empty((rows, E), dtype=torch.float32, device=xb.device)
+            check(lib.pcm_ffn32_fwd(rows, E, Hd, ptr(xb), xb.stride(0), ptr(w1b), ptr(b1), ptr(w2b), ptr(b2), float(p_drop),
+                                    ptr(seed_base), int(seed), ptr(hd), ptr(y), current_stream()), "pcm_ffn32_fwd")
+            h = hd
+        else:
+            h = K.gemm_bf16(xb, w1b, bias=b1, relu=True, out_dtype=torch.bfloat16)  # (rows, Hd) bf16
+            hd = h
+            if p_drop > 0:
+                hd = torch.empty_like(h)
+                check(lib.pcm_ffn_dropout_fwd(h.shape[0], h.shape[1], ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(hd),
+                                              current_stream()), "pcm_ffn_dropout_fwd")
+            y = K.gemm_bf16(hd, w2b, bias=b2)
         ctx.save_for_backward(xb, h, hd, w1b, w2b, seed_base)
-        ctx.cfg = (float(p_drop), int(seed))
+        ctx.cfg = (float(p_drop), int(seed), fused)
         ctx.params = (w1, b1, w2, b2)
         return y
 
@@ -986,33 +1001,39 @@ class _FFN(torch.autograd.Function):
         from ._lib import check, current_stream, lib, ptr
 
         xb, h, hd, w1b, w2b, seed_base = ctx.saved_tensors
-        p_drop, seed = ctx.cfg
+        p_drop, seed, fused = ctx.cfg
         w1, b1, w2, b2 = ctx.params
         rows, Hd = h.shape
+        dev = dy.device
         dyb, b2_done = _grad_bf16(dy, rows, dy.shape[1], b2)
-        grads = []
-        for w, a, b in ((w2, dyb, hd), ):
-            slot = _grad_slot(w)
-            dw = slot if slot is not None else torch.zeros(w.shape, dtype=torch.float32, device=dyb.device)
-            _dw(a, b, dw)
-            grads.append(None if slot is not None else dw)
-        slot = _grad_slot(b2)
-        db2 = slot if b2_done else K.colsum(dyb, slot)
-        dhd = K.gemm_bf16(dyb, w2b, b_mn=True)  # (rows, E) x W2(E, Hd) -> (rows, Hd) fp32
-        dhb = torch.empty_like(h)
+        slot2 = _grad_slot(w2)
+        dw2 = slot2 if slot2 is not None else torch.zeros(w2.shape, dtype=torch.float32, device=dev)
+        _dw(dyb, hd, dw2)
+        slotb2 = _grad_slot(b2)
+        db2 = slotb2 if b2_done else K.colsum(dyb, slotb2)
         slotb1 = _grad_slot(b1)
-        fuse_b1 = Hd <= 256 and 256 % (Hd // 8) == 0  # the gate kernel can form colsum(dh) = db1 itself
-        db1 = slotb1 if slotb1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dyb.device)
-        check(lib.pcm_ffn_relu_dropout_bwd_ex(rows, Hd, ptr(dhd), ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(dhb),
-                                              ptr(db1 if fuse_b1 else None), current_stream()), "pcm_ffn_relu_dropout_bwd_ex")
+        db1 = slotb1 if slotb1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dev)
+        dhb = torch.empty_like(h)
+        dx = None
+        if fused:
+            dx = torch.empty((rows, dy.shape[1]), dtype=torch.float32, device=dev)
+            check(lib.pcm_ffn32_bwd(rows, dy.shape[1], Hd, ptr(dyb), dyb.stride(0), ptr(hd), ptr(w1b), ptr(w2b), float(p_drop),
+                                    ptr(dhb), ptr(dx), current_stream()), "pcm_ffn32_bwd")
+            _colsum_bias(dhb, db1)
+        else:
+            dhd = K.gemm_bf16(dyb, w2b, b_mn=True)  # (rows, E) x W2(E, Hd) -> (rows, Hd) fp32
+            fuse_b1 = Hd <= 256 and 256 % (Hd // 8) == 0  # the gate kernel can form colsum(dh) = db1 itself
+            check(lib.pcm_ffn_relu_dropout_bwd_ex(rows, Hd, ptr(dhd), ptr(h), float(p_drop), ptr(seed_base), int(seed), ptr(dhb),
+                                                  ptr(db1 if fuse_b1 else None), current_stream()), "pcm_ffn_relu_dropout_bwd_ex")
+            if not fuse_b1:
+                K.colsum(dhb, db1)
+            if ctx.needs_input_grad[0]:
+                dx = K.gemm_bf16(dhb, w1b, b_mn=True)
         slot1 = _grad_slot(w1)
-        dw1 = slot1 if slot1 is not None else torch.zeros(w1.shape, dtype=torch.float32, device=dyb.device)
+        dw1 = slot1 if slot1 is not None else torch.zeros(w1.shape, dtype=torch.float32, device=dev)
         _dw(dhb, xb, dw1)
-        if not fuse_b1:
-            K.colsum(dhb, db1)
-        dx = K.gemm_bf16(dhb, w1b, b_mn=True) if ctx.needs_input_grad[0] else None
-        return (dx, None if slot1 is not None else dw1, None if slotb1 is not None else db1, grads[0],
-                None if slot is not None else db2, None, None)
+        return (dx, None if slot1 is not None else dw1, None if slotb1 is not None else db1, None if slot2 is not None else dw2,
+                None if slotb2 is not None else db2, None, None)
 
 
 def feed_forward(x, linear1, linear2, p_drop, training):

@@ -39,7 +39,7 @@ def test_policy_matches_reference_fixture(path):
     model = build_policy(cfg, rlbench).cuda().train()
     model.load_state_dict(state)
     fused_entry_points = ("pcm_flash_attn_fwd", "pcm_flash_attn_bwd", "pcm_add_dropout_ln_fwd_ex", "pcm_add_dropout_ln_bwd_ex2",
-                          "pcm_ffn_relu_dropout_bwd_ex")
+                          "pcm_ffn_relu_dropout_bwd_ex", "pcm_ffn32_fwd", "pcm_ffn32_bwd")
     before = {k: lib.calls.get(k, 0) for k in fused_entry_points}
     d = model(_to_cuda(batch))
     for k in ("a_hat", "mu", "logvar"):
@@ -58,7 +58,8 @@ def test_policy_matches_reference_fixture(path):
         ran = {k: lib.calls.get(k, 0) - before[k] for k in fused_entry_points}
         assert ran["pcm_flash_attn_fwd"] >= n_mha and ran["pcm_add_dropout_ln_fwd_ex"] >= n_ln, ran
         assert ran["pcm_flash_attn_bwd"] >= 2 * cfg["enc_layers"] + 2 and ran["pcm_add_dropout_ln_bwd_ex2"] > 0, ran
-        assert ran["pcm_ffn_relu_dropout_bwd_ex"] >= 2 * cfg["enc_layers"] + 1, ran
+        assert ran["pcm_ffn32_fwd"] >= 2 * cfg["enc_layers"] + cfg["dec_layers"], ran  # dim_feedforward 32: the fused FFN kernels
+        assert ran["pcm_ffn32_bwd"] + ran["pcm_ffn_relu_dropout_bwd_ex"] >= 2 * cfg["enc_layers"] + 1, ran
     got_nograd = sorted(k for k, p in model.named_parameters() if p.grad is None)
     assert got_nograd == sorted(nograd)
     worst = {}
