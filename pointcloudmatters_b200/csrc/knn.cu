@@ -12,6 +12,8 @@
 //   * the heap root is cached in a register, so the common reject path touches no memory;
 //   * results leave through a block-wide transposed, fully coalesced store.
 // Algorithmic traffic: 12N + 12M + 8*M*k bytes per cloud.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -139,6 +141,162 @@ __global__ void __launch_bounds__(KNN_T) knn_kernel(int b, int m, int k,
 }
 
 // ------------------------------------------------------------------------------------------
+// kNN, one WARP per query (nsample <= 31).
+//
+// The thread-per-query kernel above spends most of its issue slots in divergent heap sifts (one lane at a time, ~40
+// instructions each, ~k (1 + ln(N / k)) of them per query) and keeps 10 % of the SM's warp slots busy.  Here the 32 lanes
+// of a warp scan 32 candidates per step for one query, and the running result is a SORTED list with one entry per lane
+// (lane i = (i+1)-th smallest so far): a candidate that beats the list's threshold is inserted with two shuffles, a ballot
+// and a select -- ~8 warp instructions.
+//
+// Exactness.  The reference's output is its max-heap after heap_sort.  If the k + 1 smallest distances of a query are
+// pairwise different, the heap's final CONTENT is the unique set of the k smallest and heap_sort's output is that set in
+// ascending order, whatever the heap's internal arrangement was: the sorted list IS the reference result.  The list keeps
+// k + 1 entries for exactly this check (candidates equal to its threshold cannot change ranks 1..k and are skipped).  A
+// query that shows a tie among its k + 1 smallest is REPLAYED through the reference's heap (phase 2): an element enters
+// the reference heap iff its distance is below the k-th smallest of the prefix before it (the heap root), a condition on
+// VALUES only, so the warp finds the entering elements with the same 32-wide scan (ballot against the root), feeds them
+// to heap_sift in scan order (lane 0, shared-memory heap), and finishes with the reference's heap_sort.
+// ------------------------------------------------------------------------------------------
+constexpr int KW_WARPS = 8;
+constexpr int KW_TILE = 1024;  // source points staged per tile (float4 -> 16 KB)
+
+// insert (cd, ci) into the ascending per-lane list (bd, bi): every lane decides on its own from its entry and its left
+// neighbour's (ud, ui) -- entries <= cd stay, the first greater one takes the candidate, the rest move up by one lane
+__device__ __forceinline__ void list_insert(float& bd, int& bi, float cd, int ci, int lane) {
+    float ud = __shfl_up_sync(PCM_FULL_MASK, bd, 1);
+    const int ui = __shfl_up_sync(PCM_FULL_MASK, bi, 1);
+    if (lane == 0) ud = -INFINITY;
+    const bool stay = bd <= cd, first = ud <= cd;
+    bi = stay ? bi : (first ? ci : ui);
+    bd = stay ? bd : fmaxf(cd, ud);
+}
+
+template <int QPW>
+__global__ void __launch_bounds__(KW_WARPS * 32) knn_warp_kernel(int b, int m, int k, const float* __restrict__ xyz,
+                                                                  const float* __restrict__ new_xyz,
+                                                                  const int* __restrict__ offset,
+                                                                  const int* __restrict__ new_offset, int* __restrict__ idx,
+                                                                  float* __restrict__ dist2) {
+    __shared__ float4 tile[KW_TILE];
+    __shared__ float s_hd[KW_WARPS][QPW][32];
+    __shared__ int s_hi[KW_WARPS][QPW][32];
+    float* tile_f = reinterpret_cast<float*>(tile);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int QPC = KW_WARPS * QPW;
+    const int q0 = blockIdx.x * QPC;
+    const int q_last = min(m, q0 + QPC) - 1;
+    const int c_first = pcm_cloud_of(q0, new_offset, b);
+    const int c_last = pcm_cloud_of(q_last, new_offset, b);
+
+    float qx[QPW], qy[QPW], qz[QPW], bd[QPW], thr[QPW], thr1[QPW];  // thr = entry k (the k+1-th smallest), thr1 = entry k-1
+    int bi[QPW], qc[QPW];
+#pragma unroll
+    for (int j = 0; j < QPW; ++j) {
+        const int q = q0 + warp * QPW + j;
+        const bool act = q < m;
+        qc[j] = act ? pcm_cloud_of(q, new_offset, b) : -1;
+        qx[j] = act ? new_xyz[(size_t)q * 3 + 0] : 0.f;
+        qy[j] = act ? new_xyz[(size_t)q * 3 + 1] : 0.f;
+        qz[j] = act ? new_xyz[(size_t)q * 3 + 2] : 0.f;
+        bd[j] = 1e10f; bi[j] = -1; thr[j] = 1e10f; thr1[j] = 1e10f;
+    }
+    unsigned replay = 0;  // bit j: query j of this warp goes through the exact heap replay
+
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1) {
+#pragma unroll
+            for (int j = 0; j < QPW; ++j) {
+                s_hd[warp][j][lane] = 1e10f; s_hi[warp][j][lane] = -1;
+                thr[j] = 1e10f;  // phase 2: the heap root
+            }
+            __syncwarp();
+        }
+        for (int c = c_first; c <= c_last; ++c) {
+            const int s = c ? __ldg(offset + c - 1) : 0;
+            const int e = __ldg(offset + c);
+            unsigned mine = 0;  // queries of this warp that scan cloud c in this phase (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < QPW; ++j)
+                if (qc[j] == c && (phase == 0 || ((replay >> j) & 1u))) mine |= 1u << j;
+            for (int t0 = s; t0 < e; t0 += KW_TILE) {
+                const int cnt = min(KW_TILE, e - t0);
+                __syncthreads();
+                const float* src = xyz + (size_t)t0 * 3;
+                for (int f = tid; f < cnt * 3; f += KW_WARPS * 32) {
+                    const int pp = f / 3;
+                    tile_f[pp * 4 + (f - pp * 3)] = __ldg(src + f);
+                }
+                __syncthreads();
+                if (!mine) continue;
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const bool valid = i0 + lane < cnt;
+                    const float4 P = tile[valid ? i0 + lane : i0];
+#pragma unroll
+                    for (int j = 0; j < QPW; ++j) {
+                        if (!((mine >> j) & 1u)) continue;
+                        const float d = pcm_dist2(qx[j] - P.x, qy[j] - P.y, qz[j] - P.z);
+                        unsigned mk = __ballot_sync(PCM_FULL_MASK, valid && d < thr[j]);
+                        while (mk) {  // candidates in scan order; the threshold only falls, so each is re-tested
+                            const int sl = __ffs(mk) - 1;
+                            mk &= mk - 1;
+                            const float cd = __shfl_sync(PCM_FULL_MASK, d, sl);
+                            if (cd < thr[j]) {
+                                if (phase == 0) {
+                                    list_insert(bd[j], bi[j], cd, t0 + i0 + sl, lane);
+                                    thr[j] = fmaxf(cd, thr1[j]);  // cd < old entry k: the new entry k is max(cd, old entry k-1)
+                                    thr1[j] = __shfl_sync(PCM_FULL_MASK, bd[j], k - 1);
+                                } else {
+                                    if (lane == 0) heap_sift(s_hd[warp][j], s_hi[warp][j], 1, k, cd, t0 + i0 + sl);
+                                    __syncwarp();
+                                    thr[j] = s_hd[warp][j][0];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (phase == 0) {
+            // ties among the k + 1 smallest (entries of untouched slots, idx -1, are identical and harmless)
+#pragma unroll
+            for (int j = 0; j < QPW; ++j) {
+                const float nd = __shfl_down_sync(PCM_FULL_MASK, bd[j], 1);
+                const int ni = __shfl_down_sync(PCM_FULL_MASK, bi[j], 1);
+                const bool tie = lane < k && bd[j] == nd && !(bi[j] == -1 && ni == -1);
+                if (__ballot_sync(PCM_FULL_MASK, tie) != 0u && qc[j] >= 0) replay |= 1u << j;
+            }
+            if (!__syncthreads_or(replay != 0u)) break;  // CTA-uniform: the tile staging of phase 2 needs every warp
+        } else {
+#pragma unroll
+            for (int j = 0; j < QPW; ++j) {
+                if (!((replay >> j) & 1u)) continue;
+                if (lane == 0) heap_sort(s_hd[warp][j], s_hi[warp][j], 1, k);
+                __syncwarp();
+                bd[j] = s_hd[warp][j][lane];
+                bi[j] = s_hi[warp][j][lane];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < QPW; ++j) {
+        const int q = q0 + warp * QPW + j;
+        if (q < m && lane < k) {
+            idx[(size_t)q * k + lane] = bi[j];
+            if (dist2) dist2[(size_t)q * k + lane] = bd[j];
+        }
+    }
+}
+
+template <int QPW>
+static int launch_knn_warp(int b, int m, int k, const float* xyz, const float* new_xyz, const int* offset,
+                           const int* new_offset, int* idx, float* dist2, cudaStream_t st) {
+    knn_warp_kernel<QPW><<<pcm_divup(m, KW_WARPS * QPW), KW_WARPS * 32, 0, st>>>(b, m, k, xyz, new_xyz, offset, new_offset, idx,
+                                                                              dist2);
+    return pcm_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
 // Ball query: replaces ball_query_cuda_kernel (ball_query_cuda_kernel.cu:58-123).
 // One WARP per query: lanes scan the cloud 32 points at a time and compact the hits IN SCAN
 // ORDER (ballot + popc prefix) into a per-warp shared-memory list, replacing the reference's
@@ -254,6 +412,20 @@ PCM_API int pcm_knn_query(int b, int m, int nsample, const float* xyz, const flo
     if (m <= 0) return PCM_OK;
     if (b <= 0 || !xyz || !new_xyz || !offset || !new_offset || !idx || nsample <= 0) return PCM_EINVAL;
     if (nsample > 128) return PCM_EUNSUPPORTED;
+    // PCM_KNN_V1=1: the thread-per-query kernel for every nsample (A/B timing); it also serves nsample > 31
+    static const bool use_v1 = [] { const char* e = getenv("PCM_KNN_V1"); return e && e[0] == '1'; }();
+    if (nsample <= 31 && !use_v1) {
+        cudaStream_t st = pcm_cu_stream(stream);
+        // queries per warp: two measured best at every BASELINE shape (tools/bench_pointops.py: occupancy beats sharing the
+        // staged cloud between more queries); PCM_KNN_QPW = 1 | 2 | 4 | 8 overrides for timing
+        static const int force = [] { const char* e = getenv("PCM_KNN_QPW"); return e ? atoi(e) : 0; }();
+        switch (force) {
+            case 1: return launch_knn_warp<1>(b, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+            case 4: return launch_knn_warp<4>(b, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+            case 8: return launch_knn_warp<8>(b, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+            default: return launch_knn_warp<2>(b, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+        }
+    }
     const size_t smem = (size_t)nsample * KNN_T * 8 + (size_t)KNN_TILE * 16;
     static bool attr_set = false;
     if (!attr_set) {
