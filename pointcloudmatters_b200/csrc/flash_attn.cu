@@ -476,9 +476,11 @@ __global__ void __launch_bounds__(256) flash_delta_kernel(const __nv_bfloat16* _
                 const float2 af = __bfloat1622float2(ap[k]), cf = __bfloat1622float2(cp[k]);
                 s += af.x * cf.x + af.y * cf.y;
             }
-            float4* q = reinterpret_cast<float4*>(dq_acc + (size_t)r * 64) + l8 * 2;  // clears the dQ accumulator row
-            q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dq_acc != nullptr) {  // clears the dQ accumulator row (NULL: single key tile, dQ is stored directly)
+                float4* q = reinterpret_cast<float4*>(dq_acc + (size_t)r * 64) + l8 * 2;
+                q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         s += __shfl_xor_sync(PCM_FULL_MASK, s, 4);
         s += __shfl_xor_sync(PCM_FULL_MASK, s, 2);
@@ -723,20 +725,39 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
         // bulk tensor stores -- no red / st.global instruction streams in the softmax warps, rows past
         // L / S are clipped by the tensor maps.  Staging is shared by the 8 warps (named barrier 1).
         const bool issuer = (warp == 2 && lane == 0);
+        const bool dq_direct = n_kv == 1;  // the launcher then passes the bf16 token-major dQ map in `tdq`
         auto drain_store = [&]() {
             if (issuer) bulk_wait_read_all();  // earlier bulk operations have finished reading the staging tiles
             named_bar_sync(1, 256);
+            if (dq_direct) {
+                // a single key tile per batch*head: this dQ tile is final -- bf16, token-major, one bulk tensor store
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                st_shared_v4(sStage + sw128_off(half, row, c), __float_as_uint(__uint_as_float(v[4 * c]) * sc),
-                             __float_as_uint(__uint_as_float(v[4 * c + 1]) * sc), __float_as_uint(__uint_as_float(v[4 * c + 2]) * sc),
-                             __float_as_uint(__uint_as_float(v[4 * c + 3]) * sc));
-            fence_proxy_async();
-            named_bar_sync(1, 256);
-            if (issuer) {
-                tma_reduce_add_3d(&tdq, sStage, 0, pi << 7, pz);
-                tma_reduce_add_3d(&tdq, sStage + 16384, 32, pi << 7, pz);
-                bulk_commit();
+                for (int q = 0; q < 4; ++q)
+                    st_shared_v4(sStage + sw128_off(0, row, half * 4 + q),
+                                 pack_bf16(__uint_as_float(v[8 * q]) * sc, __uint_as_float(v[8 * q + 1]) * sc),
+                                 pack_bf16(__uint_as_float(v[8 * q + 2]) * sc, __uint_as_float(v[8 * q + 3]) * sc),
+                                 pack_bf16(__uint_as_float(v[8 * q + 4]) * sc, __uint_as_float(v[8 * q + 5]) * sc),
+                                 pack_bf16(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
+                fence_proxy_async();
+                named_bar_sync(1, 256);
+                if (issuer) {
+                    const int pb = pz / p.nh, ph = pz - pb * p.nh;
+                    tma_store_4d(&tdq, sStage, 0, ph, pb, pi << 7);
+                    bulk_commit();
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    st_shared_v4(sStage + sw128_off(half, row, c), __float_as_uint(__uint_as_float(v[4 * c]) * sc),
+                                 __float_as_uint(__uint_as_float(v[4 * c + 1]) * sc), __float_as_uint(__uint_as_float(v[4 * c + 2]) * sc),
+                                 __float_as_uint(__uint_as_float(v[4 * c + 3]) * sc));
+                fence_proxy_async();
+                named_bar_sync(1, 256);
+                if (issuer) {
+                    tma_reduce_add_3d(&tdq, sStage, 0, pi << 7, pz);
+                    tma_reduce_add_3d(&tdq, sStage + 16384, 32, pi << 7, pz);
+                    bulk_commit();
+                }
             }
             if (prev_last) {
                 if (issuer) bulk_wait_read_all();
@@ -993,7 +1014,16 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     if ((r = head_split_map(V, Z, S, &tv))) return r;
     if ((r = head_split_map(dO, Z, L, &tdo))) return r;
     CUtensorMap tdq, tdk, tdv;
-    {   // fp32 dQ accumulator (Z, L, 64): boxes of 32 columns x 128 rows
+    // One key tile per batch*head (S <= 128: decoder self-attention, CVAE encoder): every dQ tile is final when its
+    // query tile has been processed, so the kernel stores it directly (bf16, token-major) -- no zero-fill of the fp32
+    // accumulator, no reduction, no conversion kernel.
+    const bool dq_direct = S <= 128 && !(ldq % 8) && !(reinterpret_cast<uintptr_t>(dQ) & 15);
+    if (dq_direct) {  // element (d, h, b, l) at ((l * B + b) * ldq + h * 64 + d)
+        const uint64_t dims[4] = {64, (uint64_t)nh, (uint64_t)B, (uint64_t)L};
+        const uint64_t strides[3] = {128, (uint64_t)ldq * 2, (uint64_t)B * ldq * 2};
+        const uint32_t box[4] = {64, 1, 1, 128};
+        if ((r = tensor_map(dQ, false, 4, dims, strides, box, &tdq))) return r;
+    } else {  // fp32 dQ accumulator (Z, L, 64): boxes of 32 columns x 128 rows
         const uint64_t dims[3] = {64, (uint64_t)L, (uint64_t)Z};
         const uint64_t strides[2] = {256, (uint64_t)L * 256};
         const uint32_t box[3] = {32, 128, 1};
@@ -1022,7 +1052,7 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
     const long row_ctas = (rows + 31) / 32;  // 8 warps x 4 rows per CTA
     const int g = (int)(row_ctas < 148L * 8 ? (row_ctas > 0 ? row_ctas : 1) : 148L * 8);
     cudaError_t le = pcm_launch(flash_delta_kernel, dim3(g), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(dO),
-                                reinterpret_cast<const __nv_bfloat16*>(O), ldo, B, nh, L, rows, delta, dQacc);
+                                reinterpret_cast<const __nv_bfloat16*>(O), ldo, B, nh, L, rows, delta, dq_direct ? nullptr : dQacc);
     if (le != cudaSuccess) return (int)le;
     if ((r = pcm_launch_status())) return r;
     static int num_sms = 0;
@@ -1038,6 +1068,7 @@ PCM_API int pcm_flash_attn_bwd(int B, int nh, int L, int S, const void* Q, const
                  : pcm_launch(flash_bwd_kernel<false>, dim3((unsigned)grid), dim3(BWD_THREADS), BWD_SMEM, st, tq, tk, tv, tdo, tdq, tdk, tdv, p);
     if (le != cudaSuccess) return (int)le;
     if ((r = pcm_launch_status())) return r;
+    if (dq_direct) return PCM_OK;
     le = pcm_launch(flash_dq_store_kernel, dim3(g), dim3(256), 0, st, (const float*)dQacc, B, nh, L, rows,
                     reinterpret_cast<__nv_bfloat16*>(dQ), ldq);
     if (le != cudaSuccess) return (int)le;
