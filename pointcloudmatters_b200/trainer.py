@@ -388,11 +388,12 @@ class BCTrainer:
                 self.graph_disabled_reason = (f"{self._graph_misses} captures in {self._graph_lookups} steps: batch shapes "
                                               "do not repeat (ragged clouds); running eagerly")
                 self._graphs.clear()
-                return self._forward_backward(batch, zero)
+                return self._forward_backward(self._on_device(batch), zero)
             while len(self._graphs) >= self.max_cached_graphs:
                 self._graphs.popitem(last=False)
+            dev = self.flat.param.device  # (a pinned host batch is staged straight into the static inputs, see training_step)
             clone = lambda v: ({kk: clone(vv) for kk, vv in v.items()} if isinstance(v, dict)
-                               else (v.clone() if torch.is_tensor(v) else v))
+                               else (v.to(dev, copy=True) if torch.is_tensor(v) else v))
             static = clone(batch)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -408,6 +409,13 @@ class BCTrainer:
         self._reduced = reduced_inside
         return outs
 
+    def _on_device(self, batch):
+        """Host (ideally pinned) batch -> this rank's device, asynchronously; device batches pass through."""
+        dev = self.flat.param.device if self.flat is not None else next(self.policy.parameters()).device
+        mv = lambda v: ({kk: mv(vv) for kk, vv in v.items()} if isinstance(v, dict)
+                        else (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.device != dev else v))
+        return mv(batch)
+
     def _check_hints(self, pcds):
         """debug_hints=True: one device->host read per step that verifies the host-provided cloud-size hints really are
         upper bounds (fps.cu clamps the cloud to the hint, so an undersized `n_max` would silently drop points)."""
@@ -419,7 +427,10 @@ class BCTrainer:
     def training_step(self, batch):
         """One full step on this rank's shard; returns the (detached) loss dict.  With `accumulate_grad_batches`
         = k the first k-1 calls of a group only add their gradients into the flat buffer; the k-th also runs the
-        all-reduce, clip and AdamW (the kernel divides the summed gradient by world * k)."""
+        all-reduce, clip and AdamW (the kernel divides the summed gradient by world * k).
+        `batch` may live in (pinned) host memory: on the graph path its tensors are copied host->device straight into
+        the captured graph's static inputs (one asynchronous copy per tensor, no intermediate device batch); on the
+        eager path it is moved to the device first."""
         from . import functional as PF
 
         PF.DROPOUT_RNG.new_step()
@@ -437,7 +448,7 @@ class BCTrainer:
         else:
             if self.flat is None and not zero:
                 raise RuntimeError("internal: flat state must exist before an accumulation group continues")
-            losses = self._forward_backward(batch, zero)
+            losses = self._forward_backward(self._on_device(batch), zero)
             self._eager_steps += 1
             if self.flat is None:  # first step: discover never-used parameters, then go flat
                 self._build_flat()

@@ -132,3 +132,30 @@ def test_debug_hints_reject_an_undersized_n_max():
     b["pcds"]["n_max"] = 100  # clouds have 256 points
     with pytest.raises(ValueError):
         m.training_step(b, 0)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_training_step_accepts_a_pinned_host_batch(use_graph):
+    """The batch may stay in pinned host memory: the step stages it host->device itself (graph path: straight into the
+    captured graph's static inputs).  Same losses and weights as with a device-resident copy of the batch."""
+    from pointcloudmatters_b200.data import synthetic_act_batch, to_device
+
+    hosts = [synthetic_act_batch(4, 256, num_queries=12, seed=s, pin=True) for s in (5, 6)]
+    for h in hosts:
+        h["_eps"] = torch.randn(4, 32, generator=torch.Generator().manual_seed(7)).pin_memory()
+    losses = {}
+    for mode in ("device", "host"):
+        m = _module(use_cuda_graph=use_graph)
+        out = []
+        for i in range(6):
+            h = hosts[i % 2]
+            if mode == "device":
+                b = to_device(h, "cuda")
+                b["pcds"]["n_max"] = h["pcds"]["n_max"]
+            else:
+                b = h
+            out.append(float(m.training_step(b, i)))
+        losses[mode] = out
+        if use_graph:
+            assert len(m._trainer._graphs) >= 1 and m._trainer.graph_disabled_reason is None
+    assert losses["host"] == pytest.approx(losses["device"], rel=2e-3), losses
