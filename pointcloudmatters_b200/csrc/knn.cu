@@ -247,9 +247,14 @@ __global__ void __launch_bounds__(KW_WARPS * 32) knn_warp_kernel(int b, int m, i
                                     thr[j] = fmaxf(cd, thr1[j]);  // cd < old entry k: the new entry k is max(cd, old entry k-1)
                                     thr1[j] = __shfl_sync(PCM_FULL_MASK, bd[j], k - 1);
                                 } else {
-                                    if (lane == 0) heap_sift(s_hd[warp][j], s_hi[warp][j], 1, k, cd, t0 + i0 + sl);
-                                    __syncwarp();
-                                    thr[j] = s_hd[warp][j][0];
+                                    // only lane 0 touches the heap; the new root travels by shuffle (which also reconverges
+                                    // the warp), so no lane reads shared memory that lane 0 is about to rewrite
+                                    float root = 0.f;
+                                    if (lane == 0) {
+                                        heap_sift(s_hd[warp][j], s_hi[warp][j], 1, k, cd, t0 + i0 + sl);
+                                        root = s_hd[warp][j][0];
+                                    }
+                                    thr[j] = __shfl_sync(PCM_FULL_MASK, root, 0);
                                 }
                             }
                         }

@@ -29,4 +29,12 @@ net = SpUNet(6, num_classes=16, base_channels=16, channels=(16, 32, 32, 32), lay
 y = net(dict(grid_coord=out["grid_coord"], feat=out["feat"], offset=out["offset"]))
 y.pow(2).sum().backward()
 torch.cuda.synchronize()
-print("sanitize target OK:", tuple(y.shape))
+# warp-per-query kNN: a lattice cloud (distance ties -> the exact heap-replay phase) and nsample > 31 (thread-per-query kernel)
+from pointcloudmatters_b200 import pointops as P  # noqa: E402
+
+lat = torch.from_numpy((rng.integers(0, 4, (700, 3)) / 4.0).astype(np.float32)).cuda()
+off = torch.tensor([300, 700], dtype=torch.int32, device="cuda")
+for k in (16, 33):
+    ki, kd = P.knn_query(k, lat, off, lat[::3].contiguous(), torch.tensor([100, 234], dtype=torch.int32, device="cuda"))
+torch.cuda.synchronize()
+print("sanitize target OK:", tuple(y.shape), tuple(ki.shape))
