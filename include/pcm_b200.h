@@ -270,6 +270,16 @@ int pcm_sa_bwd_scatter_tokens(int m, int k, int H, int per_cloud, int batch, int
                               const unsigned char *jsel, const int *idx, const float *xyz,
                               const float *new_xyz, const float *coef, float *dPf, double *gstats,
                               pcm_stream_t stream);
+/* Cloud-slice form of pcm_sa_gather_stats: a CTA stages the Pf rows of ONE cloud, restricted to a slice of channels, in
+ * shared memory, so Pf is read from global memory once instead of once per incoming edge.  offset / new_offset:
+ * cumulative END offsets (int32, b clouds) of the source points and of the queries, as the reference's pointops take them
+ * (libs/pointops/functions/query.py:8-23); n_max: host-known upper bound of the cloud sizes.  Same results as the generic
+ * entry point (per-channel sums: summation order only).  Returns PCM_EUNSUPPORTED outside the fast path (k != 16, or a
+ * cloud slice larger than shared memory). */
+int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, const float *Pf, const float *xyz,
+                               const float *new_xyz, const int *idx, const int *offset, const int *new_offset,
+                               const float *W, int ldw, float *ymax, float *ymin, unsigned char *jmax,
+                               unsigned char *jmin, double *stats, pcm_stream_t stream);
 int pcm_sa_edge_stats(int m, int k, const int *idx, const float *xyz, const float *new_xyz,
                       float *cnt, float *sq, double *sdtot, pcm_stream_t stream);
 int pcm_sa_bwd_coef(int H, const double *gstats, const double *fstats, const double *sdtot,

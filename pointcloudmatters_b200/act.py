@@ -206,14 +206,18 @@ class ACTPCD(nn.Module):
             idx = self._sample_indices(p, o32, n_o, mask, hints)
             n_p = p[idx.long(), :].contiguous()
             knn_idx, _ = pointops.ops.KNNQuery.apply(self.pcd_nsample, p, o32, n_p, n_o, False)
+        # cloud-size bound for the set-abstraction kernels: only the plain (unmasked) sampling path has one for ALL points
+        sa_n_max = (hints or {}).get("n_max", None) or n_max
+        if mask is not None or not isinstance(sa_n_max, int):
+            sa_n_max = None
         if tokens:
             pos = getattr(self, "_presampled_pos", None)
             if pos is None or pos.dim() != 3:
                 pos = self._presampled_pos = self.coord_embedding_sine_tokens(n_p, b)
             x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn,
-                                   tokens=(b, self._n_head_rows(), pos))
+                                   tokens=(b, self._n_head_rows(), pos), n_max=sa_n_max)
         else:
-            x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn)
+            x = PF.set_abstraction(p, x, o32, n_p, n_o, knn_idx, self.linear.weight, self.bn, n_max=sa_n_max)
         if return_index:
             return [n_p, x, n_o, idx]
         return [n_p, x, n_o]

@@ -17,6 +17,8 @@
 // beta_c * Wx[c,:].(cnt_i*xyz_i - SQ_i).  All kernels are HBM/L2-bound gathers: one thread owns 4
 // channels (128-bit loads of a Pf row), a CTA owns a strip of queries, per-channel partial sums
 // live in registers and reach global memory as one fp64 atomic per channel per CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -57,6 +59,81 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
                 dz = __ldg(xyz + (size_t)i * 3 + 2) - qz;
                 if (act) pf = ld4(Pf + (size_t)i * H + c0);
             }
+            const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, pv[v])));
+                if (y > mx[v]) { mx[v] = y; amx[v] = j; }
+                if (y < mn[v]) { mn[v] = y; amn[v] = j; }
+                s1[v] += y;
+                s2[v] = fmaf(y, y, s2[v]);
+                sx[v] = fmaf(y, dx, sx[v]);
+                sy[v] = fmaf(y, dy, sy[v]);
+                sz[v] = fmaf(y, dz, sz[v]);
+            }
+        }
+        if (act) {
+            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+            *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<uchar4*>(jmax + (size_t)q * H + c0) = make_uchar4(amx[0], amx[1], amx[2], amx[3]);
+            *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            atomicAdd(stats + 0 * H + c0 + v, (double)s1[v]);
+            atomicAdd(stats + 1 * H + c0 + v, (double)s2[v]);
+            atomicAdd(stats + 2 * H + c0 + v, (double)sx[v]);
+            atomicAdd(stats + 3 * H + c0 + v, (double)sy[v]);
+            atomicAdd(stats + 4 * H + c0 + v, (double)sz[v]);
+        }
+    }
+}
+
+// Same pass for a compile-time neighbour count K <= 32 (the reference configuration has nsample = 16).  In the generic
+// kernel above every thread walks the k neighbours through a dependent chain (index load -> three coordinate loads and the
+// 16-byte Pf gather), one neighbour at a time.  Here lane j of each warp fetches neighbour j's index and offset vector
+// once per query -- K independent loads -- and the loop, fully unrolled, receives them by shuffle: the K Pf gathers of a
+// thread are independent instructions the compiler can issue ahead of the arithmetic.  Identical arithmetic, identical
+// results.
+template <int K>
+__global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
+    const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+    const int* __restrict__ idx, const float* __restrict__ W, int ldw, int m, int H,
+    float* __restrict__ ymax, float* __restrict__ ymin, unsigned char* __restrict__ jmax,
+    unsigned char* __restrict__ jmin, double* __restrict__ stats) {
+    const int c0 = threadIdx.x * 4, lane = threadIdx.x & 31;
+    const bool act = c0 < H;
+    float wx[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wx[v][d] = act ? __ldg(W + (size_t)(c0 + v) * ldw + d) : 0.f;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
+    for (int q = blockIdx.x; q < m; q += gridDim.x) {
+        const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
+        int ni = -1;
+        float ndx = 0.f, ndy = 0.f, ndz = 0.f;
+        if (lane < K) {
+            ni = __ldg(idx + (size_t)q * K + lane);
+            if (ni >= 0) {  // -1 = padding: the reference groups an all-zero row (y = 0, still counted by BN)
+                ndx = __ldg(xyz + (size_t)ni * 3 + 0) - qx;
+                ndy = __ldg(xyz + (size_t)ni * 3 + 1) - qy;
+                ndz = __ldg(xyz + (size_t)ni * 3 + 2) - qz;
+            }
+        }
+        float mx[4], mn[4];
+        int amx[4] = {0, 0, 0, 0}, amn[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { mx[v] = -INFINITY; mn[v] = INFINITY; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int i = __shfl_sync(PCM_FULL_MASK, ni, j);
+            const float dx = __shfl_sync(PCM_FULL_MASK, ndx, j), dy = __shfl_sync(PCM_FULL_MASK, ndy, j),
+                        dz = __shfl_sync(PCM_FULL_MASK, ndz, j);
+            float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i >= 0 && act) pf = ld4(Pf + (size_t)i * H + c0);
             const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -344,6 +421,151 @@ __global__ void __launch_bounds__(256) sa_bwd_dense_kernel(const float* __restri
     }
 }
 
+// ---- cloud-slice variant: the Pf rows of ONE cloud, restricted to a slice of CS channels, live in shared memory ----
+// The gather kernels above re-read every Pf row about M k / N = 8 times (1.07 GB of L2 -> SM traffic at cfg-2).  Here a CTA owns (cloud, CS-channel slice): it stages the slice of the cloud's Pf rows once
+// (n_b x CS fp32 -- 64 KB at 1024 points x 16 channels; Pf is then read from global memory exactly once in total), walks the
+// cloud's queries with CS / 4 threads per query, and gathers from shared memory.  Neighbour indices and offset vectors of a
+// query are fetched once by the query's threads (K / LPR neighbours each) and exchanged by shuffle.  Same per-element
+// arithmetic as the generic kernel: identical ymax / ymin / arg; the per-channel sums differ in summation order only (fp32
+// per thread and warp, fp64 across warps).  cfg-2: 284 us (generic kernel 433 us, its shuffle-unrolled form 307 us).
+// per-channel partial sums of a cloud-slice CTA: lanes with equal lane % LPR hold the same four channels
+template <int LPR, int CSV>
+__device__ __forceinline__ void sa_slice_reduce_impl(float (&r0)[4], float (&r1)[4], float (&r2)[4], float (&r3)[4],
+                                                     float (&r4)[4], double (*red)[CSV], int cl, int lane) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            r0[v] += __shfl_xor_sync(PCM_FULL_MASK, r0[v], o);
+            r1[v] += __shfl_xor_sync(PCM_FULL_MASK, r1[v], o);
+            r2[v] += __shfl_xor_sync(PCM_FULL_MASK, r2[v], o);
+            r3[v] += __shfl_xor_sync(PCM_FULL_MASK, r3[v], o);
+            r4[v] += __shfl_xor_sync(PCM_FULL_MASK, r4[v], o);
+        }
+        if (lane < LPR) {
+            atomicAdd(&red[0][cl * 4 + v], (double)r0[v]);
+            atomicAdd(&red[1][cl * 4 + v], (double)r1[v]);
+            atomicAdd(&red[2][cl * 4 + v], (double)r2[v]);
+            atomicAdd(&red[3][cl * 4 + v], (double)r3[v]);
+            atomicAdd(&red[4][cl * 4 + v], (double)r4[v]);
+        }
+    }
+}
+template <int LPR>
+__device__ __forceinline__ void sa_slice_reduce(float (&r0)[4], float (&r1)[4], float (&r2)[4], float (&r3)[4], float (&r4)[4],
+                                                double (*red)[LPR * 4], int cl, int lane) {
+    sa_slice_reduce_impl<LPR, LPR * 4>(r0, r1, r2, r3, r4, red, cl, lane);
+}
+
+template <int CS, int K>
+__global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
+    const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+    const int* __restrict__ idx, const int* __restrict__ offset, const int* __restrict__ new_offset,
+    const float* __restrict__ W, int ldw, int H, int n_cap, float* __restrict__ ymax, float* __restrict__ ymin,
+    unsigned char* __restrict__ jmax, unsigned char* __restrict__ jmin, double* __restrict__ stats) {
+    extern __shared__ __align__(16) float4 slice4[];  // [n_b][LPR]
+    __shared__ double red[SA_STAT_ROWS][CS];
+    constexpr int LPR = CS / 4;     // threads (float4 lanes) per row / per query
+    constexpr int QS = 256 / LPR;   // queries in flight per CTA
+    constexpr int QPW = 32 / LPR;   // queries per warp
+    constexpr int NPL = K / LPR;    // neighbours fetched per thread
+    static_assert(K % LPR == 0 && NPL >= 1, "K must be a multiple of the threads per query");
+    const int cloud = blockIdx.y, c_base = blockIdx.x * CS;
+    const int s_n = cloud ? __ldg(offset + cloud - 1) : 0;
+    const int n_b = min(__ldg(offset + cloud) - s_n, n_cap);
+    const int s_m = cloud ? __ldg(new_offset + cloud - 1) : 0, e_m = __ldg(new_offset + cloud);
+    for (int t = threadIdx.x; t < n_b * LPR; t += 256) {
+        const int r = t / LPR, l = t - r * LPR;
+        slice4[t] = ld4(Pf + (size_t)(s_n + r) * H + c_base + 4 * l);
+    }
+    for (int t = threadIdx.x; t < SA_STAT_ROWS * CS; t += 256) (&red[0][0])[t] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cl = lane % LPR, grp = lane - cl;  // grp = first lane of this query's thread group
+    const int c0 = c_base + cl * 4;
+    float wx[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wx[v][d] = __ldg(W + (size_t)(c0 + v) * ldw + d);
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
+    for (int qw = s_m + warp * QPW; qw < e_m; qw += QS) {  // warp-uniform trip count (the shuffles need every lane)
+        const int q = qw + lane / LPR;
+        const bool valid = q < e_m;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (valid) { qx = __ldg(new_xyz + (size_t)q * 3 + 0); qy = __ldg(new_xyz + (size_t)q * 3 + 1); qz = __ldg(new_xyz + (size_t)q * 3 + 2); }
+        int ni[NPL];
+        float ndx[NPL], ndy[NPL], ndz[NPL];
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {  // this thread fetches neighbours u * LPR + cl of its query
+            ni[u] = -1; ndx[u] = ndy[u] = ndz[u] = 0.f;
+            if (valid) {
+                const int i = __ldg(idx + (size_t)q * K + u * LPR + cl);
+                if (i >= 0) {  // -1 = padding: the reference groups an all-zero row (y = 0, still counted by BN)
+                    ndx[u] = __ldg(xyz + (size_t)i * 3 + 0) - qx;
+                    ndy[u] = __ldg(xyz + (size_t)i * 3 + 1) - qy;
+                    ndz[u] = __ldg(xyz + (size_t)i * 3 + 2) - qz;
+                    const int il = i - s_n;
+                    ni[u] = (il >= 0 && il < n_b) ? il : -2;  // -2: outside the staged rows (undersized hint): treated as padding
+                }
+            }
+        }
+        float mx[4], mn[4];
+        int amx[4] = {0, 0, 0, 0}, amn[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { mx[v] = -INFINITY; mn[v] = INFINITY; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int src = grp + (j % LPR), u = j / LPR;
+            const int i = __shfl_sync(PCM_FULL_MASK, ni[u], src);
+            const float dx = __shfl_sync(PCM_FULL_MASK, ndx[u], src), dy = __shfl_sync(PCM_FULL_MASK, ndy[u], src),
+                        dz = __shfl_sync(PCM_FULL_MASK, ndz[u], src);
+            float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i >= 0) pf = slice4[i * LPR + cl];
+            const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, pv[v])));
+                if (y > mx[v]) { mx[v] = y; amx[v] = j; }
+                if (y < mn[v]) { mn[v] = y; amn[v] = j; }
+                s1[v] += y;
+                s2[v] = fmaf(y, y, s2[v]);
+                sx[v] = fmaf(y, dx, sx[v]);
+                sy[v] = fmaf(y, dy, sy[v]);
+                sz[v] = fmaf(y, dz, sz[v]);
+            }
+        }
+        if (valid) {
+            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+            *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<uchar4*>(jmax + (size_t)q * H + c0) = make_uchar4(amx[0], amx[1], amx[2], amx[3]);
+            *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+        }
+    }
+    // threads of a warp that own the same channels (lane % LPR equal) are summed by shuffle; one shared atomic per warp
+    sa_slice_reduce<LPR>(s1, s2, sx, sy, sz, red, cl, lane);
+    __syncthreads();
+    for (int t = threadIdx.x; t < SA_STAT_ROWS * CS; t += 256) {
+        const int r = t / CS, c = t - r * CS;
+        atomicAdd(stats + (size_t)r * H + c_base + c, red[r][c]);
+    }
+}
+
+// slice width for a cloud bound of n_max points: the widest of 32 / 16 / 8 / 4 channels that divides H and keeps three CTAs
+// per SM (<= 72 KB of shared memory each); failing that, the widest that fits one CTA; 0 = use the generic kernels
+inline int sa_slice_width(int n_max, int H) {
+    const int cand[4] = {32, 16, 8, 4};
+    for (int c : cand)
+        if (H % c == 0 && (size_t)n_max * c * 4 <= 72 * 1024) return c;
+    for (int c : cand)
+        if (H % c == 0 && (size_t)n_max * c * 4 <= 200 * 1024) return c;
+    return 0;
+}
+template <typename Kern>
+inline cudaError_t sa_allow_smem(Kern kern, size_t smem) {
+    return smem > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) : cudaSuccess;
+}
+
 inline int sa_threads(int H) { return ((H / 4 + 31) / 32) * 32; }
 inline int sa_grid(long work) { long g = 148L * 8; return (int)(work < g ? (work > 0 ? work : 1) : g); }
 
@@ -355,8 +577,16 @@ PCM_API int pcm_sa_gather_stats(int m, int k, int H, const float* Pf, const floa
     if (m <= 0) return PCM_OK;
     if (!Pf || !xyz || !new_xyz || !idx || !W || !ymax || !ymin || !jmax || !jmin || !stats) return PCM_EINVAL;
     if (H % 4 || H > 4096 || k > 255 || k <= 0) return PCM_EUNSUPPORTED;
-    sa_gather_stats_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, k, H, ymax,
-                                                                                   ymin, jmax, jmin, stats);
+    static const bool generic_only = [] { const char* e = getenv("PCM_SA_GENERIC"); return e && e[0] == '1'; }();  // A/B timing
+    if (k == 16 && !generic_only)
+        sa_gather_stats_k_kernel<16><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, H,
+                                                                                             ymax, ymin, jmax, jmin, stats);
+    else if (k == 32 && !generic_only)
+        sa_gather_stats_k_kernel<32><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, H,
+                                                                                             ymax, ymin, jmax, jmin, stats);
+    else
+        sa_gather_stats_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, k, H, ymax,
+                                                                                       ymin, jmax, jmin, stats);
     return pcm_launch_status();
 }
 
@@ -422,6 +652,41 @@ PCM_API int pcm_sa_bwd_scatter_tokens(int m, int k, int H, int per_cloud, int ba
     if (H % 4 || H > 4096 || per_cloud <= 0 || batch <= 0 || head_rows < 0 || (long)per_cloud * batch != m) return PCM_EUNSUPPORTED;
     sa_bwd_scatter_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(dout, out, jsel, idx, xyz, new_xyz, coef, m, k, H,
                                                                                   dPf, gstats, per_cloud, batch, head_rows, dout2);
+    return pcm_launch_status();
+}
+
+// Cloud-slice form of pcm_sa_gather_stats (see sa_gather_stats_cloud_kernel): the caller also passes the cumulative cloud
+// offsets of the source points and of the queries (b clouds) and a host-known upper bound n_max of the cloud sizes.
+// Returns PCM_EUNSUPPORTED when the shape is outside the fast path (k != 16, H % 4, cloud too large for shared memory):
+// call the generic entry point then.  (The same layout was tried for the backward scatter -- sparse gradient accumulated
+// with shared-memory atomics, dPf written once -- and measured SLOWER than the global-atomic kernel: 245 vs 194 us at cfg-2.)
+PCM_API int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, const float* Pf, const float* xyz,
+                                       const float* new_xyz, const int* idx, const int* offset, const int* new_offset,
+                                       const float* W, int ldw, float* ymax, float* ymin, unsigned char* jmax,
+                                       unsigned char* jmin, double* stats, pcm_stream_t stream) {
+    if (m <= 0) return PCM_OK;
+    if (!Pf || !xyz || !new_xyz || !idx || !offset || !new_offset || !W || !ymax || !ymin || !jmax || !jmin || !stats)
+        return PCM_EINVAL;
+    if (b <= 0 || n_max <= 0) return PCM_EINVAL;
+    const int cs = k == 16 ? sa_slice_width(n_max, H) : 0;
+    if (!cs) return PCM_EUNSUPPORTED;
+    const size_t smem = (size_t)n_max * cs * 4;
+    const dim3 grid(H / cs, b);
+    cudaStream_t st = pcm_cu_stream(stream);
+    cudaError_t e = cudaSuccess;
+#define PCM_SA_FWD(CSV)                                                                                                       \
+    e = sa_allow_smem(sa_gather_stats_cloud_kernel<CSV, 16>, smem);                                                           \
+    if (e == cudaSuccess)                                                                                                     \
+        sa_gather_stats_cloud_kernel<CSV, 16><<<grid, 256, smem, st>>>(Pf, xyz, new_xyz, idx, offset, new_offset, W, ldw, H,   \
+                                                                      n_max, ymax, ymin, jmax, jmin, stats)
+    switch (cs) {
+        case 32: PCM_SA_FWD(32); break;
+        case 16: PCM_SA_FWD(16); break;
+        case 8: PCM_SA_FWD(8); break;
+        default: PCM_SA_FWD(4); break;
+    }
+#undef PCM_SA_FWD
+    if (e != cudaSuccess) return (int)e;
     return pcm_launch_status();
 }
 

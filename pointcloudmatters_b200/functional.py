@@ -1192,10 +1192,12 @@ class _SetAbstraction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, weight, gamma, beta, p, new_p, knn_idx, running_mean, running_var, eps, momentum,
-                training, feat_b=None, tok=None):
+                training, feat_b=None, tok=None, clouds=None):
         """`tok` = (batch, head_rows, pos or None, out_bf16, out_pos_bf16 or None): write the result straight into the
         transformer's seq-first token tensor (S, B, H) -- query b * M + mi -> row (head_rows + mi) * B + b; the head rows
-        are left for `fill_head_rows` -- and emit bf16(out) / bf16(out + pos), the operands of the first encoder layer."""
+        are left for `fill_head_rows` -- and emit bf16(out) / bf16(out + pos), the operands of the first encoder layer.
+        `clouds` = (offset int32 (b), new_offset int32 (b), n_max): per-cloud extents + host-known size bound -> the
+        cloud-slice gather kernel (Pf slice of a cloud in shared memory; csrc/sa_fused.cu), generic kernel otherwise."""
         from ._lib import check, current_stream, lib, ptr
 
         n, C = feat.shape
@@ -1212,8 +1214,17 @@ class _SetAbstraction(torch.autograd.Function):
         jmax = torch.empty((m, H), dtype=torch.uint8, device=dev)
         jmin = torch.empty_like(jmax)
         stats = torch.zeros((5, H), dtype=torch.float64, device=dev)
-        check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
-                                      ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
+        rc = PCM_EUNSUPPORTED
+        if clouds is not None and not _NO_SA_CLOUDS:
+            off, noff, n_max = clouds
+            rc = lib.pcm_sa_gather_stats_clouds(off.numel(), int(n_max), m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx),
+                                                ptr(off), ptr(noff), ptr(weight), weight.stride(0), ptr(ymax), ptr(ymin),
+                                                ptr(jmax), ptr(jmin), ptr(stats), st)
+            if rc != PCM_EUNSUPPORTED:
+                check(rc, "pcm_sa_gather_stats_clouds")
+        if rc == PCM_EUNSUPPORTED:
+            check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
+                                          ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
         coef = torch.empty((4, H), dtype=torch.float32, device=dev)
         n_dev = None
         if training and SYNC_BN.active():  # rows 0-1 (sum y, sum y^2) global; rows 2-4 (sum y dxyz) stay local (backward dW)
@@ -1253,8 +1264,8 @@ class _SetAbstraction(torch.autograd.Function):
         dev = Pf.device
         st = current_stream()
         dout = dout.contiguous().float()
-        dPf = torch.zeros((n, H), dtype=torch.float32, device=dev)
         gstats = torch.zeros((5, H), dtype=torch.float64, device=dev)
+        dPf = torch.zeros((n, H), dtype=torch.float32, device=dev)
         if ctx.tok is None:
             check(lib.pcm_sa_bwd_scatter(m, k, H, ptr(dout), ptr(out), ptr(jsel), ptr(knn_idx), ptr(p), ptr(new_p), ptr(coef),
                                          ptr(dPf), ptr(gstats), st), "pcm_sa_bwd_scatter")
@@ -1293,14 +1304,19 @@ class _SetAbstraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dfeat = K.gemm_bf16(dPfb, wfb, b_mn=True)  # (n, H) x Wf(H, C)
         K.gemm_bf16(dPfb, featb, a_mn=True, b_mn=True, out=dW[:, 3:], accumulate=True, split_k=0)
-        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
+        return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
 
 
-def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn, tokens=None):
+_NO_SA_CLOUDS = bool(int(os.environ.get("PCM_NO_SA_CLOUDS", "0")))  # A/B switch: generic gather / scatter kernels
+PCM_EUNSUPPORTED = -2
+
+
+def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, bn, tokens=None, n_max=None):
     """Grouped Linear(3+C -> H, no bias) + BatchNorm1d + ReLU + max over the k neighbours
     (act.py:446-460) as ONE fused operator.  feat (n, C), knn_idx (m, k) int32 (-1 = padding) -> (m, H).
     `tokens` = (batch, head_rows, pos (S, B, H) or None): return the transformer's seq-first token tensor (S, B, H)
-    instead, with the point rows filled (see `fill_head_rows` for the rest) and the bf16 operand copies attached."""
+    instead, with the point rows filled (see `fill_head_rows` for the rest) and the bf16 operand copies attached.
+    `n_max`: host-known upper bound of the cloud sizes (the batch's `n_max` hint) -> cloud-slice kernels."""
     _need_cuda(feat)
     training = bn.training or (bn.running_mean is None)
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -1334,9 +1350,13 @@ def set_abstraction(p, feat, offset, new_p, new_offset, knn_idx, linear_weight, 
         out_b = torch.empty((S, B, H), dtype=torch.bfloat16, device=feat.device)
         out_pb = torch.empty_like(out_b) if pos is not None else None
         tok = (B, head, pos, out_b, out_pb)
+    clouds = None
+    if (n_max is not None and int(n_max) > 0 and torch.is_tensor(offset) and torch.is_tensor(new_offset)
+            and offset.dtype == torch.int32 and new_offset.dtype == torch.int32 and offset.numel() == new_offset.numel()):
+        clouds = (offset.contiguous(), new_offset.contiguous(), int(n_max))
     out = _SetAbstraction.apply(feat, linear_weight, bn.weight, bn.bias, p.contiguous(), new_p.contiguous(),
                                 knn_idx.contiguous(), bn.running_mean, bn.running_var, bn.eps, momentum, training,
-                                _act_bf16(feat, feat.shape[0], C), tok)
+                                _act_bf16(feat, feat.shape[0], C), tok, clouds)
     if tok is not None:
         out._pcm_bf16 = tok[3]
         if tok[4] is not None:

@@ -32,8 +32,12 @@ def _reference(p, feat, new_p, idx, W, bn):
 @pytest.mark.parametrize("b,n,mm,k,C,H,neg", [(3, 300, 64, 16, 64, 128, False), (2, 12, 6, 16, 32, 64, True),
                                                (2, 500, 100, 8, 512, 512, True)])
 @pytest.mark.parametrize("training", [True, False])
-def test_sa_fused_matches_as_written_chain(b, n, mm, k, C, H, neg, training):
+@pytest.mark.parametrize("cloud_slices", [False, True])
+def test_sa_fused_matches_as_written_chain(b, n, mm, k, C, H, neg, training, cloud_slices):
+    """`cloud_slices`: the caller hands over the cloud offsets and a host-known size bound -> the kernels that keep a
+    cloud's Pf slice in shared memory (k = 16 only; asserted through the per-entry-point call counters)."""
     from pointcloudmatters_b200 import functional as PF
+    from pointcloudmatters_b200._lib import lib
 
     xyz, off, noff = clouds(b, n, mm, seed=3, ragged=True)
     fidx = O.farthest_point_sampling(xyz, off, noff)
@@ -64,7 +68,14 @@ def test_sa_fused_matches_as_written_chain(b, n, mm, k, C, H, neg, training):
         bn.running_mean.copy_(torch.linspace(-0.2, 0.2, H)); 
         bn.train(training)
         if fused:
-            out = PF.set_abstraction(p, feat, None, new_p, None, idx, W, bn)
+            before = dict(lib.calls)
+            if cloud_slices:
+                t_off, t_noff = torch.from_numpy(off).cuda(), torch.from_numpy(noff).cuda()
+                out = PF.set_abstraction(p, feat, t_off, new_p, t_noff, idx, W, bn, n_max=int(np.diff(off, prepend=0).max()) + 5)
+            else:
+                out = PF.set_abstraction(p, feat, None, new_p, None, idx, W, bn)
+            used = lib.calls.get("pcm_sa_gather_stats", 0) - before.get("pcm_sa_gather_stats", 0)
+            assert used == (0 if (cloud_slices and k == 16) else 1), (used, cloud_slices, k)
         else:
             out = _reference(p, feat, new_p, idx, W, bn)
         out.backward(dout)
