@@ -288,9 +288,50 @@ class _DropoutRNG:
         for t in self.base.values():
             t.add_(1)
         self.offset = 0
+        ZERO_ARENA.reset()
 
 
 DROPOUT_RNG = _DropoutRNG()
+
+
+class _ZeroArena:
+    """Small zero-initialised accumulators of a step (BatchNorm / set-abstraction statistics, loss sums, scatter counters:
+    ~20 per step, each a separate fill kernel as `torch.zeros`) are carved out of ONE zero-filled buffer per stream and
+    step: one fill instead of twenty.  A region is handed out once, so it is zero when its user first touches it.  The
+    buffer is keyed by (device, stream) -- it is filled on the stream that uses it -- and is dropped at every step
+    boundary and whenever graph capture starts or ends (a buffer filled outside a capture must not be consumed inside:
+    the replay would find it dirty)."""
+
+    CAP = 8 << 20
+
+    def __init__(self):
+        self.bufs = {}
+
+    def reset(self):
+        self.bufs.clear()
+
+    def zeros(self, shape, dtype, device):
+        device = torch.device(device)
+        n = int(math.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        if device.type != "cuda" or n > self.CAP // 4 or n == 0:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        ent = self.bufs.get(key)
+        need = (n + 255) & ~255
+        if ent is None or ent[1] + need > self.CAP or ent[2] != capturing:
+            ent = [torch.zeros(self.CAP, dtype=torch.uint8, device=device), 0, capturing]
+            self.bufs[key] = ent
+        v = ent[0][ent[1]: ent[1] + n].view(dtype).view(shape)
+        ent[1] += need
+        return v
+
+
+ZERO_ARENA = _ZeroArena()
+
+
+def _zeros(shape, dtype, device):
+    return ZERO_ARENA.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), dtype, device)
 
 
 def _workspace(name, shape, dtype, device, zero=False):
@@ -1106,7 +1147,7 @@ class _BatchNormReLU(torch.autograd.Function):
 
         R, C = y.shape
         st = current_stream()
-        stats = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+        stats = _zeros((2, C), torch.float64, y.device)
         n_dev = None
         if training:
             check(lib.pcm_bn_stats(R, C, ptr(y), ptr(stats), st), "pcm_bn_stats")
@@ -1144,7 +1185,7 @@ class _BatchNormReLU(torch.autograd.Function):
         g_slot, b_slot = _grad_slot(gamma), _grad_slot(beta)
         dg = g_slot if g_slot is not None else torch.zeros(C, dtype=torch.float32, device=y.device)
         db = b_slot if b_slot is not None else torch.zeros(C, dtype=torch.float32, device=y.device)
-        gstats = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+        gstats = _zeros((2, C), torch.float64, y.device)
         need_dy = ctx.needs_input_grad[0]
         dy = torch.empty_like(y) if need_dy else None
         dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
@@ -1213,7 +1254,7 @@ class _SetAbstraction(torch.autograd.Function):
         ymin = torch.empty_like(ymax)
         jmax = torch.empty((m, H), dtype=torch.uint8, device=dev)
         jmin = torch.empty_like(jmax)
-        stats = torch.zeros((5, H), dtype=torch.float64, device=dev)
+        stats = _zeros((5, H), torch.float64, dev)
         rc = PCM_EUNSUPPORTED
         if clouds is not None and not _NO_SA_CLOUDS:
             off, noff, n_max = clouds
@@ -1264,7 +1305,7 @@ class _SetAbstraction(torch.autograd.Function):
         dev = Pf.device
         st = current_stream()
         dout = dout.contiguous().float()
-        gstats = torch.zeros((5, H), dtype=torch.float64, device=dev)
+        gstats = _zeros((5, H), torch.float64, dev)
         dPf = torch.zeros((n, H), dtype=torch.float32, device=dev)
         if ctx.tok is None:
             check(lib.pcm_sa_bwd_scatter(m, k, H, ptr(dout), ptr(out), ptr(jsel), ptr(knn_idx), ptr(p), ptr(new_p), ptr(coef),
@@ -1276,12 +1317,12 @@ class _SetAbstraction(torch.autograd.Function):
             check(lib.pcm_sa_bwd_scatter_tokens(m, k, H, per, B, head, ptr(dout), ptr(dout2), ptr(out), ptr(jsel), ptr(knn_idx),
                                                 ptr(p), ptr(new_p), ptr(coef), ptr(dPf), ptr(gstats), st),
                   "pcm_sa_bwd_scatter_tokens")
-        cnt = torch.zeros(n, dtype=torch.float32, device=dev)
-        sq = torch.zeros((n, 3), dtype=torch.float32, device=dev)
-        sdtot = torch.zeros(3, dtype=torch.float64, device=dev)
+        cnt = _zeros((n,), torch.float32, dev)
+        sq = _zeros((n, 3), torch.float32, dev)
+        sdtot = _zeros((3,), torch.float64, dev)
         check(lib.pcm_sa_edge_stats(m, k, ptr(knn_idx), ptr(p), ptr(new_p), ptr(cnt), ptr(sq), ptr(sdtot), st),
               "pcm_sa_edge_stats")
-        dW = torch.zeros((H, 3 + C), dtype=torch.float32, device=dev)
+        dW = _zeros((H, 3 + C), torch.float32, dev)
         ab = torch.empty((2, H), dtype=torch.float32, device=dev)
         dgamma = torch.empty(H, dtype=torch.float32, device=dev)
         dbeta = torch.empty(H, dtype=torch.float32, device=dev)
@@ -1438,7 +1479,7 @@ class _ActHeadsLoss(torch.autograd.Function):
         assert hs.stride(2) == 1
         a_hat = torch.empty((B, Q, A), dtype=torch.float32, device=dev)
         pad_hat = torch.empty((B, Q, 1), dtype=torch.float32, device=dev)
-        losses = torch.zeros(3, dtype=torch.float32, device=dev) if actions is not None else None
+        losses = _zeros((3,), torch.float32, dev) if actions is not None else None
         ws = _workspace("heads_loss_ws", (4,), torch.float64, dev, zero=True)  # acc (1 double) + ticket; self-cleaning
         pad_u8 = is_pad.contiguous().view(torch.uint8) if is_pad is not None else None
         act_c = actions.contiguous().float() if actions is not None else None
