@@ -574,6 +574,29 @@ int pcm_ffn32_fwd(long long rows, int E, int Hd, const void *x, long long ldx, c
 int pcm_ffn32_bwd(long long rows, int E, int Hd, const void *dy, long long lddy, const void *hd, const void *w1,
                   const void *w2, float p_drop, void *dh, float *dx, pcm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Raw camera frames -> packed per-sample point clouds (the stage in front of pcm_grid_sample_*): the boolean-mask
+ * selections of the reference's dataset classes, for a whole batch at once, survivors in ascending point order like
+ * numpy's a[mask].
+ *   mode 0, ManiSkill2 (src/data/components/maniskill2/maniskill2_single_task_pcd_act.py:196-224): xyz = (b, P, 4) xyzw,
+ *     keep w > 0 and z > 0.005 (include_ground: x > -0.8 instead); crop = NULL or (b, 2) int32 {first row, first column}
+ *     of the crop_size x crop_size pixel window kept in every cam_h x cam_w camera image (rand_crop, :200-208).
+ *   mode 1, RLBench (src/data/components/rlbench/rlbench_single_task_act.py:266-295): xyz = (b, P, xyz_stride >= 3), keep the
+ *     points strictly inside bounds = {xmin, ymin, zmin, xmax, ymax, zmax} (float64 comparison); seg = optional (b, P)
+ *     fp32 instance ids appended to the colours as a {0, 1} channel (ids listed in `invalid` -> 0, other ids > 0 -> 1).
+ * pcm_frame_filter_count: chunk_count[(sample, chunk)], chunk = 1024 consecutive points, ceil(P / 1024) chunks per sample.
+ * pcm_frame_filter_scatter: chunk_base = exclusive prefix sum of chunk_count (int64, sample-major); out_xyz (N, 3),
+ *   out_color (N, color_ch + (seg != NULL)) fp32; color: (b, P, color_ch) uint8 or fp32.  All pointers are device
+ *   pointers except `bounds` (host). */
+int pcm_frame_filter_count(int b, long long P, int mode, const float *xyz, int xyz_stride, int include_ground,
+                           const double *bounds, const int *crop, int cam_h, int cam_w, int crop_size,
+                           int *chunk_count, pcm_stream_t stream);
+int pcm_frame_filter_scatter(int b, long long P, int mode, const float *xyz, int xyz_stride, int include_ground,
+                             const double *bounds, const int *crop, int cam_h, int cam_w, int crop_size,
+                             const void *color, int color_is_u8, int color_ch, const float *seg, const float *invalid,
+                             int n_invalid, const long long *chunk_base, float *out_xyz, float *out_color,
+                             pcm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

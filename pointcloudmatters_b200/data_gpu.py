@@ -84,3 +84,67 @@ def collate_raw_clouds(samples, device, **kw):
         pos += s
     offset = torch.tensor(sizes, dtype=torch.int64).cumsum(0)
     return grid_sample_collate(coord.to(device, non_blocking=True), color.to(device, non_blocking=True), offset.to(device), **kw)
+
+
+def _filter_frames(mode, xyz, color, *, include_ground=False, bounds=None, crop=None, cam_hw=(128, 128), crop_size=112, seg=None,
+                   invalid=()):
+    """Shared driver of the two frame filters (csrc/frame_filter.cu): flag + count per 1024-point chunk, exclusive scan,
+    ordered scatter.  Returns (coord (N, 3) f32, color (N, C) f32, offset (B) int64) on the device of `xyz`; ONE
+    device->host read (the total survivor count sizes the outputs) -- it belongs to the loader stage."""
+    import ctypes
+
+    if not xyz.is_cuda:
+        raise PcmError("the frame filters run on CUDA tensors only (no CPU fallback)")
+    b, P, stride = xyz.shape
+    dev = xyz.device
+    xyz = xyz.contiguous().float()
+    color_u8 = color.dtype == torch.uint8
+    color = color.contiguous() if color_u8 else color.contiguous().float()
+    cc = color.shape[-1]
+    chunks = (P + 1023) // 1024
+    counts = torch.empty((b, chunks), dtype=torch.int32, device=dev)
+    bnd = (ctypes.c_double * 6)(*[float(v) for v in (bounds if bounds is not None else (0,) * 6)])
+    bnd_p = ctypes.addressof(bnd) if bounds is not None else None
+    crop_t = None
+    if crop is not None:
+        crop_t = torch.as_tensor(crop, dtype=torch.int32).reshape(b, 2).to(dev).contiguous()
+    seg_t = seg.contiguous().float() if seg is not None else None
+    inv_t = torch.tensor([float(v) for v in invalid], dtype=torch.float32, device=dev) if (seg is not None and len(invalid)) else None
+    st = current_stream()
+    check(lib.pcm_frame_filter_count(b, P, mode, ptr(xyz), stride, int(include_ground), bnd_p, ptr(crop_t), cam_hw[0], cam_hw[1],
+                                     crop_size, ptr(counts), st), "pcm_frame_filter_count")
+    incl = torch.cumsum(counts.view(-1).to(torch.int64), 0)
+    base = (incl - counts.view(-1)).contiguous()
+    offset = incl.view(b, chunks)[:, -1].contiguous()
+    n = int(offset[-1])  # the one device->host read
+    out_xyz = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_ch = cc + (1 if seg is not None else 0)
+    out_color = torch.empty((n, out_ch), dtype=torch.float32, device=dev)
+    check(lib.pcm_frame_filter_scatter(b, P, mode, ptr(xyz), stride, int(include_ground), bnd_p, ptr(crop_t), cam_hw[0], cam_hw[1],
+                                       crop_size, ptr(color), int(color_u8), cc, ptr(seg_t), ptr(inv_t),
+                                       0 if inv_t is None else inv_t.numel(), ptr(base), ptr(out_xyz), ptr(out_color), st),
+          "pcm_frame_filter_scatter")
+    return out_xyz, out_color, offset
+
+
+def filter_frames_maniskill2(xyzw, rgb, include_ground=False, crop=None, cam_hw=(128, 128), crop_size=112):
+    """ManiSkill2 frames of a batch -> packed clouds (maniskill2_single_task_pcd_act.py:196-224): xyzw (B, P, 4) f32 and rgb
+    (B, P, 3) uint8 / f32 of the selected cameras (P = cams * 128 * 128, camera-major), keep w > 0 and z > 0.005 (or
+    x > -0.8 with `include_ground`); `crop` = per-sample (first row, first column) of the `rand_crop` window or None.
+    Returns (coord (N, 3), color (N, 3) raw 0..255 values, offset (B)): the inputs of `grid_sample_collate`."""
+    return _filter_frames(0, xyzw, rgb, include_ground=include_ground, crop=crop, cam_hw=cam_hw, crop_size=crop_size)
+
+
+RLBENCH_SCENE_BOUNDS = (-0.3, -0.5, 0.6, 0.7, 0.5, 1.6)  # src/data/components/rlbench/constants.py:1
+
+
+def filter_frames_rlbench(point_maps, rgbs, masks=None, bounds=RLBENCH_SCENE_BOUNDS, invalid_mask_values=(201, 204, 208, 246)):
+    """RLBench multi-view fusion + scene-bounds crop of a batch (rlbench_single_task_act.py:266-295): point_maps / rgbs
+    (B, cams, h, w, 3) (or already flattened (B, P, 3)), masks (B, cams, h, w) instance ids or None.  The cameras are
+    concatenated camera-major, points strictly inside `bounds` survive; with `masks` the colours get a fourth {0, 1}
+    channel (invalid ids -> 0, other ids > 0 -> 1).  Returns (coord (N, 3), color (N, 3 | 4), offset (B))."""
+    b = point_maps.shape[0]
+    xyz = point_maps.reshape(b, -1, 3)
+    col = rgbs.reshape(b, -1, 3)
+    seg = masks.reshape(b, -1) if masks is not None else None
+    return _filter_frames(1, xyz, col, bounds=bounds, seg=seg, invalid=invalid_mask_values)

@@ -36,5 +36,14 @@ lat = torch.from_numpy((rng.integers(0, 4, (700, 3)) / 4.0).astype(np.float32)).
 off = torch.tensor([300, 700], dtype=torch.int32, device="cuda")
 for k in (16, 33):
     ki, kd = P.knn_query(k, lat, off, lat[::3].contiguous(), torch.tensor([100, 234], dtype=torch.int32, device="cuda"))
+# raw-frame filter (both dataset families) feeding the voxel-grid stage
+from pointcloudmatters_b200.data_gpu import filter_frames_maniskill2, filter_frames_rlbench, grid_sample_collate  # noqa: E402
+
+fx = torch.from_numpy(rng.uniform(-1, 1, (2, 16384, 4)).astype(np.float32)).cuda()
+fc = torch.from_numpy(rng.integers(0, 256, (2, 16384, 3)).astype(np.uint8)).cuda()
+c3, col3, off3 = filter_frames_maniskill2(fx, fc, crop=np.array([[3, 9], [0, 15]], np.int32))
+grid_sample_collate(c3, col3, off3, grid_size=0.05)
+rp = torch.from_numpy(rng.uniform(-1, 2, (2, 2, 64, 64, 3)).astype(np.float32)).cuda()
+filter_frames_rlbench(rp, rp * 100, torch.from_numpy(rng.integers(0, 250, (2, 2, 64, 64)).astype(np.float32)).cuda())
 torch.cuda.synchronize()
-print("sanitize target OK:", tuple(y.shape), tuple(ki.shape))
+print("sanitize target OK:", tuple(y.shape), tuple(ki.shape), tuple(c3.shape))
