@@ -280,6 +280,18 @@ int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, const floa
                                const float *new_xyz, const int *idx, const int *offset, const int *new_offset,
                                const float *W, int ldw, float *ymax, float *ymin, unsigned char *jmax,
                                unsigned char *jmin, double *stats, pcm_stream_t stream);
+/* Single-extreme forms of the gather pass: BatchNorm's per-channel scale a_c = gamma_c * invstd_c has the sign of gamma_c
+ * (the nn.BatchNorm1d weight, act.py:446-460), known before the batch statistics, so only the extreme that ReLU(BN(.)) +
+ * max-pool will select is tracked: max of y where gamma >= 0, min where gamma < 0.  yext / jext replace ymax / jmax in
+ * pcm_sa_output[_tokens], which then take ymin = jmin = NULL.  Results are bit-identical to the two-extreme entry points.
+ * pcm_sa_gather_sel: nsample 16 or 32 only (PCM_EUNSUPPORTED otherwise). */
+int pcm_sa_gather_sel(int m, int k, int H, const float *Pf, const float *xyz, const float *new_xyz, const int *idx,
+                      const float *W, int ldw, const float *gamma, float *yext, unsigned char *jext, double *stats,
+                      pcm_stream_t stream);
+int pcm_sa_gather_sel_clouds(int b, int n_max, int m, int k, int H, const float *Pf, const float *xyz,
+                             const float *new_xyz, const int *idx, const int *offset, const int *new_offset,
+                             const float *W, int ldw, const float *gamma, float *yext, unsigned char *jext,
+                             double *stats, pcm_stream_t stream);
 int pcm_sa_edge_stats(int m, int k, const int *idx, const float *xyz, const float *new_xyz,
                       float *cnt, float *sq, double *sdtot, pcm_stream_t stream);
 int pcm_sa_bwd_coef(int H, const double *gstats, const double *fstats, const double *sdtot,

@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
 // once per query -- K independent loads -- and the loop, fully unrolled, receives them by shuffle: the K Pf gathers of a
 // thread are independent instructions the compiler can issue ahead of the arithmetic.  Identical arithmetic, identical
 // results.
-template <int K>
+template <int K, bool ONE>
 __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
     const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-    const int* __restrict__ idx, const float* __restrict__ W, int ldw, int m, int H,
+    const int* __restrict__ idx, const float* __restrict__ W, int ldw, const float* __restrict__ sel_gamma, int m, int H,
     float* __restrict__ ymax, float* __restrict__ ymin, unsigned char* __restrict__ jmax,
     unsigned char* __restrict__ jmin, double* __restrict__ stats) {
     const int c0 = threadIdx.x * 4, lane = threadIdx.x & 31;
@@ -110,6 +110,17 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
     for (int v = 0; v < 4; ++v)
 #pragma unroll
         for (int d = 0; d < 3; ++d) wx[v][d] = act ? __ldg(W + (size_t)(c0 + v) * ldw + d) : 0.f;
+    // ONE: only the extreme BatchNorm will select is tracked -- sign(a_c) = sign(gamma_c) is known before the statistics --
+    // by running the whole pass on s y (s = -1 where gamma < 0): max(s y) is max or min of y, the sums are mirrored exactly
+    float sg[4] = {1.f, 1.f, 1.f, 1.f};
+    if (ONE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            sg[v] = (act && __ldg(sel_gamma + c0 + v) < 0.f) ? -1.f : 1.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) wx[v][d] *= sg[v];
+        }
+    }
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
     for (int q = blockIdx.x; q < m; q += gridDim.x) {
         const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
@@ -137,9 +148,9 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
             const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, pv[v])));
+                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, ONE ? pv[v] * sg[v] : pv[v])));
                 if (y > mx[v]) { mx[v] = y; amx[v] = j; }
-                if (y < mn[v]) { mn[v] = y; amn[v] = j; }
+                if (!ONE && y < mn[v]) { mn[v] = y; amn[v] = j; }
                 s1[v] += y;
                 s2[v] = fmaf(y, y, s2[v]);
                 sx[v] = fmaf(y, dx, sx[v]);
@@ -148,11 +159,17 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
             }
         }
         if (act) {
-            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
-            *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0] * sg[0], mx[1] * sg[1], mx[2] * sg[2], mx[3] * sg[3]);
             *reinterpret_cast<uchar4*>(jmax + (size_t)q * H + c0) = make_uchar4(amx[0], amx[1], amx[2], amx[3]);
-            *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+            if (!ONE) {
+                *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+                *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+            }
         }
+    }
+    if (ONE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { s1[v] *= sg[v]; sx[v] *= sg[v]; sy[v] *= sg[v]; sz[v] *= sg[v]; }
     }
     if (act) {
 #pragma unroll
@@ -205,8 +222,9 @@ __global__ void __launch_bounds__(256) sa_output_kernel(const float* __restrict_
     for (long e = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < total; e += (long)gridDim.x * blockDim.x * 4) {
         const int c = (int)(e % H);
         const float4 a = ld4(coef + c), b = ld4(coef + H + c);
-        const float4 hi = ld4(ymax + e), lo = ld4(ymin + e);
-        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = *reinterpret_cast<const uchar4*>(jmin + e);
+        // ymin == NULL: single-extreme intermediates (pcm_sa_gather_sel*): ymax / jmax already hold the selected extreme
+        const float4 hi = ld4(ymax + e), lo = ymin ? ld4(ymin + e) : hi;
+        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = jmin ? *reinterpret_cast<const uchar4*>(jmin + e) : jh;
         float4 o;
         uchar4 js;
         o.x = fmaxf(fmaf(a.x, a.x >= 0.f ? hi.x : lo.x, b.x), 0.f); js.x = a.x >= 0.f ? jh.x : jl.x;
@@ -233,8 +251,9 @@ __global__ void __launch_bounds__(256) sa_output_tokens_kernel(
         const long row = (long)(head + (int)(q % per)) * batch + q / per;
         const long d = row * H + c;
         const float4 a = ld4(coef + c), b = ld4(coef + H + c);
-        const float4 hi = ld4(ymax + e), lo = ld4(ymin + e);
-        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = *reinterpret_cast<const uchar4*>(jmin + e);
+        // ymin == NULL: single-extreme intermediates (pcm_sa_gather_sel*): ymax / jmax already hold the selected extreme
+        const float4 hi = ld4(ymax + e), lo = ymin ? ld4(ymin + e) : hi;
+        const uchar4 jh = *reinterpret_cast<const uchar4*>(jmax + e), jl = jmin ? *reinterpret_cast<const uchar4*>(jmin + e) : jh;
         float4 o;
         uchar4 js;
         o.x = fmaxf(fmaf(a.x, a.x >= 0.f ? hi.x : lo.x, b.x), 0.f); js.x = a.x >= 0.f ? jh.x : jl.x;
@@ -457,11 +476,11 @@ __device__ __forceinline__ void sa_slice_reduce(float (&r0)[4], float (&r1)[4], 
     sa_slice_reduce_impl<LPR, LPR * 4>(r0, r1, r2, r3, r4, red, cl, lane);
 }
 
-template <int CS, int K>
+template <int CS, int K, bool ONE>
 __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
     const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
     const int* __restrict__ idx, const int* __restrict__ offset, const int* __restrict__ new_offset,
-    const float* __restrict__ W, int ldw, int H, int n_cap, float* __restrict__ ymax, float* __restrict__ ymin,
+    const float* __restrict__ W, int ldw, const float* __restrict__ sel_gamma, int H, int n_cap, float* __restrict__ ymax, float* __restrict__ ymin,
     unsigned char* __restrict__ jmax, unsigned char* __restrict__ jmin, double* __restrict__ stats) {
     extern __shared__ __align__(16) float4 slice4[];  // [n_b][LPR]
     __shared__ double red[SA_STAT_ROWS][CS];
@@ -488,6 +507,17 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
     for (int v = 0; v < 4; ++v)
 #pragma unroll
         for (int d = 0; d < 3; ++d) wx[v][d] = __ldg(W + (size_t)(c0 + v) * ldw + d);
+    // ONE: only the extreme BatchNorm will select is tracked -- sign(a_c) = sign(gamma_c) is known before the statistics --
+    // by running the whole pass on s y (s = -1 where gamma < 0): max(s y) is max or min of y, the sums are mirrored exactly
+    float sg[4] = {1.f, 1.f, 1.f, 1.f};
+    if (ONE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            sg[v] = __ldg(sel_gamma + c0 + v) < 0.f ? -1.f : 1.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) wx[v][d] *= sg[v];
+        }
+    }
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
     for (int qw = s_m + warp * QPW; qw < e_m; qw += QS) {  // warp-uniform trip count (the shuffles need every lane)
         const int q = qw + lane / LPR;
@@ -525,9 +555,9 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
             const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, pv[v])));
+                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, ONE ? pv[v] * sg[v] : pv[v])));
                 if (y > mx[v]) { mx[v] = y; amx[v] = j; }
-                if (y < mn[v]) { mn[v] = y; amn[v] = j; }
+                if (!ONE && y < mn[v]) { mn[v] = y; amn[v] = j; }
                 s1[v] += y;
                 s2[v] = fmaf(y, y, s2[v]);
                 sx[v] = fmaf(y, dx, sx[v]);
@@ -536,11 +566,17 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
             }
         }
         if (valid) {
-            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
-            *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0] * sg[0], mx[1] * sg[1], mx[2] * sg[2], mx[3] * sg[3]);
             *reinterpret_cast<uchar4*>(jmax + (size_t)q * H + c0) = make_uchar4(amx[0], amx[1], amx[2], amx[3]);
-            *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+            if (!ONE) {
+                *reinterpret_cast<float4*>(ymin + (size_t)q * H + c0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+                *reinterpret_cast<uchar4*>(jmin + (size_t)q * H + c0) = make_uchar4(amn[0], amn[1], amn[2], amn[3]);
+            }
         }
+    }
+    if (ONE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { s1[v] *= sg[v]; sx[v] *= sg[v]; sy[v] *= sg[v]; sz[v] *= sg[v]; }
     }
     // threads of a warp that own the same channels (lane % LPR equal) are summed by shuffle; one shared atomic per warp
     sa_slice_reduce<LPR>(s1, s2, sx, sy, sz, red, cl, lane);
@@ -579,11 +615,11 @@ PCM_API int pcm_sa_gather_stats(int m, int k, int H, const float* Pf, const floa
     if (H % 4 || H > 4096 || k > 255 || k <= 0) return PCM_EUNSUPPORTED;
     static const bool generic_only = [] { const char* e = getenv("PCM_SA_GENERIC"); return e && e[0] == '1'; }();  // A/B timing
     if (k == 16 && !generic_only)
-        sa_gather_stats_k_kernel<16><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, H,
-                                                                                             ymax, ymin, jmax, jmin, stats);
+        sa_gather_stats_k_kernel<16, false><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, nullptr,
+                                                                                                    m, H, ymax, ymin, jmax, jmin, stats);
     else if (k == 32 && !generic_only)
-        sa_gather_stats_k_kernel<32><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, H,
-                                                                                             ymax, ymin, jmax, jmin, stats);
+        sa_gather_stats_k_kernel<32, false><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, nullptr,
+                                                                                                    m, H, ymax, ymin, jmax, jmin, stats);
     else
         sa_gather_stats_kernel<<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, m, k, H, ymax,
                                                                                        ymin, jmax, jmin, stats);
@@ -613,7 +649,7 @@ PCM_API int pcm_sa_output(int m, int H, const float* ymax, const float* ymin, co
                           pcm_stream_t stream) {
     const long total = (long)m * H;
     if (total <= 0) return PCM_OK;
-    if (!ymax || !ymin || !jmax || !jmin || !coef || !out || !jsel) return PCM_EINVAL;
+    if (!ymax || !jmax || !coef || !out || !jsel || (!ymin != !jmin)) return PCM_EINVAL;
     if (H % 4) return PCM_EUNSUPPORTED;
     sa_output_kernel<<<sa_grid((total / 4 + 255) / 256), 256, 0, pcm_cu_stream(stream)>>>(ymax, ymin, jmax, jmin, coef, total, H, out, jsel);
     return pcm_launch_status();
@@ -635,7 +671,7 @@ PCM_API int pcm_sa_output_tokens(int m, int H, int per_cloud, int batch, int hea
                                  float* out, void* out_bf16, void* out_pos_bf16, unsigned char* jsel, pcm_stream_t stream) {
     const long total = (long)m * H;
     if (total <= 0) return PCM_OK;
-    if (!ymax || !ymin || !jmax || !jmin || !coef || !out || !jsel || (out_pos_bf16 && !pos)) return PCM_EINVAL;
+    if (!ymax || !jmax || !coef || !out || !jsel || (!ymin != !jmin) || (out_pos_bf16 && !pos)) return PCM_EINVAL;
     if (H % 4 || per_cloud <= 0 || batch <= 0 || head_rows < 0 || (long)per_cloud * batch != m) return PCM_EUNSUPPORTED;
     sa_output_tokens_kernel<<<sa_grid((total / 4 + 255) / 256), 256, 0, pcm_cu_stream(stream)>>>(
         ymax, ymin, jmax, jmin, coef, total, H, per_cloud, batch, head_rows, pos, out, reinterpret_cast<__nv_bfloat16*>(out_bf16),
@@ -660,13 +696,13 @@ PCM_API int pcm_sa_bwd_scatter_tokens(int m, int k, int H, int per_cloud, int ba
 // Returns PCM_EUNSUPPORTED when the shape is outside the fast path (k != 16, H % 4, cloud too large for shared memory):
 // call the generic entry point then.  (The same layout was tried for the backward scatter -- sparse gradient accumulated
 // with shared-memory atomics, dPf written once -- and measured SLOWER than the global-atomic kernel: 245 vs 194 us at cfg-2.)
-PCM_API int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, const float* Pf, const float* xyz,
-                                       const float* new_xyz, const int* idx, const int* offset, const int* new_offset,
-                                       const float* W, int ldw, float* ymax, float* ymin, unsigned char* jmax,
-                                       unsigned char* jmin, double* stats, pcm_stream_t stream) {
+static int sa_gather_clouds_impl(int b, int n_max, int m, int k, int H, const float* Pf, const float* xyz, const float* new_xyz,
+                                 const int* idx, const int* offset, const int* new_offset, const float* W, int ldw,
+                                 const float* sel_gamma, float* ymax, float* ymin, unsigned char* jmax, unsigned char* jmin,
+                                 double* stats, pcm_stream_t stream) {
     if (m <= 0) return PCM_OK;
-    if (!Pf || !xyz || !new_xyz || !idx || !offset || !new_offset || !W || !ymax || !ymin || !jmax || !jmin || !stats)
-        return PCM_EINVAL;
+    if (!Pf || !xyz || !new_xyz || !idx || !offset || !new_offset || !W || !ymax || !jmax || !stats) return PCM_EINVAL;
+    if (!sel_gamma && (!ymin || !jmin)) return PCM_EINVAL;
     if (b <= 0 || n_max <= 0) return PCM_EINVAL;
     const int cs = k == 16 ? sa_slice_width(n_max, H) : 0;
     if (!cs) return PCM_EUNSUPPORTED;
@@ -674,20 +710,68 @@ PCM_API int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, co
     const dim3 grid(H / cs, b);
     cudaStream_t st = pcm_cu_stream(stream);
     cudaError_t e = cudaSuccess;
-#define PCM_SA_FWD(CSV)                                                                                                       \
-    e = sa_allow_smem(sa_gather_stats_cloud_kernel<CSV, 16>, smem);                                                           \
+#define PCM_SA_FWD(CSV, ONE)                                                                                                  \
+    e = sa_allow_smem(sa_gather_stats_cloud_kernel<CSV, 16, ONE>, smem);                                                      \
     if (e == cudaSuccess)                                                                                                     \
-        sa_gather_stats_cloud_kernel<CSV, 16><<<grid, 256, smem, st>>>(Pf, xyz, new_xyz, idx, offset, new_offset, W, ldw, H,   \
-                                                                      n_max, ymax, ymin, jmax, jmin, stats)
-    switch (cs) {
-        case 32: PCM_SA_FWD(32); break;
-        case 16: PCM_SA_FWD(16); break;
-        case 8: PCM_SA_FWD(8); break;
-        default: PCM_SA_FWD(4); break;
+        sa_gather_stats_cloud_kernel<CSV, 16, ONE><<<grid, 256, smem, st>>>(Pf, xyz, new_xyz, idx, offset, new_offset, W, ldw, \
+                                                                           sel_gamma, H, n_max, ymax, ymin, jmax, jmin, stats)
+    if (sel_gamma) {
+        switch (cs) {
+            case 32: PCM_SA_FWD(32, true); break;
+            case 16: PCM_SA_FWD(16, true); break;
+            case 8: PCM_SA_FWD(8, true); break;
+            default: PCM_SA_FWD(4, true); break;
+        }
+    } else {
+        switch (cs) {
+            case 32: PCM_SA_FWD(32, false); break;
+            case 16: PCM_SA_FWD(16, false); break;
+            case 8: PCM_SA_FWD(8, false); break;
+            default: PCM_SA_FWD(4, false); break;
+        }
     }
 #undef PCM_SA_FWD
     if (e != cudaSuccess) return (int)e;
     return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_gather_stats_clouds(int b, int n_max, int m, int k, int H, const float* Pf, const float* xyz,
+                                       const float* new_xyz, const int* idx, const int* offset, const int* new_offset,
+                                       const float* W, int ldw, float* ymax, float* ymin, unsigned char* jmax,
+                                       unsigned char* jmin, double* stats, pcm_stream_t stream) {
+    return sa_gather_clouds_impl(b, n_max, m, k, H, Pf, xyz, new_xyz, idx, offset, new_offset, W, ldw, nullptr, ymax, ymin, jmax,
+                                 jmin, stats, stream);
+}
+
+// Single-extreme forms of the gather pass.  BatchNorm's per-channel scale a_c = gamma_c * invstd_c has the sign of gamma_c,
+// which is known BEFORE the batch statistics: only the extreme that will be selected is tracked (max of y where gamma >= 0,
+// min where gamma < 0) -- a third less compare / select work per edge and half the (m, H) intermediates.  yext / jext take
+// the place of ymax / jmax in pcm_sa_output[_tokens] (pass ymin = jmin = NULL there).  Bit-identical results.
+// pcm_sa_gather_sel: nsample 16 or 32 (PCM_EUNSUPPORTED otherwise); pcm_sa_gather_sel_clouds: as pcm_sa_gather_stats_clouds.
+PCM_API int pcm_sa_gather_sel(int m, int k, int H, const float* Pf, const float* xyz, const float* new_xyz, const int* idx,
+                              const float* W, int ldw, const float* gamma, float* yext, unsigned char* jext, double* stats,
+                              pcm_stream_t stream) {
+    if (m <= 0) return PCM_OK;
+    if (!Pf || !xyz || !new_xyz || !idx || !W || !gamma || !yext || !jext || !stats) return PCM_EINVAL;
+    if (H % 4 || H > 4096) return PCM_EUNSUPPORTED;
+    if (k == 16)
+        sa_gather_stats_k_kernel<16, true><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, gamma, m, H,
+                                                                                                   yext, nullptr, jext, nullptr, stats);
+    else if (k == 32)
+        sa_gather_stats_k_kernel<32, true><<<sa_grid(m), sa_threads(H), 0, pcm_cu_stream(stream)>>>(Pf, xyz, new_xyz, idx, W, ldw, gamma, m, H,
+                                                                                                   yext, nullptr, jext, nullptr, stats);
+    else
+        return PCM_EUNSUPPORTED;
+    return pcm_launch_status();
+}
+
+PCM_API int pcm_sa_gather_sel_clouds(int b, int n_max, int m, int k, int H, const float* Pf, const float* xyz,
+                                     const float* new_xyz, const int* idx, const int* offset, const int* new_offset,
+                                     const float* W, int ldw, const float* gamma, float* yext, unsigned char* jext,
+                                     double* stats, pcm_stream_t stream) {
+    if (!gamma) return PCM_EINVAL;
+    return sa_gather_clouds_impl(b, n_max, m, k, H, Pf, xyz, new_xyz, idx, offset, new_offset, W, ldw, gamma, yext, nullptr, jext,
+                                 nullptr, stats, stream);
 }
 
 PCM_API int pcm_sa_edge_stats(int m, int k, const int* idx, const float* xyz, const float* new_xyz, float* cnt,

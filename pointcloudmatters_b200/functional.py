@@ -1251,21 +1251,35 @@ class _SetAbstraction(torch.autograd.Function):
         wfb = weight[:, 3:].to(torch.bfloat16).contiguous()
         Pf = K.gemm_bf16(featb, wfb)  # (n, H) fp32: the only tensor-core work of the layer
         ymax = torch.empty((m, H), dtype=torch.float32, device=dev)
-        ymin = torch.empty_like(ymax)
         jmax = torch.empty((m, H), dtype=torch.uint8, device=dev)
-        jmin = torch.empty_like(jmax)
+        ymin = jmin = None
         stats = _zeros((5, H), torch.float64, dev)
+        # gather pass, fastest applicable form first.  Single-extreme forms: sign(BatchNorm scale) = sign(gamma) is known
+        # before the statistics, so only the extreme that will be selected is tracked (bit-identical results).
         rc = PCM_EUNSUPPORTED
-        if clouds is not None and not _NO_SA_CLOUDS:
-            off, noff, n_max = clouds
-            rc = lib.pcm_sa_gather_stats_clouds(off.numel(), int(n_max), m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx),
-                                                ptr(off), ptr(noff), ptr(weight), weight.stride(0), ptr(ymax), ptr(ymin),
-                                                ptr(jmax), ptr(jmin), ptr(stats), st)
+        if not _NO_SA_SEL:
+            if clouds is not None and not _NO_SA_CLOUDS:
+                off, noff, n_max = clouds
+                rc = lib.pcm_sa_gather_sel_clouds(off.numel(), int(n_max), m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx),
+                                                  ptr(off), ptr(noff), ptr(weight), weight.stride(0), ptr(gamma), ptr(ymax),
+                                                  ptr(jmax), ptr(stats), st)
+            if rc == PCM_EUNSUPPORTED:
+                rc = lib.pcm_sa_gather_sel(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
+                                           ptr(gamma), ptr(ymax), ptr(jmax), ptr(stats), st)
             if rc != PCM_EUNSUPPORTED:
-                check(rc, "pcm_sa_gather_stats_clouds")
+                check(rc, "pcm_sa_gather_sel")
         if rc == PCM_EUNSUPPORTED:
-            check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
-                                          ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
+            ymin, jmin = torch.empty_like(ymax), torch.empty_like(jmax)
+            if clouds is not None and not _NO_SA_CLOUDS:
+                off, noff, n_max = clouds
+                rc = lib.pcm_sa_gather_stats_clouds(off.numel(), int(n_max), m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx),
+                                                    ptr(off), ptr(noff), ptr(weight), weight.stride(0), ptr(ymax), ptr(ymin),
+                                                    ptr(jmax), ptr(jmin), ptr(stats), st)
+                if rc != PCM_EUNSUPPORTED:
+                    check(rc, "pcm_sa_gather_stats_clouds")
+            if rc == PCM_EUNSUPPORTED:
+                check(lib.pcm_sa_gather_stats(m, k, H, ptr(Pf), ptr(p), ptr(new_p), ptr(knn_idx), ptr(weight), weight.stride(0),
+                                              ptr(ymax), ptr(ymin), ptr(jmax), ptr(jmin), ptr(stats), st), "pcm_sa_gather_stats")
         coef = torch.empty((4, H), dtype=torch.float32, device=dev)
         n_dev = None
         if training and SYNC_BN.active():  # rows 0-1 (sum y, sum y^2) global; rows 2-4 (sum y dxyz) stay local (backward dW)
@@ -1348,7 +1362,8 @@ class _SetAbstraction(torch.autograd.Function):
         return dfeat, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
 
 
-_NO_SA_CLOUDS = bool(int(os.environ.get("PCM_NO_SA_CLOUDS", "0")))  # A/B switch: generic gather / scatter kernels
+_NO_SA_CLOUDS = bool(int(os.environ.get("PCM_NO_SA_CLOUDS", "0")))  # A/B switch: gather without the shared-memory cloud slice
+_NO_SA_SEL = bool(int(os.environ.get("PCM_NO_SA_SEL", "0")))  # A/B switch: track both extremes (max and min) per channel
 PCM_EUNSUPPORTED = -2
 
 

@@ -74,8 +74,11 @@ def test_sa_fused_matches_as_written_chain(b, n, mm, k, C, H, neg, training, clo
                 out = PF.set_abstraction(p, feat, t_off, new_p, t_noff, idx, W, bn, n_max=int(np.diff(off, prepend=0).max()) + 5)
             else:
                 out = PF.set_abstraction(p, feat, None, new_p, None, idx, W, bn)
-            used = lib.calls.get("pcm_sa_gather_stats", 0) - before.get("pcm_sa_gather_stats", 0)
-            assert used == (0 if (cloud_slices and k == 16) else 1), (used, cloud_slices, k)
+            used = {n: lib.calls.get(n, 0) - before.get(n, 0) for n in ("pcm_sa_gather_stats", "pcm_sa_gather_sel", "pcm_sa_gather_sel_clouds")}
+            if k == 16:  # single-extreme kernels (sign of the BatchNorm scale known up front), cloud-slice form when offsets are given
+                assert used["pcm_sa_gather_stats"] == 0 and used["pcm_sa_gather_sel_clouds" if cloud_slices else "pcm_sa_gather_sel"] == 1, used
+            else:
+                assert used["pcm_sa_gather_stats"] == 1, used
         else:
             out = _reference(p, feat, new_p, idx, W, bn)
         out.backward(dout)
