@@ -91,6 +91,51 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
     }
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per instruction, bit-identical to the scalar
+// forms -- the gather kernels are bound by their instruction count, and a thread owns four channels = two pairs
+__device__ __forceinline__ float2 pcm_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pcm_fadd2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pcm_fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
+// one edge (neighbour j) of a thread's four channels: y = Pf + Wx . d (on s y in single-extreme mode), extreme tracking,
+// the five running sums.  Same operation order as the scalar generic kernel.
+template <bool ONE>
+__device__ __forceinline__ void sa_edge(const float4 pf, float dx, float dy, float dz, int j, const float2 (&wxp)[2][3],
+                                        const float2 (&sg2)[2], float (&mx)[4], int (&amx)[4], float (&mn)[4], int (&amn)[4],
+                                        float2 (&s1)[2], float2 (&s2)[2], float2 (&sx)[2], float2 (&sy)[2], float2 (&sz)[2]) {
+    const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float2 pv = h == 0 ? make_float2(pf.x, pf.y) : make_float2(pf.z, pf.w);
+        if (ONE) pv = pcm_fmul2(pv, sg2[h]);
+        const float2 y = pcm_ffma2(wxp[h][2], dz2, pcm_ffma2(wxp[h][1], dy2, pcm_ffma2(wxp[h][0], dx2, pv)));
+        if (y.x > mx[2 * h]) { mx[2 * h] = y.x; amx[2 * h] = j; }
+        if (y.y > mx[2 * h + 1]) { mx[2 * h + 1] = y.y; amx[2 * h + 1] = j; }
+        if (!ONE) {
+            if (y.x < mn[2 * h]) { mn[2 * h] = y.x; amn[2 * h] = j; }
+            if (y.y < mn[2 * h + 1]) { mn[2 * h + 1] = y.y; amn[2 * h + 1] = j; }
+        }
+        s1[h] = pcm_fadd2(s1[h], y);
+        s2[h] = pcm_ffma2(y, y, s2[h]);
+        sx[h] = pcm_ffma2(y, dx2, sx[h]);
+        sy[h] = pcm_ffma2(y, dy2, sy[h]);
+        sz[h] = pcm_ffma2(y, dz2, sz[h]);
+    }
+}
+
 // Same pass for a compile-time neighbour count K <= 32 (the reference configuration has nsample = 16).  In the generic
 // kernel above every thread walks the k neighbours through a dependent chain (index load -> three coordinate loads and the
 // 16-byte Pf gather), one neighbour at a time.  Here lane j of each warp fetches neighbour j's index and offset vector
@@ -98,7 +143,7 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
 // thread are independent instructions the compiler can issue ahead of the arithmetic.  Identical arithmetic, identical
 // results.
 template <int K, bool ONE>
-__global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
+__global__ void __launch_bounds__(256, 3) sa_gather_stats_k_kernel(
     const float* __restrict__ Pf, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
     const int* __restrict__ idx, const float* __restrict__ W, int ldw, const float* __restrict__ sel_gamma, int m, int H,
     float* __restrict__ ymax, float* __restrict__ ymin, unsigned char* __restrict__ jmax,
@@ -121,7 +166,14 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
             for (int d = 0; d < 3; ++d) wx[v][d] *= sg[v];
         }
     }
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
+    float2 wxp[2][3], sg2[2], s1p[2], s2p[2], sxp[2], syp[2], szp[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        sg2[h] = make_float2(sg[2 * h], sg[2 * h + 1]);
+        s1p[h] = s2p[h] = sxp[h] = syp[h] = szp[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wxp[h][d] = make_float2(wx[2 * h][d], wx[2 * h + 1][d]);
+    }
     for (int q = blockIdx.x; q < m; q += gridDim.x) {
         const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1), qz = __ldg(new_xyz + (size_t)q * 3 + 2);
         int ni = -1;
@@ -145,18 +197,7 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
                         dz = __shfl_sync(PCM_FULL_MASK, ndz, j);
             float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i >= 0 && act) pf = ld4(Pf + (size_t)i * H + c0);
-            const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, ONE ? pv[v] * sg[v] : pv[v])));
-                if (y > mx[v]) { mx[v] = y; amx[v] = j; }
-                if (!ONE && y < mn[v]) { mn[v] = y; amn[v] = j; }
-                s1[v] += y;
-                s2[v] = fmaf(y, y, s2[v]);
-                sx[v] = fmaf(y, dx, sx[v]);
-                sy[v] = fmaf(y, dy, sy[v]);
-                sz[v] = fmaf(y, dz, sz[v]);
-            }
+            sa_edge<ONE>(pf, dx, dy, dz, j, wxp, sg2, mx, amx, mn, amn, s1p, s2p, sxp, syp, szp);
         }
         if (act) {
             *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0] * sg[0], mx[1] * sg[1], mx[2] * sg[2], mx[3] * sg[3]);
@@ -167,6 +208,9 @@ __global__ void __launch_bounds__(256) sa_gather_stats_k_kernel(
             }
         }
     }
+    float s1[4] = {s1p[0].x, s1p[0].y, s1p[1].x, s1p[1].y}, s2[4] = {s2p[0].x, s2p[0].y, s2p[1].x, s2p[1].y};
+    float sx[4] = {sxp[0].x, sxp[0].y, sxp[1].x, sxp[1].y}, sy[4] = {syp[0].x, syp[0].y, syp[1].x, syp[1].y};
+    float sz[4] = {szp[0].x, szp[0].y, szp[1].x, szp[1].y};
     if (ONE) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) { s1[v] *= sg[v]; sx[v] *= sg[v]; sy[v] *= sg[v]; sz[v] *= sg[v]; }
@@ -446,7 +490,9 @@ __global__ void __launch_bounds__(256) sa_bwd_dense_kernel(const float* __restri
 // cloud's queries with CS / 4 threads per query, and gathers from shared memory.  Neighbour indices and offset vectors of a
 // query are fetched once by the query's threads (K / LPR neighbours each) and exchanged by shuffle.  Same per-element
 // arithmetic as the generic kernel: identical ymax / ymin / arg; the per-channel sums differ in summation order only (fp32
-// per thread and warp, fp64 across warps).  cfg-2: 284 us (generic kernel 433 us, its shuffle-unrolled form 307 us).
+// per thread and warp, fp64 across warps).  cfg-2: 284 us (generic kernel 433 us, its shuffle-unrolled form 307 us); 256 us
+// tracking the selected extreme only, 240 us with packed FFMA2 / FADD2 arithmetic (100 registers: 2 CTAs per SM; capping the
+// registers for a third CTA spills and costs more than it gains, the 128-thread kernel above is capped at 80 instead).
 // per-channel partial sums of a cloud-slice CTA: lanes with equal lane % LPR hold the same four channels
 template <int LPR, int CSV>
 __device__ __forceinline__ void sa_slice_reduce_impl(float (&r0)[4], float (&r1)[4], float (&r2)[4], float (&r3)[4],
@@ -518,7 +564,14 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
             for (int d = 0; d < 3; ++d) wx[v][d] *= sg[v];
         }
     }
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0};
+    float2 wxp[2][3], sg2[2], s1p[2], s2p[2], sxp[2], syp[2], szp[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        sg2[h] = make_float2(sg[2 * h], sg[2 * h + 1]);
+        s1p[h] = s2p[h] = sxp[h] = syp[h] = szp[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) wxp[h][d] = make_float2(wx[2 * h][d], wx[2 * h + 1][d]);
+    }
     for (int qw = s_m + warp * QPW; qw < e_m; qw += QS) {  // warp-uniform trip count (the shuffles need every lane)
         const int q = qw + lane / LPR;
         const bool valid = q < e_m;
@@ -552,18 +605,7 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
                         dz = __shfl_sync(PCM_FULL_MASK, ndz[u], src);
             float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i >= 0) pf = slice4[i * LPR + cl];
-            const float pv[4] = {pf.x, pf.y, pf.z, pf.w};
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float y = fmaf(wx[v][2], dz, fmaf(wx[v][1], dy, fmaf(wx[v][0], dx, ONE ? pv[v] * sg[v] : pv[v])));
-                if (y > mx[v]) { mx[v] = y; amx[v] = j; }
-                if (!ONE && y < mn[v]) { mn[v] = y; amn[v] = j; }
-                s1[v] += y;
-                s2[v] = fmaf(y, y, s2[v]);
-                sx[v] = fmaf(y, dx, sx[v]);
-                sy[v] = fmaf(y, dy, sy[v]);
-                sz[v] = fmaf(y, dz, sz[v]);
-            }
+            sa_edge<ONE>(pf, dx, dy, dz, j, wxp, sg2, mx, amx, mn, amn, s1p, s2p, sxp, syp, szp);
         }
         if (valid) {
             *reinterpret_cast<float4*>(ymax + (size_t)q * H + c0) = make_float4(mx[0] * sg[0], mx[1] * sg[1], mx[2] * sg[2], mx[3] * sg[3]);
@@ -574,6 +616,9 @@ __global__ void __launch_bounds__(256) sa_gather_stats_cloud_kernel(
             }
         }
     }
+    float s1[4] = {s1p[0].x, s1p[0].y, s1p[1].x, s1p[1].y}, s2[4] = {s2p[0].x, s2p[0].y, s2p[1].x, s2p[1].y};
+    float sx[4] = {sxp[0].x, sxp[0].y, sxp[1].x, sxp[1].y}, sy[4] = {syp[0].x, syp[0].y, syp[1].x, syp[1].y};
+    float sz[4] = {szp[0].x, szp[0].y, szp[1].x, szp[1].y};
     if (ONE) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) { s1[v] *= sg[v]; sx[v] *= sg[v]; sy[v] *= sg[v]; sz[v] *= sg[v]; }
