@@ -67,6 +67,25 @@ __device__ __forceinline__ int pcm_cloud_of(int i, const int* __restrict__ offse
     return lo;
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per instruction, bit-identical to the scalar
+// forms.  Used where a kernel is bound by its instruction count (set-abstraction gather, attention softmax).
+__device__ __forceinline__ float2 pcm_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pcm_fadd2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pcm_fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 // ---- counter-based dropout RNG shared by the attention / LayerNorm kernels --------------------
 // A 64-bit splitmix mix per ROW (seed, row base index) and one cheap 32-bit hash ("lowbias32") per
 // PAIR of elements: low / high 16 bits decide the two elements.  The drop probability actually

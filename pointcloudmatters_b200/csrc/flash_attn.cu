@@ -324,14 +324,28 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                         }
                         tmem_ld_wait(v);
                         float pr[32];
+                        // exponent arguments and row sums on packed fp32 pairs (FFMA2 / FADD2: bit-identical, half the
+                        // instructions); ex2 itself is one MUFU per element
+                        const float2 sl22 = make_float2(sl2, sl2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref));
+                        for (int e = 0; e < 32; e += 2) {
+                            const float2 a = pcm_ffma2(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sl22, nm2);
+                            pr[e] = fast_exp2(a.x);
+                            pr[e + 1] = fast_exp2(a.y);
+                        }
                         if (bits != 0xFFFFFFFFu) {
 #pragma unroll
                             for (int e = 0; e < 32; ++e) pr[e] = ((bits >> e) & 1u) ? pr[e] : 0.f;
                         }
+                        {
+                            float2 l01 = make_float2(ls[0], ls[1]), l23 = make_float2(ls[2], ls[3]);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) ls[e & 3] += pr[e];
+                            for (int e = 0; e < 32; e += 4) {
+                                l01 = pcm_fadd2(l01, make_float2(pr[e], pr[e + 1]));
+                                l23 = pcm_fadd2(l23, make_float2(pr[e + 2], pr[e + 3]));
+                            }
+                            ls[0] = l01.x; ls[1] = l01.y; ls[2] = l23.x; ls[3] = l23.y;
+                        }
                         if (DROPOUT) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -375,7 +389,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                                 tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
                                 tmem_ld_wait(v);
 #pragma unroll
-                                for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                                for (int e = 0; e < 32; e += 2) {
+                                    const float2 r = pcm_fadd2(make_float2(o[c * 32 + e], o[c * 32 + e + 1]),
+                                                               make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+                                    o[c * 32 + e] = r.x; o[c * 32 + e + 1] = r.y;
+                                }
                             }
                         }
                         pv_collected = true;
@@ -419,7 +437,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) flash_fwd_kernel(const __grid_
                     tmem_ld_32x32b_x32(t_row + TM_PV + c * 32, v);
                     tmem_ld_wait(v);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(v[e]);
+                    for (int e = 0; e < 32; e += 2) {
+                        const float2 r = pcm_fadd2(make_float2(o[c * 32 + e], o[c * 32 + e + 1]),
+                                                   make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+                        o[c * 32 + e] = r.x; o[c * 32 + e + 1] = r.y;
+                    }
                 }
                 const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 const float inv = lsum > 0.f ? p.keep_scale / lsum : 0.f;
@@ -844,10 +866,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
                             tmem_ld_wait(w);
                             float pr[32], g[32];
                             uint32_t pd_pk[16], ds_pk[16];
+                            // exponent arguments and the dS arithmetic below on packed fp32 pairs (FFMA2 / FMUL2: bit-identical)
+                            const float2 sl22 = make_float2(sl2, sl2), nl2 = make_float2(-lse_r, -lse_r);
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -lse_r));
+                            for (int e = 0; e < 32; e += 2) {
+                                const float2 a = pcm_ffma2(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sl22, nl2);
+                                pr[e] = fast_exp2(a.x);
+                                pr[e + 1] = fast_exp2(a.y);
                                 g[e] = __uint_as_float(w[e]);
+                                g[e + 1] = __uint_as_float(w[e + 1]);
                             }
                             if (bits != 0xFFFFFFFFu) {  // masked keys, rows past L, columns past nkv16 (uninitialised TMEM)
 #pragma unroll
@@ -873,16 +900,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) flash_bwd_kernel(const __grid_
 #pragma unroll
                                 for (int q = 0; q < 16; ++q)
                                     pd_pk[q] = pack_bf16(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
+                                const float2 ks2 = make_float2(keep_scale, keep_scale), nd2 = make_float2(-delta_r, -delta_r);
 #pragma unroll
-                                for (int q = 0; q < 16; ++q)
-                                    ds_pk[q] = pack_bf16(pr[2 * q] * fmaf(g[2 * q], keep_scale, -delta_r),
-                                                         pr[2 * q + 1] * fmaf(g[2 * q + 1], keep_scale, -delta_r));
+                                for (int q = 0; q < 16; ++q) {
+                                    const float2 d = pcm_fmul2(make_float2(pr[2 * q], pr[2 * q + 1]),
+                                                               pcm_ffma2(make_float2(g[2 * q], g[2 * q + 1]), ks2, nd2));
+                                    ds_pk[q] = pack_bf16(d.x, d.y);
+                                }
                             } else {
 #pragma unroll
                                 for (int q = 0; q < 16; ++q) pd_pk[q] = pack_bf16(pr[2 * q], pr[2 * q + 1]);
+                                const float2 nd2 = make_float2(-delta_r, -delta_r);
 #pragma unroll
-                                for (int q = 0; q < 16; ++q)
-                                    ds_pk[q] = pack_bf16(pr[2 * q] * (g[2 * q] - delta_r), pr[2 * q + 1] * (g[2 * q + 1] - delta_r));
+                                for (int q = 0; q < 16; ++q) {
+                                    const float2 d = pcm_fmul2(make_float2(pr[2 * q], pr[2 * q + 1]),
+                                                               pcm_fadd2(make_float2(g[2 * q], g[2 * q + 1]), nd2));
+                                    ds_pk[q] = pack_bf16(d.x, d.y);
+                                }
                             }
                             if (tr && c2 == 0) TRACE(t < 7 ? 25 + 5 * (int)t : 64);
                             wait_prev();

@@ -91,25 +91,6 @@ __global__ void __launch_bounds__(256) sa_gather_stats_kernel(
     }
 }
 
-// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per instruction, bit-identical to the scalar
-// forms -- the gather kernels are bound by their instruction count, and a thread owns four channels = two pairs
-__device__ __forceinline__ float2 pcm_ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ float2 pcm_fadd2(float2 a, float2 b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ float2 pcm_fmul2(float2 a, float2 b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&r);
-}
-
 // one edge (neighbour j) of a thread's four channels: y = Pf + Wx . d (on s y in single-extreme mode), extreme tracking,
 // the five running sums.  Same operation order as the scalar generic kernel.
 template <bool ONE>
