@@ -3,8 +3,11 @@
 // kNN replaces knn_query_cuda_kernel (reference libs/pointops/src/knn_query/
 // knn_query_cuda_kernel.cu:60-104).  The reference's output ORDER under equal distances is an
 // artefact of its sequential binary max-heap (strict `d2 < root` replacement, `reheap`, then
-// `heap_sort`), so the only way to be bit-exact on every input is to replay that heap.  We keep
-// one query per thread like the reference, but
+// `heap_sort`), so the only way to be bit-exact on every input is to replay that heap -- for the
+// queries that HAVE ties.  Two kernels: knn_warp_kernel (nsample <= 31, the default: one warp per
+// query, sorted per-lane list, heap replay only for queries with a tie among their k + 1 smallest;
+// see its comment below) and knn_kernel (any nsample <= 128: always replays the heap).  The latter
+// keeps one query per thread like the reference, but
 //   * the heap lives in SHARED memory laid out [slot][thread] (bank = thread id: conflict-free
 //     for any per-thread slot), not in a 1 KB/thread local-memory stack frame;
 //   * the cloud is staged through shared memory in float4 tiles with coalesced loads, so the
