@@ -434,7 +434,9 @@ int g_ln_fwd_cap = 148 * 8;
 
 inline int ln_grid(long rows) {
     long blocks = (rows + 7) / 8;
-    const long cap = g_ln_fwd_cap > 0 ? g_ln_fwd_cap : 148L * 8;
+    // one resident wave (4 CTAs per SM): tools/bench_ln.py, 6 400 rows: 21.1 / 14.3 / 12.7 / 14.5 us at 148 / 296 / 592 / 1 184
+    // CTAs, 32 960 rows: 119 / 79 / 61.3 / 61.5 us
+    const long cap = g_ln_fwd_cap > 0 ? g_ln_fwd_cap : 148L * 4;
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
