@@ -284,6 +284,8 @@ def b200_arm(args):
             # captured graph's input buffers (inside this timed region)
             loss = module.training_step(b, i)
             if from_host:
+                if i + 1 < steps:  # input pipelining, as a prefetching loader would: the next batch's host->device copy
+                    module.prefetch(batches[(i + 1) % len(batches)])  # runs on a copy stream under this step's kernels
                 loss_host = float(loss)  # device->host read of the step result, every step
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()

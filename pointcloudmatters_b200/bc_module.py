@@ -57,6 +57,11 @@ class ACTBCModule(nn.Module):
     def _dist_kwargs(self):
         return {k: self.hparams[k] for k in ("sync_batchnorm", "overlap_allreduce", "grad_wire_dtype")}
 
+    def prefetch(self, batch) -> None:
+        """Stage the next step's pinned host batch on the device while the current step runs (BCTrainer.prefetch)."""
+        if self._trainer is not None:
+            self._trainer.prefetch(batch)
+
     def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
         """forward + backward + gradient all-reduce + clip + AdamW + LR step; returns the loss."""
         if self._trainer is None:

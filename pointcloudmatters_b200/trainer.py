@@ -378,6 +378,7 @@ class BCTrainer:
         The cache holds at most `max_cached_graphs` entries (least recently used evicted -- its private memory pool
         is released with it); when captures keep missing (ragged clouds: a new sum-N almost every batch) the
         trainer stops capturing and runs eagerly (`graph_disabled_reason` says so) instead of re-capturing each step."""
+        batch_obj = batch
         batch = self._bucket_hints(self._inputs_only(batch))
         sig = (self._signature(batch), bool(zero))
         self._graph_lookups += 1
@@ -404,10 +405,64 @@ class BCTrainer:
         else:
             self._graphs.move_to_end(sig)
         graph, static, outs, reduced_inside = entry
-        self._copy_into(static, batch)
+        pf, self._prefetched = getattr(self, "_prefetched", None), None
+        if pf is not None and pf[0] is batch_obj and pf[1] == sig[0]:
+            # the batch was staged host->device by `prefetch` while the previous step ran: device->device into the graph inputs
+            main = torch.cuda.current_stream()
+            main.wait_event(pf[3])
+            self._copy_into(static, pf[2])
+            done = torch.cuda.Event()
+            done.record(main)
+            self._stage_free[pf[1]] = done
+        else:
+            self._copy_into(static, batch)
         graph.replay()
         self._reduced = reduced_inside
         return outs
+
+    def prefetch(self, batch):
+        """Optional input pipelining for the CUDA-graph path: stage the NEXT step's pinned host batch host->device on a
+        copy stream while the current step is still running.  `training_step(batch)` called afterwards with the SAME
+        batch object then only copies device->device into the graph's inputs.  A no-op for device batches, on the eager
+        path and before the step graphs exist; a prefetched batch that is never used is simply dropped."""
+        if not (self.use_cuda_graph and self.flat is not None and self.flat.param.is_cuda and self.graph_disabled_reason is None):
+            return
+        b = self._bucket_hints(self._inputs_only(batch))
+        host = []
+        self._walk(b, lambda t: host.append(t.device.type == "cpu"))
+        if not host or not any(host):
+            return
+        key = self._signature(b)
+        if not hasattr(self, "_stages"):
+            self._stages, self._stage_free, self._copy_stream = {}, {}, torch.cuda.Stream()
+        dev = self.flat.param.device
+        stage = self._stages.get(key)
+        if stage is None:
+            if len(self._stages) >= 4:
+                self._stages.clear()
+                self._stage_free.clear()
+            mk = lambda v: ({kk: mk(vv) for kk, vv in v.items()} if isinstance(v, dict)
+                            else (torch.empty(v.shape, dtype=v.dtype, device=dev) if torch.is_tensor(v) else v))
+            stage = self._stages[key] = mk(b)
+            # once: the staging buffers were just allocated on the step's stream (they are kept for the trainer's lifetime)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+        cs = self._copy_stream
+        free = self._stage_free.get(key)
+        if free is not None:
+            cs.wait_event(free)  # the previous step's device->device copy out of this staging set has finished
+        with torch.cuda.stream(cs):
+            self._copy_into(stage, b)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._prefetched = (batch, key, stage, ev)
+
+    @staticmethod
+    def _walk(batch, fn):
+        for v in batch.values():
+            if isinstance(v, dict):
+                BCTrainer._walk(v, fn)
+            elif torch.is_tensor(v):
+                fn(v)
 
     def _on_device(self, batch):
         """Host (ideally pinned) batch -> this rank's device, asynchronously; device batches pass through."""

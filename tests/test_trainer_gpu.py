@@ -158,4 +158,31 @@ def test_training_step_accepts_a_pinned_host_batch(use_graph):
         losses[mode] = out
         if use_graph:
             assert len(m._trainer._graphs) >= 1 and m._trainer.graph_disabled_reason is None
-    assert losses["host"] == pytest.approx(losses["device"], rel=2e-3), losses
+    assert losses["host"] == pytest.approx(losses["device"], rel=1e-2), losses  # (atomics noise, see the prefetch test)
+
+
+def test_prefetch_stages_the_next_host_batch_and_changes_nothing():
+    """BCTrainer.prefetch: the next step's pinned host batch is copied on a side stream while the current step runs; the
+    step that consumes it gives the same losses as without prefetching (also when a prefetched batch is NOT the one used)."""
+    from pointcloudmatters_b200.data import synthetic_act_batch
+
+    hosts = [synthetic_act_batch(4, 256, num_queries=12, seed=s, pin=True) for s in (5, 6, 7)]
+    for h in hosts:
+        h["_eps"] = torch.randn(4, 32, generator=torch.Generator().manual_seed(7)).pin_memory()
+    losses = {}
+    for mode in ("plain", "prefetch"):
+        m = _module(use_cuda_graph=True)
+        out = []
+        for i in range(9):
+            loss = m.training_step(hosts[i % 3], i)
+            if mode == "prefetch":
+                nxt = hosts[(i + 1) % 3] if i != 5 else hosts[0]  # step 6 is handed a different batch than was prefetched
+                m.prefetch(nxt)
+            out.append(float(loss))
+        losses[mode] = out
+        assert len(m._trainer._graphs) >= 1 and m._trainer.graph_disabled_reason is None
+        if mode == "prefetch":
+            assert hasattr(m._trainer, "_stages") and len(m._trainer._stages) == 1
+    # run-to-run noise of the fp32-atomic reductions reaches ~2e-3 after a few Adam steps (see test_act_gpu); a wrong or
+    # stale batch would change the loss by tens of percent
+    assert losses["prefetch"] == pytest.approx(losses["plain"], rel=1e-2), losses
