@@ -8,9 +8,11 @@ cloud transforms (`transform_pcd`: GridSamplePCD ..., oracle/grid_sample_oracle.
   * RLBench (src/data/components/rlbench/rlbench_single_task_act.py:266-295): camera maps stacked, cast to float64,
     flattened camera-major; keep the points strictly inside SCENE_BOUNDS (rlbench/constants.py:1); `use_mask`: instance
     ids in `invalid_mask_values` -> 0, remaining ids > 0 -> 1, appended to the colours as a fourth channel.
-PARITY UNPINNED: the dataset classes cannot be imported here (h5py trajectories / RLBench pickles and their packages are
-absent) and the reference has no tests for them; the functions below are line-by-line restatements of the cited lines and
-are checked against hand-built expectations in tests/test_frame_filter_cpu.py.
+PINNED: oracle/gen_golden_frames.py runs the reference's UNMODIFIED `__getitem__` methods of both dataset classes (modules
+loaded by file path; `h5py` and the `src.utils` package front stubbed, instances made without their file-reading
+`__init__`) on seeded synthetic frames and stores what they pass to `transform_pcd` in tests/golden/frame_filter_ref.npz
+(5 cases: 1 / 2-of-3 cameras, rand_crop, include_ground, RLBench 1 / 4 cameras with masks, values on the thresholds);
+tests/test_frame_filter_cpu.py checks these functions against them bit-exactly, plus hand-built expectations.
 """
 from __future__ import annotations
 

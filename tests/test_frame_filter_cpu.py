@@ -1,7 +1,10 @@
 """oracle/frame_filter_oracle.py (numpy restatement of the reference's frame -> cloud selections) against hand-built
 expectations: the predicates, their thresholds' precision, the crop window orientation, the survivor order and the mask
 binarisation are each exercised on a case whose answer can be read off."""
+from pathlib import Path
+
 import numpy as np
+import pytest
 
 from oracle import frame_filter_oracle as FO
 
@@ -55,3 +58,31 @@ def test_rlbench_bounds_are_strict_and_masks_are_binarised():
     assert np.array_equal(col[:, 3], np.array([1.0, 0.0, -3.0], np.float32))  # valid id -> 1, invalid id -> 0, negative id kept
     c2, col2 = FO.rlbench_frame(pts, rgb)
     assert col2.shape[1] == 3 and np.array_equal(c2, c)
+
+
+# ---- pinned against the REFERENCE's own dataset __getitem__ (oracle/gen_golden_frames.py -> tests/golden/frame_filter_ref.npz) ----
+GOLD = np.load(Path(__file__).parent / "golden" / "frame_filter_ref.npz")
+MS_CASES = ("ms_1cam", "ms_2of3_crop", "ms_ground_crop")
+RL_CASES = ("rl_front", "rl_4cam_mask")
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+def test_maniskill2_oracle_matches_reference_getitem(case):
+    crop = tuple(int(v) for v in GOLD[f"{case}/crop"])
+    c, col = FO.maniskill2_frame(GOLD[f"{case}/xyzw"], GOLD[f"{case}/rgb"], include_ground=bool(GOLD[f"{case}/include_ground"]),
+                                 crop=None if crop[0] < 0 else crop)
+    ref_c, ref_col = GOLD[f"{case}/out_coord"], GOLD[f"{case}/out_color"]
+    assert ref_c.dtype == np.float32 and len(ref_c) > 5000
+    assert np.array_equal(c, ref_c)
+    assert np.array_equal(col, ref_col.astype(np.float32))
+
+
+@pytest.mark.parametrize("case", RL_CASES)
+def test_rlbench_oracle_matches_reference_getitem(case):
+    masks = GOLD[f"{case}/masks"] if bool(GOLD[f"{case}/use_mask"]) else None
+    c, col = FO.rlbench_frame(GOLD[f"{case}/point_maps"], GOLD[f"{case}/rgbs"], masks)
+    ref_c, ref_col = GOLD[f"{case}/out_coord"], GOLD[f"{case}/out_color"]
+    assert ref_c.dtype == np.float64 and len(ref_c) > 500       # the reference keeps float64 here; ToTensorPCD casts later
+    assert np.array_equal(c, ref_c.astype(np.float32)) and np.array_equal(c.astype(np.float64), ref_c)
+    assert np.array_equal(col, ref_col.astype(np.float32))
+    assert col.shape[1] == (4 if masks is not None else 3)

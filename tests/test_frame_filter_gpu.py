@@ -2,6 +2,8 @@
 survivor sets, order, coordinates, colours and per-sample offsets for both dataset families, incl. the random-crop window,
 include_ground, uint8 and fp32 colours, instance masks, samples with no survivors, and values sitting on the thresholds;
 then the composition with the voxel-grid stage (frames -> grid_sample_collate) against the oracles' composition."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -83,3 +85,32 @@ def test_frames_to_collated_batch_matches_the_oracle_pipeline():
     want = GO.grid_sample_collate(clouds, 0.02)
     for k in ("coord", "grid_coord", "feat", "offset"):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+# ---- against what the REFERENCE's own dataset __getitem__ produced (tests/golden/frame_filter_ref.npz, oracle/gen_golden_frames.py) ----
+GOLD = np.load(Path(__file__).parent / "golden" / "frame_filter_ref.npz")
+
+
+@pytest.mark.parametrize("case", ["ms_1cam", "ms_2of3_crop", "ms_ground_crop"])
+def test_maniskill2_frames_match_reference_getitem(case):
+    from pointcloudmatters_b200.data_gpu import filter_frames_maniskill2
+
+    crop = GOLD[f"{case}/crop"]
+    c, col, off = filter_frames_maniskill2(torch.from_numpy(GOLD[f"{case}/xyzw"])[None].cuda(), torch.from_numpy(GOLD[f"{case}/rgb"])[None].cuda(),
+                                           include_ground=bool(GOLD[f"{case}/include_ground"]), crop=None if crop[0] < 0 else crop[None])
+    assert int(off[-1]) == len(GOLD[f"{case}/out_coord"])
+    assert np.array_equal(c.cpu().numpy(), GOLD[f"{case}/out_coord"])
+    assert np.array_equal(col.cpu().numpy(), GOLD[f"{case}/out_color"].astype(np.float32))
+
+
+@pytest.mark.parametrize("case", ["rl_front", "rl_4cam_mask"])
+def test_rlbench_frames_match_reference_getitem(case):
+    from pointcloudmatters_b200.data_gpu import filter_frames_rlbench
+
+    use_mask = bool(GOLD[f"{case}/use_mask"])
+    masks = torch.from_numpy(GOLD[f"{case}/masks"].astype(np.float32))[None].cuda() if use_mask else None
+    c, col, off = filter_frames_rlbench(torch.from_numpy(GOLD[f"{case}/point_maps"])[None].cuda(),
+                                        torch.from_numpy(GOLD[f"{case}/rgbs"])[None].cuda(), masks)
+    assert int(off[-1]) == len(GOLD[f"{case}/out_coord"])
+    assert np.array_equal(c.cpu().numpy().astype(np.float64), GOLD[f"{case}/out_coord"])
+    assert np.array_equal(col.cpu().numpy(), GOLD[f"{case}/out_color"].astype(np.float32))
