@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) add_dropout_ln_bwd_kernel
             dh.w = rstd * (gy[v].w - c1 - xh[v].w * c2);
             if (dres) *reinterpret_cast<float4*>(dres + e) = dh;
             float4 o = dh;
-            if (dx && dx != dres) {
+            if ((dx || dx_bf16) && dx != dres) {  // dx == NULL with dx_bf16: only the bf16 copy of dx is wanted
                 if (p_drop > 0.f) {
                     const uint32_t c = (uint32_t)(v * 32 + lane);
                     const uint32_t h0 = pcm_pair_bits(rseed, 2 * c), h1 = pcm_pair_bits(rseed, 2 * c + 1);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) add_dropout_ln_bwd_kernel
                     o.z = (h1 & 0xFFFFu) >= thr16 ? dh.z * ks : 0.f;
                     o.w = (h1 >> 16) >= thr16 ? dh.w * ks : 0.f;
                 }
-                *reinterpret_cast<float4*>(dx + e) = o;
+                if (dx) *reinterpret_cast<float4*>(dx + e) = o;
             }
             if (CS) { axs[v].x += o.x; axs[v].y += o.y; axs[v].z += o.z; axs[v].w += o.w; }
             if (dx_bf16) {  // bf16 copy of dx: the operand of the sub-block's backward GEMMs
@@ -505,7 +505,8 @@ PCM_API int pcm_add_dropout_ln_fwd(long long rows, int C, const float* x, const 
 }
 
 // dres = dLN/dh; dx = dropout-backward(dres) (pass dx == dres or NULL when not needed);
-// dgamma / dbeta are ACCUMULATED (caller zero-fills); dx_bf16 (optional) = bf16(dx).
+// dgamma / dbeta are ACCUMULATED (caller zero-fills); dx_bf16 (optional) = bf16(dx).  dx == NULL with dx_bf16 given:
+// only the bf16 copy is written (the consumer is a GEMM; saves the fp32 store, 1/6 of the kernel's traffic).
 PCM_API int pcm_add_dropout_ln_bwd_ex2(long long rows, int C, const float* dy, const float* dy_b, const float* h, const float* mean,
                                        const float* rstd, const float* gamma, float p_drop,
                                        const unsigned long long* seed_base, unsigned long long seed_offset, float* dres,
@@ -513,7 +514,7 @@ PCM_API int pcm_add_dropout_ln_bwd_ex2(long long rows, int C, const float* dy, c
                                        pcm_stream_t stream) {
     if (rows <= 0) return PCM_OK;
     if (!dy || !h || !mean || !rstd || !gamma || !dgamma || !dbeta) return PCM_EINVAL;
-    if (dx_colsum && !dx) return PCM_EINVAL;
+    if (dx_colsum && !dx && !dx_bf16) return PCM_EINVAL;
     if (C % 128) return PCM_EUNSUPPORTED;
     cudaStream_t st = pcm_cu_stream(stream);
     const int grid = ln_grid_bwd(rows);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -121,6 +122,11 @@ def _grad_slot(p):
 #    a reference to the fp32 gradient (its memory cannot be recycled under a live key) and the table
 #    is emptied by the next LayerNorm backward, so a key can never outlive its tensor.
 _GRAD_BF16 = {}
+# fp32 LayerNorm-backward dx tensors that were NOT written (only their bf16 copy exists, see _AddDropoutLN.backward):
+# address -> weak reference.  A consumer that misses the side-channel entry for one that is still alive (so the address
+# cannot have been recycled) must not read it: _grad_bf16 raises instead of casting garbage.
+_DX_UNWRITTEN = {}
+_NO_LN_DX_BF16_ONLY = bool(int(os.environ.get("PCM_LN_DX_FP32", "0")))  # A/B switch: also write the fp32 dx
 # second gradient tensor travelling with the one autograd carries (two-handle outputs, see _FillHeadRows): keyed by the
 # carried gradient's address, value (second gradient, carried gradient); popped by the consumer
 _GRAD_EXTRA = {}
@@ -149,7 +155,12 @@ def _grad_bf16(g, rows, C, bias=None):
     e = _GRAD_BF16.pop(g.data_ptr(), None)
     if e is not None and e[1].data_ptr() == g.data_ptr() and e[1].numel() == g.numel() == rows * C and g.is_contiguous():
         out = e[0].view(rows, C)
+        _DX_UNWRITTEN.pop(g.data_ptr(), None)
         return (out, len(e) > 2 and e[2] is bias and bias is not None) if bias is not None else out
+    ref = _DX_UNWRITTEN.pop(g.data_ptr(), None)
+    if ref is not None and ref() is not None:
+        raise PcmError("gradient tensor holds no fp32 data (the LayerNorm backward wrote only its bf16 copy) and its "
+                       "side-channel entry is gone: backward order violated the producer-before-next-LayerNorm assumption")
     g2 = g.reshape(rows, C)
     out = K.add_cast_bf16(g2 if g2.is_contiguous() else g2.contiguous())
     return (out, False) if bias is not None else out
@@ -902,7 +913,7 @@ class _AddDropoutLN(torch.autograd.Function):
     GEMMs; the backward leaves bf16(dx) for the sub-block backward that consumes dx."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps, p_drop, want_bf16, pos, x_bias=None):
+    def forward(ctx, x, res, gamma, beta, eps, p_drop, want_bf16, pos, x_bias=None, x_exclusive=False):
         """`x_bias`: the bias Parameter of the linear layer that produced `x` (out_proj.bias / linear2.bias): its gradient
         is colsum(dx), accumulated by the backward kernel itself when the parameter owns a flat-gradient slot."""
         shape = res.shape
@@ -921,6 +932,7 @@ class _AddDropoutLN(torch.autograd.Function):
         ctx.save_for_backward(h, mean, rstd, gamma)
         ctx.cfg = (p_drop, seed_base, seed, x is not None, shape)
         ctx.params = (gamma, beta, x_bias if x is not None else None)
+        ctx.x_exclusive = bool(x_exclusive)
         yv = y.view(shape)
         # second handle on the same storage (not an autograd view of the first): consumers that use y as the
         # RESIDUAL operand of the next LayerNorm take this one, so the two gradient contributions of y arrive
@@ -937,7 +949,7 @@ class _AddDropoutLN(torch.autograd.Function):
         if dy is None:
             dy, dy_res = dy_res, None
         if dy is None:
-            return (None,) * 9
+            return (None,) * 10
         h, mean, rstd, gamma = ctx.saved_tensors
         p_drop, seed_base, seed, has_x, shape = ctx.cfg
         dy2 = dy.reshape(h.shape)
@@ -951,23 +963,33 @@ class _AddDropoutLN(torch.autograd.Function):
         g_slot, b_slot = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
         x_bias = ctx.params[2]
         xb_slot = _grad_slot(x_bias) if x_bias is not None else None
+        # x tagged with its producer's bias (`_pcm_bias`: the fused attention block / the FFN) and declared by the caller to
+        # feed nothing but this LayerNorm: that producer's backward takes bf16(dx) from the side channel and never reads
+        # the fp32 tensor, which is then left unwritten (placeholder)
+        bf16_only = has_x and x_bias is not None and ctx.x_exclusive and not _NO_LN_DX_BF16_ONLY
         dres, dx, dgamma, dbeta, dxb = K.add_dropout_ln_bwd(dy2, h, mean, rstd, gamma, p_drop, seed_base, seed, has_x,
                                                             dgamma=g_slot, dbeta=b_slot, want_dx_bf16=has_x, dy_b=dyr,
-                                                            dx_colsum=xb_slot)
+                                                            dx_colsum=xb_slot, dx_fp32=not bf16_only)
         _GRAD_BF16.clear()
         dx_out = None
         if has_x:
             dx_out = dx.view(shape)
             _GRAD_BF16[dx_out.data_ptr()] = (dxb, dx_out, x_bias if xb_slot is not None else None)
+            if bf16_only:
+                for k in [k for k, r in _DX_UNWRITTEN.items() if r() is None]:
+                    del _DX_UNWRITTEN[k]
+                _DX_UNWRITTEN[dx_out.data_ptr()] = weakref.ref(dx_out)
         return (dx_out, dres.view(shape), None if g_slot is not None else dgamma, None if b_slot is not None else dbeta,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
-def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=None):
+def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=None, x_exclusive=False):
     """LayerNorm(residual + dropout(x)) -- the post-LN epilogue of every transformer sub-block.
     `x` may be None (plain LayerNorm of `residual`).  `cast` / `cast_pos`: also produce the bf16
     operand copies bf16(y) / bf16(y + cast_pos) that the NEXT sub-block's GEMMs read (attached to the
-    returned tensor; see _act_bf16)."""
+    returned tensor; see _act_bf16).  `x_exclusive`: the caller guarantees that `x` (a fused attention block's or FFN's
+    output) is used by this call only, so its fp32 gradient need not be materialised (the producer's backward reads the
+    bf16 copy)."""
     _need_cuda(residual)
     C = residual.shape[-1]
     p_eff = p if (training and p > 0) else 0.0
@@ -981,7 +1003,7 @@ def add_dropout_layernorm(x, residual, norm, p, training, cast=False, cast_pos=N
             res_in = residual
         y, yb, ypb, y_res = _AddDropoutLN.apply(xr, res_in.contiguous(), norm.weight, norm.bias, norm.eps, p_eff, bool(cast),
                                                 None if cast_pos is None else cast_pos.detach(),
-                                                getattr(x, "_pcm_bias", None) if x is not None else None)
+                                                getattr(x, "_pcm_bias", None) if x is not None else None, bool(x_exclusive))
         y._pcm_res = y_res
         if yb is not None:
             y._pcm_bf16 = yb

@@ -224,20 +224,22 @@ def add_dropout_ln_fwd(x, res, gamma, beta, eps, p_drop, seed_base, seed_offset,
 
 
 def add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p_drop, seed_base, seed_offset, need_dx, dgamma=None, dbeta=None,
-                       want_dx_bf16=False, dy_b=None, dx_colsum=None):
+                       want_dx_bf16=False, dy_b=None, dx_colsum=None, dx_fp32=True):
     """dgamma / dbeta, when given, are ACCUMULATED into (the kernel adds with atomics); so is `dx_colsum` (C floats):
     the column sums of dx = the bias gradient of the linear layer that produced x.
+    `dx_fp32=False` (needs want_dx_bf16): the fp32 dx is NOT written -- the returned tensor is an unwritten placeholder.
     Returns (dres, dx, dgamma, dbeta, dx_bf16)."""
     rows, C = h.shape
     dres = torch.empty_like(h)
-    dx = (torch.empty_like(h) if p_drop > 0 else dres) if need_dx else None
+    dx = (torch.empty_like(h) if (p_drop > 0 or not dx_fp32) else dres) if need_dx else None
+    skip = need_dx and want_dx_bf16 and not dx_fp32
     if dgamma is None:
         dgamma = torch.zeros(C, dtype=torch.float32, device=h.device)
     if dbeta is None:
         dbeta = torch.zeros(C, dtype=torch.float32, device=h.device)
     dxb = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device) if (want_dx_bf16 and need_dx) else None
     check(lib.pcm_add_dropout_ln_bwd_ex2(rows, C, ptr(dy), ptr(dy_b), ptr(h), ptr(mean), ptr(rstd), ptr(gamma), float(p_drop),
-                                         ptr(seed_base), int(seed_offset), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                         ptr(seed_base), int(seed_offset), ptr(dres), ptr(None if skip else dx), ptr(dgamma), ptr(dbeta),
                                          ptr(dxb), ptr(dx_colsum if need_dx else None), current_stream()),
           "pcm_add_dropout_ln_bwd_ex2")
     return dres, dx, dgamma, dbeta, dxb

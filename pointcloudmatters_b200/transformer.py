@@ -54,8 +54,8 @@ class TransformerEncoderLayer(nn.Module):
         a = PF.multi_head_attention(self.self_attn, src, pos, None, None, src_key_padding_mask, tr, pos_head=pos_head)
         # norm1 feeds the FFN (bf16 copy), norm2 feeds the next layer's attention / the decoder's
         # cross-attention (bf16(y) for values, bf16(y + pos) for queries and keys)
-        src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr, cast=True)
-        return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr, cast=True, cast_pos=pos)
+        src = PF.add_dropout_layernorm(a, src, self.norm1, self.p, tr, cast=True, x_exclusive=True)
+        return PF.add_dropout_layernorm(self._ffn(src), src, self.norm2, self.p, tr, cast=True, cast_pos=pos, x_exclusive=True)
 
 
 class TransformerEncoder(nn.Module):
@@ -117,12 +117,13 @@ class TransformerDecoderLayer(nn.Module):
             t2 = ln(tgt, self.norm3)
             return tgt + PF.dropout(self._ffn(t2), self.p, tr)
         a = PF.multi_head_attention(self.self_attn, tgt, query_pos, None, None, None, tr)
-        tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr, cast_pos=query_pos)  # -> cross-attention queries
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm1, self.p, tr, cast_pos=query_pos, x_exclusive=True)  # -> cross-attention queries
         a = PF.multi_head_attention(self.multihead_attn, tgt, query_pos, memory, pos, memory_key_padding_mask, tr,
                                     mem_pos_head=pos_head, memkv=memkv)
-        tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr, cast=True)  # -> FFN
+        tgt = PF.add_dropout_layernorm(a, tgt, self.norm2, self.p, tr, cast=True, x_exclusive=True)  # -> FFN
         # -> next layer's self-attention
-        return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr, cast=True, cast_pos=query_pos)
+        return PF.add_dropout_layernorm(self._ffn(tgt), tgt, self.norm3, self.p, tr, cast=True, cast_pos=query_pos,
+                                        x_exclusive=True)
 
 
 class _FirstOfStack(torch.autograd.Function):

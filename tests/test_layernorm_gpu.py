@@ -64,6 +64,65 @@ def test_add_dropout_ln_dropout_mask_is_consistent():
     torch.testing.assert_close(x.grad[kept], (r.grad / (1 - p))[kept], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_ln_backward_bf16_only_dx_equals_the_fp32_form(p):
+    """dx_fp32=False: the kernel skips the fp32 dx store; dres, bf16(dx), dgamma / dbeta and colsum(dx) are unchanged
+    (up to the order of the atomics), and the placeholder is not touched."""
+    from pointcloudmatters_b200 import kernels as K
+
+    rows, C = 3000, 512
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h = torch.randn(rows, C, device="cuda", generator=g)
+    dy = torch.randn(rows, C, device="cuda", generator=g)
+    gamma = torch.randn(C, device="cuda", generator=g)
+    mean, rstd = h.mean(1), 1.0 / torch.sqrt(h.var(1, unbiased=False) + 1e-5)
+    sb = torch.tensor([99], dtype=torch.int64, device="cuda")
+    outs = []
+    for fp32 in (True, False):
+        cs = torch.zeros(C, device="cuda")
+        dres, dx, dg, db, dxb = K.add_dropout_ln_bwd(dy, h, mean, rstd, gamma, p, sb if p > 0 else None, 5, True, want_dx_bf16=True,
+                                                     dx_colsum=cs, dx_fp32=fp32)
+        outs.append((dres, dx, dg, db, dxb, cs))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[4], b[4])
+    assert torch.equal(a[4], a[1].bfloat16())
+    assert b[1].data_ptr() != b[0].data_ptr()
+    for i in (2, 3, 5):
+        torch.testing.assert_close(a[i], b[i], rtol=1e-4, atol=1e-3)
+
+
+def test_unwritten_dx_is_never_cast():
+    """A consumer that misses the side-channel entry of a bf16-only dx must raise, not read the placeholder."""
+    from pointcloudmatters_b200 import functional as PF
+    from pointcloudmatters_b200._lib import PcmError
+
+    C = 512
+    norm = torch.nn.LayerNorm(C).cuda()
+    bias = torch.nn.Parameter(torch.zeros(C, device="cuda"))
+    x = torch.randn(4, 8, C, device="cuda", requires_grad=True)
+    seen = {}
+
+    class Probe(torch.autograd.Function):  # stands in for a producer that tags its output but loses the side channel
+        @staticmethod
+        def forward(ctx, t):
+            return t.clone()
+
+        @staticmethod
+        def backward(ctx, gr):
+            PF._GRAD_BF16.clear()
+            try:
+                PF._grad_bf16(gr, 32, C)
+            except PcmError as e:
+                seen["err"] = str(e)
+            return torch.zeros_like(gr)
+
+    xo = Probe.apply(x)
+    xo._pcm_bias = bias
+    y = PF.add_dropout_layernorm(xo, torch.randn(4, 8, C, device="cuda"), norm, 0.1, True, x_exclusive=True)
+    y.sum().backward()
+    assert "no fp32 data" in seen.get("err", "")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_colsum(dtype):
     from pointcloudmatters_b200.kernels import colsum
