@@ -25,7 +25,7 @@ b["pcds"]["n_max"] = hb["pcds"]["n_max"]
 for i in range(3):
     module.training_step(b, i)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True, record_shapes=True) as prof:
     module.training_step(b, 3)
     torch.cuda.synchronize()
 agg = defaultdict(lambda: [0, 0.0])
@@ -42,3 +42,22 @@ tot = sum(v[1] for v in agg.values())
 print(f"# aten ops with device time, one eager cfg-2 step: {tot:.0f} us in {sum(v[0] for v in agg.values())} calls")
 for (op, site), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{t:8.1f} us {n:4d}x  {op:28s} {site}")
+
+# second view: by (op, input shapes, enclosing non-aten profiler range = the autograd node / python function that issued it)
+agg2 = defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    dt = getattr(e, "self_device_time_total", 0)
+    if not e.name.startswith("aten::") or dt <= 0:
+        continue
+    par, owner = e.cpu_parent, "(top level)"
+    while par is not None:
+        if not par.name.startswith("aten::"):
+            owner = par.name
+            break
+        par = par.cpu_parent
+    shapes = str([s for s in (e.input_shapes or []) if s])[:70]
+    agg2[(e.name, shapes, owner[:70])][0] += 1
+    agg2[(e.name, shapes, owner[:70])][1] += dt
+print("\n# by op / input shapes / issuing range")
+for (op, shp, owner), (n, t) in sorted(agg2.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f"{t:8.1f} us {n:4d}x  {op:18s} {shp:72s} {owner}")
